@@ -1,0 +1,114 @@
+/* sage2gpu.h -- C ABI of libsage2gpu: SAGE2 steps 1-3 (organise reads, prefix/suffix hash table,
+ * economy overlap graph) on one NVIDIA B200 (sm_100a).
+ *
+ * The reference has no plugin / FFI layer: its boundary is the C++ object protocol main.cpp drives
+ * (main.cpp:37-132).  Each entry point below names the reference call(s) it replaces; paths are
+ * relative to the SAGE2 source tree.  INTEGRATION.md shows the shim a maintainer adds to main.cpp
+ * and the makefile link line.
+ *
+ * Conventions: plain C types, caller-owned host buffers, library-owned device memory, no exceptions
+ * across the ABI.  Every function returns 0 on success and a non-zero code on failure;
+ * sage2gpu_last_error() then describes the failure (the reference's convention is printError ->
+ * log + exit, utils.cpp:36-40; the host shim forwards the string to it).  There is no CPU fallback:
+ * without a CUDA device sage2gpu_create() fails.
+ *
+ * Read ids are the reference's: 1-based ranks of the unique canonical reads in
+ * Read::operator< order (readLoader.cpp:11-18,215-260).
+ */
+#ifndef SAGE2GPU_H
+#define SAGE2GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sage2gpu_ctx sage2gpu_ctx;
+
+enum { SAGE2GPU_OK = 0, SAGE2GPU_ERR_CUDA = 1, SAGE2GPU_ERR_ARG = 2, SAGE2GPU_ERR_STATE = 3, SAGE2GPU_ERR_IO = 4 };
+
+/* Log counters of the reference (readLoader.cpp:164-169,257; hashTable.cpp:86,124;
+ * economyGraph.cpp:485-487,569-571) plus the workload sizes the roofline needs. */
+typedef struct {
+    uint64_t total_reads, good_reads, unique_reads, total_bp, avg_len;
+    uint64_t hash_len, distinct_keys, keys_over_threshold, table_capacity;
+    uint64_t contained_ext, contained_size, left_to_explore;
+    uint64_t edges_phase_b, candidates_c, edges_inserted_c, transitive_removed;
+    uint64_t n_edges;
+    uint64_t compare_calls;     /* V of SURVEY 8(d): gated partner comparisons in phase A */
+    uint64_t window_probes;     /* U*W table probes in phase A */
+    uint64_t slow_path_reads;
+    uint64_t record_words;      /* 64-bit words per packed read record */
+} sage2gpu_counters;
+
+/* Stage times in milliseconds (CUDA events on the context's stream; host part by steady_clock). */
+typedef struct {
+    float ingest, sort_reads, build_table, phase_a, phase_b, phase_c_dev, phase_c_host, sort_edges, total;
+} sage2gpu_timers;
+
+/* One undirected edge as OverlapGraph::convertGraph creates it (overlapGraph.cpp:84-159):
+ * from < to; `type` and `delta` describe from->to, `delta_twin` the twin to->from
+ * (type of the twin = reverseEdgeType(type), utils.cpp:212-219). */
+typedef struct {
+    uint64_t from, to;
+    uint32_t type, delta, delta_twin, reserved;
+} sage2gpu_edge;
+
+/* replaces: object construction in main.cpp:44,76,108.  device = CUDA ordinal. */
+int  sage2gpu_create(sage2gpu_ctx **ctx, int device);
+void sage2gpu_destroy(sage2gpu_ctx *ctx);
+const char *sage2gpu_last_error(const sage2gpu_ctx *ctx);
+
+/* replaces: ReadLoader::readDatasetInBytes' per-read work + organizeReads
+ * (readLoader.cpp:133-260; isGoodRead utils.cpp:144, insertReadIntoList readLoader.cpp:179).
+ * `bases` = the read sequences concatenated (ASCII, any case), read r = bases[offsets[r],
+ * offsets[r+1]).  Host buffers (pinned memory makes the upload asynchronous).  Reads with
+ * length <= min_overlap or a non-ACGT character are dropped exactly like the reference does. */
+int sage2gpu_load_reads(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
+                        int64_t n_reads, int min_overlap);
+/* Same, with both buffers already resident in this context's device memory. */
+int sage2gpu_load_reads_device(sage2gpu_ctx *ctx, const uint8_t *d_bases, const int64_t *d_offsets,
+                               int64_t n_reads, int min_overlap);
+
+/* replaces: HashTable::hashPrefixesAndSuffix (hashTable.cpp:70-128) */
+int sage2gpu_build_hash_table(sage2gpu_ctx *ctx);
+
+/* replaces: EconomyGraph::buildInitialOverlapGraph + buildOverlapGraphEconomy + sortEconomyGraph
+ * (economyGraph.cpp:37-574,896-913) and the edge selection of OverlapGraph::convertGraph
+ * (overlapGraph.cpp:93-112).  Leaves the canonical edge list on the device and a copy on the host. */
+int sage2gpu_build_overlap_graph(sage2gpu_ctx *ctx);
+
+/* All three steps back to back (main.cpp:37-132 without the file I/O). */
+int sage2gpu_run_steps123(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
+                          int64_t n_reads, int min_overlap);
+
+int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *out);
+/* Number of CUDA kernels this library has launched in this process so far (monotonic). */
+uint64_t sage2gpu_kernel_launches(void);
+int sage2gpu_get_timers(const sage2gpu_ctx *ctx, sage2gpu_timers *out);
+
+/* replaces: what steps 4-7 read through ReadLoader::getRead (readLoader.cpp:309): for ids 1..U the
+ * length, frequency and both packed strands in the REFERENCE byte layout (utils.cpp:96-119).
+ * byte_off has U+1 entries (byte_off[i-1] = start of read i); fwd/rc need byte_off[U] bytes
+ * (query with sage2gpu_reads_bytes). */
+int sage2gpu_reads_bytes(const sage2gpu_ctx *ctx, uint64_t *n_bytes);
+int sage2gpu_get_reads(sage2gpu_ctx *ctx, uint16_t *length, uint16_t *frequency, uint64_t *byte_off,
+                       uint8_t *fwd, uint8_t *rc);
+
+/* Phase A / B state for inspection: packed extension records (id | type<<32 | overhang<<33) of
+ * rightExtension / leftExtension (economyGraph.cpp:46-47) and exploredReads after phase B. */
+int sage2gpu_get_extensions(sage2gpu_ctx *ctx, uint64_t *right_ext, uint64_t *left_ext, uint8_t *explored);
+
+/* replaces: the economyGraphList hand-over to convertGraph.  capacity in edges; *n_edges receives the
+ * total (call with out=NULL to size).  Order = the order convertGraph creates / .graph3 lists them. */
+int sage2gpu_get_edges(sage2gpu_ctx *ctx, sage2gpu_edge *out, uint64_t capacity, uint64_t *n_edges);
+
+/* replaces: ReadLoader::saveReadsInFile (readLoader.cpp:270-287) and
+ * OverlapGraph::saveOverlapGraphInFile (overlapGraph.cpp:338-369): the reference's -s text formats,
+ * byte for byte, so that `SAGE2 -m 4 -i <prefix>` continues from them. */
+int sage2gpu_write_reads(sage2gpu_ctx *ctx, const char *path);
+int sage2gpu_write_graph3(sage2gpu_ctx *ctx, const char *path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,252 @@
+"""Python host side of libsage2gpu (ctypes over the C ABI in include/sage2gpu.h).
+
+`Sage2Gpu` is the thin handle; `ReadLoader`, `HashTable` and `EconomyGraph` mirror the reference's
+step-1..3 classes and method names (inputReader/readLoader.h:32-56, economyGraph/hashTable.h:20-44,
+economyGraph/economyGraph.h:32-54) so that the parity tests read like a reference driver
+(main.cpp:37-132).  There is no CPU fallback: if libsage2gpu.so is missing or no CUDA device is
+present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsage2gpu.so")
+
+
+class Sage2GpuError(RuntimeError):
+    pass
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "total_reads", "good_reads", "unique_reads", "total_bp", "avg_len",
+        "hash_len", "distinct_keys", "keys_over_threshold", "table_capacity",
+        "contained_ext", "contained_size", "left_to_explore",
+        "edges_phase_b", "candidates_c", "edges_inserted_c", "transitive_removed",
+        "n_edges", "compare_calls", "window_probes", "slow_path_reads", "record_words")]
+
+
+class Timers(C.Structure):
+    _fields_ = [(n, C.c_float) for n in (
+        "ingest", "sort_reads", "build_table", "phase_a", "phase_b", "phase_c_dev", "phase_c_host",
+        "sort_edges", "total")]
+
+
+EDGE_DT = np.dtype([("from", "<u8"), ("to", "<u8"), ("type", "<u4"), ("delta", "<u4"),
+                    ("delta_twin", "<u4"), ("reserved", "<u4")])
+
+EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2gpu_load_reads",
+           "sage2gpu_load_reads_device", "sage2gpu_build_hash_table", "sage2gpu_build_overlap_graph",
+           "sage2gpu_run_steps123", "sage2gpu_get_counters", "sage2gpu_get_timers", "sage2gpu_reads_bytes",
+           "sage2gpu_get_reads", "sage2gpu_get_extensions", "sage2gpu_get_edges", "sage2gpu_write_reads",
+           "sage2gpu_write_graph3", "sage2gpu_kernel_launches"]
+
+_lib = None
+
+
+def build_library(force: bool = False) -> None:
+    """Compile libsage2gpu.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", os.path.join(HERE, "csrc"), "-j8"]
+    if force:
+        subprocess.check_call(args + ["clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Sage2GpuError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        vp, i64, u64p = C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)
+        lib.sage2gpu_create.argtypes = [C.POINTER(vp), C.c_int]
+        lib.sage2gpu_destroy.argtypes = [vp]
+        lib.sage2gpu_destroy.restype = None
+        lib.sage2gpu_last_error.argtypes = [vp]
+        lib.sage2gpu_last_error.restype = C.c_char_p
+        lib.sage2gpu_load_reads.argtypes = [vp, vp, vp, i64, C.c_int]
+        lib.sage2gpu_load_reads_device.argtypes = [vp, vp, vp, i64, C.c_int]
+        lib.sage2gpu_build_hash_table.argtypes = [vp]
+        lib.sage2gpu_build_overlap_graph.argtypes = [vp]
+        lib.sage2gpu_run_steps123.argtypes = [vp, vp, vp, i64, C.c_int]
+        lib.sage2gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
+        lib.sage2gpu_get_timers.argtypes = [vp, C.POINTER(Timers)]
+        lib.sage2gpu_reads_bytes.argtypes = [vp, u64p]
+        lib.sage2gpu_get_reads.argtypes = [vp, vp, vp, vp, vp, vp]
+        lib.sage2gpu_get_extensions.argtypes = [vp, vp, vp, vp]
+        lib.sage2gpu_get_edges.argtypes = [vp, vp, C.c_uint64, u64p]
+        lib.sage2gpu_write_reads.argtypes = [vp, C.c_char_p]
+        lib.sage2gpu_write_graph3.argtypes = [vp, C.c_char_p]
+        lib.sage2gpu_kernel_launches.argtypes = []
+        lib.sage2gpu_kernel_launches.restype = C.c_uint64
+        _lib = lib
+    return _lib
+
+
+def kernel_launches() -> int:
+    """CUDA kernels launched by libsage2gpu in this process so far."""
+    return int(load_library().sage2gpu_kernel_launches())
+
+
+class Sage2Gpu:
+    """One libsage2gpu context = one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.sage2gpu_create(C.byref(self._h), device)
+        if rc != 0:
+            raise Sage2GpuError(f"sage2gpu_create(device={device}) failed with code {rc}: no usable CUDA device "
+                                "(libsage2gpu has no CPU fallback)")
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.sage2gpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.sage2gpu_last_error(self._h)
+            raise Sage2GpuError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ---- steps --------------------------------------------------------------------------------
+    def load_reads(self, bases: np.ndarray, offsets: np.ndarray, min_overlap: int):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep = (bases, offsets)
+        self._check(self._lib.sage2gpu_load_reads(self._h, bases.ctypes.data, offsets.ctypes.data,
+                                                  len(offsets) - 1, int(min_overlap)), "load_reads")
+
+    def load_reads_ptr(self, bases_ptr: int, offsets_ptr: int, n_reads: int, min_overlap: int, device: bool):
+        fn = self._lib.sage2gpu_load_reads_device if device else self._lib.sage2gpu_load_reads
+        self._check(fn(self._h, bases_ptr, offsets_ptr, int(n_reads), int(min_overlap)), "load_reads")
+
+    def build_hash_table(self):
+        self._check(self._lib.sage2gpu_build_hash_table(self._h), "build_hash_table")
+
+    def build_overlap_graph(self):
+        self._check(self._lib.sage2gpu_build_overlap_graph(self._h), "build_overlap_graph")
+
+    def run_steps123(self, bases, offsets, min_overlap: int):
+        self.load_reads(bases, offsets, min_overlap)
+        self.build_hash_table()
+        self.build_overlap_graph()
+
+    # ---- results ------------------------------------------------------------------------------
+    def counters(self) -> dict:
+        c = Counters()
+        self._check(self._lib.sage2gpu_get_counters(self._h, C.byref(c)), "get_counters")
+        return {n: int(getattr(c, n)) for n, _ in Counters._fields_}
+
+    def timers(self) -> dict:
+        t = Timers()
+        self._check(self._lib.sage2gpu_get_timers(self._h, C.byref(t)), "get_timers")
+        return {n: float(getattr(t, n)) for n, _ in Timers._fields_}
+
+    def reads(self) -> dict:
+        U = self.counters()["unique_reads"]
+        nb = C.c_uint64()
+        self._check(self._lib.sage2gpu_reads_bytes(self._h, C.byref(nb)), "reads_bytes")
+        out = dict(length=np.zeros(U, np.uint16), frequency=np.zeros(U, np.uint16),
+                   byte_off=np.zeros(U + 1, np.uint64), fwd=np.zeros(nb.value, np.uint8), rc=np.zeros(nb.value, np.uint8))
+        self._check(self._lib.sage2gpu_get_reads(self._h, out["length"].ctypes.data, out["frequency"].ctypes.data,
+                                                 out["byte_off"].ctypes.data, out["fwd"].ctypes.data,
+                                                 out["rc"].ctypes.data), "get_reads")
+        return out
+
+    def extensions(self) -> dict:
+        U = self.counters()["unique_reads"]
+        out = dict(right=np.zeros(U, np.uint64), left=np.zeros(U, np.uint64), explored=np.zeros(U, np.uint8))
+        self._check(self._lib.sage2gpu_get_extensions(self._h, out["right"].ctypes.data, out["left"].ctypes.data,
+                                                      out["explored"].ctypes.data), "get_extensions")
+        return out
+
+    def edges(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(self._lib.sage2gpu_get_edges(self._h, None, 0, C.byref(n)), "get_edges")
+        out = np.zeros(n.value, dtype=EDGE_DT)
+        if n.value:
+            self._check(self._lib.sage2gpu_get_edges(self._h, out.ctypes.data, n.value, C.byref(n)), "get_edges")
+        return out
+
+    def write_reads(self, path: str):
+        self._check(self._lib.sage2gpu_write_reads(self._h, path.encode()), "write_reads")
+
+    def write_graph3(self, path: str):
+        self._check(self._lib.sage2gpu_write_graph3(self._h, path.encode()), "write_graph3")
+
+
+# ---- mirrors of the reference's step 1-3 classes (main.cpp:37-132) ---------------------------------
+
+class ReadLoader:
+    """inputReader/readLoader.h:32-56."""
+
+    def __init__(self, minOvlp: int, device: int = 0):
+        self.minOverlap = int(minOvlp)
+        self.gpu = Sage2Gpu(device)
+        self.numberOfReads = self.numberOfUniqueReads = self.totalBP = 0
+        self._pending = None
+
+    def readDatasetInBytes(self, reads):
+        """`reads`: list[bytes] / (N,L) uint8 array of sequences (the FASTQ parse is the caller's)."""
+        from . import synth
+        self._pending = synth.concat(reads)
+
+    def organizeReads(self):
+        bases, offsets = self._pending
+        self.gpu.load_reads(bases, offsets, self.minOverlap)
+        c = self.gpu.counters()
+        self.numberOfReads, self.numberOfUniqueReads, self.totalBP = c["good_reads"], c["unique_reads"], c["total_bp"]
+        self.averageReadLength = c["avg_len"]
+
+    def saveReadsInFile(self, path: str):
+        self.gpu.write_reads(path)
+
+
+class HashTable:
+    """economyGraph/hashTable.h:20-44."""
+
+    def __init__(self, minOvlp: int, loader: ReadLoader):
+        self.minOverlap, self.loaderObj = int(minOvlp), loader
+
+    def hashPrefixesAndSuffix(self):
+        self.loaderObj.gpu.build_hash_table()
+        c = self.loaderObj.gpu.counters()
+        self.hashStringLength, self.sizeOfHashTable = c["hash_len"], c["table_capacity"]
+
+
+class EconomyGraph:
+    """economyGraph/economyGraph.h:32-54; the three calls of main.cpp:109-114 map onto one device pass."""
+
+    def __init__(self, minOvlp: int, hash1: HashTable):
+        self.minOverlap, self.hashObj, self.loaderObj = int(minOvlp), hash1, hash1.loaderObj
+        self._built = False
+
+    def buildInitialOverlapGraph(self):
+        self.loaderObj.gpu.build_overlap_graph()
+        self._built = True
+
+    def buildOverlapGraphEconomy(self):
+        if not self._built:
+            raise Sage2GpuError("buildInitialOverlapGraph must run first (main.cpp:109-111)")
+
+    def sortEconomyGraph(self):
+        if not self._built:
+            raise Sage2GpuError("buildInitialOverlapGraph must run first")
+
+    def saveOverlapGraphInFile(self, path: str):
+        """OverlapGraph::convertGraph + saveOverlapGraphInFile (overlapGraph.cpp:84-115,338-369)."""
+        self.loaderObj.gpu.write_graph3(path)

@@ -1,0 +1,362 @@
+// api.cu -- the C ABI of libsage2gpu (include/sage2gpu.h) over the stages in reads.cu, table.cu,
+// search.cu and graph.cu, plus the host-side seams to the reference's formats.
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../include/sage2gpu.h"
+#include "context.h"
+
+struct sage2gpu_ctx {
+    sg::Context c;
+};
+
+namespace {
+
+struct StageTimer {
+    cudaEvent_t a, b;
+    cudaStream_t st;
+    explicit StageTimer(cudaStream_t s) : st(s)
+    {
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+    float stop()
+    {
+        float ms = 0;
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
+    ~StageTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+template <typename Fn>
+int guarded(sage2gpu_ctx *ctx, Fn fn)
+{
+    if (!ctx) return SAGE2GPU_ERR_ARG;
+    try {
+        SG_CUDA(cudaSetDevice(ctx->c.device));
+        fn(ctx->c);
+        ctx->c.last_error.clear();
+        return SAGE2GPU_OK;
+    } catch (const sg::CudaError &e) {
+        ctx->c.last_error = e.what();
+        cudaGetLastError();
+        return SAGE2GPU_ERR_CUDA;
+    } catch (const std::exception &e) {
+        ctx->c.last_error = e.what();
+        return SAGE2GPU_ERR_STATE;
+    }
+}
+
+void load_common(sg::Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n, int k, bool dev)
+{
+    SG_CHECK(k >= 1 && k < 65535, "min_overlap out of range");
+    SG_CHECK(n == 0 || (bases != nullptr && offsets != nullptr), "null input");
+    c.min_overlap = k;
+    c.tm = sg::Timers();
+    {
+        StageTimer t(c.stream);
+        sg::stage_ingest_ascii(c, bases, offsets, n, dev);
+        c.tm.ingest = t.stop();
+    }
+    {
+        StageTimer t(c.stream);
+        sg::stage_organize_reads(c);
+        c.tm.sort_reads = t.stop();
+    }
+}
+
+// record (word-big-endian) -> reference bytes (utils.cpp:96-119)
+void record_to_bytes(const sg::u64 *rec, int len, uint8_t *out)
+{
+    const int nb = (len + 3) / 4;
+    for (int b = 0; b < nb; ++b) out[b] = (uint8_t)(rec[b >> 3] >> (56 - 8 * (b & 7)));
+}
+
+struct HostReads {
+    std::vector<uint16_t> len, freq;
+    std::vector<sg::u64> F, RC;
+};
+
+void fetch_reads(sg::Context &c, HostReads &h)
+{
+    SG_CHECK(c.have_reads, "no reads loaded");
+    const sg::u64 U = c.cnt.unique_reads;
+    h.len.resize(U); h.freq.resize(U); h.F.resize(U * c.SW); h.RC.resize(U * c.SW);
+    if (U == 0) return;
+    SG_CUDA(cudaMemcpyAsync(h.len.data(), c.len.p, U * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
+    SG_CUDA(cudaMemcpyAsync(h.freq.data(), c.freq.p, U * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
+    SG_CUDA(cudaMemcpyAsync(h.F.data(), c.F.p, U * c.SW * sizeof(sg::u64), cudaMemcpyDeviceToHost, c.stream));
+    SG_CUDA(cudaMemcpyAsync(h.RC.data(), c.RC.p, U * c.SW * sizeof(sg::u64), cudaMemcpyDeviceToHost, c.stream));
+    SG_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+void fetch_edges(sg::Context &c)
+{
+    SG_CHECK(c.have_graph, "overlap graph not built");
+    const sg::u64 E = c.cnt.n_edges;
+    if (c.h_edges.size() == 2 * E) return;
+    c.h_edges.resize(2 * E);
+    if (E) {
+        SG_CUDA(cudaMemcpyAsync(c.h_edges.data(), c.edges.p, 2 * E * sizeof(sg::u64), cudaMemcpyDeviceToHost, c.stream));
+        SG_CUDA(cudaStreamSynchronize(c.stream));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sage2gpu_create(sage2gpu_ctx **out, int device)
+{
+    if (!out) return SAGE2GPU_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SAGE2GPU_ERR_CUDA;
+    sage2gpu_ctx *ctx = new sage2gpu_ctx();
+    ctx->c.device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SAGE2GPU_ERR_CUDA;
+    }
+    // keep freed blocks in the stream-ordered pool: steady-state allocation is a pointer bump
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return SAGE2GPU_OK;
+}
+
+void sage2gpu_destroy(sage2gpu_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStream_t st = ctx->c.stream;
+    cudaStreamSynchronize(st);
+    {
+        sg::Context &c = ctx->c;
+        c.d_bases.release(); c.d_offsets.release(); c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
+        c.slots.release(); c.entries.release(); c.extR.release(); c.extL.release(); c.flag5.release();
+        c.cont_max.release(); c.explored.release(); c.edges.release();
+    }
+    cudaStreamSynchronize(st);
+    delete ctx;
+    cudaStreamDestroy(st);
+}
+
+const char *sage2gpu_last_error(const sage2gpu_ctx *ctx) { return ctx ? ctx->c.last_error.c_str() : "null context"; }
+
+int sage2gpu_load_reads(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int min_overlap)
+{
+    return guarded(ctx, [&](sg::Context &c) { load_common(c, bases, offsets, n_reads, min_overlap, false); });
+}
+
+int sage2gpu_load_reads_device(sage2gpu_ctx *ctx, const uint8_t *d_bases, const int64_t *d_offsets, int64_t n_reads, int min_overlap)
+{
+    return guarded(ctx, [&](sg::Context &c) { load_common(c, d_bases, d_offsets, n_reads, min_overlap, true); });
+}
+
+int sage2gpu_build_hash_table(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_build_table(c);
+        c.tm.build_table = t.stop();
+    });
+}
+
+int sage2gpu_build_overlap_graph(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.have_table, "build_hash_table must run first");
+        {
+            StageTimer t(c.stream);
+            sg::stage_phase_a(c);
+            c.tm.phase_a = t.stop();
+        }
+        {
+            StageTimer t(c.stream);
+            sg::stage_phase_b(c);
+            c.tm.phase_b = t.stop();
+        }
+        sg::stage_phase_c_and_finalize(c);
+        fetch_edges(c);
+        c.tm.total_device = c.tm.ingest + c.tm.sort_reads + c.tm.build_table + c.tm.phase_a + c.tm.phase_b +
+                            c.tm.phase_c_dev + c.tm.phase_c_host + c.tm.sort_edges;
+    });
+}
+
+int sage2gpu_run_steps123(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int min_overlap)
+{
+    int rc = sage2gpu_load_reads(ctx, bases, offsets, n_reads, min_overlap);
+    if (rc) return rc;
+    rc = sage2gpu_build_hash_table(ctx);
+    if (rc) return rc;
+    return sage2gpu_build_overlap_graph(ctx);
+}
+
+int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *o)
+{
+    if (!ctx || !o) return SAGE2GPU_ERR_ARG;
+    const sg::Counters &n = ctx->c.cnt;
+    o->total_reads = n.total_reads; o->good_reads = n.good_reads; o->unique_reads = n.unique_reads;
+    o->total_bp = n.total_bp; o->avg_len = n.avg_len;
+    o->hash_len = n.hash_len; o->distinct_keys = n.distinct_keys; o->keys_over_threshold = n.keys_over_threshold;
+    o->table_capacity = n.table_capacity;
+    o->contained_ext = n.contained_ext; o->contained_size = n.contained_size; o->left_to_explore = n.left_to_explore;
+    o->edges_phase_b = n.edges_phase_b; o->candidates_c = n.candidates_c; o->edges_inserted_c = n.edges_inserted_c;
+    o->transitive_removed = n.transitive_removed; o->n_edges = n.n_edges;
+    o->compare_calls = n.compare_calls; o->window_probes = n.window_probes; o->slow_path_reads = n.slow_path_reads;
+    o->record_words = (uint64_t)ctx->c.SW;
+    return SAGE2GPU_OK;
+}
+
+int sage2gpu_get_timers(const sage2gpu_ctx *ctx, sage2gpu_timers *o)
+{
+    if (!ctx || !o) return SAGE2GPU_ERR_ARG;
+    const sg::Timers &t = ctx->c.tm;
+    o->ingest = t.ingest; o->sort_reads = t.sort_reads; o->build_table = t.build_table; o->phase_a = t.phase_a;
+    o->phase_b = t.phase_b; o->phase_c_dev = t.phase_c_dev; o->phase_c_host = t.phase_c_host;
+    o->sort_edges = t.sort_edges; o->total = t.total_device;
+    return SAGE2GPU_OK;
+}
+
+int sage2gpu_reads_bytes(const sage2gpu_ctx *ctx, uint64_t *n_bytes)
+{
+    if (!ctx || !n_bytes) return SAGE2GPU_ERR_ARG;
+    sage2gpu_ctx *m = const_cast<sage2gpu_ctx *>(ctx);
+    return guarded(m, [&](sg::Context &c) {
+        SG_CHECK(c.have_reads, "no reads loaded");
+        const sg::u64 U = c.cnt.unique_reads;
+        std::vector<uint16_t> len(U);
+        if (U) {
+            SG_CUDA(cudaMemcpyAsync(len.data(), c.len.p, U * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
+            SG_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        uint64_t tot = 0;
+        for (sg::u64 i = 0; i < U; ++i) tot += (uint64_t)(len[i] + 3) / 4;
+        *n_bytes = tot;
+    });
+}
+
+int sage2gpu_get_reads(sage2gpu_ctx *ctx, uint16_t *length, uint16_t *frequency, uint64_t *byte_off, uint8_t *fwd, uint8_t *rc)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        HostReads h;
+        fetch_reads(c, h);
+        const sg::u64 U = c.cnt.unique_reads;
+        uint64_t off = 0;
+        for (sg::u64 i = 0; i < U; ++i) {
+            if (length) length[i] = h.len[i];
+            if (frequency) frequency[i] = h.freq[i];
+            if (byte_off) byte_off[i] = off;
+            if (fwd) record_to_bytes(&h.F[i * c.SW], h.len[i], fwd + off);
+            if (rc) record_to_bytes(&h.RC[i * c.SW], h.len[i], rc + off);
+            off += (uint64_t)(h.len[i] + 3) / 4;
+        }
+        if (byte_off) byte_off[U] = off;
+    });
+}
+
+int sage2gpu_get_extensions(sage2gpu_ctx *ctx, uint64_t *right_ext, uint64_t *left_ext, uint8_t *explored)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.have_graph, "overlap graph not built");
+        const sg::u64 U = c.cnt.unique_reads;
+        if (U == 0) return;
+        if (right_ext) SG_CUDA(cudaMemcpyAsync(right_ext, c.extR.p, U * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+        if (left_ext) SG_CUDA(cudaMemcpyAsync(left_ext, c.extL.p, U * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+        if (explored) SG_CUDA(cudaMemcpyAsync(explored, c.explored.p, U, cudaMemcpyDeviceToHost, c.stream));
+        SG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int sage2gpu_get_edges(sage2gpu_ctx *ctx, sage2gpu_edge *out, uint64_t capacity, uint64_t *n_edges)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        fetch_edges(c);
+        const sg::u64 E = c.cnt.n_edges;
+        if (n_edges) *n_edges = E;
+        if (!out) return;
+        SG_CHECK(capacity >= E, "edge buffer too small");
+        std::vector<uint16_t> len(c.cnt.unique_reads);
+        if (!len.empty()) {
+            SG_CUDA(cudaMemcpyAsync(len.data(), c.len.p, len.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
+            SG_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        for (sg::u64 e = 0; e < E; ++e) {
+            const sg::u64 w0 = c.h_edges[2 * e], w1 = c.h_edges[2 * e + 1];
+            sage2gpu_edge &x = out[e];
+            x.from = w0 >> 32; x.to = w0 & 0xFFFFFFFFull;
+            x.type = (uint32_t)(w1 >> 20) & 3u; x.delta = (uint32_t)(w1 & 0xFFFFFu);
+            const uint32_t ul = len[x.from - 1], vl = len[x.to - 1];
+            x.delta_twin = ul - (vl - x.delta);                    // overlapGraph.cpp:147
+            x.reserved = 0;
+        }
+    });
+}
+
+uint64_t sage2gpu_kernel_launches(void) { return sg::launch_counter(); }
+
+int sage2gpu_write_reads(sage2gpu_ctx *ctx, const char *path)
+{
+    int io = 0;
+    int rc = guarded(ctx, [&](sg::Context &c) {
+        HostReads h;
+        fetch_reads(c, h);
+        FILE *f = fopen(path, "wb");
+        if (!f) { io = 1; return; }
+        static const char T[4] = { 'A', 'C', 'G', 'T' };
+        const sg::u64 U = c.cnt.unique_reads;
+        fprintf(f, "%llu\n", (unsigned long long)U);
+        std::vector<char> line(2 * (size_t)(32 * c.SW) + 64);
+        for (sg::u64 i = 0; i < U; ++i) {
+            const int len = h.len[i];
+            int n = snprintf(line.data(), 64, "%u\t%u\t", (unsigned)h.freq[i], (unsigned)len);
+            for (int s = 0; s < 2; ++s) {
+                const sg::u64 *rec = (s ? h.RC.data() : h.F.data()) + i * c.SW;
+                for (int p = 0; p < len; ++p) line[n++] = T[(rec[p >> 5] >> (62 - 2 * (p & 31))) & 3];
+                line[n++] = s ? '\n' : '\t';
+            }
+            fwrite(line.data(), 1, (size_t)n, f);
+        }
+        if (fclose(f) != 0) io = 1;
+    });
+    if (rc == 0 && io) { ctx->c.last_error = std::string("cannot write ") + path; return SAGE2GPU_ERR_IO; }
+    return rc;
+}
+
+int sage2gpu_write_graph3(sage2gpu_ctx *ctx, const char *path)
+{
+    int io = 0;
+    int rc = guarded(ctx, [&](sg::Context &c) {
+        fetch_edges(c);
+        std::vector<uint16_t> len(c.cnt.unique_reads);
+        if (!len.empty()) {
+            SG_CUDA(cudaMemcpyAsync(len.data(), c.len.p, len.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
+            SG_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        FILE *f = fopen(path, "wb");
+        if (!f) { io = 1; return; }
+        // genomeSize (0 before step 5), numberOfReads, averageReadLength: overlapGraph.cpp:348-351
+        fprintf(f, "0\n%llu\n%llu\n", (unsigned long long)c.cnt.good_reads, (unsigned long long)c.cnt.avg_len);
+        const sg::u64 E = c.cnt.n_edges;
+        for (sg::u64 e = 0; e < E; ++e) {
+            const sg::u64 w0 = c.h_edges[2 * e], w1 = c.h_edges[2 * e + 1];
+            const unsigned long long a = w0 >> 32, b = w0 & 0xFFFFFFFFull;
+            const uint32_t type = (uint32_t)(w1 >> 20) & 3u, d = (uint32_t)(w1 & 0xFFFFFu);
+            const uint32_t dt = (uint32_t)len[a - 1] - ((uint32_t)len[b - 1] - d);
+            fprintf(f, "%llu\t%llu\t%u\t1\t%u\t0\t0\n\n%llu\t%llu\t%u\t1\t%u\t0\t0\n\n", a, b, type, d, b, a,
+                    sg::reverse_edge_type(type), dt);
+        }
+        if (fclose(f) != 0) io = 1;
+    });
+    if (rc == 0 && io) { ctx->c.last_error = std::string("cannot write ") + path; return SAGE2GPU_ERR_IO; }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// context.h -- device-resident state of one libsage2gpu context (one GPU, one stream).
+#pragma once
+#include <string>
+#include <vector>
+#include "core.cuh"
+#include "device_utils.cuh"
+
+namespace sg {
+
+struct Counters {
+    // step 1 (readLoader.cpp:164-169,257)
+    u64 total_reads = 0, good_reads = 0, unique_reads = 0, total_bp = 0, avg_len = 0;
+    // step 2 (hashTable.cpp:86,124)
+    u64 hash_len = 0, distinct_keys = 0, keys_over_threshold = 0, table_capacity = 0;
+    // step 3 (economyGraph.cpp:485-487,569-571)
+    u64 contained_ext = 0, contained_size = 0, left_to_explore = 0;
+    u64 edges_phase_b = 0, candidates_c = 0, edges_inserted_c = 0, transitive_removed = 0;
+    u64 n_edges = 0;
+    u64 compare_calls = 0;   // V of SURVEY 8(d) (phase A gated partner comparisons)
+    u64 window_probes = 0;   // U*W
+    u64 slow_path_reads = 0; // reads re-done by the exact sequential chain
+};
+
+struct Timers {   // milliseconds, CUDA events on the context stream
+    float ingest = 0, sort_reads = 0, dedupe = 0, build_table = 0, phase_a = 0, phase_b = 0,
+          phase_c_dev = 0, phase_c_host = 0, sort_edges = 0, total_device = 0;
+};
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int min_overlap = 0, h = 0, SW = 0;
+    Counters cnt;
+    Timers tm;
+
+    // raw input staged on device
+    DevBuf<uint8_t> d_bases;
+    DevBuf<int64_t> d_offsets;
+    u64 n_input = 0;
+    int max_len = 0;
+
+    // unique reads, ids 1..U map to index 0..U-1
+    DevBuf<u64> F, RC;          // [U*SW] records
+    DevBuf<uint16_t> len, freq; // [U]
+
+    // prefix/suffix table
+    DevBuf<u64> slots;          // [cap]
+    DevBuf<u32> entries;        // [4U]
+    u64 cap = 0;
+
+    // phase A output
+    DevBuf<u64> extR, extL;     // [U] ext_pack
+    DevBuf<uint8_t> flag5;      // [U] connections > 300
+    DevBuf<u32> cont_max;       // [U] largest (1-based) id whose scan found this read contained
+    // phase B output
+    DevBuf<uint8_t> explored;   // [U] 0 / 4 / 5 / 6
+    // edges
+    DevBuf<u64> edges;          // [2*n_edges] (w0,w1) pairs, canonical sorted after finalize
+    std::vector<u64> h_edges;   // host copy of final edges (w0,w1 interleaved)
+    bool have_reads = false, have_table = false, have_graph = false;
+};
+
+// stages (each throws sg::CudaError)
+void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident);
+void stage_organize_reads(Context &c);
+void stage_build_table(Context &c);
+void stage_phase_a(Context &c);
+void stage_phase_b(Context &c);
+void stage_phase_c_and_finalize(Context &c);
+
+}  // namespace sg

@@ -1,0 +1,258 @@
+// graph.cu -- step 3 after the search: phase B on device, phase-C candidate generation, the serial
+// phase-C walk on the host (host_phase_c.cpp), and the canonical edge list (K6).  Restates
+// EconomyGraph::buildInitialOverlapGraph phase B (economyGraph/economyGraph.cpp:455-480),
+// sortEconomyGraph (:896-913) and the part of OverlapGraph::convertGraph that decides which entries
+// become edges (overlapGraph/overlapGraph.cpp:93-112).
+#include <algorithm>
+#include "context.h"
+#include "host_phase_c.h"
+
+namespace sg {
+
+void launch_phase_c_candidates(Context &c, const u32 *s_ids, u64 nS, u32 *counts, const u32 *offsets, u64 *cand, bool fill);
+
+static unsigned big_grid(u64 n, unsigned block = 256)
+{
+    unsigned g = grid_for(n, block, 4);
+    return g > kSMs * 16u ? kSMs * 16u : g;
+}
+
+// B1: which reads have reciprocal unique extensions on both sides (economyGraph.cpp:460)
+__global__ void __launch_bounds__(256) phase_b_qualify_kernel(const u64 *__restrict__ extR, const u64 *__restrict__ extL,
+                                                               const uint8_t *__restrict__ flag5, const u32 *__restrict__ cont_max,
+                                                               u64 U, uint8_t *__restrict__ explored, unsigned long long *counters)
+{
+    unsigned long long nq = 0, n6 = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += (u64)gridDim.x * blockDim.x) {
+        const u32 id = (u32)i + 1;
+        uint8_t s = state_after_a(id, cont_max[i], flag5[i]);
+        if (s != 6) {
+            const bool q = phase_b_qualifies(extR, extL, i);
+            if (q) { s = 4; nq++; }
+        } else n6++;
+        explored[i] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { nq += __shfl_xor_sync(0xffffffffu, nq, o); n6 += __shfl_xor_sync(0xffffffffu, n6, o); }
+    if ((threadIdx.x & 31) == 0) { if (nq) atomicAdd(&counters[0], nq); if (n6) atomicAdd(&counters[1], n6); }
+}
+
+// B2: edges.  Read i (state 4) inserts i->L and i->R unless the target was already state 4 when i was
+// visited, i.e. unless the target qualifies too and has a smaller id (economyGraph.cpp:462-473).
+__global__ void __launch_bounds__(256) phase_b_edges_kernel(const u64 *__restrict__ extR, const u64 *__restrict__ extL,
+                                                             const uint8_t *__restrict__ explored, const uint16_t *__restrict__ len,
+                                                             u64 U, u64 *__restrict__ edges, unsigned long long *n_edges)
+{
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x; i0 < U; i0 += (u64)gridDim.x * blockDim.x) {
+        const u64 i = i0 + threadIdx.x;
+        EdgeRec e[2];
+        int n = 0;
+        if (i < U) n = phase_b_edges(extR, extL, explored, len, i, e);
+        // warp-aggregated append
+        const int lane = threadIdx.x & 31;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 31 && tot) base = atomicAdd(n_edges, (unsigned long long)tot);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        const u64 pos = base + (u64)(incl - n);
+        for (int t = 0; t < n; ++t) { edges[2 * (pos + t)] = e[t].w0; edges[2 * (pos + t) + 1] = e[t].w1; }
+    }
+}
+
+__global__ void __launch_bounds__(256) flag_state0_kernel(const uint8_t *__restrict__ explored, u64 U, u32 *__restrict__ flag)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += (u64)gridDim.x * blockDim.x) flag[i] = explored[i] == 0;
+}
+
+__global__ void __launch_bounds__(256) compact_ids_kernel(const u32 *__restrict__ flag, const u32 *__restrict__ idx, u64 U, u32 *__restrict__ out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += (u64)gridDim.x * blockDim.x)
+        if (flag[i]) out[idx[i]] = (u32)i;
+}
+
+void stage_phase_b(Context &c)
+{
+    cudaStream_t st = c.stream;
+    const u64 U = c.cnt.unique_reads;
+    c.explored.alloc(U, st);
+    c.edges.alloc(4 * U + 2, st);
+    c.cnt.contained_ext = c.cnt.contained_size = 0;
+    c.cnt.left_to_explore = 0; c.cnt.edges_phase_b = 0;
+    if (U == 0) return;
+    DevBuf<unsigned long long> d_cnt(3, st);
+    SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 3 * sizeof(unsigned long long), st));
+    phase_b_qualify_kernel<<<big_grid(U), 256, 0, st>>>(c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, U, c.explored.p, d_cnt.p);
+    SG_LAUNCHED();
+    phase_b_edges_kernel<<<big_grid(U), 256, 0, st>>>(c.extR.p, c.extL.p, c.explored.p, c.len.p, U, c.edges.p, d_cnt.p + 2);
+    SG_LAUNCHED();
+    unsigned long long h[3];
+    SG_CUDA(cudaMemcpyAsync(h, d_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.cnt.contained_ext = h[0];
+    c.cnt.contained_size = h[1];
+    c.cnt.left_to_explore = U - h[0] - h[1];
+    c.cnt.edges_phase_b = h[2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: drop phase-B records owned by state-0 reads (their lists are rebuilt by the host walk),
+// append the host's records, canonical radix sort, (from,to,type) dedupe keeping the smallest
+// overhang (overlapGraph.cpp:101).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flag_keep_edges_kernel(const u64 *__restrict__ edges, u64 n, const uint8_t *__restrict__ explored, u32 *__restrict__ flag)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        const u32 a = (u32)(edges[2 * e] >> 32);
+        flag[e] = explored[a - 1] != 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) split_edges_kernel(const u64 *__restrict__ edges, u64 n, const u32 *__restrict__ flag,
+                                                           const u32 *__restrict__ idx, u64 *__restrict__ w0, u64 *__restrict__ w1)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x)
+        if (!flag || flag[e]) { const u64 p = flag ? idx[e] : e; w0[p] = edges[2 * e]; w1[p] = edges[2 * e + 1]; }
+}
+
+__global__ void __launch_bounds__(256) flag_first_edge_kernel(const u64 *__restrict__ w0, const u64 *__restrict__ w1, u64 n, u32 *__restrict__ flag)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x)
+        flag[e] = (e == 0 || w0[e] != w0[e - 1] || (w1[e] >> 20) != (w1[e - 1] >> 20)) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) join_edges_kernel(const u64 *__restrict__ w0, const u64 *__restrict__ w1, u64 n,
+                                                          const u32 *__restrict__ flag, const u32 *__restrict__ idx, u64 *__restrict__ edges)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x)
+        if (flag[e]) { edges[2 * (u64)idx[e]] = w0[e]; edges[2 * (u64)idx[e] + 1] = w1[e]; }
+}
+
+void stage_phase_c_and_finalize(Context &c)
+{
+    cudaStream_t st = c.stream;
+    const u64 U = c.cnt.unique_reads;
+    c.cnt.candidates_c = c.cnt.edges_inserted_c = c.cnt.transitive_removed = 0;
+    c.cnt.n_edges = 0;
+    c.h_edges.clear();
+    if (U == 0) { c.have_graph = true; return; }
+
+    cudaEvent_t ev0, ev1, ev2;
+    SG_CUDA(cudaEventCreate(&ev0)); SG_CUDA(cudaEventCreate(&ev1)); SG_CUDA(cudaEventCreate(&ev2));
+    SG_CUDA(cudaEventRecord(ev0, st));
+
+    // ---- state-0 reads and their candidate lists -------------------------------------------------
+    DevBuf<u32> flag(U, st), idx(U, st), d_total(1, st);
+    flag_state0_kernel<<<big_grid(U), 256, 0, st>>>(c.explored.p, U, flag.p);
+    SG_LAUNCHED();
+    exclusive_scan_u32(flag.p, idx.p, U, d_total.p, st);
+    u32 nS = 0;
+    SG_CUDA(cudaMemcpyAsync(&nS, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+
+    u64 nB = c.cnt.edges_phase_b;
+    std::vector<u64> host_c_edges;     // records owned by state-0 reads after the walk
+    float host_ms = 0.f;
+    if (nS > 0) {
+        DevBuf<u32> s_ids(nS, st), counts(nS, st), offs(nS, st), d_ctotal(1, st);
+        compact_ids_kernel<<<big_grid(U), 256, 0, st>>>(flag.p, idx.p, U, s_ids.p);
+        SG_LAUNCHED();
+        launch_phase_c_candidates(c, s_ids.p, nS, counts.p, nullptr, nullptr, false);
+        exclusive_scan_u32(counts.p, offs.p, nS, d_ctotal.p, st);
+        u32 nC = 0;
+        SG_CUDA(cudaMemcpyAsync(&nC, d_ctotal.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        DevBuf<u64> cand(nC, st);
+        if (nC) launch_phase_c_candidates(c, s_ids.p, nS, counts.p, offs.p, cand.p, true);
+        c.cnt.candidates_c = nC;
+
+        // ---- host walk (serial by definition, economyGraph.cpp:513-564) -------------------------
+        PhaseCInput in;
+        std::vector<u32> h_sids(nS), h_off((size_t)nS + 1);
+        std::vector<u64> h_cand(nC), h_edgesB(2 * nB);
+        std::vector<uint16_t> h_len(U);
+        SG_CUDA(cudaMemcpyAsync(h_sids.data(), s_ids.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(h_off.data(), offs.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        if (nC) SG_CUDA(cudaMemcpyAsync(h_cand.data(), cand.p, nC * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        if (nB) SG_CUDA(cudaMemcpyAsync(h_edgesB.data(), c.edges.p, 2 * nB * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(h_len.data(), c.len.p, U * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaEventRecord(ev1, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        h_off[nS] = nC;
+        in.U = U; in.len = h_len.data(); in.nS = nS; in.s_ids = h_sids.data(); in.cand_off = h_off.data();
+        in.cand = h_cand.data(); in.nB = nB; in.edgesB = h_edgesB.data();
+        PhaseCOutput out;
+        host_ms = run_host_phase_c(in, out);
+        c.cnt.edges_inserted_c = out.inserted;
+        c.cnt.transitive_removed = out.removed;
+        host_c_edges.swap(out.edges);
+    } else {
+        SG_CUDA(cudaEventRecord(ev1, st));
+    }
+
+    // ---- assemble the final record set on device --------------------------------------------------
+    const u64 nH = host_c_edges.size() / 2;
+    DevBuf<u32> eflag, eidx, d_keep(1, st);
+    u64 nKeep = nB;
+    if (nS > 0 && nB > 0) {
+        eflag.alloc(nB, st); eidx.alloc(nB, st);
+        flag_keep_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, c.explored.p, eflag.p);
+        SG_LAUNCHED();
+        exclusive_scan_u32(eflag.p, eidx.p, nB, d_keep.p, st);
+        u32 k32 = 0;
+        SG_CUDA(cudaMemcpyAsync(&k32, d_keep.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        nKeep = k32;
+    }
+    const u64 nAll = nKeep + nH;
+    if (nAll == 0) {
+        SG_CUDA(cudaEventRecord(ev2, st));
+        SG_CUDA(cudaEventSynchronize(ev2));
+        c.have_graph = true;
+        c.tm.phase_c_host = host_ms;
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+        return;
+    }
+    DevBuf<u64> a0(nAll, st), a1(nAll, st), b0(nAll, st), b1(nAll, st);
+    if (nB) {
+        split_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, eflag.p, eidx.p, a0.p, b0.p);
+        SG_LAUNCHED();
+    }
+    if (nH) {
+        DevBuf<u64> tmp(2 * nH, st);
+        SG_CUDA(cudaMemcpyAsync(tmp.p, host_c_edges.data(), 2 * nH * sizeof(u64), cudaMemcpyHostToDevice, st));
+        split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(tmp.p, nH, nullptr, nullptr, a0.p + nKeep, b0.p + nKeep);
+        SG_LAUNCHED();
+        SG_CUDA(cudaStreamSynchronize(st));   // host_c_edges / tmp lifetime
+    }
+    SortCols cols;
+    cols.a[0] = a0.p; cols.a[1] = a1.p; cols.b[0] = b0.p; cols.b[1] = b1.p; cols.v[0] = cols.v[1] = nullptr;
+    int cur = 0;
+    cur = radix_sort_varying(cols, cur, nAll, true, st);     // (type, overhang)
+    cur = radix_sort_varying(cols, cur, nAll, false, st);    // (from, to)
+    DevBuf<u32> fflag(nAll, st), fidx(nAll, st), d_ne(1, st);
+    flag_first_edge_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll, fflag.p);
+    SG_LAUNCHED();
+    exclusive_scan_u32(fflag.p, fidx.p, nAll, d_ne.p, st);
+    u32 nE = 0;
+    SG_CUDA(cudaMemcpyAsync(&nE, d_ne.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.edges.alloc(2 * (u64)nE, st);
+    join_edges_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll, fflag.p, fidx.p, c.edges.p);
+    SG_LAUNCHED();
+    SG_CUDA(cudaEventRecord(ev2, st));
+    SG_CUDA(cudaEventSynchronize(ev2));
+    c.cnt.n_edges = nE;
+    float ms01 = 0, ms12 = 0;
+    cudaEventElapsedTime(&ms01, ev0, ev1);
+    cudaEventElapsedTime(&ms12, ev1, ev2);
+    c.tm.phase_c_dev = ms01;
+    c.tm.phase_c_host = host_ms;
+    c.tm.sort_edges = ms12 - host_ms > 0 ? ms12 - host_ms : 0;
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+    c.have_graph = true;
+}
+
+}  // namespace sg

@@ -1,0 +1,203 @@
+// host_phase_c.cpp -- EconomyGraph::buildOverlapGraphEconomy (economyGraph/economyGraph.cpp:495-574)
+// with insertAllEdgesOfRead's search replaced by the GPU's candidate lists.
+//
+// Why this is on the host: the walk is a FIFO breadth-first traversal whose edge insertions depend
+// on which reads were explored before (:605), followed by Myers marking whose outcome depends on list
+// order (:643-679).  SURVEY.md section 8(f) N1 lists moving it to the device as the next step.
+//
+// Only the nodes the walk can touch get adjacency lists: S (state 0 after phase B) and the phase-B
+// neighbours of S (whose lists markTransitiveEdge scans, :653).  Everything else keeps the device's
+// phase-B records untouched.  What leaves this function: for every a in S, the entries of list[a]
+// with id > a after the walk, i.e. exactly what convertGraph would consume (overlapGraph.cpp:103).
+#include "host_phase_c.h"
+
+#include <algorithm>
+#include <chrono>
+#include <unordered_map>
+
+namespace sg {
+namespace {
+
+struct HEdge { uint32_t id; uint8_t type, mark; uint32_t length; };
+
+inline uint32_t rev_type(uint32_t t) { return t == 0 ? 3u : (t == 3 ? 0u : t); }
+
+// compareLengthBased, economyGraph.cpp:853-871
+inline bool by_length_desc(const HEdge &a, const HEdge &b)
+{
+    if (a.length != b.length) return a.length > b.length;
+    if (a.id != b.id) return a.id > b.id;
+    return a.type > b.type;
+}
+
+struct Walk {
+    const PhaseCInput &in;
+    std::unordered_map<uint32_t, uint32_t> slot;   // read id (1-based) -> local node
+    std::vector<std::vector<HEdge>> adj;
+    std::vector<uint8_t> state;                    // 0/1/2 for S nodes, 4 for everything else
+    std::vector<uint8_t> marked;
+    std::vector<uint32_t> node_id;
+    uint64_t inserted = 0, removed = 0;
+
+    explicit Walk(const PhaseCInput &i) : in(i) {}
+
+    uint32_t node(uint32_t id, uint8_t st)
+    {
+        auto it = slot.find(id);
+        if (it != slot.end()) return it->second;
+        const uint32_t n = (uint32_t)adj.size();
+        slot.emplace(id, n);
+        adj.emplace_back();
+        state.push_back(st);
+        marked.push_back(0);
+        node_id.push_back(id);
+        return n;
+    }
+
+    // insertEdgeEconomy, economyGraph.cpp:813-849 (both endpoints are S nodes here)
+    void insert_edge(uint32_t nu, uint32_t nv, uint32_t delta, uint32_t type)
+    {
+        const uint32_t u = node_id[nu], v = node_id[nv];
+        const uint32_t lu = in.len[u - 1], lv = in.len[v - 1];
+        const uint32_t delta2 = lu - (lv - delta);
+        adj[nu].push_back(HEdge{ v, (uint8_t)type, 0, delta & 0xFFFFFu });
+        adj[nv].push_back(HEdge{ u, (uint8_t)rev_type(type), 0, delta2 & 0xFFFFFu });
+    }
+
+    // insertAllEdgesOfRead, economyGraph.cpp:580-638
+    void insert_all(uint32_t n1)
+    {
+        if (state[n1] != 0) return;
+        state[n1] = 1;
+        const uint32_t s = n1;    // S nodes occupy local slots 0..nS-1 in s_ids order
+        uint64_t cnt = 0;
+        for (uint32_t q = in.cand_off[s]; q < in.cand_off[s + 1]; ++q) {
+            const uint64_t cw = in.cand[q];
+            const uint32_t read2 = (uint32_t)(cw >> 32);
+            const uint32_t n2 = slot.find(read2)->second;
+            if (state[n2] != 0) continue;                                   // :605
+            uint32_t delta = (uint32_t)(cw & 0xFFFFFu);
+            if (delta & 0x80000u) delta |= 0xFFF00000u;                     // sign-extend the int32 overhang
+            insert_edge(n1, n2, delta, (uint32_t)((cw >> 20) & 3u));
+            cnt++;
+        }
+        if (adj[n1].size() > 1) std::sort(adj[n1].begin(), adj[n1].end(), by_length_desc);   // :634
+        inserted += 2 * cnt;
+    }
+
+    // markTransitiveEdge, economyGraph.cpp:643-679
+    void mark_transitive(uint32_t nf)
+    {
+        std::vector<HEdge> &lf = adj[nf];
+        for (auto &e : lf) marked[slot.find(e.id)->second] = 1;
+        for (auto &e : lf) {
+            const uint32_t na = slot.find(e.id)->second;
+            if (marked[na] != 1) continue;
+            for (auto &f : adj[na]) {
+                auto itb = slot.find(f.id);
+                if (itb == slot.end()) continue;      // not adjacent to any S read: cannot be in play
+                const uint32_t nb = itb->second;
+                if (marked[nb] != 1) continue;
+                const uint32_t t1 = e.type, t2 = f.type;
+                if ((t1 == 0 || t1 == 2) && (t2 == 0 || t2 == 1)) marked[nb] = 2;
+                else if ((t1 == 1 || t1 == 3) && (t2 == 2 || t2 == 3)) marked[nb] = 2;
+            }
+        }
+        for (auto &e : lf) if (marked[slot.find(e.id)->second] == 2) e.mark = 1;
+        for (auto &e : lf) marked[slot.find(e.id)->second] = 0;
+        marked[nf] = 0;
+        state[nf] = 2;
+    }
+
+    // removeTransitiveEdges, economyGraph.cpp:681-707
+    void remove_transitive(uint32_t n)
+    {
+        std::vector<HEdge> &l = adj[n];
+        size_t w = 0;
+        for (size_t r = 0; r < l.size(); ++r) if (!l[r].mark) l[w++] = l[r];
+        removed += l.size() - w;
+        l.resize(w);
+    }
+};
+
+}  // namespace
+
+float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    Walk w(in);
+    w.slot.reserve(in.nS * 4 + 16);
+    for (uint64_t s = 0; s < in.nS; ++s) w.node(in.s_ids[s] + 1, 0);
+    const uint32_t nS = (uint32_t)in.nS;
+
+    // phase-B neighbours of S, then every phase-B entry of every needed node
+    for (uint64_t e = 0; e < in.nB; ++e) {
+        const uint32_t a = (uint32_t)(in.edgesB[2 * e] >> 32), b = (uint32_t)in.edgesB[2 * e];
+        const auto ia = w.slot.find(a), ib = w.slot.find(b);
+        const bool a_in_s = ia != w.slot.end() && ia->second < nS;
+        const bool b_in_s = ib != w.slot.end() && ib->second < nS;
+        if (a_in_s && ib == w.slot.end()) w.node(b, 4);
+        if (b_in_s && ia == w.slot.end()) w.node(a, 4);
+    }
+    for (uint64_t e = 0; e < in.nB; ++e) {
+        const uint64_t w0 = in.edgesB[2 * e], w1 = in.edgesB[2 * e + 1];
+        const uint32_t a = (uint32_t)(w0 >> 32), b = (uint32_t)w0;
+        const uint32_t type = (uint32_t)(w1 >> 20) & 3u, length = (uint32_t)(w1 & 0xFFFFFu);
+        const auto ia = w.slot.find(a), ib = w.slot.find(b);
+        if (ia != w.slot.end()) w.adj[ia->second].push_back(HEdge{ b, (uint8_t)type, 0, length });
+        if (ib != w.slot.end()) {
+            const uint32_t la = in.len[a - 1], lb = in.len[b - 1];
+            w.adj[ib->second].push_back(HEdge{ a, (uint8_t)rev_type(type), 0, (la - (lb - length)) & 0xFFFFFu });
+        }
+    }
+
+    // buildOverlapGraphEconomy, economyGraph.cpp:513-564
+    std::vector<uint32_t> queue;
+    queue.reserve(nS);
+    for (uint32_t i = 0; i < nS; ++i) {
+        if (w.state[i] != 0) continue;
+        queue.clear();
+        size_t start = 0;
+        queue.push_back(i);
+        while (start < queue.size()) {
+            const uint32_t n1 = queue[start++];
+            if (w.state[n1] == 0) w.insert_all(n1);
+            if (w.adj[n1].empty()) continue;                                 // :525
+            if (w.state[n1] == 1) {
+                for (size_t x = 0; x < w.adj[n1].size(); ++x) {
+                    const uint32_t n2 = w.slot.find(w.adj[n1][x].id)->second;
+                    if (w.state[n2] == 0) { queue.push_back(n2); w.insert_all(n2); }
+                }
+                w.mark_transitive(n1);
+            }
+            if (w.state[n1] == 2) {
+                for (size_t x = 0; x < w.adj[n1].size(); ++x) {
+                    const uint32_t n2 = w.slot.find(w.adj[n1][x].id)->second;
+                    if (w.state[n2] != 1) continue;
+                    for (size_t y = 0; y < w.adj[n2].size(); ++y) {
+                        const uint32_t n3 = w.slot.find(w.adj[n2][y].id)->second;
+                        if (w.state[n3] == 0) { queue.push_back(n3); w.insert_all(n3); }
+                    }
+                    w.mark_transitive(n2);
+                }
+                w.remove_transitive(n1);
+            }
+        }
+    }
+
+    // what convertGraph consumes from the lists of S reads (overlapGraph.cpp:93-112)
+    out.edges.clear();
+    for (uint32_t i = 0; i < nS; ++i) {
+        const uint32_t a = w.node_id[i];
+        for (const HEdge &e : w.adj[i])
+            if (e.id > a) {
+                out.edges.push_back(((uint64_t)a << 32) | e.id);
+                out.edges.push_back(((uint64_t)e.type << 20) | e.length);
+            }
+    }
+    out.inserted = w.inserted;
+    out.removed = w.removed;
+    return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace sg

@@ -1,0 +1,28 @@
+// host_phase_c.h -- the serial phase-C walk (economyGraph.cpp:495-707) on the host, fed with the
+// candidate lists the GPU produced.  Product code (part of libsage2gpu); shares nothing with oracle/.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace sg {
+
+struct PhaseCInput {
+    uint64_t U;
+    const uint16_t *len;        // [U], index = readId-1
+    uint64_t nS;
+    const uint32_t *s_ids;      // [nS] 0-based ids of reads in state 0 after phase B, ascending
+    const uint32_t *cand_off;   // [nS+1]
+    const uint64_t *cand;       // read2(1-based)<<32 | edgeType<<20 | overhang20, reference order
+    uint64_t nB;
+    const uint64_t *edgesB;     // [2*nB] canonical phase-B records (w0,w1), any order
+};
+
+struct PhaseCOutput {
+    std::vector<uint64_t> edges;    // (w0,w1) canonical records owned by state-0 reads (from = that read)
+    uint64_t inserted = 0, removed = 0;
+};
+
+// returns elapsed host milliseconds
+float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out);
+
+}  // namespace sg

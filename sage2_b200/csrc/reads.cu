@@ -1,0 +1,252 @@
+// reads.cu -- step 1 on device: filter + canonicalise + 2-bit pack (K1), sort + dedupe with
+// frequencies + packed reverse complements (K2).  Restates ReadLoader::readDatasetInBytes /
+// insertReadIntoList / organizeReads (inputReader/readLoader.cpp:133-260) and the utils.cpp helpers
+// they call (isGoodRead :144, reverseComplement :73, charsToBytes :96).
+#include "context.h"
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------------
+// K1: one warp per read.  Lane l of round w handles base 32w+l, so one round assembles exactly one
+// 64-bit record word of the read and one of its reverse complement (two __reduce_or_sync each).
+// Bad reads (length <= k, non-ACGT, utils.cpp:144-166) become all-ones records that sort last.
+// ------------------------------------------------------------------------------------------------
+constexpr int K1_WARPS = 8;
+
+__global__ void __launch_bounds__(K1_WARPS * 32) max_len_kernel(const int64_t *__restrict__ off, u64 n, int *out)
+{
+    int m = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const int64_t d = off[i + 1] - off[i];
+        const int l = d > 0x7FFFFFFF ? 0x7FFFFFFF : (int)d;
+        m = l > m ? l : m;
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+__global__ void __launch_bounds__(K1_WARPS * 32) pack_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ off,
+                                                              u64 n, int k, int SW, u64 *__restrict__ rec,
+                                                              unsigned long long *counters /*[0]=good,[1]=bp*/)
+{
+    __shared__ u64 sF[K1_WARPS][kMaxWords], sR[K1_WARPS][kMaxWords];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 nwarps = (u64)gridDim.x * K1_WARPS;
+    unsigned long long good = 0, bp = 0;
+    for (u64 r = (u64)blockIdx.x * K1_WARPS + warp; r < n; r += nwarps) {
+        const int64_t o = off[r];
+        const int64_t len64 = off[r + 1] - o;
+        const int max_ok = 32 * SW - 8;
+        bool bad = len64 <= (int64_t)k || len64 > (int64_t)max_ok;
+        const int len = bad ? 0 : (int)len64;
+        bool invalid = false;
+        for (int w = 0; w < SW; ++w) {
+            const int p = 32 * w + lane;
+            u32 cf = 0, cr = 0;
+            if (p < len) {
+                const u32 a = bases[o + p], b = bases[o + len - 1 - p];
+                const u32 au = a & 0xDFu;
+                invalid |= !(au == 'A' || au == 'C' || au == 'G' || au == 'T');
+                cf = ((a >> 1) ^ (a >> 2)) & 3u;             // A0 C1 G2 T3, case-insensitive
+                cr = 3u - (((b >> 1) ^ (b >> 2)) & 3u);      // complement of the mirrored base
+            }
+            const int sh = 30 - 2 * (lane & 15);
+            const u32 fhi = __reduce_or_sync(0xffffffffu, lane < 16 ? cf << sh : 0u);
+            const u32 flo = __reduce_or_sync(0xffffffffu, lane >= 16 ? cf << sh : 0u);
+            const u32 rhi = __reduce_or_sync(0xffffffffu, lane < 16 ? cr << sh : 0u);
+            const u32 rlo = __reduce_or_sync(0xffffffffu, lane >= 16 ? cr << sh : 0u);
+            if (lane == 0) {
+                sF[warp][w] = ((u64)fhi << 32) | flo;
+                sR[warp][w] = ((u64)rhi << 32) | rlo;
+            }
+        }
+        bad |= __any_sync(0xffffffffu, invalid);
+        __syncwarp();
+        // canonical orientation: keep the read iff read < revcomp (readLoader.cpp:195)
+        const u64 f = lane < SW ? sF[warp][lane] : 0ull, q = lane < SW ? sR[warp][lane] : 0ull;
+        const unsigned diff = __ballot_sync(0xffffffffu, f != q);
+        bool use_rc = false;
+        if (diff) {
+            const int first = __ffs(diff) - 1;
+            use_rc = __shfl_sync(0xffffffffu, (int)(q < f), first) != 0;
+        }
+        if (lane < SW) {
+            u64 v = use_rc ? q : f;
+            if (lane == SW - 1) v |= (u64)len;
+            rec[r * SW + lane] = bad ? ~0ull : v;
+        }
+        if (!bad) { good++; bp += (unsigned long long)len; }
+        __syncwarp();
+    }
+    if (lane == 0 && good) {
+        atomicAdd(&counters[0], good);
+        atomicAdd(&counters[1], bp);
+    }
+}
+
+void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident)
+{
+    cudaStream_t st = c.stream;
+    SG_CHECK(n_reads >= 0, "negative read count");
+    SG_CHECK((u64)n_reads < 0x3FFFFFFFull, "at most 2^30-1 reads per context");
+    c.n_input = (u64)n_reads;
+    c.have_reads = c.have_table = c.have_graph = false;
+    c.cnt = Counters();
+    c.cnt.total_reads = (u64)n_reads;
+    c.h = hash_len_for(c.min_overlap);
+    c.cnt.hash_len = (u64)c.h;
+    if (n_reads == 0) { c.SW = 1; c.max_len = 0; return; }
+
+    const uint8_t *d_b = bases;
+    const int64_t *d_o = offsets;
+    if (!device_resident) {
+        const int64_t total = offsets[n_reads];
+        c.d_offsets.alloc((size_t)n_reads + 1, st);
+        c.d_bases.alloc((size_t)total, st);
+        SG_CUDA(cudaMemcpyAsync(c.d_offsets.p, offsets, ((size_t)n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (total) SG_CUDA(cudaMemcpyAsync(c.d_bases.p, bases, (size_t)total, cudaMemcpyHostToDevice, st));
+        d_b = c.d_bases.p; d_o = c.d_offsets.p;
+    }
+    // longest read decides the record stride
+    DevBuf<int> d_max(1, st);
+    SG_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int), st));
+    unsigned g = grid_for((u64)n_reads, K1_WARPS * 32, 4);
+    if (g > kSMs * 8) g = kSMs * 8;
+    max_len_kernel<<<g, K1_WARPS * 32, 0, st>>>(d_o, (u64)n_reads, d_max.p);
+    SG_LAUNCHED();
+    int max_len = 0;
+    SG_CUDA(cudaMemcpyAsync(&max_len, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (max_len > 32 * kMaxWords - 8) max_len = 32 * kMaxWords - 8;   // longer reads are dropped as bad
+    if (max_len < 1) max_len = 1;
+    c.max_len = max_len;
+    c.SW = words_for_len(max_len);
+    {   // the search kernels are instantiated for these strides (search.cu SG_DISPATCH_SW)
+        static const int kStrides[] = { 2, 3, 4, 5, 6, 8, 12, 16, 32 };
+        for (int s : kStrides) if (s >= c.SW) { c.SW = s; break; }
+    }
+
+    // K1
+    DevBuf<u64> rec((size_t)n_reads * c.SW, st);
+    DevBuf<unsigned long long> d_cnt(2, st);
+    SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), st));
+    unsigned gp = grid_for((u64)n_reads, 1, K1_WARPS);
+    if (gp > kSMs * 16) gp = kSMs * 16;
+    pack_kernel<<<gp, K1_WARPS * 32, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, c.SW, rec.p, d_cnt.p);
+    SG_LAUNCHED();
+    unsigned long long h_cnt[2];
+    SG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.cnt.good_reads = h_cnt[0];
+    c.cnt.total_bp = h_cnt[1];
+    c.cnt.avg_len = h_cnt[0] ? h_cnt[1] / h_cnt[0] : 0;        // readLoader.cpp:161 integer division
+    c.F = std::move(rec);                                      // raw (unsorted, with bad reads) until organize
+    c.d_bases.release();
+    c.d_offsets.release();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: LSD radix sort of a permutation over the record words (last word first), dedupe.
+// ------------------------------------------------------------------------------------------------
+__global__ void iota_kernel(u32 *v, u64 n)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) v[i] = (u32)i;
+}
+
+__global__ void gather_word_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ perm, u64 n, int SW, int w, u64 *__restrict__ key)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        key[i] = rec[(u64)perm[i] * SW + w];
+}
+
+__global__ void unique_flag_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ perm, u64 n_good, int SW, u32 *__restrict__ flag)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_good; i += (u64)gridDim.x * blockDim.x) {
+        u32 f = 1;
+        if (i > 0) {
+            const u64 *a = rec + (u64)perm[i] * SW, *b = rec + (u64)perm[i - 1] * SW;
+            f = 0;
+            for (int w = 0; w < SW; ++w) f |= (a[w] != b[w]);
+        }
+        flag[i] = f;
+    }
+}
+
+__global__ void unique_write_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ perm, const u32 *__restrict__ flag,
+                                    const u32 *__restrict__ uidx, u64 n_good, int SW,
+                                    u64 *__restrict__ F, u64 *__restrict__ RC, uint16_t *__restrict__ len, u32 *__restrict__ start)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_good; i += (u64)gridDim.x * blockDim.x) {
+        if (!flag[i]) continue;
+        const u32 u = uidx[i];
+        const u64 *a = rec + (u64)perm[i] * SW;
+        u64 f[kMaxWords], r[kMaxWords];
+        for (int w = 0; w < SW; ++w) f[w] = a[w];
+        const int l = rec_len(f, SW);
+        revcomp_record(f, r, SW, l);
+        for (int w = 0; w < SW; ++w) { F[(u64)u * SW + w] = f[w]; RC[(u64)u * SW + w] = r[w]; }
+        len[u] = (uint16_t)l;
+        start[u] = (u32)i;
+    }
+}
+
+__global__ void freq_kernel(const u32 *__restrict__ start, u64 U, u64 n_good, uint16_t *__restrict__ freq)
+{
+    for (u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += (u64)gridDim.x * blockDim.x) {
+        const u64 e = (u + 1 < U) ? start[u + 1] : n_good;
+        freq[u] = (uint16_t)(e - start[u]);       // uint16_t frequency wraps like readLoader.cpp:234
+    }
+}
+
+static unsigned big_grid(u64 n, unsigned block = 256)
+{
+    unsigned g = grid_for(n, block, 4);
+    return g > kSMs * 16u ? kSMs * 16u : g;
+}
+
+void stage_organize_reads(Context &c)
+{
+    cudaStream_t st = c.stream;
+    const u64 n = c.n_input, n_good = c.cnt.good_reads;
+    const int SW = c.SW;
+    c.cnt.unique_reads = 0;
+    if (n == 0 || n_good == 0) {
+        c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
+        c.have_reads = true;
+        return;
+    }
+    DevBuf<u64> rec = std::move(c.F);
+    DevBuf<u64> ka(n, st), kb(n, st);
+    DevBuf<u32> va(n, st), vb(n, st);
+    iota_kernel<<<big_grid(n), 256, 0, st>>>(va.p, n);
+    SG_LAUNCHED();
+    SortCols cols;
+    cols.a[0] = ka.p; cols.a[1] = kb.p; cols.b[0] = cols.b[1] = nullptr; cols.v[0] = va.p; cols.v[1] = vb.p;
+    int cur = 0;
+    for (int w = SW - 1; w >= 0; --w) {
+        gather_word_kernel<<<big_grid(n), 256, 0, st>>>(rec.p, cols.v[cur], n, SW, w, cols.a[cur]);
+        SG_LAUNCHED();
+        cur = radix_sort_varying(cols, cur, n, false, st);
+    }
+    const u32 *perm = cols.v[cur];
+    DevBuf<u32> flag(n_good, st), uidx(n_good, st), d_total(1, st);
+    unique_flag_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, perm, n_good, SW, flag.p);
+    SG_LAUNCHED();
+    exclusive_scan_u32(flag.p, uidx.p, n_good, d_total.p, st);
+    u32 U = 0;
+    SG_CUDA(cudaMemcpyAsync(&U, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.cnt.unique_reads = U;
+    c.F.alloc((size_t)U * SW, st);
+    c.RC.alloc((size_t)U * SW, st);
+    c.len.alloc(U, st);
+    c.freq.alloc(U, st);
+    DevBuf<u32> start(U, st);
+    unique_write_kernel<<<big_grid(n_good, 128), 128, 0, st>>>(rec.p, perm, flag.p, uidx.p, n_good, SW, c.F.p, c.RC.p, c.len.p, start.p);
+    SG_LAUNCHED();
+    freq_kernel<<<big_grid(U), 256, 0, st>>>(start.p, U, n_good, c.freq.p);
+    SG_LAUNCHED();
+    c.have_reads = true;
+}
+
+}  // namespace sg

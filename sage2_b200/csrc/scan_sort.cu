@@ -1,0 +1,239 @@
+// scan_sort.cu -- exclusive scan and stable LSD radix sort (sm_100a, hand written).
+//
+// Radix sort, one 1..8-bit digit per pass, three launches per pass:
+//   rs_hist    : per-tile digit histogram               -> tileHist[digit][tile]
+//   scan       : exclusive scan of the flattened array  -> global base of (digit, tile)
+//   rs_scatter : stable rank inside the tile (warp match_any ranking, warps own contiguous item
+//                ranges so tile order == input order) and scatter of every column.
+// HBM traffic per pass: key column read twice, every column read once and written once.
+#include "device_utils.cuh"
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ u32 block_exclusive_scan_256(u32 v, u32 *smem /*[8]*/, u32 &block_total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) smem[warp] = x;
+    __syncthreads();
+    u32 warp_prefix = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        u32 s = smem[w];
+        if (w < warp) warp_prefix += s;
+        total += s;
+    }
+    block_total = total;
+    __syncthreads();
+    return warp_prefix + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const u32 *__restrict__ in, u32 *__restrict__ sums, u64 n)
+{
+    __shared__ u32 sm[8];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) s += in[base + i];
+    u32 total;
+    block_exclusive_scan_256(s, sm, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_kernel(const u32 *in, u32 *out, u64 n, const u32 *__restrict__ block_prefix, u32 *d_total)
+{
+    __shared__ u32 sm[8];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    u32 v[SCAN_ITEMS];
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0u; s += v[i]; }
+    u32 total;
+    u32 ex = block_exclusive_scan_256(s, sm, total);
+    if (block_prefix) ex += block_prefix[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+    if (d_total && gridDim.x == 1 && threadIdx.x == 0) *d_total = total;
+}
+
+void exclusive_scan_u32(const u32 *in, u32 *out, u64 n, u32 *d_total, cudaStream_t st)
+{
+    if (n == 0) {
+        if (d_total) SG_CUDA(cudaMemsetAsync(d_total, 0, sizeof(u32), st));
+        return;
+    }
+    const u64 nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb == 1) {
+        scan_tile_kernel<<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr, d_total);
+        SG_LAUNCHED();
+        return;
+    }
+    DevBuf<u32> sums(nb, st);
+    scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, sums.p, n);
+    SG_LAUNCHED();
+    exclusive_scan_u32(sums.p, sums.p, nb, d_total, st);
+    scan_tile_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, sums.p, nullptr);
+    SG_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------------
+// OR / AND reduction of a key column
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) or_and_kernel(const u64 *__restrict__ keys, u64 n, u64 *out)
+{
+    u64 o = 0, a = ~0ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = keys[i];
+        o |= k; a &= k;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        o |= __shfl_xor_sync(0xffffffffu, o, s);
+        a &= __shfl_xor_sync(0xffffffffu, a, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr((unsigned long long *)&out[0], (unsigned long long)o);
+        atomicAnd((unsigned long long *)&out[1], (unsigned long long)a);
+    }
+}
+
+void reduce_or_and_u64(const u64 *keys, u64 n, u64 *d_or_and, cudaStream_t st)
+{
+    const u64 init[2] = { 0ull, ~0ull };
+    SG_CUDA(cudaMemcpyAsync(d_or_and, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (n == 0) return;
+    unsigned g = grid_for(n, 256, 8);
+    if (g > kSMs * 8) g = kSMs * 8;
+    or_and_kernel<<<g, 256, 0, st>>>(keys, n, d_or_and);
+    SG_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix sort
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;                         // per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 4096 records per block
+constexpr int RS_WARP_ITEMS = 32 * RS_ITEMS;         // contiguous range owned by one warp
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const u64 *__restrict__ key, u64 n, int shift, u32 mask,
+                                                              u32 *__restrict__ tile_hist, u32 num_tiles)
+{
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const u64 idx = base + (u64)i * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(u32)(key[idx] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x <= mask) tile_hist[(u64)threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__restrict__ key, u64 n, int shift, u32 mask,
+                                                                 const u32 *__restrict__ tile_off, u32 num_tiles,
+                                                                 const u64 *__restrict__ a_in, u64 *__restrict__ a_out,
+                                                                 const u64 *__restrict__ b_in, u64 *__restrict__ b_out,
+                                                                 const u32 *__restrict__ v_in, u32 *__restrict__ v_out)
+{
+    __shared__ u32 whist[RS_WARPS][256];
+    __shared__ u32 dbase[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+
+    const u64 wbase = (u64)blockIdx.x * RS_TILE + (u64)warp * RS_WARP_ITEMS;
+    u32 packed[RS_ITEMS];    // digit | rank-in-warp << 8
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const u64 idx = wbase + (u64)r * 32 + lane;
+        const bool valid = idx < n;
+        const u32 d = valid ? ((u32)(key[idx] >> shift) & mask) : 0xFFFFFFFFu;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        const unsigned peers = __match_any_sync(0xffffffffu, d) & vm;
+        u32 rank = 0;
+        if (valid) rank = whist[warp][d] + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (valid && lane == (__ffs(peers) - 1)) whist[warp][d] += __popc(peers);
+        __syncwarp();
+        packed[r] = valid ? (d | (rank << 8)) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    // exclusive scan over warps for every digit + global base of (digit, tile)
+    {
+        const int d = threadIdx.x;
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { const u32 t = whist[w][d]; whist[w][d] = run; run += t; }
+        dbase[d] = ((u32)d <= mask) ? tile_off[(u64)d * num_tiles + blockIdx.x] : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        if (packed[r] == 0xFFFFFFFFu) continue;
+        const u64 idx = wbase + (u64)r * 32 + lane;
+        const u32 d = packed[r] & 0xFF;
+        const u64 pos = (u64)dbase[d] + whist[warp][d] + (packed[r] >> 8);
+        a_out[pos] = a_in[idx];
+        if (b_in) b_out[pos] = b_in[idx];
+        if (v_in) v_out[pos] = v_in[idx];
+    }
+}
+
+int radix_sort_bits(SortCols &c, int cur, u64 n, bool use_b, int lo, int hi, cudaStream_t st)
+{
+    if (n <= 1 || hi <= lo) return cur;
+    SG_CHECK(n < 0xFFFFFFFFull, "radix sort supports < 2^32 records");
+    const int bits = hi - lo;
+    const int passes = (bits + 7) / 8;
+    const int width = (bits + passes - 1) / passes;
+    const u32 num_tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
+    DevBuf<u32> hist((u64)256 * num_tiles, st);
+    int shift = lo;
+    for (int p = 0; p < passes; ++p) {
+        const int w = (hi - shift) < width ? (hi - shift) : width;
+        const u32 mask = (1u << w) - 1u;
+        const u64 *key = use_b ? c.b[cur] : c.a[cur];
+        rs_hist_kernel<<<num_tiles, RS_THREADS, 0, st>>>(key, n, shift, mask, hist.p, num_tiles);
+        SG_LAUNCHED();
+        exclusive_scan_u32(hist.p, hist.p, (u64)(mask + 1) * num_tiles, nullptr, st);
+        rs_scatter_kernel<<<num_tiles, RS_THREADS, 0, st>>>(key, n, shift, mask, hist.p, num_tiles,
+                                                            c.a[cur], c.a[cur ^ 1], c.b[cur], c.b[cur ^ 1],
+                                                            c.v[cur], c.v[cur ^ 1]);
+        SG_LAUNCHED();
+        cur ^= 1;
+        shift += w;
+    }
+    return cur;
+}
+
+int radix_sort_varying(SortCols &c, int cur, u64 n, bool use_b, cudaStream_t st)
+{
+    if (n <= 1) return cur;
+    DevBuf<u64> oa(2, st);
+    reduce_or_and_u64(use_b ? c.b[cur] : c.a[cur], n, oa.p, st);
+    u64 h[2];
+    SG_CUDA(cudaMemcpyAsync(h, oa.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    const u64 varying = h[0] ^ h[1];
+    if (varying == 0) return cur;
+    const int lo = __builtin_ctzll(varying), hi = 64 - __builtin_clzll(varying);
+    return radix_sort_bits(c, cur, n, use_b, lo, hi, st);
+}
+
+}  // namespace sg

@@ -1,0 +1,82 @@
+"""ctypes loader for tests/host_emul.cpp (TEST INFRASTRUCTURE: CPU emulation that drives the product's
+core.cuh primitives + host_phase_c.cpp; see the header of host_emul.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "_build", "host_emul.so")
+SRCS = [os.path.join(HERE, "host_emul.cpp"), os.path.join(ROOT, "sage2_b200", "csrc", "host_phase_c.cpp")]
+DEPS = SRCS + [os.path.join(ROOT, "sage2_b200", "csrc", "core.cuh"), os.path.join(ROOT, "sage2_b200", "csrc", "host_phase_c.h")]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO] + SRCS)
+        _lib = C.CDLL(SO)
+        _lib.hemu_run.restype = C.c_void_p
+        _lib.hemu_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        _lib.hemu_free.argtypes = [C.c_void_p]
+        _lib.hemu_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.hemu_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 9
+        _lib.hemu_get_bases.restype = C.c_uint64
+        _lib.hemu_get_bases.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.hemu_pack.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        _lib.hemu_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        _lib.hemu_key.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.hemu_overlap.restype = C.c_int
+        _lib.hemu_overlap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    return _lib
+
+
+class EmuRun:
+    def __init__(self, bases, offsets, k):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        L = lib()
+        h = L.hemu_run(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k)
+        sz = np.zeros(12, dtype=np.uint64)
+        L.hemu_sizes(h, sz.ctypes.data)
+        (self.U, self.SW, self.N, self.total_bp, self.n_edges, self.over, self.distinct, self.compare_calls,
+         self.inserted, self.removed, self.contained, self.contained_size) = (int(x) for x in sz)
+        U, SW, E = self.U, self.SW, self.n_edges
+        self.F = np.zeros(U * SW, np.uint64); self.RC = np.zeros(U * SW, np.uint64)
+        self.len = np.zeros(U, np.uint16); self.freq = np.zeros(U, np.uint16)
+        self.extR = np.zeros(U, np.uint64); self.extL = np.zeros(U, np.uint64)
+        self.explored_a = np.zeros(U, np.uint8); self.explored_b = np.zeros(U, np.uint8)
+        self.edges = np.zeros(2 * E, np.uint64)
+        L.hemu_copy(h, *(a.ctypes.data for a in (self.F, self.RC, self.len, self.freq, self.extR, self.extL,
+                                                  self.explored_a, self.explored_b, self.edges)))
+        L.hemu_free(h)
+        self.F = self.F.reshape(U, SW); self.RC = self.RC.reshape(U, SW)
+
+
+def records_to_bytes(rec: np.ndarray, lens: np.ndarray) -> np.ndarray:
+    """(U,SW) word-big-endian records -> concatenated reference-layout bytes (utils.cpp:96-119)."""
+    if len(rec) == 0:
+        return np.zeros(0, np.uint8)
+    be = rec.astype(">u8").view(np.uint8).reshape(len(rec), -1)
+    nb = (lens.astype(np.int64) + 3) // 4
+    mask = np.arange(be.shape[1])[None, :] < nb[:, None]
+    return be[mask]
+
+
+def unpack_ext(e: np.ndarray):
+    return (e & np.uint64(0xFFFFFFFF)).astype(np.uint64), ((e >> np.uint64(32)) & np.uint64(1)).astype(np.uint32), \
+        ((e >> np.uint64(33)) & np.uint64(0x3FFFFF)).astype(np.uint32)
+
+
+def unpack_edges(w: np.ndarray):
+    w0, w1 = w[0::2], w[1::2]
+    return (w0 >> np.uint64(32)).astype(np.uint64), (w0 & np.uint64(0xFFFFFFFF)).astype(np.uint64), \
+        ((w1 >> np.uint64(20)) & np.uint64(3)).astype(np.uint32), (w1 & np.uint64(0xFFFFF)).astype(np.uint32)

@@ -1,0 +1,242 @@
+// host_emul.cpp -- TEST INFRASTRUCTURE.  Drives the product's own host/device primitives
+// (sage2_b200/csrc/core.cuh) and its host phase-C walk (host_phase_c.cpp) sequentially on the CPU,
+// with std::sort / std::map standing in for the CUDA radix sort and open-addressing index.  It lets
+// the `-m "not gpu"` suite check the bit arithmetic, the extension state machine, phase B and the
+// phase-C walk against the oracle without a GPU.  It is NOT a fallback: nothing in sage2_b200 links it.
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <vector>
+#include "../sage2_b200/csrc/core.cuh"
+#include "../sage2_b200/csrc/host_phase_c.h"
+
+using namespace sg;
+
+namespace {
+
+struct Emu {
+    int SW = 1, k = 0, h = 0;
+    u64 total = 0, good = 0, total_bp = 0, U = 0;
+    std::vector<u64> F, RC;
+    std::vector<uint16_t> len, freq;
+    std::vector<u64> extR, extL;
+    std::vector<uint8_t> explored_a, explored_b;
+    std::vector<u64> edges;     // (w0,w1) final
+    u64 over = 0, distinct = 0, compare_calls = 0, inserted = 0, removed = 0, contained = 0, contained_size = 0;
+};
+
+int code_of(uint8_t c) { return ((c >> 1) ^ (c >> 2)) & 3; }
+bool valid_char(uint8_t c) { c &= 0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+void pack_record(const uint8_t *s, int len, int SW, u64 *rec, bool rc)
+{
+    for (int w = 0; w < SW; ++w) rec[w] = 0;
+    for (int p = 0; p < len; ++p) {
+        const int c = rc ? 3 - code_of(s[len - 1 - p]) : code_of(s[p]);
+        rec[p >> 5] |= (u64)c << (62 - 2 * (p & 31));
+    }
+    rec[SW - 1] |= (u64)len;
+}
+
+void run(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
+{
+    e.k = k; e.h = hash_len_for(k); e.total = (u64)n;
+    const int h = e.h;
+    int max_len = 1;
+    for (int64_t r = 0; r < n; ++r) max_len = std::max<int64_t>(max_len, std::min<int64_t>(off[r + 1] - off[r], 32 * kMaxWords - 8));
+    int SW = words_for_len(max_len);
+    static const int kStrides[] = { 2, 3, 4, 5, 6, 8, 12, 16, 32 };
+    for (int s : kStrides) if (s >= SW) { SW = s; break; }
+    e.SW = SW;
+
+    // K1
+    std::vector<std::vector<u64>> recs;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t l = off[r + 1] - off[r];
+        if (l <= k || l > 32 * SW - 8) continue;
+        const uint8_t *s = bases + off[r];
+        bool ok = true;
+        for (int p = 0; p < l; ++p) ok &= valid_char(s[p]);
+        if (!ok) continue;
+        std::vector<u64> f(SW), q(SW);
+        pack_record(s, (int)l, SW, f.data(), false);
+        pack_record(s, (int)l, SW, q.data(), true);
+        recs.push_back(q < f ? q : f);
+        e.good++; e.total_bp += (u64)l;
+    }
+    // K2
+    std::sort(recs.begin(), recs.end());
+    for (size_t i = 0; i < recs.size(); ++i) {
+        if (i == 0 || recs[i] != recs[i - 1]) {
+            e.F.insert(e.F.end(), recs[i].begin(), recs[i].end());
+            e.len.push_back((uint16_t)rec_len(recs[i].data(), SW));
+            e.freq.push_back(0);
+        }
+        e.freq.back()++;
+    }
+    const u64 U = e.U = e.len.size();
+    e.RC.resize(U * SW);
+    for (u64 i = 0; i < U; ++i) revcomp_record(&e.F[i * SW], &e.RC[i * SW], SW, e.len[i]);
+
+    // K3
+    std::map<std::pair<u64, u64>, std::vector<u32>> table;
+    for (u64 i = 0; i < U; ++i)
+        for (int t = 0; t < 4; ++t) {
+            u64 v0, v1;
+            entry_key(&e.F[i * SW], &e.RC[i * SW], SW, e.len[i], h, t, v0, v1);
+            table[std::make_pair(v0, v1)].push_back((u32)(i * 4 + t));
+        }
+    e.distinct = table.size();
+    for (auto &kv : table) if (kv.second.size() >= (size_t)kHashThreshold) e.over++;
+
+    // K4 phase A
+    e.extR.assign(U, 0); e.extL.assign(U, 0);
+    std::vector<uint8_t> flag5(U, 0);
+    std::vector<u32> cont_max(U, 0);
+    std::vector<u64> prevR(SW), prevL(SW);
+    for (u64 i = 0; i < U; ++i) {
+        const u64 *Xf = &e.F[i * SW], *Xr = &e.RC[i * SW];
+        const int len1 = e.len[i];
+        ExtState st;
+        ext_init(st);
+        for (int j = 0; j <= len1 - h; ++j) {
+            u64 v0, v1;
+            extract_key(Xf, SW, j, h, v0, v1);
+            auto it = table.find(std::make_pair(v0, v1));
+            if (it == table.end() || it->second.size() >= (size_t)kHashThreshold) continue;
+            ext_new_window(st);
+            for (u32 ent : it->second) {
+                const u32 rid2 = ent >> 2;
+                const int type = (int)(ent & 3);
+                const bool right = !(type & 1);
+                if (rid2 == (u32)i || !(right ? gate_right(j, len1, k) : gate_left(j, k, h))) continue;
+                const u64 *Q = (partner_uses_rc(type) ? &e.RC[0] : &e.F[0]) + (u64)rid2 * SW;
+                const int len2 = e.len[rid2];
+                bool cont;
+                e.compare_calls++;
+                const bool ok = overlap_equal(right ? Xf : Xr, len1, right ? j : len1 - j - h, Q, len2, SW, cont);
+                if (ok && cont) cont_max[rid2] = std::max(cont_max[rid2], (u32)(i + 1));
+                if (!(ok && !cont)) continue;
+                if (right) ext_right_hit(st, prevR.data(), Q, SW, rid2 + 1, type >> 1, j, len1, len2);
+                else ext_left_hit(st, prevL.data(), Q, SW, rid2 + 1, type >> 1, j, h, len1, len2);
+            }
+        }
+        flag5[i] = st.connections > kConnectionsLimit;
+        const bool amb = st.itsAmbigR == 1 || st.itsAmbigL == 1;
+        e.extR[i] = ext_pack(st.Rid, st.Rtype, amb ? 0u : st.Rlen);
+        e.extL[i] = ext_pack(st.Lid, st.Ltype, amb ? 0u : st.Llen);
+    }
+    // phase B
+    e.explored_a.resize(U); e.explored_b.resize(U);
+    for (u64 i = 0; i < U; ++i) {
+        uint8_t s = state_after_a((u32)i + 1, cont_max[i], flag5[i]);
+        e.explored_a[i] = s;
+        if (s != 6) { if (phase_b_qualifies(e.extR.data(), e.extL.data(), i)) { s = 4; e.contained++; } }
+        else e.contained_size++;
+        e.explored_b[i] = s;
+    }
+    std::vector<u64> edgesB;
+    for (u64 i = 0; i < U; ++i) {
+        EdgeRec r[2];
+        const int nr = phase_b_edges(e.extR.data(), e.extL.data(), e.explored_b.data(), e.len.data(), i, r);
+        for (int t = 0; t < nr; ++t) { edgesB.push_back(r[t].w0); edgesB.push_back(r[t].w1); }
+    }
+    // K5 candidates + host walk
+    std::vector<u32> s_ids, cand_off;
+    std::vector<u64> cand;
+    for (u64 i = 0; i < U; ++i) {
+        if (e.explored_b[i] != 0) continue;
+        s_ids.push_back((u32)i);
+        cand_off.push_back((u32)cand.size());
+        const u64 *Xf = &e.F[i * SW], *Xr = &e.RC[i * SW];
+        const int len1 = e.len[i];
+        for (int j = 0; j <= len1 - h; ++j) {
+            u64 v0, v1;
+            extract_key(Xf, SW, j, h, v0, v1);
+            auto it = table.find(std::make_pair(v0, v1));
+            if (it == table.end() || it->second.size() >= (size_t)kHashThreshold) continue;
+            for (u32 ent : it->second) {
+                const u32 rid2 = ent >> 2;
+                const int type = (int)(ent & 3);
+                const bool right = !(type & 1);
+                if (rid2 == (u32)i || e.explored_b[rid2] != 0 || !(right ? gate_right(j, len1, k) : gate_left(j, k, h))) continue;
+                const u64 *Q = (partner_uses_rc(type) ? &e.RC[0] : &e.F[0]) + (u64)rid2 * SW;
+                bool cont;
+                if (overlap_equal(right ? Xf : Xr, len1, right ? j : len1 - j - h, Q, e.len[rid2], SW, cont))
+                    cand.push_back(candidate_record(type, j, h, len1, e.len[rid2], rid2));
+            }
+        }
+    }
+    cand_off.push_back((u32)cand.size());
+    std::vector<u64> all;
+    if (!s_ids.empty()) {
+        PhaseCInput in;
+        in.U = U; in.len = e.len.data(); in.nS = s_ids.size(); in.s_ids = s_ids.data(); in.cand_off = cand_off.data();
+        in.cand = cand.data(); in.nB = edgesB.size() / 2; in.edgesB = edgesB.data();
+        PhaseCOutput out;
+        run_host_phase_c(in, out);
+        e.inserted = out.inserted; e.removed = out.removed;
+        all = out.edges;
+    }
+    for (size_t x = 0; x < edgesB.size(); x += 2)
+        if (e.explored_b[(edgesB[x] >> 32) - 1] != 0) { all.push_back(edgesB[x]); all.push_back(edgesB[x + 1]); }
+    // K6
+    std::vector<std::pair<u64, u64>> recs2;
+    for (size_t x = 0; x < all.size(); x += 2) recs2.emplace_back(all[x], all[x + 1]);
+    std::sort(recs2.begin(), recs2.end());
+    for (size_t x = 0; x < recs2.size(); ++x) {
+        if (x > 0 && recs2[x].first == recs2[x - 1].first && (recs2[x].second >> 20) == (recs2[x - 1].second >> 20)) continue;
+        e.edges.push_back(recs2[x].first); e.edges.push_back(recs2[x].second);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void *hemu_run(const uint8_t *bases, const int64_t *off, int64_t n, int k)
+{
+    Emu *e = new Emu();
+    run(*e, bases, off, n, k);
+    return e;
+}
+void hemu_free(void *p) { delete (Emu *)p; }
+// sizes: [0]=U [1]=SW [2]=good [3]=total_bp [4]=n_edges [5]=over [6]=distinct [7]=compare_calls [8]=inserted
+//        [9]=removed [10]=contained [11]=contained_size
+void hemu_sizes(void *p, uint64_t *o)
+{
+    Emu *e = (Emu *)p;
+    o[0] = e->U; o[1] = (u64)e->SW; o[2] = e->good; o[3] = e->total_bp; o[4] = e->edges.size() / 2; o[5] = e->over;
+    o[6] = e->distinct; o[7] = e->compare_calls; o[8] = e->inserted; o[9] = e->removed; o[10] = e->contained;
+    o[11] = e->contained_size;
+}
+void hemu_copy(void *p, uint64_t *F, uint64_t *RC, uint16_t *len, uint16_t *freq, uint64_t *extR, uint64_t *extL,
+               uint8_t *expl_a, uint8_t *expl_b, uint64_t *edges)
+{
+    Emu *e = (Emu *)p;
+    if (F) memcpy(F, e->F.data(), e->F.size() * 8);
+    if (RC) memcpy(RC, e->RC.data(), e->RC.size() * 8);
+    if (len) memcpy(len, e->len.data(), e->len.size() * 2);
+    if (freq) memcpy(freq, e->freq.data(), e->freq.size() * 2);
+    if (extR) memcpy(extR, e->extR.data(), e->extR.size() * 8);
+    if (extL) memcpy(extL, e->extL.data(), e->extL.size() * 8);
+    if (expl_a) memcpy(expl_a, e->explored_a.data(), e->explored_a.size());
+    if (expl_b) memcpy(expl_b, e->explored_b.data(), e->explored_b.size());
+    if (edges) memcpy(edges, e->edges.data(), e->edges.size() * 8);
+}
+
+// unit-level entry points
+uint64_t hemu_get_bases(const uint64_t *rec, int SW, int s, int nb) { return get_bases(rec, SW, s, nb); }
+void hemu_pack(const uint8_t *s, int len, int SW, uint64_t *rec, int rc) { pack_record(s, len, SW, rec, rc != 0); }
+void hemu_revcomp(const uint64_t *F, uint64_t *R, int SW, int len) { revcomp_record(F, R, SW, len); }
+void hemu_key(const uint64_t *rec, int SW, int j, int h, uint64_t *v) { extract_key(rec, SW, j, h, v[0], v[1]); }
+int hemu_overlap(const uint64_t *X, int lenX, int start, const uint64_t *Y, int lenY, int SW, int *contained)
+{
+    bool c;
+    const bool ok = overlap_equal(X, lenX, start, Y, lenY, SW, c);
+    *contained = c;
+    return ok;
+}
+
+}  // extern "C"

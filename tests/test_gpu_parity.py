@@ -1,0 +1,142 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every stage of the CUDA path, called through
+the C ABI, must equal the oracle on the same seeded inputs; the text outputs must be byte-identical
+to the UNMODIFIED reference's (md5s in tests/golden/golden.json)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import datasets
+import emul
+from oracle import oracle
+from sage2_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+SMALL = ["clean", "k31", "k70", "k64", "err", "rep", "hicopy", "deep", "varlen", "varlen_err", "deep_varlen",
+         "tandem", "mixed", "empty", "allbad", "single"]
+
+
+def _md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def _get(name):
+    return datasets.get(name) if name in datasets.DATASETS else synth.config(name)
+
+
+def _run_gpu(reads, k):
+    loader = api.ReadLoader(k)
+    loader.readDatasetInBytes(reads)
+    loader.organizeReads()
+    table = api.HashTable(k, loader)
+    table.hashPrefixesAndSuffix()
+    graph = api.EconomyGraph(k, table)
+    graph.buildInitialOverlapGraph()
+    graph.buildOverlapGraphEconomy()
+    graph.sortEconomyGraph()
+    return loader, graph
+
+
+def _compare(o, gpu):
+    c = gpu.counters()
+    assert c["good_reads"] == o.N and c["unique_reads"] == o.U and c["avg_len"] == o.avg_len
+    assert c["distinct_keys"] == o.distinct_keys and c["keys_over_threshold"] == o.keys_over_threshold
+    assert c["compare_calls"] == o.compare_calls
+    assert (c["contained_ext"], c["contained_size"], c["left_to_explore"]) == (o.contained_ext, o.contained_size, o.left_to_explore)
+    assert (c["edges_inserted_c"], c["transitive_removed"]) == (o.edges_inserted_c, o.transitive_removed)
+    r = gpu.reads()
+    np.testing.assert_array_equal(r["length"], o.length[1:])
+    np.testing.assert_array_equal(r["frequency"], o.frequency[1:])
+    np.testing.assert_array_equal(r["fwd"], o.fwd)
+    np.testing.assert_array_equal(r["rc"], o.rc)
+    x = gpu.extensions()
+    for mine, ref in ((x["right"], o.right_ext), (x["left"], o.left_ext)):
+        i, t, l = emul.unpack_ext(mine)
+        np.testing.assert_array_equal(i, ref["id"][1:])
+        has = i != 0
+        np.testing.assert_array_equal(t[has], ref["type"][1:][has])
+        np.testing.assert_array_equal(l[has], ref["length"][1:][has])
+    np.testing.assert_array_equal(x["explored"], o.explored_b[1:])
+    e = gpu.edges()
+    assert len(e) == o.n_edges
+    for f in ("from", "to", "type", "delta", "delta_twin"):
+        np.testing.assert_array_equal(e[f], o.edges[f])
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_every_stage_equals_oracle(name, tmp_path):
+    reads, k = _get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    loader, graph = _run_gpu(reads, k)
+    _compare(o, loader.gpu)
+    loader.saveReadsInFile(str(tmp_path / "g.reads"))
+    graph.saveOverlapGraphInFile(str(tmp_path / "g.graph3"))
+    if name in GOLD:       # bytes the unmodified reference wrote for the same input
+        assert _md5(tmp_path / "g.reads") == GOLD[name]["reads_md5"]
+        assert _md5(tmp_path / "g.graph3") == GOLD[name]["graph3_md5"]
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg4mini"])
+def test_baseline_configs_byte_identical_to_reference(name, tmp_path):
+    reads, k = _get(name)
+    loader, graph = _run_gpu(reads, k)
+    loader.saveReadsInFile(str(tmp_path / "g.reads"))
+    graph.saveOverlapGraphInFile(str(tmp_path / "g.graph3"))
+    g = GOLD[name]
+    c = loader.gpu.counters()
+    assert c["unique_reads"] == g["unique_reads"] and c["good_reads"] == g["good_reads"]
+    assert c["contained_ext"] == g["contained_ext"] and c["left_to_explore"] == g["left_to_explore"]
+    assert c["edges_inserted_c"] == g["edges_inserted"] and c["transitive_removed"] == g["transitive_removed"]
+    assert _md5(tmp_path / "g.reads") == g["reads_md5"]
+    assert _md5(tmp_path / "g.graph3") == g["graph3_md5"]
+
+
+def test_rerun_same_context_is_idempotent():
+    reads, k = _get("rep")
+    b, off = synth.concat(reads)
+    gpu = api.Sage2Gpu(0)
+    gpu.run_steps123(b, off, k)
+    e1 = gpu.edges().copy()
+    gpu.run_steps123(b, off, k)
+    e2 = gpu.edges()
+    np.testing.assert_array_equal(e1, e2)
+
+
+def test_input_order_does_not_matter():
+    """Read ids are ranks in the sorted unique set: shuffling the input must not change any output."""
+    reads, k = _get("err")
+    b, off = synth.concat(reads)
+    gpu = api.Sage2Gpu(0)
+    gpu.run_steps123(b, off, k)
+    e1 = gpu.edges().copy()
+    perm = np.random.default_rng(1).permutation(len(reads))
+    b2, off2 = synth.concat(reads[perm])
+    gpu.run_steps123(b2, off2, k)
+    np.testing.assert_array_equal(e1, gpu.edges())
+
+
+def test_cfg2_full_size_properties():
+    """BASELINE config #2 at full size: structural invariants that do not need the oracle."""
+    reads, k = _get("cfg2")
+    b, off = synth.concat(reads)
+    gpu = api.Sage2Gpu(0)
+    gpu.run_steps123(b, off, k)
+    c = gpu.counters()
+    assert c["good_reads"] == len(reads)
+    r = gpu.reads()
+    assert int(r["frequency"].astype(np.int64).sum()) == len(reads)         # dedupe conserves reads
+    e = gpu.edges()
+    assert c["n_edges"] == len(e) > 0
+    assert np.all(e["from"] < e["to"]) and np.all(e["to"] <= c["unique_reads"])
+    key = (e["from"].astype(np.uint64) << np.uint64(34)) | (e["to"].astype(np.uint64) << np.uint64(2)) | e["type"].astype(np.uint64)
+    assert np.all(np.diff(key.astype(np.int64)) > 0)                        # canonical order, (from,to,type) unique
+    # fixed-length reads: the twin overhang equals the overhang, and an error-free random genome is a chain
+    assert np.all(e["delta"] == e["delta_twin"])
+    assert c["contained_ext"] + c["left_to_explore"] + c["contained_size"] == c["unique_reads"]
+    assert c["left_to_explore"] <= 8
