@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s through SAGE2's overlap-graph build (reference steps 1-3) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+A "step" is one complete pass of the hot path over one batch of synthetic reads: ingest (filter,
+canonicalise, 2-bit pack), sort + dedupe, prefix/suffix table, phase A search + extension state
+machine, phase B, phase-C candidates + host walk, canonical edge sort.  The workload is BASELINE.json
+config #2 (4.6 Mbp random genome, 150 bp paired-end, 100x, -k 63): 3,066,666 input reads per step.
+
+  value   : whole-job input reads/s with the ASCII reads already resident in HBM.
+  e2e     : the same through the C ABI with HOST (pinned) buffers: H2D of the reads and D2H of the
+            edge list are inside the timed region.
+  roofline: the phase-A search kernel against the measured HBM copy peak (MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference: the UNMODIFIED reference's steps 1-3 (oracle/_ref/ref_steps123,
+            built from /root/reference in the build container) on the box's host cores, on a bounded
+            cfg2-shaped sample.
+
+N > 1 (torchrun, one rank per GPU): round 1 runs N independent replicas (each rank builds the graph
+of its own cfg2-shaped read set, different seed); no data-path collective, scaling "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads/sec through exact-overlap graph build (SAGE2 steps 1-3)"
+UNIT = "reads/s"
+
+
+def make_workload(name: str, seed_shift: int = 0, genome_size: int | None = None):
+    from sage2_b200 import synth
+    if name != "cfg2":
+        reads, k = synth.config(name)
+        return reads, k, {"workload": name}
+    G = genome_size or 4_600_000
+    g = synth.random_genome(G, 4600 + 7919 * seed_shift)
+    reads = synth.paired_reads(g, 150, 100, seed=4601 + 7919 * seed_shift, mu=450, sigma=30)
+    return reads, 63, {"workload": "cfg2: synthetic 4.6 Mbp random genome, 150 bp paired-end, 100x, -k 63",
+                       "genome_bp": G, "read_len": 150, "coverage": 100, "k": 63}
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the reference on the host cores -------------------------------------------------------------
+
+def reference_run(reads, k, tmpdir: str, threads: int | None = None) -> dict:
+    """One run of the unmodified reference's steps 1-3 (oracle/_ref/ref_steps123) on `reads`."""
+    from oracle import oracle
+    from sage2_b200 import synth
+    fq = os.path.join(tmpdir, "sample.fastq")
+    synth.write_fastq(fq, reads)
+    env = dict(os.environ)
+    if threads:
+        env["OMP_NUM_THREADS"] = str(threads)
+    if os.access(oracle.REF_STEPS, os.X_OK):
+        out = subprocess.run([oracle.REF_STEPS, fq, str(k)], env=env, check=True, capture_output=True, text=True).stdout
+        d = json.loads(out.strip().splitlines()[-1])
+        d["kind"] = "reference"
+        return d
+    # the reference did not travel: time the C port instead
+    b, off = synth.concat(reads)
+    t = time.perf_counter()
+    o = oracle.OracleRun(b, off, k, threads or 0)
+    dt = time.perf_counter() - t
+    return {"input_reads": len(reads), "unique_reads": o.U, "edges": o.n_edges, "threads": threads or os.cpu_count(),
+            "t_steps123": dt, "kind": "port"}
+
+
+def sample_workload(target_seconds: float, tmpdir: str):
+    """A cfg2-shaped sample (same read length, coverage, k; smaller genome) sized for ~target_seconds."""
+    probe_reads, k, _ = make_workload("cfg2", genome_size=150_000)
+    d = reference_run(probe_reads, k, tmpdir)
+    rate = d["input_reads"] / max(d["t_steps123"], 1e-3)
+    want_reads = min(3_066_666, max(100_000, int(rate * target_seconds)))
+    G = max(150_000, min(4_600_000, int(want_reads * 150 / 100)))
+    return make_workload("cfg2", genome_size=G)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tmp = tempfile.mkdtemp(prefix="sage2_ref_")
+    per_step = max(4.0, 170.0 / max(1, args.steps + args.warmup))
+    reads, k, cfg = sample_workload(min(25.0, per_step), tmp)
+    times, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = reference_run(reads, k, tmp)
+        if i >= args.warmup:
+            times.append(last["t_steps123"])
+    ms = 1000.0 * float(np.mean(times))
+    value = len(reads) / (ms / 1000.0)
+    sample = f"cfg2-shaped sample: {cfg['genome_bp']} bp genome, {len(reads)} reads, steps 1-3 without FASTQ parse / text output"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "impl": "reference",
+            "config": dict(cfg, workload=cfg["workload"], sample_reads=len(reads)),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last.get("threads"), "kind": last["kind"], "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "reference_breakdown_s": {k2: v for k2, v in last.items() if k2.startswith("t_")}}
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm -----------------------------------------------------------------------------------
+
+def algorithmic_bytes_phase_a(c: dict, read_len: int) -> float:
+    """SURVEY.md 8(d) restricted to the phase-A launch: stream the packed reads once, one 32-B sector
+    per window probe, one sector-rounded packed partner read per gated comparison, 16 B of extension
+    records out per read."""
+    U, V, probes = c["unique_reads"], c["compare_calls"], c["window_probes"]
+    packed = (read_len + 3) // 4
+    B = 32 * ((packed + 31) // 32)
+    return float(U * packed + 32 * probes + B * V + 16 * U)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sage2_b200 import api, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    reads, k, cfg = make_workload(args.workload, seed_shift=rank)
+    n_reads = len(reads)
+    read_len = int(reads.shape[1]) if isinstance(reads, np.ndarray) and reads.ndim == 2 else 0
+    bases, offsets = synth.concat(reads)
+    h_bases = torch.from_numpy(bases).pin_memory()
+    h_off = torch.from_numpy(offsets).pin_memory()
+    d_bases = h_bases.cuda(non_blocking=False)
+    d_off = h_off.cuda(non_blocking=False)
+    gpu = api.Sage2Gpu(local)
+    stream = torch.cuda.ExternalStream(gpu.stream_ptr(), device=torch.device("cuda", local))
+
+    def step_device():
+        gpu.load_reads_ptr(d_bases.data_ptr(), d_off.data_ptr(), n_reads, k, device=True)
+        gpu.build_hash_table()
+        gpu.build_overlap_graph()
+
+    def step_host():
+        gpu.load_reads_ptr(h_bases.data_ptr(), h_off.data_ptr(), n_reads, k, device=False)
+        gpu.build_hash_table()
+        gpu.build_overlap_graph()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = api.kernel_launches()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        stage = {}
+        for _ in range(steps):
+            fn()
+            for kk, vv in gpu.timers().items():
+                stage[kk] = stage.get(kk, 0.0) + vv
+        ev1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        dev_ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), api.kernel_launches() - l0, {a: b / steps for a, b in stage.items()}
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    dev_ms, wall_ms, launches, stage = timed(step_device, args.steps)
+    counters = gpu.counters()
+    clocks = sampler.stop() if sampler else None
+    step_host()
+    e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_host, args.steps)
+    n_edges = gpu.counters()["n_edges"]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = dev_ms / args.steps
+    value = world * n_reads / (ms_per_step / 1000.0)
+    e2e_value = world * n_reads / (e2e_dev_ms / args.steps / 1000.0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    abytes = algorithmic_bytes_phase_a(counters, read_len or counters["avg_len"])
+    ka_ms = stage["phase_a_kernel"]
+    achieved = abytes / (ka_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "phase_a_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": abytes, "kernel_ms": ka_ms,
+                "kernel_share_of_step": ka_ms / ms_per_step}
+
+    # reference's CPU path on a bounded sample of the same workload (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        tmp = tempfile.mkdtemp(prefix="sage2_cpu_")
+        s_reads, s_k, s_cfg = sample_workload(15.0, tmp)
+        d = reference_run(s_reads, s_k, tmp)
+        cpu = {"value": d["input_reads"] / d["t_steps123"], "unit": UNIT, "cores": d.get("threads"), "kind": d["kind"],
+               "sample": f"cfg2-shaped sample: {s_cfg['genome_bp']} bp genome, {len(s_reads)} reads, steps 1-3 "
+                         f"({d['t_steps123']:.1f} s) without FASTQ parse / text output",
+               "breakdown_s": {k2: v for k2, v in d.items() if k2.startswith("t_")}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": dict(cfg, parallelism=("single GPU" if world == 1 else f"{world} independent replicas, no collective"),
+                       reads_per_step_per_gpu=n_reads, l2_policy="inputs (460 MB ASCII + working set) larger than the 126 MB L2",
+                       timing="CUDA events on the library stream around all steps, max over ranks"),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bases.nbytes + offsets.nbytes),
+                "d2h_bytes_per_step": int(16 * n_edges), "ms_per_step": e2e_dev_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "edges_per_sec": world * counters["n_edges"] / (ms_per_step / 1000.0),
+        "wall_ms_per_step": wall_ms / args.steps,
+        "stage_ms": stage,
+        "counters": {kk: counters[kk] for kk in ("good_reads", "unique_reads", "distinct_keys", "compare_calls",
+                                                  "window_probes", "n_edges", "left_to_explore", "record_words")},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

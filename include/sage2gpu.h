@@ -43,6 +43,7 @@ typedef struct {
 /* Stage times in milliseconds (CUDA events on the context's stream; host part by steady_clock). */
 typedef struct {
     float ingest, sort_reads, build_table, phase_a, phase_b, phase_c_dev, phase_c_host, sort_edges, total;
+    float phase_a_kernel;   /* the phase-A search kernel alone (events around the launch) */
 } sage2gpu_timers;
 
 /* One undirected edge as OverlapGraph::convertGraph creates it (overlapGraph.cpp:84-159):
@@ -85,6 +86,8 @@ int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *out);
 /* Number of CUDA kernels this library has launched in this process so far (monotonic). */
 uint64_t sage2gpu_kernel_launches(void);
 int sage2gpu_get_timers(const sage2gpu_ctx *ctx, sage2gpu_timers *out);
+/* The cudaStream_t every kernel of this context is launched on (for external CUDA-event timing). */
+void *sage2gpu_stream(const sage2gpu_ctx *ctx);
 
 /* replaces: what steps 4-7 read through ReadLoader::getRead (readLoader.cpp:309): for ids 1..U the
  * length, frequency and both packed strands in the REFERENCE byte layout (utils.cpp:96-119).

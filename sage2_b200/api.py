@@ -34,7 +34,7 @@ class Counters(C.Structure):
 class Timers(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "ingest", "sort_reads", "build_table", "phase_a", "phase_b", "phase_c_dev", "phase_c_host",
-        "sort_edges", "total")]
+        "sort_edges", "total", "phase_a_kernel")]
 
 
 EDGE_DT = np.dtype([("from", "<u8"), ("to", "<u8"), ("type", "<u4"), ("delta", "<u4"),
@@ -44,7 +44,7 @@ EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2g
            "sage2gpu_load_reads_device", "sage2gpu_build_hash_table", "sage2gpu_build_overlap_graph",
            "sage2gpu_run_steps123", "sage2gpu_get_counters", "sage2gpu_get_timers", "sage2gpu_reads_bytes",
            "sage2gpu_get_reads", "sage2gpu_get_extensions", "sage2gpu_get_edges", "sage2gpu_write_reads",
-           "sage2gpu_write_graph3", "sage2gpu_kernel_launches"]
+           "sage2gpu_write_graph3", "sage2gpu_kernel_launches", "sage2gpu_stream"]
 
 _lib = None
 
@@ -83,6 +83,8 @@ def load_library():
         lib.sage2gpu_get_edges.argtypes = [vp, vp, C.c_uint64, u64p]
         lib.sage2gpu_write_reads.argtypes = [vp, C.c_char_p]
         lib.sage2gpu_write_graph3.argtypes = [vp, C.c_char_p]
+        lib.sage2gpu_stream.argtypes = [vp]
+        lib.sage2gpu_stream.restype = vp
         lib.sage2gpu_kernel_launches.argtypes = []
         lib.sage2gpu_kernel_launches.restype = C.c_uint64
         _lib = lib
@@ -144,6 +146,10 @@ class Sage2Gpu:
         self.load_reads(bases, offsets, min_overlap)
         self.build_hash_table()
         self.build_overlap_graph()
+
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this context (e.g. for torch.cuda.ExternalStream)."""
+        return int(self._lib.sage2gpu_stream(self._h) or 0)
 
     # ---- results ------------------------------------------------------------------------------
     def counters(self) -> dict:

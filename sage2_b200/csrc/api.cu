@@ -221,9 +221,11 @@ int sage2gpu_get_timers(const sage2gpu_ctx *ctx, sage2gpu_timers *o)
     const sg::Timers &t = ctx->c.tm;
     o->ingest = t.ingest; o->sort_reads = t.sort_reads; o->build_table = t.build_table; o->phase_a = t.phase_a;
     o->phase_b = t.phase_b; o->phase_c_dev = t.phase_c_dev; o->phase_c_host = t.phase_c_host;
-    o->sort_edges = t.sort_edges; o->total = t.total_device;
+    o->sort_edges = t.sort_edges; o->total = t.total_device; o->phase_a_kernel = t.phase_a_kernel;
     return SAGE2GPU_OK;
 }
+
+void *sage2gpu_stream(const sage2gpu_ctx *ctx) { return ctx ? (void *)ctx->c.stream : nullptr; }
 
 int sage2gpu_reads_bytes(const sage2gpu_ctx *ctx, uint64_t *n_bytes)
 {

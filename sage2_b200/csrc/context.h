@@ -23,7 +23,7 @@ struct Counters {
 
 struct Timers {   // milliseconds, CUDA events on the context stream
     float ingest = 0, sort_reads = 0, dedupe = 0, build_table = 0, phase_a = 0, phase_b = 0,
-          phase_c_dev = 0, phase_c_host = 0, sort_edges = 0, total_device = 0;
+          phase_c_dev = 0, phase_c_host = 0, sort_edges = 0, total_device = 0, phase_a_kernel = 0;
 };
 
 struct Context {

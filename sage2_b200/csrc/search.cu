@@ -320,13 +320,19 @@ void stage_phase_a(Context &c)
     DevBuf<unsigned long long> d_counters(2, st);
     SG_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(unsigned long long), st));
     const SearchParams P = make_params(c);
+    cudaEvent_t e0, e1;
+    SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
+    SG_CUDA(cudaEventRecord(e0, st));
     SG_DISPATCH_SW(c.SW, launch_phase_a<SWC>(c, P, d_counters.p));
     SG_LAUNCHED();
+    SG_CUDA(cudaEventRecord(e1, st));
     unsigned long long h[2];
     SG_CUDA(cudaMemcpyAsync(h, d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     c.cnt.compare_calls = h[0];
     c.cnt.window_probes = h[1];
+    cudaEventElapsedTime(&c.tm.phase_a_kernel, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
 // used by graph.cu
