@@ -36,8 +36,9 @@ typedef struct {
     uint64_t n_edges;
     uint64_t compare_calls;     /* V of SURVEY 8(d): gated partner comparisons in phase A */
     uint64_t window_probes;     /* U*W table probes in phase A */
-    uint64_t slow_path_reads;
+    uint64_t slow_path_reads;   /* reads whose extension chain ran hit by hit (ambiguity / multi-hit windows) */
     uint64_t record_words;      /* 64-bit words per packed read record */
+    uint64_t probe_restarts;    /* reads redone with verified probes after a tag collision */
 } sage2gpu_counters;
 
 /* Stage times in milliseconds (CUDA events on the context's stream; host part by steady_clock). */

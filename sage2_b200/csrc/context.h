@@ -18,7 +18,8 @@ struct Counters {
     u64 n_edges = 0;
     u64 compare_calls = 0;   // V of SURVEY 8(d) (phase A gated partner comparisons)
     u64 window_probes = 0;   // U*W
-    u64 slow_path_reads = 0; // reads re-done by the exact sequential chain
+    u64 slow_path_reads = 0; // reads that left the parallel fast mode for the exact sequential chain
+    u64 probe_restarts = 0;  // reads redone with verified probes after a 24-bit tag collision
 };
 
 struct Timers {   // milliseconds, CUDA events on the context stream

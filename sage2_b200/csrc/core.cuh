@@ -103,9 +103,12 @@ SG_HD void revcomp_record(const u64 *F, u64 *R, int SW, int len)
 // 0 fwd prefix, 1 fwd suffix, 2 revcomp prefix, 3 revcomp suffix.  Entries are sorted by
 // (key, readId, type) so that every key's entries are contiguous and already in the reference's
 // bucket order (insertion order, hashTable.cpp:94-109).  The open-addressing index maps
-// key -> (offset, count) with one 64-bit slot per distinct key:
-//   [63:40] 24-bit tag of the key hash   [39:33] min(count,127)   [32:0] offset of the first entry
+// key -> bucket with one 64-bit slot per distinct key:
+//   [63:40] 24-bit tag of the key hash   [39:33] min(count,127)
+//   [32:0]  count == 1: the entry itself (no second hop);  count > 1: offset of the first entry
 // A slot is never 0 when occupied (count >= 1).  count >= 100 means "masked" (hashTable.cpp:116-121).
+// Slots are grouped in 32-byte SECTORS of 4: a key's home is a sector (one DRAM sector per probe),
+// insertion and search walk the 4 slots of a sector in order, then the next sector.
 SG_HD u64 mix64(u64 x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
@@ -120,15 +123,16 @@ SG_HD u64 mulhi64(u64 a, u64 b)
     return (u64)(((unsigned __int128)a * b) >> 64);
 #endif
 }
-SG_HD u64 slot_home(u64 hsh, u64 cap) { return mulhi64(hsh, cap); }
+constexpr int kSlotsPerSector = 4;
+SG_HD u64 home_sector(u64 hsh, u64 nsec) { return mulhi64(hsh, nsec); }
 SG_HD u64 slot_tag(u64 hsh) { return hsh & 0xFFFFFFull; }
-SG_HD u64 slot_encode(u64 hsh, u64 count, u64 offset)
+SG_HD u64 slot_encode(u64 hsh, u64 count, u64 payload)
 {
-    return (slot_tag(hsh) << 40) | ((count > 127 ? 127ull : count) << 33) | offset;
+    return (slot_tag(hsh) << 40) | ((count > 127 ? 127ull : count) << 33) | payload;
 }
 SG_HD u64 slot_get_tag(u64 s) { return s >> 40; }
 SG_HD u32 slot_get_count(u64 s) { return (u32)((s >> 33) & 127); }
-SG_HD u64 slot_get_offset(u64 s) { return s & 0x1FFFFFFFFull; }
+SG_HD u64 slot_get_payload(u64 s) { return s & 0x1FFFFFFFFull; }
 
 // Key of table entry `type` of a read (hashTable.cpp:98-101)
 SG_HD void entry_key(const u64 *F, const u64 *RC, int SW, int len, int h, int type, u64 &v0, u64 &v1)

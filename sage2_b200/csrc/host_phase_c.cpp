@@ -36,12 +36,12 @@ struct Walk {
     std::vector<std::vector<HEdge>> adj;
     std::vector<uint8_t> state;                    // 0/1/2 for S nodes, 4 for everything else
     std::vector<uint8_t> marked;
-    std::vector<uint32_t> node_id;
+    std::vector<uint32_t> node_id, node_len;
     uint64_t inserted = 0, removed = 0;
 
     explicit Walk(const PhaseCInput &i) : in(i) {}
 
-    uint32_t node(uint32_t id, uint8_t st)
+    uint32_t node(uint32_t id, uint8_t st, uint32_t len)
     {
         auto it = slot.find(id);
         if (it != slot.end()) return it->second;
@@ -51,6 +51,7 @@ struct Walk {
         state.push_back(st);
         marked.push_back(0);
         node_id.push_back(id);
+        node_len.push_back(len);
         return n;
     }
 
@@ -58,7 +59,7 @@ struct Walk {
     void insert_edge(uint32_t nu, uint32_t nv, uint32_t delta, uint32_t type)
     {
         const uint32_t u = node_id[nu], v = node_id[nv];
-        const uint32_t lu = in.len[u - 1], lv = in.len[v - 1];
+        const uint32_t lu = node_len[nu], lv = node_len[nv];
         const uint32_t delta2 = lu - (lv - delta);
         adj[nu].push_back(HEdge{ v, (uint8_t)type, 0, delta & 0xFFFFFu });
         adj[nv].push_back(HEdge{ u, (uint8_t)rev_type(type), 0, delta2 & 0xFFFFFu });
@@ -127,7 +128,7 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
     const auto t0 = std::chrono::steady_clock::now();
     Walk w(in);
     w.slot.reserve(in.nS * 4 + 16);
-    for (uint64_t s = 0; s < in.nS; ++s) w.node(in.s_ids[s] + 1, 0);
+    for (uint64_t s = 0; s < in.nS; ++s) w.node(in.s_ids[s] + 1, 0, in.s_len[s]);
     const uint32_t nS = (uint32_t)in.nS;
 
     // phase-B neighbours of S, then every phase-B entry of every needed node
@@ -136,8 +137,8 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
         const auto ia = w.slot.find(a), ib = w.slot.find(b);
         const bool a_in_s = ia != w.slot.end() && ia->second < nS;
         const bool b_in_s = ib != w.slot.end() && ib->second < nS;
-        if (a_in_s && ib == w.slot.end()) w.node(b, 4);
-        if (b_in_s && ia == w.slot.end()) w.node(a, 4);
+        if (a_in_s && ib == w.slot.end()) w.node(b, 4, in.edgesB_len[e] >> 16);
+        if (b_in_s && ia == w.slot.end()) w.node(a, 4, in.edgesB_len[e] & 0xFFFFu);
     }
     for (uint64_t e = 0; e < in.nB; ++e) {
         const uint64_t w0 = in.edgesB[2 * e], w1 = in.edgesB[2 * e + 1];
@@ -146,7 +147,7 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
         const auto ia = w.slot.find(a), ib = w.slot.find(b);
         if (ia != w.slot.end()) w.adj[ia->second].push_back(HEdge{ b, (uint8_t)type, 0, length });
         if (ib != w.slot.end()) {
-            const uint32_t la = in.len[a - 1], lb = in.len[b - 1];
+            const uint32_t la = in.edgesB_len[e] & 0xFFFFu, lb = in.edgesB_len[e] >> 16;
             w.adj[ib->second].push_back(HEdge{ a, (uint8_t)rev_type(type), 0, (la - (lb - length)) & 0xFFFFFu });
         }
     }

@@ -7,14 +7,15 @@
 namespace sg {
 
 struct PhaseCInput {
-    uint64_t U;
-    const uint16_t *len;        // [U], index = readId-1
     uint64_t nS;
     const uint32_t *s_ids;      // [nS] 0-based ids of reads in state 0 after phase B, ascending
+    const uint16_t *s_len;      // [nS] their lengths
     const uint32_t *cand_off;   // [nS+1]
     const uint64_t *cand;       // read2(1-based)<<32 | edgeType<<20 | overhang20, reference order
     uint64_t nB;
-    const uint64_t *edgesB;     // [2*nB] canonical phase-B records (w0,w1), any order
+    const uint64_t *edgesB;     // [2*nB] canonical phase-B records (w0,w1), any order: every record with an
+                                // endpoint in S or adjacent (by a phase-B record) to a read in S
+    const uint32_t *edgesB_len; // [nB] len(from) | len(to) << 16
 };
 
 struct PhaseCOutput {

@@ -3,24 +3,39 @@
 // insertAllEdgesOfRead (:580-638), HashTable::hashTableSearch (hashTable.cpp:193-231) and
 // compareStringInBytes[Previous] (economyGraph.cpp:712-808).
 //
-// One warp per read.  Lanes probe 32 consecutive windows at once (key extraction by funnel shifts from
-// the read's words in shared memory, one slot sector per probe); every found window's bucket is then
-// expanded 32 entries at a time: each lane fetches one partner record in the orientation the entry
-// type asks for and verifies the whole overlap by XOR under a mask (which also re-verifies the key).
-// Accepted hits are fed, in the reference's order (window ascending, bucket order), to the
-// unique-extension state machine of core.cuh.
+// One warp per read, three stages per 32 windows:
+//   1. PROBE   lane l derives the key of window base+l by funnel shifts from the read's words in shared
+//              memory and reads ONE 32-byte sector of the slot index (4 slots).  A 24-bit tag match is
+//              taken as "found" (verified in stage 2); a match on a masked key (>= 100 entries) is
+//              verified at once through the bucket's first read, exactly like hashTableSearch.
+//   2. VERIFY  the (window, bucket entry) pairs of all found windows are flattened into a queue in the
+//              reference's order (window ascending, bucket order) and consumed 32 at a time: every
+//              lane fetches one partner record in the orientation its entry type asks for and checks
+//              the whole overlap by XOR under a mask; the first entry of every bucket also proves the
+//              key (a tag collision restarts the read with verified probes).
+//   3. EXTEND  the accepted hits of a round feed the unique-extension state machine.  FAST mode checks
+//              every hit against the previous hit of its side in parallel (records exchanged through
+//              shared memory): as long as no window holds two hits of one side and every adjacent pair
+//              is consistent, the reference's chain (economyGraph.cpp:94-437) reduces to "first right
+//              hit, last left hit, not ambiguous".  The first round that breaks this converts the
+//              state to core.cuh's ExtState and the rest of the read runs the reference's sequential
+//              chain hit by hit (EXACT mode) -- still with parallel fetch and verification.
 #include "context.h"
 
 namespace sg {
-
-constexpr int SR_WARPS = 8;
 
 struct SearchParams {
     const u64 *F, *RC;
     const u64 *slots;
     const u32 *entries;
-    u64 cap, U;
+    u64 nsec, U;
     int h, k;
+};
+
+template <int SW>
+struct SearchCfg {
+    static constexpr int WARPS = SW <= 8 ? 8 : (SW <= 16 ? 4 : 2);
+    static constexpr int SWP = SW | 1;          // odd record stride in shared memory (bank spread)
 };
 
 template <int SW>
@@ -39,53 +54,68 @@ __device__ __forceinline__ void t_extract_key(const u64 *X, int j, int h, u64 &v
     else { v0 = t_window32<SW>(X, j) >> (64 - 2 * (h - 32)); v1 = t_window32<SW>(X, j + h - 32); }
 }
 
-// X (shared / global pointer, dynamic word index) against Y (registers, static index)
-template <int SW>
-__device__ __forceinline__ bool t_overlap_equal(const u64 *X, int lenX, int start, const u64 (&Y)[SW], int lenY, bool &contained)
+// X[start+t] == Y[t] for t in [0, ov): X is indexed dynamically (shared / global pointer), Y statically
+// (registers or a pointer).  `key_bad` = a mismatch inside the first h bases (the hash key).
+template <int SW, typename YT>
+__device__ __forceinline__ bool t_overlap_equal(const u64 *X, int lenX, int start, const YT &Y, int lenY, int h,
+                                                bool &contained, bool &key_bad)
 {
     const int rem = lenX - start;
     contained = lenY <= rem;
     const int ov = contained ? lenY : rem;
-    u64 acc = 0;
+    u64 acc = 0, acck = 0;
 #pragma unroll
     for (int w = 0; w < SW; ++w) {
         const int nb = ov - 32 * w;
         if (nb > 0) {
             const u64 m = nb >= 32 ? ~0ull : ~(~0ull >> (2 * nb));
-            acc |= (t_window32<SW>(X, start + 32 * w) ^ Y[w]) & m;
+            const u64 d = (t_window32<SW>(X, start + 32 * w) ^ Y[w]) & m;
+            acc |= d;
+            if (w < 2) {
+                const int kb = h - 32 * w;      // h <= 64: the key lives in the first two words
+                if (kb > 0) acck |= d & (kb >= 32 ? ~0ull : ~(~0ull >> (2 * kb)));
+            }
         }
     }
+    key_bad = acck != 0;
     return acc == 0;
 }
 
-// hashTableSearch: linear probe; a slot whose tag matches is confirmed by re-extracting the key from
-// its first entry's read (hashTable.cpp:203-220); masked keys (>= 100 entries) read as absent.
+// hashTableSearch (hashTable.cpp:193-231) on the sector index.  cnt == 0: absent (or masked).
+// `exact`: confirm every tag match by re-extracting the key from the bucket's first read (:203-220);
+// otherwise only masked keys are confirmed here and the caller proves the key in stage 2.
 template <int SW>
-__device__ __forceinline__ bool probe_key(const SearchParams &P, u64 v0, u64 v1, u32 &off, u32 &cnt)
+__device__ __forceinline__ void probe_window(const SearchParams &P, u64 v0, u64 v1, bool exact, u64 &payload, u32 &cnt)
 {
+    payload = 0; cnt = 0;
     const u64 hsh = hash_key(v0, v1);
     const u64 tag = slot_tag(hsh);
-    u64 s = slot_home(hsh, P.cap);
+    u64 sec = home_sector(hsh, P.nsec);
     for (;;) {
-        const u64 slot = __ldg(&P.slots[s]);
-        if (slot == 0) return false;
-        if (slot_get_tag(slot) == tag) {
-            const u64 o = slot_get_offset(slot);
-            const u32 ent = __ldg(&P.entries[o]);
-            const u64 rid = ent >> 2;
-            const int type = (int)(ent & 3);
-            const u64 *X = ((type & 2) ? P.RC : P.F) + rid * SW;
-            const int l = (int)(__ldg(&X[SW - 1]) & 0xFFFF);
-            u64 w0, w1;
-            t_extract_key<SW>(X, (type & 1) ? l - P.h : 0, P.h, w0, w1);
-            if (w0 == v0 && w1 == v1) {
-                const u32 c = slot_get_count(slot);
-                if (c >= (u32)kHashThreshold) return false;
-                off = (u32)o; cnt = c;
-                return true;
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(P.slots + kSlotsPerSector * sec);
+        const ulonglong2 a = __ldg(p), b = __ldg(p + 1);
+        const u64 s[4] = { a.x, a.y, b.x, b.y };
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const u64 slot = s[t];
+            if (slot == 0) return;
+            if (slot_get_tag(slot) != tag) continue;
+            const u32 c = slot_get_count(slot);
+            if (exact || c >= (u32)kHashThreshold) {
+                const u32 ent = c == 1 ? (u32)slot_get_payload(slot) : __ldg(&P.entries[slot_get_payload(slot)]);
+                const u64 rid = ent >> 2;
+                const int type = (int)(ent & 3);
+                const u64 *X = ((type & 2) ? P.RC : P.F) + rid * SW;
+                const int l = (int)(__ldg(&X[SW - 1]) & 0xFFFF);
+                u64 w0, w1;
+                t_extract_key<SW>(X, (type & 1) ? l - P.h : 0, P.h, w0, w1);
+                if (w0 != v0 || w1 != v1) continue;            // tag collision: keep probing
+                if (c >= (u32)kHashThreshold) return;         // masked key reads as absent (:203)
             }
+            payload = slot_get_payload(slot); cnt = c;
+            return;
         }
-        s = (s + 1 == P.cap) ? 0 : s + 1;
+        sec = (sec + 1 == P.nsec) ? 0 : sec + 1;
     }
 }
 
@@ -96,99 +126,257 @@ __device__ __forceinline__ void load_record(const u64 *src, u64 (&q)[SW])
     for (int w = 0; w < SW; ++w) q[w] = __ldg(&src[w]);
 }
 
+// queue item: [32:0] entry (inline) or index into entries | [49:34] window | bit 50 first entry of its
+// bucket | bit 51 inline
+__device__ __forceinline__ u64 make_item(int jj, bool first, bool inl, u64 payload)
+{
+    return payload | ((u64)jj << 34) | ((u64)first << 50) | ((u64)inl << 51);
+}
+
 // ------------------------------------------------------------------------------------------------
-// K4: phase A, exact sequential chain (reference order).
+// K4: phase A
 // ------------------------------------------------------------------------------------------------
 template <int SW>
-__global__ void __launch_bounds__(SR_WARPS * 32)
+__global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32)
 phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, uint8_t *__restrict__ flag5,
                u32 *__restrict__ cont_max, unsigned long long *__restrict__ counters)
 {
-    __shared__ u64 sXf[SR_WARPS][SW], sXr[SR_WARPS][SW], sPrevR[SR_WARPS][SW], sPrevL[SR_WARPS][SW], sQ[SR_WARPS][SW];
-    __shared__ ExtState sState[SR_WARPS];
+    constexpr int WARPS = SearchCfg<SW>::WARPS, SWP = SearchCfg<SW>::SWP;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ u64 sXf[WARPS][SW], sXr[WARPS][SW], sPrevR[WARPS][SW], sPrevL[WARPS][SW];
+    __shared__ u64 sQ[WARPS][32 * SWP];
+    __shared__ u64 sItem[WARPS][32];
+    __shared__ ExtState sState[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 *Xf = sXf[warp], *Xr = sXr[warp];
+    u64 *Xf = sXf[warp], *Xr = sXr[warp], *prevR = sPrevR[warp], *prevL = sPrevL[warp], *Qs = sQ[warp], *items = sItem[warp];
     ExtState &st = sState[warp];
-    const u64 nwarps = (u64)gridDim.x * SR_WARPS;
-    unsigned long long calls = 0, probes = 0;
+    const u64 nwarps = (u64)gridDim.x * WARPS;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long calls = 0, probes = 0, n_exact = 0, n_restart = 0;
 
-    for (u64 i = (u64)blockIdx.x * SR_WARPS + warp; i < P.U; i += nwarps) {
+    for (u64 i = (u64)blockIdx.x * WARPS + warp; i < P.U; i += nwarps) {
         if (lane < SW) { Xf[lane] = P.F[i * SW + lane]; Xr[lane] = P.RC[i * SW + lane]; }
-        if (lane == 0) ext_init(st);
         __syncwarp();
         const int len1 = (int)(Xf[SW - 1] & 0xFFFF);
         const int W = len1 - P.h + 1;
-        for (int base = 0; base < W; base += 32) {
+        bool exact_probe = false;
+
+    restart:
+        // warp-uniform scan state (FAST mode); `exact` switches to the ExtState in shared memory
+        bool exact = false, hasR = false, hasL = false;
+        u32 Rid = 0, Rtype = 0, Rlen = 0, Lid = 0, Ltype = 0, Llen = 0, connections = 0;
+        int cJR = 0, cLenR = 0, firstJR = 0, cJL = 0, cLenL = 0, curWin = -1;
+        unsigned long long my_calls = 0, my_probes = 0;
+        int qn = 0;                                   // items waiting in `items`
+
+        for (int base = 0; base < W || qn > 0; base += 32) {
+            // ---- stage 1: probe -------------------------------------------------------------------
+            u64 payload = 0;
+            u32 cnt = 0;
             const int j = base + lane;
-            bool found = false;
-            u32 off = 0, cnt = 0;
             if (j < W) {
                 u64 v0, v1;
                 t_extract_key<SW>(Xf, j, P.h, v0, v1);
-                found = probe_key<SW>(P, v0, v1, off, cnt);
-                probes++;
+                probe_window<SW>(P, v0, v1, exact_probe, payload, cnt);
             }
-            unsigned fm = __ballot_sync(0xffffffffu, found);
-            while (fm) {
-                const int l = __ffs(fm) - 1;
-                fm &= fm - 1;
-                const int jj = base + l;
-                const u32 o = __shfl_sync(0xffffffffu, off, l), c = __shfl_sync(0xffffffffu, cnt, l);
-                if (lane == 0) ext_new_window(st);
-                __syncwarp();
-                const bool gateR = gate_right(jj, len1, P.k), gateL = gate_left(jj, P.k, P.h);
-                for (u32 e0 = 0; e0 < c; e0 += 32) {
-                    const u32 e = e0 + lane;
-                    bool hit = false, right = false;
-                    u32 rid2 = 0;
-                    int len2 = 0, type = 0;
-                    u64 q[SW];
-                    if (e < c) {
-                        const u32 ent = __ldg(&P.entries[o + e]);
-                        rid2 = ent >> 2; type = (int)(ent & 3);
-                        right = !(type & 1);
-                        if (rid2 != (u32)i && (right ? gateR : gateL)) {
-                            const bool use_rc = partner_uses_rc(type);
-                            load_record<SW>((use_rc ? P.RC : P.F) + (u64)rid2 * SW, q);
-                            len2 = (int)(q[SW - 1] & 0xFFFF);
-                            bool contained;
-                            calls++;
-                            const bool ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, contained);
-                            if (ok && contained) atomicMax(&cont_max[rid2], (u32)(i + 1));   // economyGraph.cpp:735
-                            hit = ok && !contained;
-                        }
-                    }
-                    unsigned hm = __ballot_sync(0xffffffffu, hit);
-                    while (hm) {
-                        const int b = __ffs(hm) - 1;
-                        hm &= hm - 1;
-                        if (lane == b) {
-                            u64 *Q = sQ[warp];
+            u32 incl = cnt;
 #pragma unroll
-                            for (int w = 0; w < SW; ++w) Q[w] = q[w];
-                            if (right) ext_right_hit(st, sPrevR[warp], Q, SW, rid2 + 1, type >> 1, jj, len1, len2);
-                            else ext_left_hit(st, sPrevL[warp], Q, SW, rid2 + 1, type >> 1, jj, P.h, len1, len2);
+            for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+            const int T = (int)__shfl_sync(FULL, incl, 31);
+            const bool last_chunk = base + 32 >= W;
+            int consumed = 0;
+
+            // ---- stage 2 + 3: rounds of 32 items ------------------------------------------------------
+            for (;;) {
+                const int avail = qn + (T - consumed);
+                if (avail == 0 || (avail < 32 && !last_chunk)) break;
+                const int take = avail < 32 ? avail : 32;
+                // lanes [0,qn) take queued items, lanes [qn,take) items consumed.. of this chunk
+                u64 item = 0;
+                {
+                    int t = consumed + lane - qn;
+                    const bool from_chunk = lane >= qn && lane < take;
+                    if (t < 0) t = 0;
+                    if (t >= T) t = T > 0 ? T - 1 : 0;
+                    int lo = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const u32 pm = __shfl_sync(FULL, incl, lo + step - 1);
+                        if (pm <= (u32)t) lo += step;
+                    }
+                    if (lo > 31) lo = 31;
+                    const u32 ex = __shfl_sync(FULL, incl - cnt, lo);
+                    const u32 c = __shfl_sync(FULL, cnt, lo);
+                    const u64 pay = __shfl_sync(FULL, payload, lo);
+                    const u32 e = (u32)t - ex;
+                    if (from_chunk) item = make_item(base + lo, e == 0, c == 1, c == 1 ? pay : pay + e);
+                    else if (lane < qn) item = items[lane];
+                }
+                consumed += take - qn;
+                qn = 0;
+                const bool valid = lane < take;
+
+                // ---- verify ---------------------------------------------------------------------------
+                const int jj = (int)((item >> 34) & 0xFFFF);
+                const bool first = (item >> 50) & 1, inl = (item >> 51) & 1;
+                bool hit = false, right = false, fp = false;
+                u32 rid2 = 0;
+                int len2 = 0, type = 0;
+                if (valid) {
+                    const u32 ent = inl ? (u32)(item & 0xFFFFFFFFull) : __ldg(&P.entries[item & 0x1FFFFFFFFull]);
+                    rid2 = ent >> 2; type = (int)(ent & 3);
+                    right = !(type & 1);
+                    const bool need = rid2 != (u32)i && (right ? gate_right(jj, len1, P.k) : gate_left(jj, P.k, P.h));
+                    if (need || first) {
+                        u64 q[SW];
+                        load_record<SW>((partner_uses_rc(type) ? P.RC : P.F) + (u64)rid2 * SW, q);
+                        len2 = (int)(q[SW - 1] & 0xFFFF);
+                        bool contained, key_bad;
+                        const bool ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, P.h, contained, key_bad);
+                        fp = first && key_bad;
+                        if (need) {
+                            my_calls++;
+                            if (ok && contained) atomicMax(&cont_max[rid2], (u32)(i + 1));      // economyGraph.cpp:735
+                            hit = ok && !contained;
+                            if (hit) {
+#pragma unroll
+                                for (int w = 0; w < SW; ++w) Qs[lane * SWP + w] = q[w];
+                            }
                         }
-                        __syncwarp();
                     }
                 }
+                if (__any_sync(FULL, fp)) {          // tag collision: redo this read with verified probes
+                    exact_probe = true;
+                    n_restart++;
+                    __syncwarp();
+                    goto restart;
+                }
+                unsigned hm = __ballot_sync(FULL, hit);
+                if (hm == 0) continue;
+                __syncwarp();
+
+                // ---- extend -------------------------------------------------------------------------
+                if (!exact) {
+                    const unsigned mR = __ballot_sync(FULL, hit && right), mL = hm & ~mR;
+                    const unsigned lower = (right ? mR : mL) & lt_mask;
+                    const int src = lower ? 31 - __clz(lower) : -1;
+                    const int pj = __shfl_sync(FULL, jj, src < 0 ? lane : src);
+                    const int plen = __shfl_sync(FULL, len2, src < 0 ? lane : src);
+                    bool anomaly = false;
+                    if (hit) {
+                        const u64 *prec = nullptr;
+                        int prevJ = 0, prevLen = 0;
+                        if (src >= 0) { prec = Qs + src * SWP; prevJ = pj; prevLen = plen; }
+                        else if (right ? hasR : hasL) { prec = right ? prevR : prevL; prevJ = right ? cJR : cJL; prevLen = right ? cLenR : cLenL; }
+                        if (prec) {
+                            bool c2, kb;
+                            const u64 *mine = Qs + lane * SWP;
+                            if (prevJ == jj) anomaly = true;                      // two hits of one side in one window
+                            else if (right) anomaly = !t_overlap_equal<SW>(prec, prevLen, jj - prevJ, mine, len2, 0, c2, kb);   // :110-112
+                            else anomaly = !t_overlap_equal<SW>(mine, len2, jj - prevJ, prec, prevLen, 0, c2, kb);             // :295-297
+                        }
+                    }
+                    if (!__any_sync(FULL, anomaly)) {
+                        __syncwarp();
+                        if (mR) {
+                            if (!hasR) {      // rightExtension = the first right hit (longest overlap), :96-108
+                                const int f = __ffs(mR) - 1;
+                                const int jf = __shfl_sync(FULL, jj, f), lf = __shfl_sync(FULL, len2, f);
+                                Rid = __shfl_sync(FULL, rid2, f) + 1; Rtype = (u32)(__shfl_sync(FULL, type, f) >> 1);
+                                Rlen = (u32)(lf - (len1 - jf)); firstJR = jf; hasR = true;
+                            }
+                            const int l = 31 - __clz(mR);
+                            cJR = __shfl_sync(FULL, jj, l); cLenR = __shfl_sync(FULL, len2, l);
+                            if (lane < SW) prevR[lane] = Qs[l * SWP + lane];
+                        }
+                        if (mL) {             // leftExtension = the last left hit (longest overlap), :281-357
+                            const int l = 31 - __clz(mL);
+                            cJL = __shfl_sync(FULL, jj, l); cLenL = __shfl_sync(FULL, len2, l);
+                            Lid = __shfl_sync(FULL, rid2, l) + 1; Ltype = (u32)(__shfl_sync(FULL, type, l) >> 1);
+                            Llen = (u32)(cLenL - cJL - P.h); hasL = true;
+                            if (lane < SW) prevL[lane] = Qs[l * SWP + lane];
+                        }
+                        connections += (u32)__popc(hm);
+                        __syncwarp();
+                        continue;
+                    }
+                    // convert to the reference's sequential state as of just before this round
+                    exact = true;
+                    n_exact++;
+                    curWin = __shfl_sync(FULL, jj, __ffs(hm) - 1);
+                    if (lane == 0) {
+                        ext_init(st);
+                        st.Rid = Rid; st.Rtype = Rtype; st.Rlen = Rlen; st.Lid = Lid; st.Ltype = Ltype; st.Llen = Llen;
+                        st.prevJR = cJR; st.prevLenR = cLenR; st.prevPL = len1 - cJL - P.h; st.prevLenL = cLenL;
+                        st.markAmbigR = (hasR && cJR == curWin) ? 1 : 0;
+                        st.markFirstR = (hasR && firstJR == curWin) ? 1 : 0;
+                        st.markAmbigL = (hasL && cJL == curWin) ? 1 : 0;
+                        st.connections = connections;
+                    }
+                    __syncwarp();
+                }
+                while (hm) {
+                    const int b = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    const int jb = __shfl_sync(FULL, jj, b);
+                    if (jb != curWin) { curWin = jb; if (lane == 0) ext_new_window(st); }      // :86-88
+                    __syncwarp();
+                    if (lane == b) {
+                        if (right) ext_right_hit(st, prevR, Qs + lane * SWP, SW, rid2 + 1, type >> 1, jj, len1, len2);
+                        else ext_left_hit(st, prevL, Qs + lane * SWP, SW, rid2 + 1, type >> 1, jj, P.h, len1, len2);
+                    }
+                    __syncwarp();
+                }
             }
+            // leftover items of this chunk wait for the next one
+            {
+                const int rem = T - consumed;      // < 32 - qn
+                int t = consumed + lane;
+                const bool mine = lane < rem;
+                if (t >= T) t = T > 0 ? T - 1 : 0;
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const u32 pm = __shfl_sync(FULL, incl, lo + step - 1);
+                    if (pm <= (u32)t) lo += step;
+                }
+                if (lo > 31) lo = 31;
+                const u32 ex = __shfl_sync(FULL, incl - cnt, lo);
+                const u32 c = __shfl_sync(FULL, cnt, lo);
+                const u64 pay = __shfl_sync(FULL, payload, lo);
+                const u32 e = (u32)t - ex;
+                if (mine) items[qn + lane] = make_item(base + lo, e == 0, c == 1, c == 1 ? pay : pay + e);
+                qn += rem;
+                __syncwarp();
+            }
+            my_probes += (j < W);
         }
         __syncwarp();
         if (lane == 0) {
-            flag5[i] = st.connections > kConnectionsLimit ? 1 : 0;              // :443
-            const bool amb = st.itsAmbigR == 1 || st.itsAmbigL == 1;           // :446-450
-            extR[i] = ext_pack(st.Rid, st.Rtype, amb ? 0u : st.Rlen);
-            extL[i] = ext_pack(st.Lid, st.Ltype, amb ? 0u : st.Llen);
+            if (exact) {
+                flag5[i] = st.connections > kConnectionsLimit ? 1 : 0;              // :443
+                const bool amb = st.itsAmbigR == 1 || st.itsAmbigL == 1;           // :446-450
+                extR[i] = ext_pack(st.Rid, st.Rtype, amb ? 0u : st.Rlen);
+                extL[i] = ext_pack(st.Lid, st.Ltype, amb ? 0u : st.Llen);
+            } else {
+                flag5[i] = connections > kConnectionsLimit ? 1 : 0;
+                extR[i] = ext_pack(Rid, Rtype, Rlen);
+                extL[i] = ext_pack(Lid, Ltype, Llen);
+            }
         }
+        calls += my_calls; probes += my_probes;
         __syncwarp();
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
-        calls += __shfl_xor_sync(0xffffffffu, calls, s);
-        probes += __shfl_xor_sync(0xffffffffu, probes, s);
+        calls += __shfl_xor_sync(FULL, calls, s);
+        probes += __shfl_xor_sync(FULL, probes, s);
     }
-    if (lane == 0) { atomicAdd(&counters[0], calls); atomicAdd(&counters[1], probes); }
+    if (lane == 0) {
+        atomicAdd(&counters[0], calls); atomicAdd(&counters[1], probes);
+        if (n_exact) atomicAdd(&counters[2], n_exact);
+        if (n_restart) atomicAdd(&counters[3], n_restart);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -199,15 +387,16 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
 // candidate = read2(1-based) << 32 | edgeType << 20 | (overhang & 0xFFFFF)
 // ------------------------------------------------------------------------------------------------
 template <int SW, bool FILL>
-__global__ void __launch_bounds__(SR_WARPS * 32)
+__global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32)
 phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint8_t *__restrict__ explored,
                u32 *__restrict__ counts, const u32 *__restrict__ offsets, u64 *__restrict__ cand)
 {
-    __shared__ u64 sXf[SR_WARPS][SW], sXr[SR_WARPS][SW];
+    constexpr int WARPS = SearchCfg<SW>::WARPS;
+    __shared__ u64 sXf[WARPS][SW], sXr[WARPS][SW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *Xf = sXf[warp], *Xr = sXr[warp];
-    const u64 nwarps = (u64)gridDim.x * SR_WARPS;
-    for (u64 s = (u64)blockIdx.x * SR_WARPS + warp; s < nS; s += nwarps) {
+    const u64 nwarps = (u64)gridDim.x * WARPS;
+    for (u64 s = (u64)blockIdx.x * WARPS + warp; s < nS; s += nwarps) {
         const u64 i = s_ids[s];      // 0-based
         if (lane < SW) { Xf[lane] = P.F[i * SW + lane]; Xr[lane] = P.RC[i * SW + lane]; }
         __syncwarp();
@@ -217,36 +406,36 @@ phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint
         const u64 out_base = FILL ? offsets[s] : 0;
         for (int base = 0; base < W; base += 32) {
             const int j = base + lane;
-            bool found = false;
-            u32 off = 0, cnt = 0;
+            u64 payload = 0;
+            u32 cnt = 0;
             if (j < W) {
                 u64 v0, v1;
                 t_extract_key<SW>(Xf, j, P.h, v0, v1);
-                found = probe_key<SW>(P, v0, v1, off, cnt);
+                probe_window<SW>(P, v0, v1, true, payload, cnt);
             }
-            unsigned fm = __ballot_sync(0xffffffffu, found);
+            unsigned fm = __ballot_sync(0xffffffffu, cnt != 0);
             while (fm) {
                 const int l = __ffs(fm) - 1;
                 fm &= fm - 1;
                 const int jj = base + l;
-                const u32 o = __shfl_sync(0xffffffffu, off, l), c = __shfl_sync(0xffffffffu, cnt, l);
+                const u64 pay = __shfl_sync(0xffffffffu, payload, l);
+                const u32 c = __shfl_sync(0xffffffffu, cnt, l);
                 const bool gateR = gate_right(jj, len1, P.k), gateL = gate_left(jj, P.k, P.h);
                 for (u32 e0 = 0; e0 < c; e0 += 32) {
                     const u32 e = e0 + lane;
                     bool ok = false;
                     u64 rec = 0;
                     if (e < c) {
-                        const u32 ent = __ldg(&P.entries[o + e]);
+                        const u32 ent = c == 1 ? (u32)pay : __ldg(&P.entries[pay + e]);
                         const u32 rid2 = ent >> 2;
                         const int type = (int)(ent & 3);
                         const bool right = !(type & 1);
                         if (rid2 != (u32)i && explored[rid2] == 0 && (right ? gateR : gateL)) {
-                            const bool use_rc = partner_uses_rc(type);
                             u64 q[SW];
-                            load_record<SW>((use_rc ? P.RC : P.F) + (u64)rid2 * SW, q);
+                            load_record<SW>((partner_uses_rc(type) ? P.RC : P.F) + (u64)rid2 * SW, q);
                             const int len2 = (int)(q[SW - 1] & 0xFFFF);
-                            bool contained;
-                            ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, contained);
+                            bool contained, kb;
+                            ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, 0, contained, kb);
                             rec = candidate_record(type, jj, P.h, len1, len2, rid2);
                         }
                     }
@@ -264,10 +453,10 @@ phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static unsigned search_grid(u64 n_reads)
+static unsigned search_grid(u64 n_reads, int warps, int blocks_per_sm)
 {
-    u64 g = (n_reads + SR_WARPS - 1) / SR_WARPS;
-    const u64 cap = (u64)kSMs * 8;
+    u64 g = (n_reads + warps - 1) / warps;
+    const u64 cap = (u64)kSMs * blocks_per_sm;
     if (g > cap) g = cap;
     if (g == 0) g = 1;
     return (unsigned)g;
@@ -276,14 +465,22 @@ static unsigned search_grid(u64 n_reads)
 template <int SW>
 static void launch_phase_a(Context &c, const SearchParams &P, unsigned long long *d_counters)
 {
-    phase_a_kernel<SW><<<search_grid(P.U), SR_WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters);
+    constexpr int WARPS = SearchCfg<SW>::WARPS;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_kernel<SW>, WARPS * 32, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    phase_a_kernel<SW><<<search_grid(P.U, WARPS, blocks_per_sm), WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters);
 }
 
 template <int SW>
 static void launch_phase_c(Context &c, const SearchParams &P, const u32 *s_ids, u64 nS, u32 *counts, const u32 *offsets, u64 *cand, bool fill)
 {
-    if (fill) phase_c_kernel<SW, true><<<search_grid(nS), SR_WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
-    else phase_c_kernel<SW, false><<<search_grid(nS), SR_WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
+    constexpr int WARPS = SearchCfg<SW>::WARPS;
+    const unsigned g = search_grid(nS, WARPS, 8);
+    if (fill) phase_c_kernel<SW, true><<<g, WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
+    else phase_c_kernel<SW, false><<<g, WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
 }
 
 #define SG_DISPATCH_SW(SWV, CALL)                                                       \
@@ -304,7 +501,7 @@ static SearchParams make_params(const Context &c)
 {
     SearchParams P;
     P.F = c.F.p; P.RC = c.RC.p; P.slots = c.slots.p; P.entries = c.entries.p;
-    P.cap = c.cap; P.U = c.cnt.unique_reads; P.h = c.h; P.k = c.min_overlap;
+    P.nsec = c.cap / kSlotsPerSector; P.U = c.cnt.unique_reads; P.h = c.h; P.k = c.min_overlap;
     return P;
 }
 
@@ -314,11 +511,11 @@ void stage_phase_a(Context &c)
     SG_CHECK(c.have_table, "build_hash_table must run before the overlap search");
     const u64 U = c.cnt.unique_reads;
     c.extR.alloc(U, st); c.extL.alloc(U, st); c.flag5.alloc(U, st); c.cont_max.alloc(U, st);
-    c.cnt.compare_calls = 0; c.cnt.window_probes = 0;
+    c.cnt.compare_calls = 0; c.cnt.window_probes = 0; c.cnt.slow_path_reads = 0; c.cnt.probe_restarts = 0;
     if (U == 0) return;
     SG_CUDA(cudaMemsetAsync(c.cont_max.p, 0, U * sizeof(u32), st));
-    DevBuf<unsigned long long> d_counters(2, st);
-    SG_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(unsigned long long), st));
+    DevBuf<unsigned long long> d_counters(4, st);
+    SG_CUDA(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(unsigned long long), st));
     const SearchParams P = make_params(c);
     cudaEvent_t e0, e1;
     SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
@@ -326,11 +523,13 @@ void stage_phase_a(Context &c)
     SG_DISPATCH_SW(c.SW, launch_phase_a<SWC>(c, P, d_counters.p));
     SG_LAUNCHED();
     SG_CUDA(cudaEventRecord(e1, st));
-    unsigned long long h[2];
+    unsigned long long h[4];
     SG_CUDA(cudaMemcpyAsync(h, d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     c.cnt.compare_calls = h[0];
     c.cnt.window_probes = h[1];
+    c.cnt.slow_path_reads = h[2];
+    c.cnt.probe_restarts = h[3];
     cudaEventElapsedTime(&c.tm.phase_a_kernel, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 }

@@ -5,8 +5,9 @@
 // (readId asc, type asc) order; a key with >= 100 entries is invisible to searches.  Layout:
 //   entries[4U]  : (readId0<<2 | type), radix-sorted by the exact 128-bit key (stable, so each key's
 //                  run is already in bucket order),
-//   slots[cap]   : open-addressing index (linear probing, load <= 0.5) filled with 64-bit atomicCAS,
-//                  one slot per DISTINCT key: tag | min(count,127) | offset (core.cuh).
+//   slots[cap]   : open-addressing index (linear probing over 32-byte sectors of 4 slots, load <= 0.5)
+//                  filled with 64-bit atomicCAS, one slot per DISTINCT key: tag | min(count,127) |
+//                  (the entry itself when count == 1, else the offset of the key's run) (core.cuh).
 #include "context.h"
 
 namespace sg {
@@ -39,8 +40,9 @@ __global__ void __launch_bounds__(256) group_start_kernel(const u32 *__restrict_
 }
 
 __global__ void __launch_bounds__(256) index_insert_kernel(const u64 *__restrict__ k0, const u64 *__restrict__ k1,
-                                                            const u32 *__restrict__ gstart, u64 D, u64 n,
-                                                            u64 *__restrict__ slots, u64 cap, unsigned long long *over)
+                                                            const u32 *__restrict__ val, const u32 *__restrict__ gstart,
+                                                            u64 D, u64 n, u64 *__restrict__ slots, u64 nsec,
+                                                            unsigned long long *over)
 {
     unsigned long long my_over = 0;
     for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < D; g += (u64)gridDim.x * blockDim.x) {
@@ -49,12 +51,14 @@ __global__ void __launch_bounds__(256) index_insert_kernel(const u64 *__restrict
         const u64 count = e - p;
         if (count >= (u64)kHashThreshold) my_over++;
         const u64 hsh = hash_key(k0[p], k1[p]);
-        const u64 v = slot_encode(hsh, count, p);
-        u64 s = slot_home(hsh, cap);
-        for (;;) {
-            const unsigned long long old = atomicCAS((unsigned long long *)&slots[s], 0ull, (unsigned long long)v);
-            if (old == 0ull) break;
-            s = (s + 1 == cap) ? 0 : s + 1;
+        const u64 v = slot_encode(hsh, count, count == 1 ? (u64)val[p] : p);
+        u64 sec = home_sector(hsh, nsec);
+        bool done = false;
+        while (!done) {
+#pragma unroll
+            for (int t = 0; t < kSlotsPerSector && !done; ++t)
+                done = atomicCAS((unsigned long long *)&slots[kSlotsPerSector * sec + t], 0ull, (unsigned long long)v) == 0ull;
+            sec = (sec + 1 == nsec) ? 0 : sec + 1;
         }
     }
     if (my_over) atomicAdd(over, my_over);
@@ -100,13 +104,14 @@ void stage_build_table(Context &c)
     group_start_kernel<<<big_grid(n), 256, 0, st>>>(flag.p, gidx.p, n, gstart.p);
     SG_LAUNCHED();
 
-    u64 cap = 2 * (u64)D;
-    if (cap < 1024) cap = 1024;
+    u64 nsec = (2 * (u64)D + kSlotsPerSector - 1) / kSlotsPerSector;    // load factor <= 0.5
+    if (nsec < 256) nsec = 256;
+    const u64 cap = nsec * kSlotsPerSector;
     c.slots.alloc(cap, st);
     SG_CUDA(cudaMemsetAsync(c.slots.p, 0, cap * sizeof(u64), st));
     DevBuf<unsigned long long> d_over(1, st);
     SG_CUDA(cudaMemsetAsync(d_over.p, 0, sizeof(unsigned long long), st));
-    index_insert_kernel<<<big_grid(D), 256, 0, st>>>(cols.a[cur], cols.b[cur], gstart.p, D, n, c.slots.p, cap, d_over.p);
+    index_insert_kernel<<<big_grid(D), 256, 0, st>>>(cols.a[cur], cols.b[cur], cols.v[cur], gstart.p, D, n, c.slots.p, nsec, d_over.p);
     SG_LAUNCHED();
     unsigned long long over = 0;
     SG_CUDA(cudaMemcpyAsync(&over, d_over.p, sizeof(over), cudaMemcpyDeviceToHost, st));

@@ -45,10 +45,10 @@ class EmuRun:
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         L = lib()
         h = L.hemu_run(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k)
-        sz = np.zeros(12, dtype=np.uint64)
+        sz = np.zeros(13, dtype=np.uint64)
         L.hemu_sizes(h, sz.ctypes.data)
         (self.U, self.SW, self.N, self.total_bp, self.n_edges, self.over, self.distinct, self.compare_calls,
-         self.inserted, self.removed, self.contained, self.contained_size) = (int(x) for x in sz)
+         self.inserted, self.removed, self.contained, self.contained_size, self.slow_reads) = (int(x) for x in sz)
         U, SW, E = self.U, self.SW, self.n_edges
         self.F = np.zeros(U * SW, np.uint64); self.RC = np.zeros(U * SW, np.uint64)
         self.len = np.zeros(U, np.uint16); self.freq = np.zeros(U, np.uint16)

@@ -4,6 +4,7 @@
 // the `-m "not gpu"` suite check the bit arithmetic, the extension state machine, phase B and the
 // phase-C walk against the oracle without a GPU.  It is NOT a fallback: nothing in sage2_b200 links it.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <map>
@@ -23,7 +24,7 @@ struct Emu {
     std::vector<u64> extR, extL;
     std::vector<uint8_t> explored_a, explored_b;
     std::vector<u64> edges;     // (w0,w1) final
-    u64 over = 0, distinct = 0, compare_calls = 0, inserted = 0, removed = 0, contained = 0, contained_size = 0;
+    u64 over = 0, distinct = 0, compare_calls = 0, inserted = 0, removed = 0, contained = 0, contained_size = 0, slow_reads = 0;
 };
 
 int code_of(uint8_t c) { return ((c >> 1) ^ (c >> 2)) & 3; }
@@ -90,25 +91,41 @@ void run(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
     e.distinct = table.size();
     for (auto &kv : table) if (kv.second.size() >= (size_t)kHashThreshold) e.over++;
 
-    // K4 phase A
+    // K4 phase A: the kernel's round structure (search.cu): the (window, bucket entry) items of a read are
+    // consumed 32 at a time; a round is evaluated in FAST mode (every hit checked against the previous hit
+    // of its side only) until the first anomaly, then converted to the reference's sequential chain.
+    // With SAGE2_EMUL_EXACT_ONLY set the plain sequential chain runs instead (cross-check of the hybrid).
     e.extR.assign(U, 0); e.extL.assign(U, 0);
     std::vector<uint8_t> flag5(U, 0);
     std::vector<u32> cont_max(U, 0);
     std::vector<u64> prevR(SW), prevL(SW);
+    const bool exact_only = getenv("SAGE2_EMUL_EXACT_ONLY") != nullptr;
+    struct Item { int jj; u32 ent; };
+    struct Hit { int jj; bool right; u32 rid2; int type; int len2; const u64 *Q; };
+    std::vector<Item> items;
+    std::vector<Hit> hits;
     for (u64 i = 0; i < U; ++i) {
         const u64 *Xf = &e.F[i * SW], *Xr = &e.RC[i * SW];
         const int len1 = e.len[i];
-        ExtState st;
-        ext_init(st);
+        items.clear();
         for (int j = 0; j <= len1 - h; ++j) {
             u64 v0, v1;
             extract_key(Xf, SW, j, h, v0, v1);
             auto it = table.find(std::make_pair(v0, v1));
             if (it == table.end() || it->second.size() >= (size_t)kHashThreshold) continue;
-            ext_new_window(st);
-            for (u32 ent : it->second) {
-                const u32 rid2 = ent >> 2;
-                const int type = (int)(ent & 3);
+            for (u32 ent : it->second) items.push_back(Item{ j, ent });
+        }
+        ExtState st;
+        ext_init(st);
+        bool exact = exact_only, hasR = false, hasL = false;
+        u32 Rid = 0, Rtype = 0, Rlen = 0, Lid = 0, Ltype = 0, Llen = 0, connections = 0;
+        int cJR = 0, cLenR = 0, firstJR = 0, cJL = 0, cLenL = 0, curWin = -1;
+        for (size_t r0 = 0; r0 < items.size(); r0 += 32) {
+            hits.clear();
+            for (size_t x = r0; x < std::min(items.size(), r0 + 32); ++x) {
+                const int j = items[x].jj;
+                const u32 rid2 = items[x].ent >> 2;
+                const int type = (int)(items[x].ent & 3);
                 const bool right = !(type & 1);
                 if (rid2 == (u32)i || !(right ? gate_right(j, len1, k) : gate_left(j, k, h))) continue;
                 const u64 *Q = (partner_uses_rc(type) ? &e.RC[0] : &e.F[0]) + (u64)rid2 * SW;
@@ -117,15 +134,67 @@ void run(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
                 e.compare_calls++;
                 const bool ok = overlap_equal(right ? Xf : Xr, len1, right ? j : len1 - j - h, Q, len2, SW, cont);
                 if (ok && cont) cont_max[rid2] = std::max(cont_max[rid2], (u32)(i + 1));
-                if (!(ok && !cont)) continue;
-                if (right) ext_right_hit(st, prevR.data(), Q, SW, rid2 + 1, type >> 1, j, len1, len2);
-                else ext_left_hit(st, prevL.data(), Q, SW, rid2 + 1, type >> 1, j, h, len1, len2);
+                if (ok && !cont) hits.push_back(Hit{ j, right, rid2, type, len2, Q });
+            }
+            if (hits.empty()) continue;
+            if (!exact) {
+                bool anomaly = false;
+                for (size_t x = 0; x < hits.size() && !anomaly; ++x) {
+                    const Hit &hx = hits[x];
+                    const u64 *prec = nullptr;
+                    int prevJ = 0, prevLen = 0;
+                    for (size_t y = x; y-- > 0;)
+                        if (hits[y].right == hx.right) { prec = hits[y].Q; prevJ = hits[y].jj; prevLen = hits[y].len2; break; }
+                    if (!prec && (hx.right ? hasR : hasL)) {
+                        prec = hx.right ? prevR.data() : prevL.data();
+                        prevJ = hx.right ? cJR : cJL; prevLen = hx.right ? cLenR : cLenL;
+                    }
+                    if (!prec) continue;
+                    bool c2;
+                    if (prevJ == hx.jj) anomaly = true;
+                    else if (hx.right) anomaly = !overlap_equal(prec, prevLen, hx.jj - prevJ, hx.Q, hx.len2, SW, c2);
+                    else anomaly = !overlap_equal(hx.Q, hx.len2, hx.jj - prevJ, prec, prevLen, SW, c2);
+                }
+                if (!anomaly) {
+                    for (const Hit &hx : hits) {
+                        if (hx.right) {
+                            if (!hasR) { Rid = hx.rid2 + 1; Rtype = (u32)(hx.type >> 1); Rlen = (u32)(hx.len2 - (len1 - hx.jj)); firstJR = hx.jj; hasR = true; }
+                            cJR = hx.jj; cLenR = hx.len2; copy_rec(prevR.data(), hx.Q, SW);
+                        } else {
+                            Lid = hx.rid2 + 1; Ltype = (u32)(hx.type >> 1); Llen = (u32)(hx.len2 - hx.jj - h); hasL = true;
+                            cJL = hx.jj; cLenL = hx.len2; copy_rec(prevL.data(), hx.Q, SW);
+                        }
+                    }
+                    connections += (u32)hits.size();
+                    continue;
+                }
+                exact = true;
+                e.slow_reads++;
+                curWin = hits[0].jj;
+                ext_init(st);
+                st.Rid = Rid; st.Rtype = Rtype; st.Rlen = Rlen; st.Lid = Lid; st.Ltype = Ltype; st.Llen = Llen;
+                st.prevJR = cJR; st.prevLenR = cLenR; st.prevPL = len1 - cJL - h; st.prevLenL = cLenL;
+                st.markAmbigR = (hasR && cJR == curWin) ? 1 : 0;
+                st.markFirstR = (hasR && firstJR == curWin) ? 1 : 0;
+                st.markAmbigL = (hasL && cJL == curWin) ? 1 : 0;
+                st.connections = connections;
+            }
+            for (const Hit &hx : hits) {
+                if (hx.jj != curWin) { curWin = hx.jj; ext_new_window(st); }
+                if (hx.right) ext_right_hit(st, prevR.data(), hx.Q, SW, hx.rid2 + 1, hx.type >> 1, hx.jj, len1, hx.len2);
+                else ext_left_hit(st, prevL.data(), hx.Q, SW, hx.rid2 + 1, hx.type >> 1, hx.jj, h, len1, hx.len2);
             }
         }
-        flag5[i] = st.connections > kConnectionsLimit;
-        const bool amb = st.itsAmbigR == 1 || st.itsAmbigL == 1;
-        e.extR[i] = ext_pack(st.Rid, st.Rtype, amb ? 0u : st.Rlen);
-        e.extL[i] = ext_pack(st.Lid, st.Ltype, amb ? 0u : st.Llen);
+        if (exact) {
+            flag5[i] = st.connections > kConnectionsLimit;
+            const bool amb = st.itsAmbigR == 1 || st.itsAmbigL == 1;
+            e.extR[i] = ext_pack(st.Rid, st.Rtype, amb ? 0u : st.Rlen);
+            e.extL[i] = ext_pack(st.Lid, st.Ltype, amb ? 0u : st.Llen);
+        } else {
+            flag5[i] = connections > kConnectionsLimit;
+            e.extR[i] = ext_pack(Rid, Rtype, Rlen);
+            e.extL[i] = ext_pack(Lid, Ltype, Llen);
+        }
     }
     // phase B
     e.explored_a.resize(U); e.explored_b.resize(U);
@@ -171,9 +240,28 @@ void run(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
     cand_off.push_back((u32)cand.size());
     std::vector<u64> all;
     if (!s_ids.empty()) {
+        // what graph.cu hands over: lengths of the S reads, and only the phase-B records that touch S or a
+        // phase-B neighbour of S, each with the lengths of its endpoints
+        std::vector<uint16_t> s_len;
+        for (u32 sid : s_ids) s_len.push_back(e.len[sid]);
+        std::vector<uint8_t> needed(U, 0);
+        for (u32 sid : s_ids) needed[sid] = 1;
+        for (size_t x = 0; x < edgesB.size(); x += 2) {
+            const u32 a = (u32)(edgesB[x] >> 32) - 1, b = (u32)edgesB[x] - 1;
+            if (e.explored_b[a] == 0) needed[b] = 1;
+            if (e.explored_b[b] == 0) needed[a] = 1;
+        }
+        std::vector<u64> selB;
+        std::vector<u32> selLen;
+        for (size_t x = 0; x < edgesB.size(); x += 2) {
+            const u32 a = (u32)(edgesB[x] >> 32) - 1, b = (u32)edgesB[x] - 1;
+            if (!needed[a] && !needed[b]) continue;
+            selB.push_back(edgesB[x]); selB.push_back(edgesB[x + 1]);
+            selLen.push_back((u32)e.len[a] | ((u32)e.len[b] << 16));
+        }
         PhaseCInput in;
-        in.U = U; in.len = e.len.data(); in.nS = s_ids.size(); in.s_ids = s_ids.data(); in.cand_off = cand_off.data();
-        in.cand = cand.data(); in.nB = edgesB.size() / 2; in.edgesB = edgesB.data();
+        in.nS = s_ids.size(); in.s_ids = s_ids.data(); in.s_len = s_len.data(); in.cand_off = cand_off.data();
+        in.cand = cand.data(); in.nB = selB.size() / 2; in.edgesB = selB.data(); in.edgesB_len = selLen.data();
         PhaseCOutput out;
         run_host_phase_c(in, out);
         e.inserted = out.inserted; e.removed = out.removed;
@@ -203,13 +291,13 @@ void *hemu_run(const uint8_t *bases, const int64_t *off, int64_t n, int k)
 }
 void hemu_free(void *p) { delete (Emu *)p; }
 // sizes: [0]=U [1]=SW [2]=good [3]=total_bp [4]=n_edges [5]=over [6]=distinct [7]=compare_calls [8]=inserted
-//        [9]=removed [10]=contained [11]=contained_size
+//        [9]=removed [10]=contained [11]=contained_size [12]=reads that left the fast mode
 void hemu_sizes(void *p, uint64_t *o)
 {
     Emu *e = (Emu *)p;
     o[0] = e->U; o[1] = (u64)e->SW; o[2] = e->good; o[3] = e->total_bp; o[4] = e->edges.size() / 2; o[5] = e->over;
     o[6] = e->distinct; o[7] = e->compare_calls; o[8] = e->inserted; o[9] = e->removed; o[10] = e->contained;
-    o[11] = e->contained_size;
+    o[11] = e->contained_size; o[12] = e->slow_reads;
 }
 void hemu_copy(void *p, uint64_t *F, uint64_t *RC, uint16_t *len, uint16_t *freq, uint64_t *extR, uint64_t *extL,
                uint8_t *expl_a, uint8_t *expl_b, uint64_t *edges)
