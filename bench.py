@@ -194,10 +194,16 @@ def run_ours(args):
         gpu.build_hash_table()
         gpu.build_overlap_graph()
 
+    h_edges = {"buf": None}
+
     def step_host():
+        # the call a user of the C ABI makes: host buffers in, edge list back in host memory
         gpu.load_reads_ptr(h_bases.data_ptr(), h_off.data_ptr(), n_reads, k, device=False)
         gpu.build_hash_table()
         gpu.build_overlap_graph()
+        if h_edges["buf"] is None:
+            h_edges["buf"] = torch.empty(2 * max(1, gpu.counters()["n_edges"]), dtype=torch.int64).pin_memory()
+        gpu.edges_packed_into(h_edges["buf"].data_ptr(), h_edges["buf"].numel() // 2)
 
     def barrier():
         torch.cuda.synchronize()

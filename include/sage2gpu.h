@@ -71,17 +71,35 @@ int sage2gpu_load_reads(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *
 int sage2gpu_load_reads_device(sage2gpu_ctx *ctx, const uint8_t *d_bases, const int64_t *d_offsets,
                                int64_t n_reads, int min_overlap);
 
+/* The same as sage2gpu_load_reads, streamed: the reference reads its input record by record
+ * (readLoader.cpp:146-160); the host parser fills one pinned chunk while the previous one is uploaded.
+ * offsets has n_reads+1 entries relative to `bases` (read r = bases[offsets[r], offsets[r+1])).  A chunk's
+ * buffers may be reused as soon as a LATER call to _append or _finish has returned.  _finish runs the
+ * filter / pack / sort / dedupe of organizeReads. */
+int sage2gpu_load_begin(sage2gpu_ctx *ctx, int min_overlap);
+int sage2gpu_load_append(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads);
+int sage2gpu_load_finish(sage2gpu_ctx *ctx);
+/* Page-locked host memory for the buffers above (plain malloc'ed memory works too, synchronously). */
+void *sage2gpu_host_alloc(uint64_t n_bytes);
+void sage2gpu_host_free(void *p);
+
 /* replaces: HashTable::hashPrefixesAndSuffix (hashTable.cpp:70-128) */
 int sage2gpu_build_hash_table(sage2gpu_ctx *ctx);
 
 /* replaces: EconomyGraph::buildInitialOverlapGraph + buildOverlapGraphEconomy + sortEconomyGraph
  * (economyGraph.cpp:37-574,896-913) and the edge selection of OverlapGraph::convertGraph
- * (overlapGraph.cpp:93-112).  Leaves the canonical edge list on the device and a copy on the host. */
+ * (overlapGraph.cpp:93-112).  Leaves the canonical edge list on the device; sage2gpu_get_edges[_packed],
+ * sage2gpu_write_graph3 bring it to the host. */
 int sage2gpu_build_overlap_graph(sage2gpu_ctx *ctx);
 
 /* All three steps back to back (main.cpp:37-132 without the file I/O). */
 int sage2gpu_run_steps123(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
                           int64_t n_reads, int min_overlap);
+
+/* Measurement aid (no reference counterpart): GB/s this GPU sustains on uniformly random, independent
+ * `granule_bytes` (16/32/64) gathers over `footprint_bytes` of device memory -- the random-sector
+ * roofline of the probe / partner-fetch traffic. */
+int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int granule_bytes, uint64_t n_loads, double *gbps);
 
 int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *out);
 /* Number of CUDA kernels this library has launched in this process so far (monotonic). */
@@ -105,6 +123,11 @@ int sage2gpu_get_extensions(sage2gpu_ctx *ctx, uint64_t *right_ext, uint64_t *le
 /* replaces: the economyGraphList hand-over to convertGraph.  capacity in edges; *n_edges receives the
  * total (call with out=NULL to size).  Order = the order convertGraph creates / .graph3 lists them. */
 int sage2gpu_get_edges(sage2gpu_ctx *ctx, sage2gpu_edge *out, uint64_t capacity, uint64_t *n_edges);
+
+/* Same list, undecoded, copied straight into the caller's (ideally pinned) buffer: two 64-bit words per
+ * edge, w0 = from << 32 | to, w1 = type << 20 | delta; the twin's delta is len(from) - (len(to) - delta)
+ * (overlapGraph.cpp:147).  capacity in edges. */
+int sage2gpu_get_edges_packed(sage2gpu_ctx *ctx, uint64_t *out, uint64_t capacity, uint64_t *n_edges);
 
 /* replaces: ReadLoader::saveReadsInFile (readLoader.cpp:270-287) and
  * OverlapGraph::saveOverlapGraphInFile (overlapGraph.cpp:338-369): the reference's -s text formats,

@@ -41,10 +41,11 @@ EDGE_DT = np.dtype([("from", "<u8"), ("to", "<u8"), ("type", "<u4"), ("delta", "
                     ("delta_twin", "<u4"), ("reserved", "<u4")])
 
 EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2gpu_load_reads",
+           "sage2gpu_load_begin", "sage2gpu_load_append", "sage2gpu_load_finish", "sage2gpu_host_alloc", "sage2gpu_host_free",
            "sage2gpu_load_reads_device", "sage2gpu_build_hash_table", "sage2gpu_build_overlap_graph",
            "sage2gpu_run_steps123", "sage2gpu_get_counters", "sage2gpu_get_timers", "sage2gpu_reads_bytes",
-           "sage2gpu_get_reads", "sage2gpu_get_extensions", "sage2gpu_get_edges", "sage2gpu_write_reads",
-           "sage2gpu_write_graph3", "sage2gpu_kernel_launches", "sage2gpu_stream"]
+           "sage2gpu_get_reads", "sage2gpu_get_extensions", "sage2gpu_get_edges", "sage2gpu_get_edges_packed", "sage2gpu_write_reads",
+           "sage2gpu_write_graph3", "sage2gpu_kernel_launches", "sage2gpu_stream", "sage2gpu_measure_gather"]
 
 _lib = None
 
@@ -72,6 +73,13 @@ def load_library():
         lib.sage2gpu_last_error.restype = C.c_char_p
         lib.sage2gpu_load_reads.argtypes = [vp, vp, vp, i64, C.c_int]
         lib.sage2gpu_load_reads_device.argtypes = [vp, vp, vp, i64, C.c_int]
+        lib.sage2gpu_load_begin.argtypes = [vp, C.c_int]
+        lib.sage2gpu_load_append.argtypes = [vp, vp, vp, i64]
+        lib.sage2gpu_load_finish.argtypes = [vp]
+        lib.sage2gpu_host_alloc.argtypes = [C.c_uint64]
+        lib.sage2gpu_host_alloc.restype = vp
+        lib.sage2gpu_host_free.argtypes = [vp]
+        lib.sage2gpu_host_free.restype = None
         lib.sage2gpu_build_hash_table.argtypes = [vp]
         lib.sage2gpu_build_overlap_graph.argtypes = [vp]
         lib.sage2gpu_run_steps123.argtypes = [vp, vp, vp, i64, C.c_int]
@@ -81,8 +89,10 @@ def load_library():
         lib.sage2gpu_get_reads.argtypes = [vp, vp, vp, vp, vp, vp]
         lib.sage2gpu_get_extensions.argtypes = [vp, vp, vp, vp]
         lib.sage2gpu_get_edges.argtypes = [vp, vp, C.c_uint64, u64p]
+        lib.sage2gpu_get_edges_packed.argtypes = [vp, vp, C.c_uint64, u64p]
         lib.sage2gpu_write_reads.argtypes = [vp, C.c_char_p]
         lib.sage2gpu_write_graph3.argtypes = [vp, C.c_char_p]
+        lib.sage2gpu_measure_gather.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(C.c_double)]
         lib.sage2gpu_stream.argtypes = [vp]
         lib.sage2gpu_stream.restype = vp
         lib.sage2gpu_kernel_launches.argtypes = []
@@ -136,6 +146,19 @@ class Sage2Gpu:
         fn = self._lib.sage2gpu_load_reads_device if device else self._lib.sage2gpu_load_reads
         self._check(fn(self._h, bases_ptr, offsets_ptr, int(n_reads), int(min_overlap)), "load_reads")
 
+    def load_reads_chunked(self, bases: np.ndarray, offsets: np.ndarray, min_overlap: int, reads_per_chunk: int):
+        """Streamed upload (sage2gpu_load_begin/_append/_finish); same result as load_reads."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep = (bases, offsets)
+        n = len(offsets) - 1
+        self._check(self._lib.sage2gpu_load_begin(self._h, int(min_overlap)), "load_begin")
+        for r0 in range(0, n, reads_per_chunk):
+            r1 = min(n, r0 + reads_per_chunk)
+            self._check(self._lib.sage2gpu_load_append(self._h, bases.ctypes.data, offsets[r0:r1 + 1].ctypes.data, r1 - r0),
+                        "load_append")
+        self._check(self._lib.sage2gpu_load_finish(self._h), "load_finish")
+
     def build_hash_table(self):
         self._check(self._lib.sage2gpu_build_hash_table(self._h), "build_hash_table")
 
@@ -146,6 +169,13 @@ class Sage2Gpu:
         self.load_reads(bases, offsets, min_overlap)
         self.build_hash_table()
         self.build_overlap_graph()
+
+    def measure_gather(self, footprint_bytes: int, granule_bytes: int = 32, n_loads: int = 1 << 28) -> float:
+        """GB/s of random `granule_bytes` gathers over `footprint_bytes` (the random-sector roofline)."""
+        g = C.c_double()
+        self._check(self._lib.sage2gpu_measure_gather(self._h, int(footprint_bytes), int(granule_bytes), int(n_loads),
+                                                      C.byref(g)), "measure_gather")
+        return float(g.value)
 
     def stream_ptr(self) -> int:
         """cudaStream_t of this context (e.g. for torch.cuda.ExternalStream)."""
@@ -187,6 +217,12 @@ class Sage2Gpu:
         if n.value:
             self._check(self._lib.sage2gpu_get_edges(self._h, out.ctypes.data, n.value, C.byref(n)), "get_edges")
         return out
+
+    def edges_packed_into(self, out_ptr: int, capacity: int) -> int:
+        """Raw (w0, w1) edge words straight into a caller buffer (e.g. pinned); returns the edge count."""
+        n = C.c_uint64()
+        self._check(self._lib.sage2gpu_get_edges_packed(self._h, out_ptr, int(capacity), C.byref(n)), "get_edges_packed")
+        return int(n.value)
 
     def write_reads(self, path: str):
         self._check(self._lib.sage2gpu_write_reads(self._h, path.encode()), "write_reads")

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libsage2gpu (include/sage2gpu.h) over the stages in reads.cu, table.cu,
 // search.cu and graph.cu, plus the host-side seams to the reference's formats.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "../../include/sage2gpu.h"
@@ -121,6 +122,9 @@ int sage2gpu_create(sage2gpu_ctx **out, int device)
         delete ctx;
         return SAGE2GPU_ERR_CUDA;
     }
+    // the search kernels gather random 32-byte sectors (slot index, partner reads): do not let L2 fetch
+    // 64/128-byte granules from HBM for them
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, getenv("SAGE2GPU_L2_GRANULE") ? (size_t)atoi(getenv("SAGE2GPU_L2_GRANULE")) : 32);
     // keep freed blocks in the stream-ordered pool: steady-state allocation is a pointer bump
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -139,11 +143,12 @@ void sage2gpu_destroy(sage2gpu_ctx *ctx)
     cudaStreamSynchronize(st);
     {
         sg::Context &c = ctx->c;
-        c.d_bases.release(); c.d_offsets.release(); c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
+        c.d_bases.release(); c.d_offsets.release(); c.up_d_bases.release(); c.up_d_offsets.release(); c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
         c.slots.release(); c.entries.release(); c.extR.release(); c.extL.release(); c.flag5.release();
         c.cont_max.release(); c.explored.release(); c.edges.release();
     }
     cudaStreamSynchronize(st);
+    if (ctx->c.up_event) cudaEventDestroy(ctx->c.up_event);
     delete ctx;
     cudaStreamDestroy(st);
 }
@@ -159,6 +164,60 @@ int sage2gpu_load_reads_device(sage2gpu_ctx *ctx, const uint8_t *d_bases, const 
 {
     return guarded(ctx, [&](sg::Context &c) { load_common(c, d_bases, d_offsets, n_reads, min_overlap, true); });
 }
+
+// ---- streamed upload: the FASTA/Q parser fills one pinned chunk while the previous one is copied ----
+int sage2gpu_load_begin(sage2gpu_ctx *ctx, int min_overlap)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(min_overlap >= 1 && min_overlap < 65535, "min_overlap out of range");
+        c.min_overlap = min_overlap;
+        c.tm = sg::Timers();
+        c.have_reads = c.have_table = c.have_graph = false;
+        c.up_reads = 0; c.up_bases = 0; c.up_open = true;
+        if (!c.up_event) SG_CUDA(cudaEventCreateWithFlags(&c.up_event, cudaEventDisableTiming));
+    });
+}
+
+int sage2gpu_load_append(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.up_open, "sage2gpu_load_begin must be called first");
+        SG_CHECK(n_reads >= 0 && (n_reads == 0 || (bases && offsets)), "bad chunk");
+        SG_CUDA(cudaEventSynchronize(c.up_event));          // the previous chunk's host buffers are free again
+        if (n_reads == 0) return;
+        sg::stage_upload_chunk(c, bases, offsets, n_reads);
+        SG_CUDA(cudaEventRecord(c.up_event, c.stream));
+    });
+}
+
+int sage2gpu_load_finish(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.up_open, "sage2gpu_load_begin must be called first");
+        c.up_open = false;
+        SG_CUDA(cudaEventSynchronize(c.up_event));
+        {
+            StageTimer t(c.stream);
+            sg::stage_ingest_ascii(c, c.up_d_bases.p, c.up_d_offsets.p, (int64_t)c.up_reads, true);
+            c.up_d_bases.release(); c.up_d_offsets.release();
+            c.tm.ingest = t.stop();
+        }
+        {
+            StageTimer t(c.stream);
+            sg::stage_organize_reads(c);
+            c.tm.sort_reads = t.stop();
+        }
+    });
+}
+
+void *sage2gpu_host_alloc(uint64_t n_bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n_bytes ? n_bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void sage2gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int sage2gpu_build_hash_table(sage2gpu_ctx *ctx)
 {
@@ -184,7 +243,6 @@ int sage2gpu_build_overlap_graph(sage2gpu_ctx *ctx)
             c.tm.phase_b = t.stop();
         }
         sg::stage_phase_c_and_finalize(c);
-        fetch_edges(c);
         c.tm.total_device = c.tm.ingest + c.tm.sort_reads + c.tm.build_table + c.tm.phase_a + c.tm.phase_b +
                             c.tm.phase_c_dev + c.tm.phase_c_host + c.tm.sort_edges;
     });
@@ -300,6 +358,27 @@ int sage2gpu_get_edges(sage2gpu_ctx *ctx, sage2gpu_edge *out, uint64_t capacity,
             x.delta_twin = ul - (vl - x.delta);                    // overlapGraph.cpp:147
             x.reserved = 0;
         }
+    });
+}
+
+int sage2gpu_get_edges_packed(sage2gpu_ctx *ctx, uint64_t *out, uint64_t capacity, uint64_t *n_edges)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.have_graph, "overlap graph not built");
+        const sg::u64 E = c.cnt.n_edges;
+        if (n_edges) *n_edges = E;
+        if (!out || E == 0) return;
+        SG_CHECK(capacity >= E, "edge buffer too small");
+        SG_CUDA(cudaMemcpyAsync(out, c.edges.p, 2 * E * sizeof(sg::u64), cudaMemcpyDeviceToHost, c.stream));
+        SG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int granule_bytes, uint64_t n_loads, double *gbps)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(gbps != nullptr, "null result pointer");
+        *gbps = (double)sg::gather_bench(footprint_bytes, granule_bytes, n_loads, c.stream);
     });
 }
 

@@ -40,6 +40,12 @@ struct Context {
     DevBuf<int64_t> d_offsets;
     u64 n_input = 0;
     int max_len = 0;
+    // streamed upload (sage2gpu_load_begin / _append / _finish): growing device copies of the chunks
+    DevBuf<uint8_t> up_d_bases;
+    DevBuf<int64_t> up_d_offsets;   // [up_reads + 1], absolute
+    u64 up_reads = 0, up_bases = 0;
+    bool up_open = false;
+    cudaEvent_t up_event = nullptr;
 
     // unique reads, ids 1..U map to index 0..U-1
     DevBuf<u64> F, RC;          // [U*SW] records
@@ -64,6 +70,7 @@ struct Context {
 
 // stages (each throws sg::CudaError)
 void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident);
+void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads);
 void stage_organize_reads(Context &c);
 void stage_build_table(Context &c);
 void stage_phase_a(Context &c);

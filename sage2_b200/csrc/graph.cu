@@ -73,6 +73,47 @@ __global__ void __launch_bounds__(256) compact_ids_kernel(const u32 *__restrict_
         if (flag[i]) out[idx[i]] = (u32)i;
 }
 
+// Phase-C hand-over: the host walk touches S (state 0 after phase B) and the phase-B neighbours of S,
+// whose whole lists markTransitiveEdge scans (economyGraph.cpp:653).  mark_neighbours flags those
+// neighbours, flag_needed_edges selects every phase-B record with an endpoint in S or flagged.
+__global__ void __launch_bounds__(256) mark_neighbours_kernel(const u64 *__restrict__ edges, u64 n, const uint8_t *__restrict__ explored,
+                                                               uint8_t *__restrict__ nbr)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        const u64 w0 = edges[2 * e];
+        const u32 a = (u32)(w0 >> 32) - 1, b = (u32)w0 - 1;
+        if (explored[a] == 0) nbr[b] = 1;
+        if (explored[b] == 0) nbr[a] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) flag_needed_edges_kernel(const u64 *__restrict__ edges, u64 n, const uint8_t *__restrict__ explored,
+                                                                 const uint8_t *__restrict__ nbr, u32 *__restrict__ flag)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        const u64 w0 = edges[2 * e];
+        const u32 a = (u32)(w0 >> 32) - 1, b = (u32)w0 - 1;
+        flag[e] = (explored[a] == 0 || explored[b] == 0 || nbr[a] || nbr[b]) ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_needed_edges_kernel(const u64 *__restrict__ edges, u64 n, const u32 *__restrict__ flag,
+                                                                   const u32 *__restrict__ idx, const uint16_t *__restrict__ len,
+                                                                   u64 *__restrict__ out, u32 *__restrict__ out_len)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        if (!flag[e]) continue;
+        const u64 w0 = edges[2 * e], p = idx[e];
+        out[2 * p] = w0; out[2 * p + 1] = edges[2 * e + 1];
+        out_len[p] = (u32)len[(u32)(w0 >> 32) - 1] | ((u32)len[(u32)w0 - 1] << 16);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_len_kernel(const u32 *__restrict__ ids, u64 n, const uint16_t *__restrict__ len, uint16_t *__restrict__ out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = len[ids[i]];
+}
+
 void stage_phase_b(Context &c)
 {
     cudaStream_t st = c.stream;
@@ -169,20 +210,47 @@ void stage_phase_c_and_finalize(Context &c)
         c.cnt.candidates_c = nC;
 
         // ---- host walk (serial by definition, economyGraph.cpp:513-564) -------------------------
+        // only the phase-B records the walk can touch leave the device
+        DevBuf<uint8_t> nbr(U, st);
+        DevBuf<u32> nflag, nidx, d_nsel(1, st), selLen;
+        DevBuf<u64> selB;
+        DevBuf<uint16_t> sLen(nS, st);
+        u32 nSel = 0;
+        gather_len_kernel<<<big_grid(nS), 256, 0, st>>>(s_ids.p, nS, c.len.p, sLen.p);
+        SG_LAUNCHED();
+        if (nB) {
+            nflag.alloc(nB, st); nidx.alloc(nB, st);
+            SG_CUDA(cudaMemsetAsync(nbr.p, 0, U, st));
+            mark_neighbours_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, c.explored.p, nbr.p);
+            SG_LAUNCHED();
+            flag_needed_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, c.explored.p, nbr.p, nflag.p);
+            SG_LAUNCHED();
+            exclusive_scan_u32(nflag.p, nidx.p, nB, d_nsel.p, st);
+            SG_CUDA(cudaMemcpyAsync(&nSel, d_nsel.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaStreamSynchronize(st));
+            selB.alloc(2 * (u64)nSel, st); selLen.alloc(nSel, st);
+            if (nSel) {
+                gather_needed_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, nflag.p, nidx.p, c.len.p, selB.p, selLen.p);
+                SG_LAUNCHED();
+            }
+        }
         PhaseCInput in;
-        std::vector<u32> h_sids(nS), h_off((size_t)nS + 1);
-        std::vector<u64> h_cand(nC), h_edgesB(2 * nB);
-        std::vector<uint16_t> h_len(U);
+        std::vector<u32> h_sids(nS), h_off((size_t)nS + 1), h_selLen(nSel);
+        std::vector<u64> h_cand(nC), h_selB(2 * (u64)nSel);
+        std::vector<uint16_t> h_slen(nS);
         SG_CUDA(cudaMemcpyAsync(h_sids.data(), s_ids.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaMemcpyAsync(h_off.data(), offs.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(h_slen.data(), sLen.p, nS * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
         if (nC) SG_CUDA(cudaMemcpyAsync(h_cand.data(), cand.p, nC * sizeof(u64), cudaMemcpyDeviceToHost, st));
-        if (nB) SG_CUDA(cudaMemcpyAsync(h_edgesB.data(), c.edges.p, 2 * nB * sizeof(u64), cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(h_len.data(), c.len.p, U * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        if (nSel) {
+            SG_CUDA(cudaMemcpyAsync(h_selB.data(), selB.p, 2 * (u64)nSel * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaMemcpyAsync(h_selLen.data(), selLen.p, nSel * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        }
         SG_CUDA(cudaEventRecord(ev1, st));
         SG_CUDA(cudaStreamSynchronize(st));
         h_off[nS] = nC;
-        in.U = U; in.len = h_len.data(); in.nS = nS; in.s_ids = h_sids.data(); in.cand_off = h_off.data();
-        in.cand = h_cand.data(); in.nB = nB; in.edgesB = h_edgesB.data();
+        in.nS = nS; in.s_ids = h_sids.data(); in.s_len = h_slen.data(); in.cand_off = h_off.data();
+        in.cand = h_cand.data(); in.nB = nSel; in.edgesB = h_selB.data(); in.edgesB_len = h_selLen.data();
         PhaseCOutput out;
         host_ms = run_host_phase_c(in, out);
         c.cnt.edges_inserted_c = out.inserted;

@@ -84,6 +84,40 @@ __global__ void __launch_bounds__(K1_WARPS * 32) pack_kernel(const uint8_t *__re
     }
 }
 
+// One chunk of the streamed upload: append the bases, append the offsets rebased to the running total.
+__global__ void __launch_bounds__(256) rebase_offsets_kernel(const int64_t *__restrict__ in, int64_t n, int64_t delta, int64_t *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] + delta;
+}
+
+template <typename T>
+static void grow(DevBuf<T> &b, size_t used, size_t need, cudaStream_t st)
+{
+    if (need <= b.n) return;
+    size_t cap = b.n ? b.n : (size_t)1 << 20;
+    while (cap < need) cap += cap / 2 + 1;
+    DevBuf<T> nb(cap, st);
+    if (used) SG_CUDA(cudaMemcpyAsync(nb.p, b.p, used * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    b = std::move(nb);
+}
+
+void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads)
+{
+    cudaStream_t st = c.stream;
+    const int64_t first = offsets[0], nb = offsets[n_reads] - first;
+    SG_CHECK(nb >= 0, "offsets must be non-decreasing");
+    SG_CHECK(c.up_reads + (u64)n_reads < 0x3FFFFFFFull, "at most 2^30-1 reads per context");
+    grow(c.up_d_bases, (size_t)c.up_bases, (size_t)(c.up_bases + (u64)nb), st);
+    grow(c.up_d_offsets, (size_t)(c.up_reads ? c.up_reads + 1 : 0), (size_t)(c.up_reads + (u64)n_reads + 1), st);
+    if (nb) SG_CUDA(cudaMemcpyAsync(c.up_d_bases.p + c.up_bases, bases + first, (size_t)nb, cudaMemcpyHostToDevice, st));
+    DevBuf<int64_t> tmp((size_t)n_reads + 1, st);
+    SG_CUDA(cudaMemcpyAsync(tmp.p, offsets, ((size_t)n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    rebase_offsets_kernel<<<grid_for((u64)n_reads + 1, 256, 4), 256, 0, st>>>(tmp.p, n_reads + 1, (int64_t)c.up_bases - first, c.up_d_offsets.p + c.up_reads);
+    SG_LAUNCHED();
+    c.up_reads += (u64)n_reads;
+    c.up_bases += (u64)nb;
+}
+
 void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident)
 {
     cudaStream_t st = c.stream;

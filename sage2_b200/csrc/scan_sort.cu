@@ -236,4 +236,61 @@ int radix_sort_varying(SortCols &c, int cur, u64 n, bool use_b, cudaStream_t st)
     return radix_sort_bits(c, cur, n, use_b, lo, hi, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// random-sector gather microbenchmark: the denominator SURVEY.md 8(d) asks for.  Every thread reads
+// `per_thread` independent, uniformly random, `granule`-byte aligned blocks (32 or 64 bytes) of a
+// buffer far larger than L2 and folds them into one word.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_bench_kernel(const uint4 *__restrict__ buf, u64 n_granules, int vec_per_granule,
+                                                            int per_thread, u64 seed, u32 *__restrict__ out)
+{
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 x = (tid + 1) * 0x9e3779b97f4a7c15ull + seed;
+    u32 acc = 0;
+    for (int r = 0; r < per_thread; r += 4) {
+        uint4 v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+            const u64 g = __umul64hi(x, n_granules);
+            const uint4 *p = buf + g * vec_per_granule;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q < vec_per_granule) v[u][q] = __ldg(p + q);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q < vec_per_granule) acc ^= v[u][q].x ^ v[u][q].y ^ v[u][q].z ^ v[u][q].w;
+    }
+    out[tid] = acc;
+}
+
+float gather_bench(u64 footprint_bytes, int granule_bytes, u64 n_loads, cudaStream_t st)
+{
+    SG_CHECK(granule_bytes == 16 || granule_bytes == 32 || granule_bytes == 64, "granule must be 16, 32 or 64 bytes");
+    const int vpg = granule_bytes / 16, per_thread = 64;
+    const u64 n_granules = footprint_bytes / (u64)granule_bytes;
+    SG_CHECK(n_granules > 0, "empty footprint");
+    u64 threads = n_loads / per_thread;
+    threads = (threads + 255) / 256 * 256;
+    DevBuf<uint4> buf((size_t)(n_granules * vpg), st);
+    DevBuf<u32> out((size_t)threads, st);
+    SG_CUDA(cudaMemsetAsync(buf.p, 1, buf.bytes(), st));
+    cudaEvent_t e0, e1;
+    SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int it = 0; it < 4; ++it) {
+        SG_CUDA(cudaEventRecord(e0, st));
+        gather_bench_kernel<<<(unsigned)(threads / 256), 256, 0, st>>>(buf.p, n_granules, vpg, per_thread, 1234 + it, out.p);
+        SG_LAUNCHED();
+        SG_CUDA(cudaEventRecord(e1, st));
+        SG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return (float)((double)threads * per_thread * granule_bytes / (best * 1e-3) / 1e9);
+}
+
 }  // namespace sg

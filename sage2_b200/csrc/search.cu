@@ -20,6 +20,7 @@
 //              hit, last left hit, not ambiguous".  The first round that breaks this converts the
 //              state to core.cuh's ExtState and the rest of the read runs the reference's sequential
 //              chain hit by hit (EXACT mode) -- still with parallel fetch and verification.
+#include <stdlib.h>
 #include "context.h"
 
 namespace sg {
@@ -54,27 +55,49 @@ __device__ __forceinline__ void t_extract_key(const u64 *X, int j, int h, u64 &v
     else { v0 = t_window32<SW>(X, j) >> (64 - 2 * (h - 32)); v1 = t_window32<SW>(X, j + h - 32); }
 }
 
-// X[start+t] == Y[t] for t in [0, ov): X is indexed dynamically (shared / global pointer), Y statically
-// (registers or a pointer).  `key_bad` = a mismatch inside the first h bases (the hash key).
+// masks of the first h bases (the hash key) inside the first two words of a compare
+__device__ __forceinline__ void key_masks(int h, u64 &km0, u64 &km1)
+{
+    km0 = h >= 32 ? ~0ull : ~(~0ull >> (2 * h));
+    km1 = h <= 32 ? 0ull : (h >= 64 ? ~0ull : ~(~0ull >> (2 * (h - 32))));
+}
+
+// 64 bits starting `s` bits (0..63) into the 128-bit string a:b, by two 32-bit funnel shifts
+__device__ __forceinline__ u64 funnel64(u64 a, u64 b, bool upper, unsigned s5)
+{
+    const u32 ah = (u32)(a >> 32), al = (u32)a, bh = (u32)(b >> 32), bl = (u32)b;
+    const u32 x0 = upper ? al : ah, x1 = upper ? bh : al, x2 = upper ? bl : bh;
+    return ((u64)__funnelshift_l(x1, x0, s5) << 32) | __funnelshift_l(x2, x1, s5);
+}
+
+// X[start+t] == Y[t] for t in [0, ov), ov = min(lenY, lenX-start): X is indexed dynamically (a shared
+// memory record with one readable word after it), Y statically (registers or a pointer).  Whole words
+// are compared by XOR, the last one under a mask.  `key_bad` = a mismatch under the key masks km0/km1.
 template <int SW, typename YT>
-__device__ __forceinline__ bool t_overlap_equal(const u64 *X, int lenX, int start, const YT &Y, int lenY, int h,
+__device__ __forceinline__ bool t_overlap_equal(const u64 *X, int lenX, int start, const YT &Y, int lenY, u64 km0, u64 km1,
                                                 bool &contained, bool &key_bad)
 {
     const int rem = lenX - start;
     contained = lenY <= rem;
     const int ov = contained ? lenY : rem;
+    const int wb = ov >> 5;                              // words [0,wb) whole, word wb under bm
+    const u64 bm = ~(~0ull >> ((ov & 31) * 2));          // 0 when ov is a multiple of 32
+    const int i0 = start >> 5;
+    const unsigned s = (unsigned)(start & 31) * 2;
+    const bool upper = s >= 32;
+    const unsigned s5 = s & 31;
     u64 acc = 0, acck = 0;
+    u64 a = X[i0];
 #pragma unroll
     for (int w = 0; w < SW; ++w) {
-        const int nb = ov - 32 * w;
-        if (nb > 0) {
-            const u64 m = nb >= 32 ? ~0ull : ~(~0ull >> (2 * nb));
-            const u64 d = (t_window32<SW>(X, start + 32 * w) ^ Y[w]) & m;
+        if (w <= wb) {
+            const u64 b = X[i0 + w + 1];
+            u64 d = funnel64(a, b, upper, s5) ^ Y[w];
+            if (w == wb) d &= bm;
             acc |= d;
-            if (w < 2) {
-                const int kb = h - 32 * w;      // h <= 64: the key lives in the first two words
-                if (kb > 0) acck |= d & (kb >= 32 ? ~0ull : ~(~0ull >> (2 * kb)));
-            }
+            if (w == 0) acck |= d & km0;
+            if (w == 1) acck |= d & km1;
+            a = b;
         }
     }
     key_bad = acck != 0;
@@ -136,15 +159,15 @@ __device__ __forceinline__ u64 make_item(int jj, bool first, bool inl, u64 paylo
 // ------------------------------------------------------------------------------------------------
 // K4: phase A
 // ------------------------------------------------------------------------------------------------
-template <int SW>
-__global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32)
+template <int SW, int MINB>
+__global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32, MINB)
 phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, uint8_t *__restrict__ flag5,
                u32 *__restrict__ cont_max, unsigned long long *__restrict__ counters)
 {
     constexpr int WARPS = SearchCfg<SW>::WARPS, SWP = SearchCfg<SW>::SWP;
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ u64 sXf[WARPS][SW], sXr[WARPS][SW], sPrevR[WARPS][SW], sPrevL[WARPS][SW];
-    __shared__ u64 sQ[WARPS][32 * SWP];
+    __shared__ u64 sXf[WARPS][SW + 1], sXr[WARPS][SW + 1], sPrevR[WARPS][SW + 1], sPrevL[WARPS][SW + 1];   // +1: t_overlap_equal reads one word past
+    __shared__ u64 sQ[WARPS][32 * SWP + 1];
     __shared__ u64 sItem[WARPS][32];
     __shared__ ExtState sState[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -153,6 +176,9 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
     const u64 nwarps = (u64)gridDim.x * WARPS;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long calls = 0, probes = 0, n_exact = 0, n_restart = 0;
+    u64 km0, km1;
+    key_masks(P.h, km0, km1);
+    if (lane == 0) { Xf[SW] = 0; Xr[SW] = 0; prevR[SW] = 0; prevL[SW] = 0; }
 
     for (u64 i = (u64)blockIdx.x * WARPS + warp; i < P.U; i += nwarps) {
         if (lane < SW) { Xf[lane] = P.F[i * SW + lane]; Xr[lane] = P.RC[i * SW + lane]; }
@@ -232,7 +258,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                         load_record<SW>((partner_uses_rc(type) ? P.RC : P.F) + (u64)rid2 * SW, q);
                         len2 = (int)(q[SW - 1] & 0xFFFF);
                         bool contained, key_bad;
-                        const bool ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, P.h, contained, key_bad);
+                        const bool ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, km0, km1, contained, key_bad);
                         fp = first && key_bad;
                         if (need) {
                             my_calls++;
@@ -272,8 +298,8 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                             bool c2, kb;
                             const u64 *mine = Qs + lane * SWP;
                             if (prevJ == jj) anomaly = true;                      // two hits of one side in one window
-                            else if (right) anomaly = !t_overlap_equal<SW>(prec, prevLen, jj - prevJ, mine, len2, 0, c2, kb);   // :110-112
-                            else anomaly = !t_overlap_equal<SW>(mine, len2, jj - prevJ, prec, prevLen, 0, c2, kb);             // :295-297
+                            else if (right) anomaly = !t_overlap_equal<SW>(prec, prevLen, jj - prevJ, mine, len2, 0ull, 0ull, c2, kb);   // :110-112
+                            else anomaly = !t_overlap_equal<SW>(mine, len2, jj - prevJ, prec, prevLen, 0ull, 0ull, c2, kb);             // :295-297
                         }
                     }
                     if (!__any_sync(FULL, anomaly)) {
@@ -392,9 +418,10 @@ phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint
                u32 *__restrict__ counts, const u32 *__restrict__ offsets, u64 *__restrict__ cand)
 {
     constexpr int WARPS = SearchCfg<SW>::WARPS;
-    __shared__ u64 sXf[WARPS][SW], sXr[WARPS][SW];
+    __shared__ u64 sXf[WARPS][SW + 1], sXr[WARPS][SW + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *Xf = sXf[warp], *Xr = sXr[warp];
+    if (lane == 0) { Xf[SW] = 0; Xr[SW] = 0; }
     const u64 nwarps = (u64)gridDim.x * WARPS;
     for (u64 s = (u64)blockIdx.x * WARPS + warp; s < nS; s += nwarps) {
         const u64 i = s_ids[s];      // 0-based
@@ -435,7 +462,7 @@ phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint
                             load_record<SW>((partner_uses_rc(type) ? P.RC : P.F) + (u64)rid2 * SW, q);
                             const int len2 = (int)(q[SW - 1] & 0xFFFF);
                             bool contained, kb;
-                            ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, 0, contained, kb);
+                            ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, 0ull, 0ull, contained, kb);
                             rec = candidate_record(type, jj, P.h, len1, len2, rid2);
                         }
                     }
@@ -462,16 +489,30 @@ static unsigned search_grid(u64 n_reads, int warps, int blocks_per_sm)
     return (unsigned)g;
 }
 
-template <int SW>
-static void launch_phase_a(Context &c, const SearchParams &P, unsigned long long *d_counters)
+template <int SW, int MINB>
+static void launch_phase_a_v(Context &c, const SearchParams &P, unsigned long long *d_counters)
 {
     constexpr int WARPS = SearchCfg<SW>::WARPS;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_kernel<SW>, WARPS * 32, 0));
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_kernel<SW, MINB>, WARPS * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    phase_a_kernel<SW><<<search_grid(P.U, WARPS, blocks_per_sm), WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters);
+    phase_a_kernel<SW, MINB><<<search_grid(P.U, WARPS, blocks_per_sm), WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters);
+}
+
+// MINB = resident blocks per SM the register budget is cut for (occupancy against spills).
+template <int SW>
+static void launch_phase_a(Context &c, const SearchParams &P, unsigned long long *d_counters)
+{
+    if constexpr (SW <= 8) {
+        static const int minb = [] { const char *e = getenv("SAGE2GPU_PA_MINB"); return e ? atoi(e) : 3; }();
+        if (minb <= 2) launch_phase_a_v<SW, 2>(c, P, d_counters);
+        else if (minb == 3) launch_phase_a_v<SW, 3>(c, P, d_counters);
+        else launch_phase_a_v<SW, 4>(c, P, d_counters);
+    } else {
+        launch_phase_a_v<SW, 1>(c, P, d_counters);
+    }
 }
 
 template <int SW>
