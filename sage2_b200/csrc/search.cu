@@ -125,7 +125,7 @@ __device__ __forceinline__ void probe_window(const SearchParams &P, u64 v0, u64 
             if (slot_get_tag(slot) != tag) continue;
             const u32 c = slot_get_count(slot);
             if (exact || c >= (u32)kHashThreshold) {
-                const u32 ent = c == 1 ? (u32)slot_get_payload(slot) : __ldg(&P.entries[slot_get_payload(slot)]);
+                const u32 ent = (c == 1 || c >= (u32)kHashThreshold) ? (u32)slot_get_payload(slot) : __ldg(&P.entries[slot_get_payload(slot)]);
                 const u64 rid = ent >> 2;
                 const int type = (int)(ent & 3);
                 const u64 *X = ((type & 2) ? P.RC : P.F) + rid * SW;

@@ -3,65 +3,124 @@
 //
 // Observable semantics kept exactly: key (h = min(k,64) bases) -> all (readId,type) sharing it, in
 // (readId asc, type asc) order; a key with >= 100 entries is invisible to searches.  Layout:
-//   entries[4U]  : (readId0<<2 | type), radix-sorted by the exact 128-bit key (stable, so each key's
-//                  run is already in bucket order),
-//   slots[cap]   : open-addressing index (linear probing over 32-byte sectors of 4 slots, load <= 0.5)
-//                  filled with 64-bit atomicCAS, one slot per DISTINCT key: tag | min(count,127) |
-//                  (the entry itself when count == 1, else the offset of the key's run) (core.cuh).
+//   slots[cap]   : open-addressing index, one 64-bit slot per DISTINCT key, grouped in 32-byte sectors
+//                  of 4 (a probe reads one sector), filled with 64-bit atomicCAS:
+//                  tag | min(count,127) | payload (core.cuh).  payload = the key's only entry
+//                  (count == 1), a representative entry (count >= 100, masked) or the offset of the
+//                  key's run in entries[] (2 <= count <= 99).
+//   entries[M]   : (readId0<<2 | type) of every key with 2..99 entries, each run sorted ascending, which
+//                  is the reference's bucket order (insertion order, hashTable.cpp:94-109).
+// Like the reference (hashTable.cpp:150-160) a slot does not store its 128-bit key: a tag match is
+// confirmed by re-extracting the key from the read of the slot's representative entry.
+//
+// Four passes over the 4U entries, no sort:
+//   1 insert  : find-or-claim the key's slot (atomicCAS on an empty slot, saturating CAS increment of
+//               the count on a match), remember the slot per entry
+//   2 offsets : exclusive scan of the 2..99 counts over the slot array, rewrite those slots' payload
+//   3 fill    : every entry of such a key takes the next position of its run (atomic cursor)
+//   4 order   : insertion sort of every run (< 100 entries)
 #include "context.h"
 
 namespace sg {
 
-__global__ void __launch_bounds__(256) gen_entries_kernel(const u64 *__restrict__ F, const u64 *__restrict__ RC,
-                                                           const uint16_t *__restrict__ len, u64 U, int SW, int h,
-                                                           u64 *__restrict__ k0, u64 *__restrict__ k1, u32 *__restrict__ val)
+constexpr u64 kCountOne = 1ull << 33;
+
+__device__ __forceinline__ u64 load_slot(const u64 *p) { return *reinterpret_cast<const volatile u64 *>(p); }
+
+__global__ void __launch_bounds__(256) table_insert_kernel(const u64 *__restrict__ F, const u64 *__restrict__ RC,
+                                                            const uint16_t *__restrict__ len, u64 U, int SW, int h,
+                                                            u64 *__restrict__ slots, u64 nsec, u32 *__restrict__ where)
 {
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < 4 * U; t += (u64)gridDim.x * blockDim.x) {
         const u64 rid = t >> 2;
         const int type = (int)(t & 3);
-        const u64 *X = ((type & 2) ? RC : F) + rid * SW;
-        const int l = len[rid];
         u64 v0, v1;
-        extract_key(X, SW, (type & 1) ? l - h : 0, h, v0, v1);
-        k0[t] = v0; k1[t] = v1; val[t] = (u32)t;
-    }
-}
-
-__global__ void __launch_bounds__(256) key_flag_kernel(const u64 *__restrict__ k0, const u64 *__restrict__ k1, u64 n, u32 *__restrict__ flag)
-{
-    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x)
-        flag[p] = (p == 0 || k0[p] != k0[p - 1] || k1[p] != k1[p - 1]) ? 1u : 0u;
-}
-
-__global__ void __launch_bounds__(256) group_start_kernel(const u32 *__restrict__ flag, const u32 *__restrict__ gidx, u64 n, u32 *__restrict__ gstart)
-{
-    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x)
-        if (flag[p]) gstart[gidx[p]] = (u32)p;
-}
-
-__global__ void __launch_bounds__(256) index_insert_kernel(const u64 *__restrict__ k0, const u64 *__restrict__ k1,
-                                                            const u32 *__restrict__ val, const u32 *__restrict__ gstart,
-                                                            u64 D, u64 n, u64 *__restrict__ slots, u64 nsec,
-                                                            unsigned long long *over)
-{
-    unsigned long long my_over = 0;
-    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < D; g += (u64)gridDim.x * blockDim.x) {
-        const u64 p = gstart[g];
-        const u64 e = (g + 1 < D) ? gstart[g + 1] : n;
-        const u64 count = e - p;
-        if (count >= (u64)kHashThreshold) my_over++;
-        const u64 hsh = hash_key(k0[p], k1[p]);
-        const u64 v = slot_encode(hsh, count, count == 1 ? (u64)val[p] : p);
+        entry_key(F + rid * SW, RC + rid * SW, SW, len[rid], h, type, v0, v1);
+        const u64 hsh = hash_key(v0, v1);
+        const u64 tag = slot_tag(hsh);
         u64 sec = home_sector(hsh, nsec);
         bool done = false;
         while (!done) {
-#pragma unroll
-            for (int t = 0; t < kSlotsPerSector && !done; ++t)
-                done = atomicCAS((unsigned long long *)&slots[kSlotsPerSector * sec + t], 0ull, (unsigned long long)v) == 0ull;
+            for (int q = 0; q < kSlotsPerSector && !done; ++q) {
+                u64 *sp = slots + kSlotsPerSector * sec + q;
+                u64 cur = load_slot(sp);
+                if (cur == 0) {
+                    const u64 old = atomicCAS((unsigned long long *)sp, 0ull, (unsigned long long)slot_encode(hsh, 1, t));
+                    if (old == 0) { where[t] = (u32)(kSlotsPerSector * sec + q); done = true; break; }
+                    cur = old;
+                }
+                if (slot_get_tag(cur) != tag) continue;
+                // same tag: same key?  (the representative entry never changes once the slot is claimed)
+                const u32 rep = (u32)slot_get_payload(cur);
+                const u64 r2 = rep >> 2;
+                u64 w0, w1;
+                entry_key(F + r2 * SW, RC + r2 * SW, SW, len[r2], h, (int)(rep & 3), w0, w1);
+                if (w0 != v0 || w1 != v1) continue;
+                while (slot_get_count(cur) < 127) {            // saturating: >= 100 is all a search needs to know
+                    const u64 old = atomicCAS((unsigned long long *)sp, (unsigned long long)cur, (unsigned long long)(cur + kCountOne));
+                    if (old == cur) break;
+                    cur = old;
+                }
+                where[t] = (u32)(kSlotsPerSector * sec + q);
+                done = true;
+            }
             sec = (sec + 1 == nsec) ? 0 : sec + 1;
         }
     }
-    if (my_over) atomicAdd(over, my_over);
+}
+
+// pass 2a: run length of every slot that owns a run in entries[]; distinct / masked key counters
+__global__ void __launch_bounds__(256) table_runs_kernel(const u64 *__restrict__ slots, u64 cap, u32 *__restrict__ run, unsigned long long *counters)
+{
+    unsigned long long distinct = 0, over = 0;
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (u64)gridDim.x * blockDim.x) {
+        const u64 v = slots[s];
+        const u32 c = v ? slot_get_count(v) : 0u;
+        run[s] = (c >= 2 && c < (u32)kHashThreshold) ? c : 0u;
+        distinct += v != 0;
+        over += c >= (u32)kHashThreshold;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { distinct += __shfl_xor_sync(0xffffffffu, distinct, o); over += __shfl_xor_sync(0xffffffffu, over, o); }
+    if ((threadIdx.x & 31) == 0) { if (distinct) atomicAdd(&counters[0], distinct); if (over) atomicAdd(&counters[1], over); }
+}
+
+// pass 2b: payload of run-owning slots := offset of the run
+__global__ void __launch_bounds__(256) table_offsets_kernel(u64 *__restrict__ slots, u64 cap, const u32 *__restrict__ run, const u32 *__restrict__ off)
+{
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (u64)gridDim.x * blockDim.x)
+        if (run[s]) slots[s] = (slots[s] & ~0x1FFFFFFFFull) | (u64)off[s];
+}
+
+// pass 3: entries of run-owning keys take the next free position of their run
+__global__ void __launch_bounds__(256) table_fill_kernel(const u64 *__restrict__ slots, const u32 *__restrict__ where, u64 n,
+                                                          u32 *__restrict__ cursor, u32 *__restrict__ entries)
+{
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
+        const u64 v = slots[where[t]];
+        const u32 c = slot_get_count(v);
+        if (c < 2 || c >= (u32)kHashThreshold) continue;
+        const u64 off = slot_get_payload(v);
+        entries[off + atomicAdd(&cursor[off], 1u)] = (u32)t;
+    }
+}
+
+// pass 4: bucket order = (readId asc, type asc) = entry value ascending
+__global__ void __launch_bounds__(256) table_order_kernel(const u64 *__restrict__ slots, u64 cap, u32 *__restrict__ entries)
+{
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (u64)gridDim.x * blockDim.x) {
+        const u64 v = slots[s];
+        if (v == 0) continue;
+        const u32 c = slot_get_count(v);
+        if (c < 2 || c >= (u32)kHashThreshold) continue;
+        u32 *e = entries + slot_get_payload(v);
+        for (u32 a = 1; a < c; ++a) {
+            const u32 x = e[a];
+            u32 b = a;
+            while (b > 0 && e[b - 1] > x) { e[b] = e[b - 1]; --b; }
+            e[b] = x;
+        }
+    }
 }
 
 static unsigned big_grid(u64 n, unsigned block = 256)
@@ -82,48 +141,46 @@ void stage_build_table(Context &c)
     const u64 n = 4 * U;
     SG_CHECK(n < 0xFFFFFFFFull, "at most 2^30-1 unique reads per context");
 
-    DevBuf<u64> a0(n, st), a1(n, st), b0(n, st), b1(n, st);
-    DevBuf<u32> v0(n, st), v1(n, st);
-    gen_entries_kernel<<<big_grid(n), 256, 0, st>>>(c.F.p, c.RC.p, c.len.p, U, SW, h, a0.p, b0.p, v0.p);
-    SG_LAUNCHED();
-    SortCols cols;
-    cols.a[0] = a0.p; cols.a[1] = a1.p; cols.b[0] = b0.p; cols.b[1] = b1.p; cols.v[0] = v0.p; cols.v[1] = v1.p;
-    int cur = 0;
-    // LSD: low key word (last 32 bases) first, then the leading bases (all zero when h <= 32)
-    cur = radix_sort_bits(cols, cur, n, true, 0, 2 * (h < 32 ? h : 32), st);
-    if (h > 32) cur = radix_sort_bits(cols, cur, n, false, 0, 2 * (h - 32), st);
-
-    DevBuf<u32> flag(n, st), gidx(n, st), d_total(1, st);
-    key_flag_kernel<<<big_grid(n), 256, 0, st>>>(cols.a[cur], cols.b[cur], n, flag.p);
-    SG_LAUNCHED();
-    exclusive_scan_u32(flag.p, gidx.p, n, d_total.p, st);
-    u32 D = 0;
-    SG_CUDA(cudaMemcpyAsync(&D, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
-    DevBuf<u32> gstart(D, st);
-    group_start_kernel<<<big_grid(n), 256, 0, st>>>(flag.p, gidx.p, n, gstart.p);
-    SG_LAUNCHED();
-
-    u64 nsec = (2 * (u64)D + kSlotsPerSector - 1) / kSlotsPerSector;    // load factor <= 0.5
+    // load factor <= 2/3 even if all 4U keys are distinct (typically ~0.5)
+    u64 nsec = (n + n / 2 + kSlotsPerSector - 1) / kSlotsPerSector;
     if (nsec < 256) nsec = 256;
     const u64 cap = nsec * kSlotsPerSector;
+    SG_CHECK(cap < 0xFFFFFFFFull, "slot index too large for one context");
     c.slots.alloc(cap, st);
     SG_CUDA(cudaMemsetAsync(c.slots.p, 0, cap * sizeof(u64), st));
-    DevBuf<unsigned long long> d_over(1, st);
-    SG_CUDA(cudaMemsetAsync(d_over.p, 0, sizeof(unsigned long long), st));
-    index_insert_kernel<<<big_grid(D), 256, 0, st>>>(cols.a[cur], cols.b[cur], cols.v[cur], gstart.p, D, n, c.slots.p, nsec, d_over.p);
-    SG_LAUNCHED();
-    unsigned long long over = 0;
-    SG_CUDA(cudaMemcpyAsync(&over, d_over.p, sizeof(over), cudaMemcpyDeviceToHost, st));
 
-    // keep the sorted entry column
-    c.entries.alloc(n, st);
-    SG_CUDA(cudaMemcpyAsync(c.entries.p, cols.v[cur], n * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    DevBuf<u32> where(n, st);
+    table_insert_kernel<<<big_grid(n), 256, 0, st>>>(c.F.p, c.RC.p, c.len.p, U, SW, h, c.slots.p, nsec, where.p);
+    SG_LAUNCHED();
+
+    DevBuf<u32> run(cap, st), off(cap, st), d_total(1, st);
+    DevBuf<unsigned long long> d_cnt(2, st);
+    SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), st));
+    table_runs_kernel<<<big_grid(cap), 256, 0, st>>>(c.slots.p, cap, run.p, d_cnt.p);
+    SG_LAUNCHED();
+    exclusive_scan_u32(run.p, off.p, cap, d_total.p, st);
+    u32 M = 0;
+    unsigned long long h_cnt[2];
+    SG_CUDA(cudaMemcpyAsync(&M, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
+
+    c.entries.alloc(M, st);
+    if (M) {
+        table_offsets_kernel<<<big_grid(cap), 256, 0, st>>>(c.slots.p, cap, run.p, off.p);
+        SG_LAUNCHED();
+        DevBuf<u32> cursor(M, st);
+        SG_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)M * sizeof(u32), st));
+        table_fill_kernel<<<big_grid(n), 256, 0, st>>>(c.slots.p, where.p, n, cursor.p, c.entries.p);
+        SG_LAUNCHED();
+        table_order_kernel<<<big_grid(cap), 256, 0, st>>>(c.slots.p, cap, c.entries.p);
+        SG_LAUNCHED();
+        SG_CUDA(cudaStreamSynchronize(st));     // cursor / where lifetimes end here
+    }
     c.cap = cap;
     c.cnt.table_capacity = cap;
-    c.cnt.distinct_keys = D;
-    c.cnt.keys_over_threshold = over;
+    c.cnt.distinct_keys = h_cnt[0];
+    c.cnt.keys_over_threshold = h_cnt[1];
     c.have_table = true;
 }
 
