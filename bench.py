@@ -211,6 +211,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_step = []
+
     def timed(fn, steps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -218,14 +220,18 @@ def run_ours(args):
         t0 = time.perf_counter()
         ev0.record(stream)
         stage = {}
+        marks = [ev0]
         for _ in range(steps):
             fn()
             for kk, vv in gpu.timers().items():
                 stage[kk] = stage.get(kk, 0.0) + vv
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record(stream)
         ev1.record(stream)
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1000.0
         dev_ms = ev0.elapsed_time(ev1)
+        per_step.append([round(a.elapsed_time(b), 3) for a, b in zip(marks[:-1], marks[1:])])
         t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -233,7 +239,7 @@ def run_ours(args):
 
     for _ in range(max(3, args.warmup)):
         step_device()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("SAGE2_BENCH_NO_SAMPLER") else None
     dev_ms, wall_ms, launches, stage = timed(step_device, args.steps)
     counters = gpu.counters()
     clocks = sampler.stop() if sampler else None
@@ -291,6 +297,7 @@ def run_ours(args):
         "edges_per_sec": world * counters["n_edges"] / (ms_per_step / 1000.0),
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms": stage,
+        "per_step_ms": {"device_resident": per_step[0], "e2e": per_step[1]},
         "counters": {kk: counters[kk] for kk in ("good_reads", "unique_reads", "distinct_keys", "compare_calls",
                                                   "window_probes", "n_edges", "left_to_explore", "record_words")},
     }

@@ -98,8 +98,9 @@ int sage2gpu_run_steps123(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t
 
 /* Measurement aid (no reference counterpart): GB/s this GPU sustains on uniformly random, independent
  * `granule_bytes` (16/32/64) gathers over `footprint_bytes` of device memory -- the random-sector
- * roofline of the probe / partner-fetch traffic. */
-int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int granule_bytes, uint64_t n_loads, double *gbps);
+ * roofline of the probe / partner-fetch traffic.  mode 0: 128-bit loads; 1: 256-bit loads
+ * (granule 32/64); 2: a 64-byte granule fetched by a lane pair, one 256-bit load each. */
+int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int granule_bytes, uint64_t n_loads, int mode, double *gbps);
 
 int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *out);
 /* Number of CUDA kernels this library has launched in this process so far (monotonic). */

@@ -92,7 +92,7 @@ def load_library():
         lib.sage2gpu_get_edges_packed.argtypes = [vp, vp, C.c_uint64, u64p]
         lib.sage2gpu_write_reads.argtypes = [vp, C.c_char_p]
         lib.sage2gpu_write_graph3.argtypes = [vp, C.c_char_p]
-        lib.sage2gpu_measure_gather.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(C.c_double)]
+        lib.sage2gpu_measure_gather.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
         lib.sage2gpu_stream.argtypes = [vp]
         lib.sage2gpu_stream.restype = vp
         lib.sage2gpu_kernel_launches.argtypes = []
@@ -170,11 +170,11 @@ class Sage2Gpu:
         self.build_hash_table()
         self.build_overlap_graph()
 
-    def measure_gather(self, footprint_bytes: int, granule_bytes: int = 32, n_loads: int = 1 << 28) -> float:
+    def measure_gather(self, footprint_bytes: int, granule_bytes: int = 32, n_loads: int = 1 << 28, mode: int = 0) -> float:
         """GB/s of random `granule_bytes` gathers over `footprint_bytes` (the random-sector roofline)."""
         g = C.c_double()
         self._check(self._lib.sage2gpu_measure_gather(self._h, int(footprint_bytes), int(granule_bytes), int(n_loads),
-                                                      C.byref(g)), "measure_gather")
+                                                      int(mode), C.byref(g)), "measure_gather")
         return float(g.value)
 
     def stream_ptr(self) -> int:

@@ -85,12 +85,12 @@ void fetch_reads(sg::Context &c, HostReads &h)
 {
     SG_CHECK(c.have_reads, "no reads loaded");
     const sg::u64 U = c.cnt.unique_reads;
-    h.len.resize(U); h.freq.resize(U); h.F.resize(U * c.SW); h.RC.resize(U * c.SW);
+    h.len.resize(U); h.freq.resize(U); h.F.resize(U * c.SWS); h.RC.resize(U * c.SWS);
     if (U == 0) return;
     SG_CUDA(cudaMemcpyAsync(h.len.data(), c.len.p, U * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
     SG_CUDA(cudaMemcpyAsync(h.freq.data(), c.freq.p, U * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
-    SG_CUDA(cudaMemcpyAsync(h.F.data(), c.F.p, U * c.SW * sizeof(sg::u64), cudaMemcpyDeviceToHost, c.stream));
-    SG_CUDA(cudaMemcpyAsync(h.RC.data(), c.RC.p, U * c.SW * sizeof(sg::u64), cudaMemcpyDeviceToHost, c.stream));
+    SG_CUDA(cudaMemcpyAsync(h.F.data(), c.F.p, U * c.SWS * sizeof(sg::u64), cudaMemcpyDeviceToHost, c.stream));
+    SG_CUDA(cudaMemcpyAsync(h.RC.data(), c.RC.p, U * c.SWS * sizeof(sg::u64), cudaMemcpyDeviceToHost, c.stream));
     SG_CUDA(cudaStreamSynchronize(c.stream));
 }
 
@@ -315,8 +315,8 @@ int sage2gpu_get_reads(sage2gpu_ctx *ctx, uint16_t *length, uint16_t *frequency,
             if (length) length[i] = h.len[i];
             if (frequency) frequency[i] = h.freq[i];
             if (byte_off) byte_off[i] = off;
-            if (fwd) record_to_bytes(&h.F[i * c.SW], h.len[i], fwd + off);
-            if (rc) record_to_bytes(&h.RC[i * c.SW], h.len[i], rc + off);
+            if (fwd) record_to_bytes(&h.F[i * c.SWS], h.len[i], fwd + off);
+            if (rc) record_to_bytes(&h.RC[i * c.SWS], h.len[i], rc + off);
             off += (uint64_t)(h.len[i] + 3) / 4;
         }
         if (byte_off) byte_off[U] = off;
@@ -374,11 +374,11 @@ int sage2gpu_get_edges_packed(sage2gpu_ctx *ctx, uint64_t *out, uint64_t capacit
     });
 }
 
-int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int granule_bytes, uint64_t n_loads, double *gbps)
+int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int granule_bytes, uint64_t n_loads, int mode, double *gbps)
 {
     return guarded(ctx, [&](sg::Context &c) {
         SG_CHECK(gbps != nullptr, "null result pointer");
-        *gbps = (double)sg::gather_bench(footprint_bytes, granule_bytes, n_loads, c.stream);
+        *gbps = (double)sg::gather_bench(footprint_bytes, granule_bytes, n_loads, mode, c.stream);
     });
 }
 
@@ -400,7 +400,7 @@ int sage2gpu_write_reads(sage2gpu_ctx *ctx, const char *path)
             const int len = h.len[i];
             int n = snprintf(line.data(), 64, "%u\t%u\t", (unsigned)h.freq[i], (unsigned)len);
             for (int s = 0; s < 2; ++s) {
-                const sg::u64 *rec = (s ? h.RC.data() : h.F.data()) + i * c.SW;
+                const sg::u64 *rec = (s ? h.RC.data() : h.F.data()) + i * c.SWS;
                 for (int p = 0; p < len; ++p) line[n++] = T[(rec[p >> 5] >> (62 - 2 * (p & 31))) & 3];
                 line[n++] = s ? '\n' : '\t';
             }

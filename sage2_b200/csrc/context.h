@@ -31,7 +31,7 @@ struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string last_error;
-    int min_overlap = 0, h = 0, SW = 0;
+    int min_overlap = 0, h = 0, SW = 0, SWS = 0;     // SW = words per record, SWS = storage stride of F / RC
     Counters cnt;
     Timers tm;
 
@@ -48,7 +48,7 @@ struct Context {
     cudaEvent_t up_event = nullptr;
 
     // unique reads, ids 1..U map to index 0..U-1
-    DevBuf<u64> F, RC;          // [U*SW] records
+    DevBuf<u64> F, RC;          // [U*SWS] records (SW words used, stride SWS = storage_words(SW))
     DevBuf<uint16_t> len, freq; // [U]
 
     // prefix/suffix table

@@ -28,6 +28,9 @@ constexpr int kHashThreshold = 100;    // hashTable.cpp:76
 constexpr u32 kConnectionsLimit = 300; // economyGraph.cpp:43
 
 SG_HD int words_for_len(int max_len) { return (2 * max_len + 16 + 63) / 64; }
+// F / RC storage stride in words: whole 32-byte sectors, a power-of-two number of them per record, so
+// that a record never straddles a 128-byte line and 1/2/4/8 lanes fetch it with one 256-bit load each.
+SG_HD int storage_words(int SW) { return SW <= 4 ? 4 : (SW <= 8 ? 8 : (SW <= 16 ? 16 : 32)); }
 SG_HD int rec_len(const u64 *rec, int SW) { return (int)(rec[SW - 1] & 0xFFFFull); }
 SG_HD int hash_len_for(int min_overlap) { return min_overlap > 64 ? 64 : min_overlap; }  // hashTable.cpp:78-81
 

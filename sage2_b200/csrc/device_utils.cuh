@@ -100,6 +100,6 @@ int radix_sort_bits(SortCols &c, int cur, u64 n, bool use_b, int lo, int hi, cud
 int radix_sort_varying(SortCols &c, int cur, u64 n, bool use_b, cudaStream_t st);
 
 // GB/s of uniformly random `granule_bytes` gathers over `footprint_bytes` of HBM (best of 3 after warm-up).
-float gather_bench(u64 footprint_bytes, int granule_bytes, u64 n_loads, cudaStream_t st);
+float gather_bench(u64 footprint_bytes, int granule_bytes, u64 n_loads, int mode, cudaStream_t st);
 
 }  // namespace sg

@@ -207,7 +207,7 @@ __global__ void unique_flag_kernel(const u64 *__restrict__ rec, const u32 *__res
 }
 
 __global__ void unique_write_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ perm, const u32 *__restrict__ flag,
-                                    const u32 *__restrict__ uidx, u64 n_good, int SW,
+                                    const u32 *__restrict__ uidx, u64 n_good, int SW, int SWS,
                                     u64 *__restrict__ F, u64 *__restrict__ RC, uint16_t *__restrict__ len, u32 *__restrict__ start)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_good; i += (u64)gridDim.x * blockDim.x) {
@@ -218,7 +218,7 @@ __global__ void unique_write_kernel(const u64 *__restrict__ rec, const u32 *__re
         for (int w = 0; w < SW; ++w) f[w] = a[w];
         const int l = rec_len(f, SW);
         revcomp_record(f, r, SW, l);
-        for (int w = 0; w < SW; ++w) { F[(u64)u * SW + w] = f[w]; RC[(u64)u * SW + w] = r[w]; }
+        for (int w = 0; w < SWS; ++w) { F[(u64)u * SWS + w] = w < SW ? f[w] : 0ull; RC[(u64)u * SWS + w] = w < SW ? r[w] : 0ull; }
         len[u] = (uint16_t)l;
         start[u] = (u32)i;
     }
@@ -271,12 +271,13 @@ void stage_organize_reads(Context &c)
     SG_CUDA(cudaMemcpyAsync(&U, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     c.cnt.unique_reads = U;
-    c.F.alloc((size_t)U * SW, st);
-    c.RC.alloc((size_t)U * SW, st);
+    c.SWS = storage_words(SW);
+    c.F.alloc((size_t)U * c.SWS, st);
+    c.RC.alloc((size_t)U * c.SWS, st);
     c.len.alloc(U, st);
     c.freq.alloc(U, st);
     DevBuf<u32> start(U, st);
-    unique_write_kernel<<<big_grid(n_good, 128), 128, 0, st>>>(rec.p, perm, flag.p, uidx.p, n_good, SW, c.F.p, c.RC.p, c.len.p, start.p);
+    unique_write_kernel<<<big_grid(n_good, 128), 128, 0, st>>>(rec.p, perm, flag.p, uidx.p, n_good, SW, c.SWS, c.F.p, c.RC.p, c.len.p, start.p);
     SG_LAUNCHED();
     freq_kernel<<<big_grid(U), 256, 0, st>>>(start.p, U, n_good, c.freq.p);
     SG_LAUNCHED();

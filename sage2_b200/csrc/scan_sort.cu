@@ -265,13 +265,50 @@ __global__ void __launch_bounds__(256) gather_bench_kernel(const uint4 *__restri
     out[tid] = acc;
 }
 
-float gather_bench(u64 footprint_bytes, int granule_bytes, u64 n_loads, cudaStream_t st)
+__device__ __forceinline__ void ldg256(const void *p, u64 (&v)[4])
+{
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+
+// mode 1: a granule of 32 / 64 bytes = one / two 256-bit loads of one lane.
+// mode 2: a 64-byte granule split over a lane pair, one 256-bit load each (one L1 request, two sectors).
+__global__ void __launch_bounds__(256) gather_bench256_kernel(const uint8_t *__restrict__ buf, u64 n_granules, int granule, int mode,
+                                                               int per_thread, u64 seed, u32 *__restrict__ out)
+{
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stream_id = mode == 2 ? (tid >> 1) : tid;
+    u64 x = (stream_id + 1) * 0x9e3779b97f4a7c15ull + seed;
+    u64 acc = 0;
+    for (int r = 0; r < per_thread; r += 4) {
+        u64 v[4][2][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+            const u64 g = __umul64hi(x, n_granules);
+            const uint8_t *p = buf + g * (u64)granule;
+            if (mode == 2) { ldg256(p + 32 * (tid & 1), v[u][0]); }
+            else {
+                ldg256(p, v[u][0]);
+                if (granule == 64) ldg256(p + 32, v[u][1]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            acc ^= v[u][0][0] ^ v[u][0][1] ^ v[u][0][2] ^ v[u][0][3];
+            if (mode != 2 && granule == 64) acc ^= v[u][1][0] ^ v[u][1][1] ^ v[u][1][2] ^ v[u][1][3];
+        }
+    }
+    out[tid] = (u32)(acc ^ (acc >> 32));
+}
+
+float gather_bench(u64 footprint_bytes, int granule_bytes, u64 n_loads, int mode, cudaStream_t st)
 {
     SG_CHECK(granule_bytes == 16 || granule_bytes == 32 || granule_bytes == 64, "granule must be 16, 32 or 64 bytes");
+    SG_CHECK(mode >= 0 && mode <= 2 && (mode == 0 || granule_bytes >= 32) && (mode != 2 || granule_bytes == 64), "bad gather mode");
     const int vpg = granule_bytes / 16, per_thread = 64;
     const u64 n_granules = footprint_bytes / (u64)granule_bytes;
     SG_CHECK(n_granules > 0, "empty footprint");
-    u64 threads = n_loads / per_thread;
+    u64 threads = n_loads / per_thread * (mode == 2 ? 2 : 1);
     threads = (threads + 255) / 256 * 256;
     DevBuf<uint4> buf((size_t)(n_granules * vpg), st);
     DevBuf<u32> out((size_t)threads, st);
@@ -281,7 +318,8 @@ float gather_bench(u64 footprint_bytes, int granule_bytes, u64 n_loads, cudaStre
     float best = 1e30f;
     for (int it = 0; it < 4; ++it) {
         SG_CUDA(cudaEventRecord(e0, st));
-        gather_bench_kernel<<<(unsigned)(threads / 256), 256, 0, st>>>(buf.p, n_granules, vpg, per_thread, 1234 + it, out.p);
+        if (mode == 0) gather_bench_kernel<<<(unsigned)(threads / 256), 256, 0, st>>>(buf.p, n_granules, vpg, per_thread, 1234 + it, out.p);
+        else gather_bench256_kernel<<<(unsigned)(threads / 256), 256, 0, st>>>((const uint8_t *)buf.p, n_granules, granule_bytes, mode, per_thread, 1234 + it, out.p);
         SG_LAUNCHED();
         SG_CUDA(cudaEventRecord(e1, st));
         SG_CUDA(cudaEventSynchronize(e1));
@@ -290,7 +328,8 @@ float gather_bench(u64 footprint_bytes, int granule_bytes, u64 n_loads, cudaStre
         if (it > 0 && ms < best) best = ms;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    return (float)((double)threads * per_thread * granule_bytes / (best * 1e-3) / 1e9);
+    const double granules = (double)threads * per_thread / (mode == 2 ? 2 : 1);
+    return (float)(granules * granule_bytes / (best * 1e-3) / 1e9);
 }
 
 }  // namespace sg

@@ -33,10 +33,18 @@ struct SearchParams {
     int h, k;
 };
 
+// 256-bit read-only load: one 32-byte sector per lane and instruction (LDG.E.256 on sm_100a)
+__device__ __forceinline__ void ldg256(const u64 *p, u64 (&v)[4])
+{
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+
 template <int SW>
 struct SearchCfg {
     static constexpr int WARPS = SW <= 8 ? 8 : (SW <= 16 ? 4 : 2);
-    static constexpr int SWP = SW | 1;          // odd record stride in shared memory (bank spread)
+    static constexpr int SWS = SW <= 4 ? 4 : (SW <= 8 ? 8 : (SW <= 16 ? 16 : 32));   // == storage_words(SW): F / RC stride
+    static constexpr int LPI = SWS / 4;          // lanes that fetch one partner record together (one sector each)
+    static constexpr int SWP = SWS + 1;          // odd record stride in shared memory (bank spread) + the word read past
 };
 
 template <int SW>
@@ -115,9 +123,8 @@ __device__ __forceinline__ void probe_window(const SearchParams &P, u64 v0, u64 
     const u64 tag = slot_tag(hsh);
     u64 sec = home_sector(hsh, P.nsec);
     for (;;) {
-        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(P.slots + kSlotsPerSector * sec);
-        const ulonglong2 a = __ldg(p), b = __ldg(p + 1);
-        const u64 s[4] = { a.x, a.y, b.x, b.y };
+        u64 s[4];
+        ldg256(P.slots + kSlotsPerSector * sec, s);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const u64 slot = s[t];
@@ -128,7 +135,7 @@ __device__ __forceinline__ void probe_window(const SearchParams &P, u64 v0, u64 
                 const u32 ent = (c == 1 || c >= (u32)kHashThreshold) ? (u32)slot_get_payload(slot) : __ldg(&P.entries[slot_get_payload(slot)]);
                 const u64 rid = ent >> 2;
                 const int type = (int)(ent & 3);
-                const u64 *X = ((type & 2) ? P.RC : P.F) + rid * SW;
+                const u64 *X = ((type & 2) ? P.RC : P.F) + rid * SearchCfg<SW>::SWS;
                 const int l = (int)(__ldg(&X[SW - 1]) & 0xFFFF);
                 u64 w0, w1;
                 t_extract_key<SW>(X, (type & 1) ? l - P.h : 0, P.h, w0, w1);
@@ -164,10 +171,10 @@ __global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32, MINB)
 phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, uint8_t *__restrict__ flag5,
                u32 *__restrict__ cont_max, unsigned long long *__restrict__ counters)
 {
-    constexpr int WARPS = SearchCfg<SW>::WARPS, SWP = SearchCfg<SW>::SWP;
+    constexpr int WARPS = SearchCfg<SW>::WARPS, SWP = SearchCfg<SW>::SWP, SWS = SearchCfg<SW>::SWS, LPI = SearchCfg<SW>::LPI, IPI = 32 / LPI;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ u64 sXf[WARPS][SW + 1], sXr[WARPS][SW + 1], sPrevR[WARPS][SW + 1], sPrevL[WARPS][SW + 1];   // +1: t_overlap_equal reads one word past
-    __shared__ u64 sQ[WARPS][32 * SWP + 1];
+    __shared__ u64 sQ[WARPS][32 * SWP];
     __shared__ u64 sItem[WARPS][32];
     __shared__ ExtState sState[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -181,7 +188,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
     if (lane == 0) { Xf[SW] = 0; Xr[SW] = 0; prevR[SW] = 0; prevL[SW] = 0; }
 
     for (u64 i = (u64)blockIdx.x * WARPS + warp; i < P.U; i += nwarps) {
-        if (lane < SW) { Xf[lane] = P.F[i * SW + lane]; Xr[lane] = P.RC[i * SW + lane]; }
+        if (lane < SW) { Xf[lane] = P.F[i * SWS + lane]; Xr[lane] = P.RC[i * SWS + lane]; }
         __syncwarp();
         const int len1 = (int)(Xf[SW - 1] & 0xFFFF);
         const int W = len1 - P.h + 1;
@@ -245,30 +252,43 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                 // ---- verify ---------------------------------------------------------------------------
                 const int jj = (int)((item >> 34) & 0xFFFF);
                 const bool first = (item >> 50) & 1, inl = (item >> 51) & 1;
-                bool hit = false, right = false, fp = false;
+                bool hit = false, right = false, fp = false, need = false, load = false;
                 u32 rid2 = 0;
                 int len2 = 0, type = 0;
+                const u64 *rec = P.F;
                 if (valid) {
                     const u32 ent = inl ? (u32)(item & 0xFFFFFFFFull) : __ldg(&P.entries[item & 0x1FFFFFFFFull]);
                     rid2 = ent >> 2; type = (int)(ent & 3);
                     right = !(type & 1);
-                    const bool need = rid2 != (u32)i && (right ? gate_right(jj, len1, P.k) : gate_left(jj, P.k, P.h));
-                    if (need || first) {
-                        u64 q[SW];
-                        load_record<SW>((partner_uses_rc(type) ? P.RC : P.F) + (u64)rid2 * SW, q);
-                        len2 = (int)(q[SW - 1] & 0xFFFF);
-                        bool contained, key_bad;
-                        const bool ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, km0, km1, contained, key_bad);
-                        fp = first && key_bad;
-                        if (need) {
-                            my_calls++;
-                            if (ok && contained) atomicMax(&cont_max[rid2], (u32)(i + 1));      // economyGraph.cpp:735
-                            hit = ok && !contained;
-                            if (hit) {
+                    need = rid2 != (u32)i && (right ? gate_right(jj, len1, P.k) : gate_left(jj, P.k, P.h));
+                    load = need || first;
+                    rec = (partner_uses_rc(type) ? P.RC : P.F) + (u64)rid2 * SWS;
+                }
+                // partner records -> shared memory, LPI lanes per record with one 256-bit load each: one memory
+                // request per record, however many sectors it spans
 #pragma unroll
-                                for (int w = 0; w < SW; ++w) Qs[lane * SWP + w] = q[w];
-                            }
-                        }
+                for (int a = 0; a < LPI; ++a) {
+                    const int src = IPI * a + lane / LPI, part = lane % LPI;
+                    const u64 *base = reinterpret_cast<const u64 *>(__shfl_sync(FULL, (unsigned long long)rec, src));
+                    const bool fetch = __shfl_sync(FULL, (int)load, src) != 0 && 4 * part < SW;
+                    if (fetch) {
+                        u64 v[4];
+                        ldg256(base + 4 * part, v);
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) Qs[src * SWP + 4 * part + w] = v[w];
+                    }
+                }
+                __syncwarp();
+                if (load) {
+                    const u64 *Y = Qs + lane * SWP;
+                    len2 = (int)(Y[SW - 1] & 0xFFFF);
+                    bool contained, key_bad;
+                    const bool ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, Y, len2, km0, km1, contained, key_bad);
+                    fp = first && key_bad;
+                    if (need) {
+                        my_calls++;
+                        if (ok && contained) atomicMax(&cont_max[rid2], (u32)(i + 1));      // economyGraph.cpp:735
+                        hit = ok && !contained;
                     }
                 }
                 if (__any_sync(FULL, fp)) {          // tag collision: redo this read with verified probes
@@ -278,8 +298,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                     goto restart;
                 }
                 unsigned hm = __ballot_sync(FULL, hit);
-                if (hm == 0) continue;
-                __syncwarp();
+                if (hm == 0) { __syncwarp(); continue; }
 
                 // ---- extend -------------------------------------------------------------------------
                 if (!exact) {
@@ -425,7 +444,7 @@ phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint
     const u64 nwarps = (u64)gridDim.x * WARPS;
     for (u64 s = (u64)blockIdx.x * WARPS + warp; s < nS; s += nwarps) {
         const u64 i = s_ids[s];      // 0-based
-        if (lane < SW) { Xf[lane] = P.F[i * SW + lane]; Xr[lane] = P.RC[i * SW + lane]; }
+        if (lane < SW) { Xf[lane] = P.F[i * SearchCfg<SW>::SWS + lane]; Xr[lane] = P.RC[i * SearchCfg<SW>::SWS + lane]; }
         __syncwarp();
         const int len1 = (int)(Xf[SW - 1] & 0xFFFF);
         const int W = len1 - P.h + 1;
@@ -459,7 +478,7 @@ phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint
                         const bool right = !(type & 1);
                         if (rid2 != (u32)i && explored[rid2] == 0 && (right ? gateR : gateL)) {
                             u64 q[SW];
-                            load_record<SW>((partner_uses_rc(type) ? P.RC : P.F) + (u64)rid2 * SW, q);
+                            load_record<SW>((partner_uses_rc(type) ? P.RC : P.F) + (u64)rid2 * SearchCfg<SW>::SWS, q);
                             const int len2 = (int)(q[SW - 1] & 0xFFFF);
                             bool contained, kb;
                             ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, q, len2, 0ull, 0ull, contained, kb);

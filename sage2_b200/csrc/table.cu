@@ -28,14 +28,14 @@ constexpr u64 kCountOne = 1ull << 33;
 __device__ __forceinline__ u64 load_slot(const u64 *p) { return *reinterpret_cast<const volatile u64 *>(p); }
 
 __global__ void __launch_bounds__(256) table_insert_kernel(const u64 *__restrict__ F, const u64 *__restrict__ RC,
-                                                            const uint16_t *__restrict__ len, u64 U, int SW, int h,
+                                                            const uint16_t *__restrict__ len, u64 U, int SW, int SWS, int h,
                                                             u64 *__restrict__ slots, u64 nsec, u32 *__restrict__ where)
 {
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < 4 * U; t += (u64)gridDim.x * blockDim.x) {
         const u64 rid = t >> 2;
         const int type = (int)(t & 3);
         u64 v0, v1;
-        entry_key(F + rid * SW, RC + rid * SW, SW, len[rid], h, type, v0, v1);
+        entry_key(F + rid * SWS, RC + rid * SWS, SW, len[rid], h, type, v0, v1);
         const u64 hsh = hash_key(v0, v1);
         const u64 tag = slot_tag(hsh);
         u64 sec = home_sector(hsh, nsec);
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) table_insert_kernel(const u64 *__restrict
                 const u32 rep = (u32)slot_get_payload(cur);
                 const u64 r2 = rep >> 2;
                 u64 w0, w1;
-                entry_key(F + r2 * SW, RC + r2 * SW, SW, len[r2], h, (int)(rep & 3), w0, w1);
+                entry_key(F + r2 * SWS, RC + r2 * SWS, SW, len[r2], h, (int)(rep & 3), w0, w1);
                 if (w0 != v0 || w1 != v1) continue;
                 while (slot_get_count(cur) < 127) {            // saturating: >= 100 is all a search needs to know
                     const u64 old = atomicCAS((unsigned long long *)sp, (unsigned long long)cur, (unsigned long long)(cur + kCountOne));
@@ -150,7 +150,7 @@ void stage_build_table(Context &c)
     SG_CUDA(cudaMemsetAsync(c.slots.p, 0, cap * sizeof(u64), st));
 
     DevBuf<u32> where(n, st);
-    table_insert_kernel<<<big_grid(n), 256, 0, st>>>(c.F.p, c.RC.p, c.len.p, U, SW, h, c.slots.p, nsec, where.p);
+    table_insert_kernel<<<big_grid(n), 256, 0, st>>>(c.F.p, c.RC.p, c.len.p, U, SW, c.SWS, h, c.slots.p, nsec, where.p);
     SG_LAUNCHED();
 
     DevBuf<u32> run(cap, st), off(cap, st), d_total(1, st);
