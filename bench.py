@@ -16,8 +16,9 @@ config #2 (4.6 Mbp random genome, 150 bp paired-end, 100x, -k 63): 3,066,666 inp
             built from /root/reference in the build container) on the box's host cores, on a bounded
             cfg2-shaped sample.
 
-N > 1 (torchrun, one rank per GPU): round 1 runs N independent replicas (each rank builds the graph
-of its own cfg2-shaped read set, different seed); no data-path collective, scaling "weak".
+N > 1 (torchrun, one rank per GPU): ONE cfg2 read set for the whole job; reads and table are
+replicated, phase A is partitioned by read id and followed by one NCCL exchange (sage2_b200/multi.py);
+total work is fixed, so scaling is "strong".
 """
 from __future__ import annotations
 
@@ -54,44 +55,45 @@ def make_workload(name: str, seed_shift: int = 0, genome_size: int | None = None
 # ---- clocks ------------------------------------------------------------------------------------
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons during the timed region, read through NVML in a background thread
+    (a polling `nvidia-smi -lms` subprocess was measured to stall kernel launches for tens of ms)."""
 
-    def __init__(self, index: int):
-        self.rows, self.p = [], None
+    def __init__(self, index: int, period_s: float = 0.1):
+        self.rows, self.stop_flag, self.t, self.err = [], threading.Event(), None, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.period = period_s
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except OSError:
-            self.p = None
+        except Exception as e:      # noqa: BLE001 - any NVML problem just means "no clock record"
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            self.stop_flag.wait(self.period)
 
     def stop(self) -> dict:
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + str(self.err)]}
+        self.stop_flag.set()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
+        sm = [c for c, _ in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max, "reasons": reasons,
+                "samples": len(sm), "source": "NVML"}
 
 
 # ---- the reference on the host cores -------------------------------------------------------------
@@ -156,11 +158,11 @@ def run_reference_arm(args):
 
 # ---- our arm -----------------------------------------------------------------------------------
 
-def algorithmic_bytes_phase_a(c: dict, read_len: int) -> float:
+def algorithmic_bytes_phase_a(c: dict, read_len: int, n_slice: int | None = None) -> float:
     """SURVEY.md 8(d) restricted to the phase-A launch: stream the packed reads once, one 32-B sector
     per window probe, one sector-rounded packed partner read per gated comparison, 16 B of extension
     records out per read."""
-    U, V, probes = c["unique_reads"], c["compare_calls"], c["window_probes"]
+    U, V, probes = (n_slice if n_slice is not None else c["unique_reads"]), c["compare_calls"], c["window_probes"]
     packed = (read_len + 3) // 4
     B = 32 * ((packed + 31) // 32)
     return float(U * packed + 32 * probes + B * V + 16 * U)
@@ -178,7 +180,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    reads, k, cfg = make_workload(args.workload, seed_shift=rank)
+    # N > 1: ONE read set for the whole job (same seed on every rank); phase A is partitioned by read id and followed
+    # by one NCCL exchange (sage2_b200/multi.py); reads and table are replicated
+    from sage2_b200 import multi
+    reads, k, cfg = make_workload(args.workload, seed_shift=0)
     n_reads = len(reads)
     read_len = int(reads.shape[1]) if isinstance(reads, np.ndarray) and reads.ndim == 2 else 0
     bases, offsets = synth.concat(reads)
@@ -189,18 +194,28 @@ def run_ours(args):
     gpu = api.Sage2Gpu(local)
     stream = torch.cuda.ExternalStream(gpu.stream_ptr(), device=torch.device("cuda", local))
 
+    dev = torch.device("cuda", local)
+    comm = {"sent": 0, "h2d": 0}
+
     def step_device():
         gpu.load_reads_ptr(d_bases.data_ptr(), d_off.data_ptr(), n_reads, k, device=True)
         gpu.build_hash_table()
-        gpu.build_overlap_graph()
+        comm["sent"] = multi.build_overlap_graph(gpu, rank, world, dev)
 
     h_edges = {"buf": None}
 
     def step_host():
         # the call a user of the C ABI makes: host buffers in, edge list back in host memory
-        gpu.load_reads_ptr(h_bases.data_ptr(), h_off.data_ptr(), n_reads, k, device=False)
+        if world == 1:
+            gpu.load_reads_ptr(h_bases.data_ptr(), h_off.data_ptr(), n_reads, k, device=False)
+            comm["h2d"] = int(bases.nbytes + offsets.nbytes)
+        else:       # each rank moves 1/N of the input over PCIe, NVLink all-gather completes it
+            with torch.cuda.stream(stream):
+                tb, to, comm["h2d"] = multi.upload_partitioned(h_bases, h_off, rank, world, dev)
+            stream.synchronize()
+            gpu.load_reads_ptr(tb.data_ptr(), to.data_ptr(), n_reads, k, device=True)
         gpu.build_hash_table()
-        gpu.build_overlap_graph()
+        multi.build_overlap_graph(gpu, rank, world, dev)
         if h_edges["buf"] is None:
             h_edges["buf"] = torch.empty(2 * max(1, gpu.counters()["n_edges"]), dtype=torch.int64).pin_memory()
         gpu.edges_packed_into(h_edges["buf"].data_ptr(), h_edges["buf"].numel() // 2)
@@ -248,27 +263,42 @@ def run_ours(args):
     n_edges = gpu.counters()["n_edges"]
 
     if rank != 0:
+        gpu.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
     ms_per_step = dev_ms / args.steps
-    value = world * n_reads / (ms_per_step / 1000.0)
-    e2e_value = world * n_reads / (e2e_dev_ms / args.steps / 1000.0)
+    value = n_reads / (ms_per_step / 1000.0)             # one job: every rank worked on the same n_reads
+    e2e_value = n_reads / (e2e_dev_ms / args.steps / 1000.0)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    abytes = algorithmic_bytes_phase_a(counters, read_len or counters["avg_len"])
+    n_slice = min(counters["unique_reads"], -(-counters["unique_reads"] // world))      # rank 0's share of the reads
+    abytes = algorithmic_bytes_phase_a(counters, read_len or counters["avg_len"], n_slice)
+    traffic = None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "phase_a_traffic.json")))
+        if world == 1 and prof.get("workload") == args.workload:
+            traffic = float(prof["dram_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        pass
+    gather = None
+    if not args.no_gather:
+        # the random-access ceiling of this GPU, measured now: uniformly random 64-byte blocks
+        # fetched by lane pairs / 32-byte sectors by single lanes over 8 GiB
+        gather = {"gbs_64B_blocks": gpu.measure_gather(8 << 30, 64, 1 << 27, 2), "gbs_32B_sectors": gpu.measure_gather(8 << 30, 32, 1 << 27, 1),
+                  "footprint_gib": 8}
     ka_ms = stage["phase_a_kernel"]
     achieved = abytes / (ka_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "kernel": "phase_a_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": abytes, "kernel_ms": ka_ms,
-                "kernel_share_of_step": ka_ms / ms_per_step}
+                "kernel_share_of_step": ka_ms / ms_per_step, "random_gather_peak": gather}
 
     # reference's CPU path on a bounded sample of the same workload (rank 0, N=1 only)
     cpu = None
@@ -283,18 +313,20 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": dict(cfg, parallelism=("single GPU" if world == 1 else f"{world} independent replicas, no collective"),
-                       reads_per_step_per_gpu=n_reads, l2_policy="inputs (460 MB ASCII + working set) larger than the 126 MB L2",
+        "config": dict(cfg, parallelism=("single GPU" if world == 1 else
+                                         f"{world} GPUs: reads + table replicated, phase A partitioned by read id, "
+                                         f"one NCCL exchange (all-gather + all-reduce MAX, {comm['sent']} B sent per rank)"),
+                       reads_per_step=n_reads, l2_policy="inputs (460 MB ASCII + working set) larger than the 126 MB L2",
                        timing="CUDA events on the library stream around all steps, max over ranks"),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bases.nbytes + offsets.nbytes),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(comm["h2d"]) * world,
                 "d2h_bytes_per_step": int(16 * n_edges), "ms_per_step": e2e_dev_ms / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "edges_per_sec": world * counters["n_edges"] / (ms_per_step / 1000.0),
+        "edges_per_sec": counters["n_edges"] / (ms_per_step / 1000.0),
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms": stage,
         "per_step_ms": {"device_resident": per_step[0], "e2e": per_step[1]},
@@ -302,6 +334,7 @@ def run_ours(args):
                                                   "window_probes", "n_edges", "left_to_explore", "record_words")},
     }
     print(json.dumps(line), flush=True)
+    gpu.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -314,6 +347,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="skip the random-gather ceiling microbenchmark")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

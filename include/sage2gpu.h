@@ -92,6 +92,19 @@ int sage2gpu_build_hash_table(sage2gpu_ctx *ctx);
  * sage2gpu_write_graph3 bring it to the host. */
 int sage2gpu_build_overlap_graph(sage2gpu_ctx *ctx);
 
+/* Multi-GPU form of the same step: phase A is independent per read
+ * (the reference's `omp for`, economyGraph.cpp:71), so with the reads and the table present on every GPU rank
+ * `rank` of `world` searches only read ids [rank*chunk, (rank+1)*chunk), chunk = ceil(U/world).
+ * sage2gpu_phase_a_buffers exposes the device arrays (length world*chunk; uint64 extension records of
+ * rightExtension / leftExtension, uint8 "connections > 300" flags, uint32 largest id that contains the
+ * read) for the one exchange step -- all-gather of the first three, all-reduce(MAX) of the last, e.g.
+ * NCCL through sage2_b200/multi.py -- after which sage2gpu_finish_graph runs phases B and C and the
+ * canonical edge sort.  build_overlap_graph == phase_a_partition(0, 1) + finish_graph. */
+int sage2gpu_phase_a_partition(sage2gpu_ctx *ctx, int rank, int world);
+int sage2gpu_phase_a_buffers(sage2gpu_ctx *ctx, void **right_ext, void **left_ext, void **over_limit, void **contained_by,
+                             uint64_t *reads_per_rank, uint64_t *unique_reads);
+int sage2gpu_finish_graph(sage2gpu_ctx *ctx);
+
 /* All three steps back to back (main.cpp:37-132 without the file I/O). */
 int sage2gpu_run_steps123(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
                           int64_t n_reads, int min_overlap);

@@ -43,6 +43,7 @@ EDGE_DT = np.dtype([("from", "<u8"), ("to", "<u8"), ("type", "<u4"), ("delta", "
 EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2gpu_load_reads",
            "sage2gpu_load_begin", "sage2gpu_load_append", "sage2gpu_load_finish", "sage2gpu_host_alloc", "sage2gpu_host_free",
            "sage2gpu_load_reads_device", "sage2gpu_build_hash_table", "sage2gpu_build_overlap_graph",
+           "sage2gpu_phase_a_partition", "sage2gpu_phase_a_buffers", "sage2gpu_finish_graph",
            "sage2gpu_run_steps123", "sage2gpu_get_counters", "sage2gpu_get_timers", "sage2gpu_reads_bytes",
            "sage2gpu_get_reads", "sage2gpu_get_extensions", "sage2gpu_get_edges", "sage2gpu_get_edges_packed", "sage2gpu_write_reads",
            "sage2gpu_write_graph3", "sage2gpu_kernel_launches", "sage2gpu_stream", "sage2gpu_measure_gather"]
@@ -82,6 +83,9 @@ def load_library():
         lib.sage2gpu_host_free.restype = None
         lib.sage2gpu_build_hash_table.argtypes = [vp]
         lib.sage2gpu_build_overlap_graph.argtypes = [vp]
+        lib.sage2gpu_phase_a_partition.argtypes = [vp, C.c_int, C.c_int]
+        lib.sage2gpu_phase_a_buffers.argtypes = [vp] + [C.POINTER(vp)] * 4 + [u64p, u64p]
+        lib.sage2gpu_finish_graph.argtypes = [vp]
         lib.sage2gpu_run_steps123.argtypes = [vp, vp, vp, i64, C.c_int]
         lib.sage2gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
         lib.sage2gpu_get_timers.argtypes = [vp, C.POINTER(Timers)]
@@ -164,6 +168,21 @@ class Sage2Gpu:
 
     def build_overlap_graph(self):
         self._check(self._lib.sage2gpu_build_overlap_graph(self._h), "build_overlap_graph")
+
+    def phase_a_partition(self, rank: int, world: int):
+        self._check(self._lib.sage2gpu_phase_a_partition(self._h, int(rank), int(world)), "phase_a_partition")
+
+    def phase_a_buffers(self) -> dict:
+        """Device pointers of the phase-A arrays (length world*chunk) for the multi-GPU exchange."""
+        p = [C.c_void_p() for _ in range(4)]
+        chunk, U = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sage2gpu_phase_a_buffers(self._h, *(C.byref(x) for x in p), C.byref(chunk), C.byref(U)),
+                    "phase_a_buffers")
+        return {"right": p[0].value or 0, "left": p[1].value or 0, "over_limit": p[2].value or 0,
+                "contained_by": p[3].value or 0, "chunk": int(chunk.value), "unique_reads": int(U.value)}
+
+    def finish_graph(self):
+        self._check(self._lib.sage2gpu_finish_graph(self._h), "finish_graph")
 
     def run_steps123(self, bases, offsets, min_overlap: int):
         self.load_reads(bases, offsets, min_overlap)

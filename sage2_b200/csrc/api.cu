@@ -228,6 +228,48 @@ int sage2gpu_build_hash_table(sage2gpu_ctx *ctx)
     });
 }
 
+static void finish_graph(sg::Context &c)
+{
+    SG_CHECK(c.have_phase_a, "phase A must run first");
+    {
+        StageTimer t(c.stream);
+        sg::stage_phase_b(c);
+        c.tm.phase_b = t.stop();
+    }
+    sg::stage_phase_c_and_finalize(c);
+    c.tm.total_device = c.tm.ingest + c.tm.sort_reads + c.tm.build_table + c.tm.phase_a + c.tm.phase_b +
+                        c.tm.phase_c_dev + c.tm.phase_c_host + c.tm.sort_edges;
+}
+
+int sage2gpu_phase_a_partition(sage2gpu_ctx *ctx, int rank, int world)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.have_table, "build_hash_table must run first");
+        StageTimer t(c.stream);
+        sg::stage_phase_a(c, rank, world);
+        c.tm.phase_a = t.stop();
+    });
+}
+
+int sage2gpu_phase_a_buffers(sage2gpu_ctx *ctx, void **right_ext, void **left_ext, void **over_limit, void **contained_by,
+                             uint64_t *reads_per_rank, uint64_t *unique_reads)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.have_phase_a, "phase A must run first");
+        if (right_ext) *right_ext = c.extR.p;
+        if (left_ext) *left_ext = c.extL.p;
+        if (over_limit) *over_limit = c.flag5.p;
+        if (contained_by) *contained_by = c.cont_max.p;
+        if (reads_per_rank) *reads_per_rank = c.pa_chunk;
+        if (unique_reads) *unique_reads = c.cnt.unique_reads;
+    });
+}
+
+int sage2gpu_finish_graph(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) { finish_graph(c); });
+}
+
 int sage2gpu_build_overlap_graph(sage2gpu_ctx *ctx)
 {
     return guarded(ctx, [&](sg::Context &c) {
@@ -237,14 +279,7 @@ int sage2gpu_build_overlap_graph(sage2gpu_ctx *ctx)
             sg::stage_phase_a(c);
             c.tm.phase_a = t.stop();
         }
-        {
-            StageTimer t(c.stream);
-            sg::stage_phase_b(c);
-            c.tm.phase_b = t.stop();
-        }
-        sg::stage_phase_c_and_finalize(c);
-        c.tm.total_device = c.tm.ingest + c.tm.sort_reads + c.tm.build_table + c.tm.phase_a + c.tm.phase_b +
-                            c.tm.phase_c_dev + c.tm.phase_c_host + c.tm.sort_edges;
+        finish_graph(c);
     });
 }
 

@@ -65,7 +65,9 @@ struct Context {
     // edges
     DevBuf<u64> edges;          // [2*n_edges] (w0,w1) pairs, canonical sorted after finalize
     std::vector<u64> h_edges;   // host copy of final edges (w0,w1 interleaved)
-    bool have_reads = false, have_table = false, have_graph = false;
+    bool have_reads = false, have_table = false, have_phase_a = false, have_graph = false;
+    u64 pa_chunk = 0;           // reads per rank in the last phase-A call (partition_chunk)
+    int pa_world = 1;
 };
 
 // stages (each throws sg::CudaError)
@@ -73,7 +75,7 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
 void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads);
 void stage_organize_reads(Context &c);
 void stage_build_table(Context &c);
-void stage_phase_a(Context &c);
+void stage_phase_a(Context &c, int rank = 0, int world = 1);   // rank's slice of the reads; arrays padded to world * chunk
 void stage_phase_b(Context &c);
 void stage_phase_c_and_finalize(Context &c);
 

@@ -258,6 +258,9 @@ SG_HD u64 candidate_record(int type, int j, int h, int len1, int len2, u32 rid2_
     return ((u64)(rid2_0based + 1) << 32) | ((u64)etype << 20) | ((u32)ovlp & 0xFFFFFu);
 }
 
+// ---- multi-GPU: reads (as query sources) are block-partitioned by id, the last rank's slice may be short ----
+SG_HD u64 partition_chunk(u64 U, int world) { return world <= 1 ? U : (U + (u64)world - 1) / (u64)world; }
+
 // ---- phase B (economyGraph.cpp:455-480) ---------------------------------------------------------------
 // State after phase A.  The reference writes 6 from any thread (:735) and 5 from the owner (:444); a
 // 1-thread run resolves that race by time order, reproduced here: the containing scan with the largest

@@ -298,8 +298,12 @@ void stage_phase_c_and_finalize(Context &c)
     SortCols cols;
     cols.a[0] = a0.p; cols.a[1] = a1.p; cols.b[0] = b0.p; cols.b[1] = b1.p; cols.v[0] = cols.v[1] = nullptr;
     int cur = 0;
-    cur = radix_sort_varying(cols, cur, nAll, true, st);     // (type, overhang)
-    cur = radix_sort_varying(cols, cur, nAll, false, st);    // (from, to)
+    // stable LSD passes, least significant field first; the bit ranges are known, no reduction / host round trip
+    int id_bits = 1;
+    while ((U >> id_bits) != 0) ++id_bits;                   // ids are 1..U
+    cur = radix_sort_bits(cols, cur, nAll, true, 0, 22, st);                 // w1: type << 20 | overhang
+    cur = radix_sort_bits(cols, cur, nAll, false, 0, id_bits, st);           // w0: to
+    cur = radix_sort_bits(cols, cur, nAll, false, 32, 32 + id_bits, st);     // w0: from
     DevBuf<u32> fflag(nAll, st), fidx(nAll, st), d_ne(1, st);
     flag_first_edge_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll, fflag.p);
     SG_LAUNCHED();

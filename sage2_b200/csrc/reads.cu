@@ -180,7 +180,9 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: LSD radix sort of a permutation over the record words (last word first), dedupe.
+// K2: sort a permutation of the good reads by record (= Read::operator<), dedupe.  Eight stable 8-bit radix
+// passes on the first record word (32 bases) + an in-place fix of the short runs of equal first words by
+// the remaining words; inputs with very long runs fall back to LSD passes over every word.
 // ------------------------------------------------------------------------------------------------
 __global__ void iota_kernel(u32 *v, u64 n)
 {
@@ -238,6 +240,48 @@ static unsigned big_grid(u64 n, unsigned block = 256)
     return g > kSMs * 16u ? kSMs * 16u : g;
 }
 
+// good reads only: bad ones were packed as all-ones records
+__global__ void flag_good_kernel(const u64 *__restrict__ rec, u64 n, int SW, u32 *__restrict__ flag)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        flag[i] = (rec[i * SW + SW - 1] & 0xFFFFull) != 0xFFFFull;
+}
+
+__global__ void compact_good_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ flag, const u32 *__restrict__ idx, u64 n, int SW,
+                                    u64 *__restrict__ key, u32 *__restrict__ val)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if (flag[i]) { key[idx[i]] = rec[i * SW]; val[idx[i]] = (u32)i; }
+}
+
+// After the sort by the first word (32 bases): order every run of equal first words by the remaining words.
+// Runs are short (duplicate reads, shared 32-mers); a run longer than kTieLimit raises `overflow` and the
+// caller falls back to the full word-by-word LSD sort.
+constexpr int kTieLimit = 512;
+__device__ __forceinline__ bool rec_less_tail(const u64 *a, const u64 *b, int SW)
+{
+    for (int w = 1; w < SW; ++w) { const u64 x = a[w], y = b[w]; if (x != y) return x < y; }
+    return false;
+}
+__global__ void __launch_bounds__(256) tie_fix_kernel(const u64 *__restrict__ rec, const u64 *__restrict__ key, u32 *__restrict__ perm, u64 n, int SW,
+                                                        u32 *__restrict__ overflow)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = key[i];
+        if ((i > 0 && key[i - 1] == k) || i + 1 >= n || key[i + 1] != k) continue;      // not the head of a run of >= 2
+        u64 e = i + 2;
+        while (e < n && key[e] == k && e - i <= (u64)kTieLimit) ++e;
+        if (e - i > (u64)kTieLimit) { *overflow = 1u; continue; }
+        for (u64 a = i + 1; a < e; ++a) {
+            const u32 x = perm[a];
+            const u64 *rx = rec + (u64)x * SW;
+            u64 b = a;
+            while (b > i && rec_less_tail(rx, rec + (u64)perm[b - 1] * SW, SW)) { perm[b] = perm[b - 1]; --b; }
+            perm[b] = x;
+        }
+    }
+}
+
 void stage_organize_reads(Context &c)
 {
     cudaStream_t st = c.stream;
@@ -250,26 +294,45 @@ void stage_organize_reads(Context &c)
         return;
     }
     DevBuf<u64> rec = std::move(c.F);
-    DevBuf<u64> ka(n, st), kb(n, st);
-    DevBuf<u32> va(n, st), vb(n, st);
-    iota_kernel<<<big_grid(n), 256, 0, st>>>(va.p, n);
-    SG_LAUNCHED();
+    DevBuf<u64> ka(n_good, st), kb(n_good, st);
+    DevBuf<u32> va(n_good, st), vb(n_good, st);
+    {   // indices and first words of the good reads, input order
+        DevBuf<u32> gflag(n, st), gidx(n, st);
+        flag_good_kernel<<<big_grid(n), 256, 0, st>>>(rec.p, n, SW, gflag.p);
+        SG_LAUNCHED();
+        exclusive_scan_u32(gflag.p, gidx.p, n, nullptr, st);
+        compact_good_kernel<<<big_grid(n), 256, 0, st>>>(rec.p, gflag.p, gidx.p, n, SW, ka.p, va.p);
+        SG_LAUNCHED();
+    }
     SortCols cols;
     cols.a[0] = ka.p; cols.a[1] = kb.p; cols.b[0] = cols.b[1] = nullptr; cols.v[0] = va.p; cols.v[1] = vb.p;
-    int cur = 0;
-    for (int w = SW - 1; w >= 0; --w) {
-        gather_word_kernel<<<big_grid(n), 256, 0, st>>>(rec.p, cols.v[cur], n, SW, w, cols.a[cur]);
+    int cur = radix_sort_bits(cols, 0, n_good, false, 0, 64, st);      // 8 passes on the first 32 bases
+    DevBuf<u32> d_flags(2, st);          // [0] tie-run overflow, [1] unique count
+    SG_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(u32), st));
+    if (SW > 1) {
+        tie_fix_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, cols.a[cur], cols.v[cur], n_good, SW, d_flags.p);
         SG_LAUNCHED();
-        cur = radix_sort_varying(cols, cur, n, false, st);
+    }
+    DevBuf<u32> flag(n_good, st), uidx(n_good, st);
+    u32 h_flags[2] = { 0, 0 };
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        unique_flag_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, cols.v[cur], n_good, SW, flag.p);
+        SG_LAUNCHED();
+        exclusive_scan_u32(flag.p, uidx.p, n_good, d_flags.p + 1, st);
+        SG_CUDA(cudaMemcpyAsync(h_flags, d_flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        if (!h_flags[0] || attempt == 1) break;
+        // a run of more than kTieLimit equal first words (low-complexity input): sort by every remaining word,
+        // last word first (stable LSD passes; the first word is already the most significant key)
+        SG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(u32), st));
+        for (int w = SW - 1; w >= 0; --w) {
+            gather_word_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, cols.v[cur], n_good, SW, w, cols.a[cur]);
+            SG_LAUNCHED();
+            cur = radix_sort_varying(cols, cur, n_good, false, st);
+        }
     }
     const u32 *perm = cols.v[cur];
-    DevBuf<u32> flag(n_good, st), uidx(n_good, st), d_total(1, st);
-    unique_flag_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, perm, n_good, SW, flag.p);
-    SG_LAUNCHED();
-    exclusive_scan_u32(flag.p, uidx.p, n_good, d_total.p, st);
-    u32 U = 0;
-    SG_CUDA(cudaMemcpyAsync(&U, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
+    const u32 U = h_flags[1];
     c.cnt.unique_reads = U;
     c.SWS = storage_words(SW);
     c.F.alloc((size_t)U * c.SWS, st);

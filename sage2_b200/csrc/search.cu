@@ -30,6 +30,7 @@ struct SearchParams {
     const u64 *slots;
     const u32 *entries;
     u64 nsec, U;
+    u64 lo, hi;         // phase A handles read indices [lo, hi)
     int h, k;
 };
 
@@ -187,7 +188,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
     key_masks(P.h, km0, km1);
     if (lane == 0) { Xf[SW] = 0; Xr[SW] = 0; prevR[SW] = 0; prevL[SW] = 0; }
 
-    for (u64 i = (u64)blockIdx.x * WARPS + warp; i < P.U; i += nwarps) {
+    for (u64 i = P.lo + (u64)blockIdx.x * WARPS + warp; i < P.hi; i += nwarps) {
         if (lane < SW) { Xf[lane] = P.F[i * SWS + lane]; Xr[lane] = P.RC[i * SWS + lane]; }
         __syncwarp();
         const int len1 = (int)(Xf[SW - 1] & 0xFFFF);
@@ -517,7 +518,7 @@ static void launch_phase_a_v(Context &c, const SearchParams &P, unsigned long lo
         SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_kernel<SW, MINB>, WARPS * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    phase_a_kernel<SW, MINB><<<search_grid(P.U, WARPS, blocks_per_sm), WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters);
+    phase_a_kernel<SW, MINB><<<search_grid(P.hi - P.lo, WARPS, blocks_per_sm), WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters);
 }
 
 // MINB = resident blocks per SM the register budget is cut for (occupancy against spills).
@@ -561,27 +562,40 @@ static SearchParams make_params(const Context &c)
 {
     SearchParams P;
     P.F = c.F.p; P.RC = c.RC.p; P.slots = c.slots.p; P.entries = c.entries.p;
-    P.nsec = c.cap / kSlotsPerSector; P.U = c.cnt.unique_reads; P.h = c.h; P.k = c.min_overlap;
+    P.nsec = c.cap / kSlotsPerSector; P.U = c.cnt.unique_reads; P.lo = 0; P.hi = P.U; P.h = c.h; P.k = c.min_overlap;
     return P;
 }
 
-void stage_phase_a(Context &c)
+void stage_phase_a(Context &c, int rank, int world)
 {
     cudaStream_t st = c.stream;
     SG_CHECK(c.have_table, "build_hash_table must run before the overlap search");
+    SG_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
     const u64 U = c.cnt.unique_reads;
-    c.extR.alloc(U, st); c.extL.alloc(U, st); c.flag5.alloc(U, st); c.cont_max.alloc(U, st);
+    const u64 chunk = partition_chunk(U, world), padded = chunk * (u64)world;
+    c.pa_chunk = chunk; c.pa_world = world;
+    c.have_phase_a = false; c.have_graph = false;
+    c.extR.alloc(padded, st); c.extL.alloc(padded, st); c.flag5.alloc(padded, st); c.cont_max.alloc(padded, st);
     c.cnt.compare_calls = 0; c.cnt.window_probes = 0; c.cnt.slow_path_reads = 0; c.cnt.probe_restarts = 0;
-    if (U == 0) return;
-    SG_CUDA(cudaMemsetAsync(c.cont_max.p, 0, U * sizeof(u32), st));
+    if (U == 0) { c.have_phase_a = true; return; }
+    if (world > 1) {      // slices of other ranks (and the padding) are defined before the exchange overwrites them
+        SG_CUDA(cudaMemsetAsync(c.extR.p, 0, padded * sizeof(u64), st));
+        SG_CUDA(cudaMemsetAsync(c.extL.p, 0, padded * sizeof(u64), st));
+        SG_CUDA(cudaMemsetAsync(c.flag5.p, 0, padded, st));
+    }
+    SG_CUDA(cudaMemsetAsync(c.cont_max.p, 0, padded * sizeof(u32), st));
     DevBuf<unsigned long long> d_counters(4, st);
     SG_CUDA(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(unsigned long long), st));
-    const SearchParams P = make_params(c);
+    SearchParams P = make_params(c);
+    P.lo = (u64)rank * chunk < U ? (u64)rank * chunk : U;
+    P.hi = P.lo + chunk < U ? P.lo + chunk : U;
     cudaEvent_t e0, e1;
     SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
     SG_CUDA(cudaEventRecord(e0, st));
-    SG_DISPATCH_SW(c.SW, launch_phase_a<SWC>(c, P, d_counters.p));
-    SG_LAUNCHED();
+    if (P.hi > P.lo) {
+        SG_DISPATCH_SW(c.SW, launch_phase_a<SWC>(c, P, d_counters.p));
+        SG_LAUNCHED();
+    }
     SG_CUDA(cudaEventRecord(e1, st));
     unsigned long long h[4];
     SG_CUDA(cudaMemcpyAsync(h, d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -592,6 +606,7 @@ void stage_phase_a(Context &c)
     c.cnt.probe_restarts = h[3];
     cudaEventElapsedTime(&c.tm.phase_a_kernel, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c.have_phase_a = true;
 }
 
 // used by graph.cu

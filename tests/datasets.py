@@ -107,6 +107,17 @@ def _mixed():
     return out, 45
 
 
+def _adapter():
+    # 1,500 distinct reads that share their first 40 bases (more than the read sort's tie-run limit) + normal reads
+    g = synth.random_genome(60_000, 36)
+    reads = synth.to_list(synth.paired_reads(g, 100, 30, seed=37, mu=300, sigma=20))
+    rng = np.random.default_rng(38)
+    head = b"ACGTTGCAAGCTTGCATGCCTGCAGGTCGACTCTAGAGGA"
+    for _ in range(1500):
+        reads.append(head + bytes(rng.choice(list(b"ACGT"), size=60).astype(np.uint8)))
+    return reads, 45
+
+
 def _empty():
     return [], 40
 
@@ -122,7 +133,7 @@ def _single():
 DATASETS = {
     "clean": _clean, "k31": _k31, "k70": _k70, "k64": _k64, "err": _err, "rep": _rep,
     "hicopy": _hicopy, "deep": _deep, "varlen": _varlen, "varlen_err": _varlen_err,
-    "deep_varlen": _deep_varlen, "tandem": _tandem, "mixed": _mixed,
+    "deep_varlen": _deep_varlen, "tandem": _tandem, "mixed": _mixed, "adapter": _adapter,
     "empty": _empty, "allbad": _allbad, "single": _single,
 }
 

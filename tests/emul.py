@@ -27,6 +27,12 @@ def lib():
         _lib.hemu_run.restype = C.c_void_p
         _lib.hemu_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         _lib.hemu_free.argtypes = [C.c_void_p]
+        _lib.hemu_prepare.restype = C.c_void_p
+        _lib.hemu_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        _lib.hemu_phase_a.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _lib.hemu_phase_a_arrays.restype = C.c_uint64
+        _lib.hemu_phase_a_arrays.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
+        _lib.hemu_finish.argtypes = [C.c_void_p]
         _lib.hemu_sizes.argtypes = [C.c_void_p, C.c_void_p]
         _lib.hemu_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 9
         _lib.hemu_get_bases.restype = C.c_uint64
@@ -40,11 +46,26 @@ def lib():
 
 
 class EmuRun:
-    def __init__(self, bases, offsets, k):
+    """Whole pipeline at once, or (rank, world, exchange) the multi-GPU split: steps 1-2, the rank's slice of
+    phase A, `exchange(views, chunk)` on in-place numpy views of the padded phase-A arrays, then the rest."""
+
+    def __init__(self, bases, offsets, k, rank=0, world=1, exchange=None):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         L = lib()
-        h = L.hemu_run(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k)
+        if exchange is None:
+            h = L.hemu_run(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k)
+        else:
+            h = L.hemu_prepare(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k)
+            L.hemu_phase_a(h, rank, world)
+            p = [C.c_void_p() for _ in range(4)]
+            n = int(L.hemu_phase_a_arrays(h, *(C.byref(x) for x in p)))
+            if n:
+                mk = lambda ptr, ct, dt: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).view(dt)
+                views = {"right": mk(p[0], C.c_uint64, np.int64), "left": mk(p[1], C.c_uint64, np.int64),
+                         "over_limit": mk(p[2], C.c_uint8, np.uint8), "contained_by": mk(p[3], C.c_uint32, np.int32)}
+                exchange(views, n // world)
+            L.hemu_finish(h)
         sz = np.zeros(13, dtype=np.uint64)
         L.hemu_sizes(h, sz.ctypes.data)
         (self.U, self.SW, self.N, self.total_bp, self.n_edges, self.over, self.distinct, self.compare_calls,

@@ -24,6 +24,9 @@ struct Emu {
     std::vector<u64> extR, extL;
     std::vector<uint8_t> explored_a, explored_b;
     std::vector<u64> edges;     // (w0,w1) final
+    std::map<std::pair<u64, u64>, std::vector<u32>> table;
+    std::vector<uint8_t> flag5;
+    std::vector<u32> cont_max;
     u64 over = 0, distinct = 0, compare_calls = 0, inserted = 0, removed = 0, contained = 0, contained_size = 0, slow_reads = 0;
 };
 
@@ -40,7 +43,7 @@ void pack_record(const uint8_t *s, int len, int SW, u64 *rec, bool rc)
     rec[SW - 1] |= (u64)len;
 }
 
-void run(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
+void prepare(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
 {
     e.k = k; e.h = hash_len_for(k); e.total = (u64)n;
     const int h = e.h;
@@ -81,7 +84,7 @@ void run(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
     for (u64 i = 0; i < U; ++i) revcomp_record(&e.F[i * SW], &e.RC[i * SW], SW, e.len[i]);
 
     // K3
-    std::map<std::pair<u64, u64>, std::vector<u32>> table;
+    auto &table = e.table;
     for (u64 i = 0; i < U; ++i)
         for (int t = 0; t < 4; ++t) {
             u64 v0, v1;
@@ -91,20 +94,31 @@ void run(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
     e.distinct = table.size();
     for (auto &kv : table) if (kv.second.size() >= (size_t)kHashThreshold) e.over++;
 
+}
+
+// rank's slice of the reads (sage2gpu_phase_a_partition); arrays padded to world * chunk
+void phase_a(Emu &e, int rank, int world)
+{
+    const int SW = e.SW, k = e.k, h = e.h;
+    const u64 U = e.U;
+    auto &table = e.table;
+    const u64 chunk = partition_chunk(U, world), padded = chunk * (u64)world;
+    const u64 lo = std::min<u64>(U, (u64)rank * chunk), hi = std::min<u64>(U, lo + chunk);
     // K4 phase A: the kernel's round structure (search.cu): the (window, bucket entry) items of a read are
     // consumed 32 at a time; a round is evaluated in FAST mode (every hit checked against the previous hit
     // of its side only) until the first anomaly, then converted to the reference's sequential chain.
     // With SAGE2_EMUL_EXACT_ONLY set the plain sequential chain runs instead (cross-check of the hybrid).
-    e.extR.assign(U, 0); e.extL.assign(U, 0);
-    std::vector<uint8_t> flag5(U, 0);
-    std::vector<u32> cont_max(U, 0);
+    e.extR.assign(padded, 0); e.extL.assign(padded, 0);
+    e.flag5.assign(padded, 0); e.cont_max.assign(padded, 0);
+    auto &flag5 = e.flag5;
+    auto &cont_max = e.cont_max;
     std::vector<u64> prevR(SW), prevL(SW);
     const bool exact_only = getenv("SAGE2_EMUL_EXACT_ONLY") != nullptr;
     struct Item { int jj; u32 ent; };
     struct Hit { int jj; bool right; u32 rid2; int type; int len2; const u64 *Q; };
     std::vector<Item> items;
     std::vector<Hit> hits;
-    for (u64 i = 0; i < U; ++i) {
+    for (u64 i = lo; i < hi; ++i) {
         const u64 *Xf = &e.F[i * SW], *Xr = &e.RC[i * SW];
         const int len1 = e.len[i];
         items.clear();
@@ -196,6 +210,15 @@ void run(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
             e.extL[i] = ext_pack(Lid, Ltype, Llen);
         }
     }
+}
+
+void finish(Emu &e)
+{
+    const int SW = e.SW, k = e.k, h = e.h;
+    const u64 U = e.U;
+    auto &table = e.table;
+    auto &flag5 = e.flag5;
+    auto &cont_max = e.cont_max;
     // phase B
     e.explored_a.resize(U); e.explored_b.resize(U);
     for (u64 i = 0; i < U; ++i) {
@@ -286,9 +309,27 @@ extern "C" {
 void *hemu_run(const uint8_t *bases, const int64_t *off, int64_t n, int k)
 {
     Emu *e = new Emu();
-    run(*e, bases, off, n, k);
+    prepare(*e, bases, off, n, k);
+    phase_a(*e, 0, 1);
+    finish(*e);
     return e;
 }
+// the multi-GPU split: prepare (steps 1-2), rank's phase-A slice, [exchange by the caller], finish
+void *hemu_prepare(const uint8_t *bases, const int64_t *off, int64_t n, int k)
+{
+    Emu *e = new Emu();
+    prepare(*e, bases, off, n, k);
+    return e;
+}
+void hemu_phase_a(void *p, int rank, int world) { phase_a(*(Emu *)p, rank, world); }
+// pointers to the padded phase-A arrays (u64, u64, u8, u32) and their length
+uint64_t hemu_phase_a_arrays(void *p, uint64_t **extR, uint64_t **extL, uint8_t **flag5, uint32_t **cont_max)
+{
+    Emu *e = (Emu *)p;
+    *extR = e->extR.data(); *extL = e->extL.data(); *flag5 = e->flag5.data(); *cont_max = e->cont_max.data();
+    return e->extR.size();
+}
+void hemu_finish(void *p) { finish(*(Emu *)p); }
 void hemu_free(void *p) { delete (Emu *)p; }
 // sizes: [0]=U [1]=SW [2]=good [3]=total_bp [4]=n_edges [5]=over [6]=distinct [7]=compare_calls [8]=inserted
 //        [9]=removed [10]=contained [11]=contained_size [12]=reads that left the fast mode
@@ -307,8 +348,8 @@ void hemu_copy(void *p, uint64_t *F, uint64_t *RC, uint16_t *len, uint16_t *freq
     if (RC) memcpy(RC, e->RC.data(), e->RC.size() * 8);
     if (len) memcpy(len, e->len.data(), e->len.size() * 2);
     if (freq) memcpy(freq, e->freq.data(), e->freq.size() * 2);
-    if (extR) memcpy(extR, e->extR.data(), e->extR.size() * 8);
-    if (extL) memcpy(extL, e->extL.data(), e->extL.size() * 8);
+    if (extR) memcpy(extR, e->extR.data(), e->U * 8);
+    if (extL) memcpy(extL, e->extL.data(), e->U * 8);
     if (expl_a) memcpy(expl_a, e->explored_a.data(), e->explored_a.size());
     if (expl_b) memcpy(expl_b, e->explored_b.data(), e->explored_b.size());
     if (edges) memcpy(edges, e->edges.data(), e->edges.size() * 8);

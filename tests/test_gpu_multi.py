@@ -1,0 +1,59 @@
+"""Two real GPUs (skipped on a one-GPU box): torchrun-style ranks over NCCL build one graph with the
+partitioned phase A + exchange of sage2_b200/multi.py; every rank must hold the oracle's edge list."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import datasets
+from oracle import oracle
+from sage2_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, out):
+    import torch.distributed as dist
+    from sage2_b200 import api, multi
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        reads, k = datasets.get(name)
+        b, off = synth.concat(reads)
+        hb, ho = torch.from_numpy(b).pin_memory(), torch.from_numpy(off).pin_memory()
+        dev = torch.device("cuda", rank)
+        tb, to, _ = multi.upload_partitioned(hb, ho, rank, world, dev)
+        torch.cuda.synchronize()
+        g = api.Sage2Gpu(rank)
+        g.load_reads_ptr(tb.data_ptr(), to.data_ptr(), len(off) - 1, k, device=True)
+        g.build_hash_table()
+        multi.build_overlap_graph(g, rank, world, dev)
+        np.save(os.path.join(out, f"edges{rank}.npy"), g.edges())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("name", ["rep", "varlen_err"])
+def test_two_gpus_one_graph(name, tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), name, str(tmp_path)), nprocs=2, join=True)
+    reads, k = datasets.get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    for r in range(2):
+        e = np.load(tmp_path / f"edges{r}.npy")
+        assert len(e) == o.n_edges
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], o.edges[f])

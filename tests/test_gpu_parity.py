@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 SMALL = ["clean", "k31", "k70", "k64", "err", "rep", "hicopy", "deep", "varlen", "varlen_err", "deep_varlen",
-         "tandem", "mixed", "empty", "allbad", "single"]
+         "tandem", "mixed", "adapter", "empty", "allbad", "single"]
 
 
 def _md5(path):
@@ -140,3 +140,46 @@ def test_cfg2_full_size_properties():
     assert np.all(e["delta"] == e["delta_twin"])
     assert c["contained_ext"] + c["left_to_explore"] + c["contained_size"] == c["unique_reads"]
     assert c["left_to_explore"] <= 8
+
+
+@pytest.mark.parametrize("name,world", [("rep", 2), ("deep_varlen", 3), ("varlen_err", 4)])
+def test_partitioned_phase_a_slices_compose(name, world):
+    """The multi-GPU form on one GPU: `world` contexts hold the same reads and table, each searches its
+    slice (sage2gpu_phase_a_partition); the exchange of sage2_b200/multi.py is done here with plain device
+    copies (all-gather of the slices, element-wise max of the containment ids); every context must then
+    finish with the oracle's graph."""
+    import torch
+    from sage2_b200 import multi
+    reads, k = _get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    dev = torch.device("cuda", 0)
+    ctxs, views = [], []
+    for r in range(world):
+        g = api.Sage2Gpu(0)
+        g.load_reads(b, off, k)
+        g.build_hash_table()
+        g.phase_a_partition(r, world)
+        ctxs.append(g)
+        views.append(multi.device_views(g.phase_a_buffers(), world, dev))
+    chunk = ctxs[0].phase_a_buffers()["chunk"]
+    assert chunk == -(-o.U // world)
+    torch.cuda.synchronize()
+    full = {key: torch.cat([views[r][key][r * chunk:(r + 1) * chunk] for r in range(world)]) for key in ("right", "left", "over_limit")}
+    cmax = torch.stack([v["contained_by"] for v in views]).max(dim=0).values
+    for v in views:
+        for key in full:
+            v[key].copy_(full[key])
+        v["contained_by"].copy_(cmax)
+    torch.cuda.synchronize()
+    total_calls = 0
+    for g in ctxs:
+        total_calls += g.counters()["compare_calls"]
+        g.finish_graph()
+        e = g.edges()
+        assert len(e) == o.n_edges
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], o.edges[f])
+        x = g.extensions()
+        np.testing.assert_array_equal(x["explored"], o.explored_b[1:])
+    assert total_calls == o.compare_calls

@@ -12,7 +12,7 @@ from oracle import oracle
 from sage2_b200 import synth
 
 NAMES = ["clean", "k31", "k70", "k64", "err", "rep", "hicopy", "deep", "varlen", "varlen_err", "deep_varlen",
-         "tandem", "mixed", "empty", "allbad", "single"]
+         "tandem", "mixed", "adapter", "empty", "allbad", "single"]
 
 
 def compare_stage_outputs(o, U, lens, freq, F, RC, extR, extL, explored_b, edges, explored_a=None):

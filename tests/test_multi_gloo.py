@@ -1,0 +1,67 @@
+"""N > 1 on the CPU (world_size 2 and 3, gloo): the partition arithmetic and the one exchange step of the
+multi-GPU build (sage2_b200/multi.py: all-gather of the extension records / flags, all-reduce MAX of the
+containment ids), driven with the CPU emulation's phase-A slices.  Every rank must end with the oracle's
+edge list."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import datasets
+import emul
+from oracle import oracle
+from sage2_b200 import multi, synth
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        reads, k = datasets.get(name)
+        b, off = synth.concat(reads)
+        sent = []
+
+        def exchange(views, chunk):
+            tv = {key: torch.from_numpy(v) for key, v in views.items()}      # share memory with the emulator's arrays
+            sent.append(multi.exchange_phase_a(tv, chunk, rank, world))
+
+        e = emul.EmuRun(b, off, k, rank=rank, world=world, exchange=exchange)
+        np.save(os.path.join(out, f"edges{rank}.npy"), e.edges)
+        np.save(os.path.join(out, f"ext{rank}.npy"), np.stack([e.extR, e.extL]))
+        np.save(os.path.join(out, f"sent{rank}.npy"), np.array(sent + [e.U]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,world", [("rep", 2), ("varlen_err", 2), ("deep_varlen", 3), ("single", 2)])
+def test_partitioned_phase_a_with_exchange_equals_oracle(name, world, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    reads, k = datasets.get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    for r in range(world):
+        a, bb, t, d = emul.unpack_edges(np.load(tmp_path / f"edges{r}.npy"))
+        assert len(a) == o.n_edges
+        np.testing.assert_array_equal(a, o.edges["from"])
+        np.testing.assert_array_equal(bb, o.edges["to"])
+        np.testing.assert_array_equal(t, o.edges["type"])
+        np.testing.assert_array_equal(d, o.edges["delta"])
+        ext = np.load(tmp_path / f"ext{r}.npy")
+        np.testing.assert_array_equal(emul.unpack_ext(ext[0])[0], o.right_ext["id"][1:])
+        np.testing.assert_array_equal(emul.unpack_ext(ext[1])[0], o.left_ext["id"][1:])
+        sent = np.load(tmp_path / f"sent{r}.npy")
+        U = int(sent[-1])
+        chunk = -(-U // world)
+        assert int(sent[0]) == chunk * (8 + 8 + 1) + chunk * world * 4
