@@ -40,6 +40,12 @@ __device__ __forceinline__ void ldg256(const u64 *p, u64 (&v)[4])
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
 }
 
+// FAST-mode scan state of one read (warp-uniform): first right hit, last left hit, last hit of each side
+struct FastState {
+    u32 Rid = 0, Rtype = 0, Rlen = 0, Lid = 0, Ltype = 0, Llen = 0, connections = 0;
+    int cJR = 0, cLenR = 0, firstJR = 0, cJL = 0, cLenL = 0;
+};
+
 template <int SW>
 struct SearchCfg {
     static constexpr int WARPS = SW <= 8 ? 8 : (SW <= 16 ? 4 : 2);
@@ -178,14 +184,14 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
     __shared__ u64 sQ[WARPS][32 * SWP];
     __shared__ u64 sItem[WARPS][32];
     __shared__ ExtState sState[WARPS];
+    __shared__ FastState sFast[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *Xf = sXf[warp], *Xr = sXr[warp], *prevR = sPrevR[warp], *prevL = sPrevL[warp], *Qs = sQ[warp], *items = sItem[warp];
     ExtState &st = sState[warp];
+    FastState &fs = sFast[warp];
     const u64 nwarps = (u64)gridDim.x * WARPS;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned long long calls = 0, probes = 0, n_exact = 0, n_restart = 0;
-    u64 km0, km1;
-    key_masks(P.h, km0, km1);
+    unsigned calls = 0, probes = 0, n_exact = 0, n_restart = 0;      // per warp: far below 2^32
     if (lane == 0) { Xf[SW] = 0; Xr[SW] = 0; prevR[SW] = 0; prevL[SW] = 0; }
 
     for (u64 i = P.lo + (u64)blockIdx.x * WARPS + warp; i < P.hi; i += nwarps) {
@@ -197,11 +203,13 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
 
     restart:
         // warp-uniform scan state (FAST mode); `exact` switches to the ExtState in shared memory
+        // (the FAST-mode values live in shared memory, `fs`, written by lane 0 once per round)
         bool exact = false, hasR = false, hasL = false;
-        u32 Rid = 0, Rtype = 0, Rlen = 0, Lid = 0, Ltype = 0, Llen = 0, connections = 0;
-        int cJR = 0, cLenR = 0, firstJR = 0, cJL = 0, cLenL = 0, curWin = -1;
-        unsigned long long my_calls = 0, my_probes = 0;
+        int curWin = -1;
+        unsigned my_calls = 0, my_probes = 0;
         int qn = 0;                                   // items waiting in `items`
+        if (lane == 0) fs = FastState();
+        __syncwarp();
 
         for (int base = 0; base < W || qn > 0; base += 32) {
             // ---- stage 1: probe -------------------------------------------------------------------
@@ -284,6 +292,8 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                     const u64 *Y = Qs + lane * SWP;
                     len2 = (int)(Y[SW - 1] & 0xFFFF);
                     bool contained, key_bad;
+                    u64 km0, km1;
+                    key_masks(P.h, km0, km1);
                     const bool ok = t_overlap_equal<SW>(right ? Xf : Xr, len1, right ? jj : len1 - jj - P.h, Y, len2, km0, km1, contained, key_bad);
                     fp = first && key_bad;
                     if (need) {
@@ -313,7 +323,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                         const u64 *prec = nullptr;
                         int prevJ = 0, prevLen = 0;
                         if (src >= 0) { prec = Qs + src * SWP; prevJ = pj; prevLen = plen; }
-                        else if (right ? hasR : hasL) { prec = right ? prevR : prevL; prevJ = right ? cJR : cJL; prevLen = right ? cLenR : cLenL; }
+                        else if (right ? hasR : hasL) { prec = right ? prevR : prevL; prevJ = right ? fs.cJR : fs.cJL; prevLen = right ? fs.cLenR : fs.cLenL; }
                         if (prec) {
                             bool c2, kb;
                             const u64 *mine = Qs + lane * SWP;
@@ -328,21 +338,26 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                             if (!hasR) {      // rightExtension = the first right hit (longest overlap), :96-108
                                 const int f = __ffs(mR) - 1;
                                 const int jf = __shfl_sync(FULL, jj, f), lf = __shfl_sync(FULL, len2, f);
-                                Rid = __shfl_sync(FULL, rid2, f) + 1; Rtype = (u32)(__shfl_sync(FULL, type, f) >> 1);
-                                Rlen = (u32)(lf - (len1 - jf)); firstJR = jf; hasR = true;
+                                const u32 rf = __shfl_sync(FULL, rid2, f);
+                                const int tf = __shfl_sync(FULL, type, f);
+                                if (lane == 0) { fs.Rid = rf + 1; fs.Rtype = (u32)(tf >> 1); fs.Rlen = (u32)(lf - (len1 - jf)); fs.firstJR = jf; }
+                                hasR = true;
                             }
                             const int l = 31 - __clz(mR);
-                            cJR = __shfl_sync(FULL, jj, l); cLenR = __shfl_sync(FULL, len2, l);
+                            const int jl = __shfl_sync(FULL, jj, l), ll = __shfl_sync(FULL, len2, l);
+                            if (lane == 0) { fs.cJR = jl; fs.cLenR = ll; }
                             if (lane < SW) prevR[lane] = Qs[l * SWP + lane];
                         }
                         if (mL) {             // leftExtension = the last left hit (longest overlap), :281-357
                             const int l = 31 - __clz(mL);
-                            cJL = __shfl_sync(FULL, jj, l); cLenL = __shfl_sync(FULL, len2, l);
-                            Lid = __shfl_sync(FULL, rid2, l) + 1; Ltype = (u32)(__shfl_sync(FULL, type, l) >> 1);
-                            Llen = (u32)(cLenL - cJL - P.h); hasL = true;
+                            const int jl = __shfl_sync(FULL, jj, l), ll = __shfl_sync(FULL, len2, l);
+                            const u32 rl = __shfl_sync(FULL, rid2, l);
+                            const int tl = __shfl_sync(FULL, type, l);
+                            if (lane == 0) { fs.cJL = jl; fs.cLenL = ll; fs.Lid = rl + 1; fs.Ltype = (u32)(tl >> 1); fs.Llen = (u32)(ll - jl - P.h); }
+                            hasL = true;
                             if (lane < SW) prevL[lane] = Qs[l * SWP + lane];
                         }
-                        connections += (u32)__popc(hm);
+                        if (lane == 0) fs.connections += (u32)__popc(hm);
                         __syncwarp();
                         continue;
                     }
@@ -352,12 +367,12 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                     curWin = __shfl_sync(FULL, jj, __ffs(hm) - 1);
                     if (lane == 0) {
                         ext_init(st);
-                        st.Rid = Rid; st.Rtype = Rtype; st.Rlen = Rlen; st.Lid = Lid; st.Ltype = Ltype; st.Llen = Llen;
-                        st.prevJR = cJR; st.prevLenR = cLenR; st.prevPL = len1 - cJL - P.h; st.prevLenL = cLenL;
-                        st.markAmbigR = (hasR && cJR == curWin) ? 1 : 0;
-                        st.markFirstR = (hasR && firstJR == curWin) ? 1 : 0;
-                        st.markAmbigL = (hasL && cJL == curWin) ? 1 : 0;
-                        st.connections = connections;
+                        st.Rid = fs.Rid; st.Rtype = fs.Rtype; st.Rlen = fs.Rlen; st.Lid = fs.Lid; st.Ltype = fs.Ltype; st.Llen = fs.Llen;
+                        st.prevJR = fs.cJR; st.prevLenR = fs.cLenR; st.prevPL = len1 - fs.cJL - P.h; st.prevLenL = fs.cLenL;
+                        st.markAmbigR = (hasR && fs.cJR == curWin) ? 1 : 0;
+                        st.markFirstR = (hasR && fs.firstJR == curWin) ? 1 : 0;
+                        st.markAmbigL = (hasL && fs.cJL == curWin) ? 1 : 0;
+                        st.connections = fs.connections;
                     }
                     __syncwarp();
                 }
@@ -405,9 +420,9 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                 extR[i] = ext_pack(st.Rid, st.Rtype, amb ? 0u : st.Rlen);
                 extL[i] = ext_pack(st.Lid, st.Ltype, amb ? 0u : st.Llen);
             } else {
-                flag5[i] = connections > kConnectionsLimit ? 1 : 0;
-                extR[i] = ext_pack(Rid, Rtype, Rlen);
-                extL[i] = ext_pack(Lid, Ltype, Llen);
+                flag5[i] = fs.connections > kConnectionsLimit ? 1 : 0;
+                extR[i] = ext_pack(fs.Rid, fs.Rtype, fs.Rlen);
+                extL[i] = ext_pack(fs.Lid, fs.Ltype, fs.Llen);
             }
         }
         calls += my_calls; probes += my_probes;
@@ -419,9 +434,9 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
         probes += __shfl_xor_sync(FULL, probes, s);
     }
     if (lane == 0) {
-        atomicAdd(&counters[0], calls); atomicAdd(&counters[1], probes);
-        if (n_exact) atomicAdd(&counters[2], n_exact);
-        if (n_restart) atomicAdd(&counters[3], n_restart);
+        atomicAdd(&counters[0], (unsigned long long)calls); atomicAdd(&counters[1], (unsigned long long)probes);
+        if (n_exact) atomicAdd(&counters[2], (unsigned long long)n_exact);
+        if (n_restart) atomicAdd(&counters[3], (unsigned long long)n_restart);
     }
 }
 
@@ -526,10 +541,11 @@ template <int SW>
 static void launch_phase_a(Context &c, const SearchParams &P, unsigned long long *d_counters)
 {
     if constexpr (SW <= 8) {
-        static const int minb = [] { const char *e = getenv("SAGE2GPU_PA_MINB"); return e ? atoi(e) : 3; }();
+        static const int minb = [] { const char *e = getenv("SAGE2GPU_PA_MINB"); return e ? atoi(e) : 4; }();
         if (minb <= 2) launch_phase_a_v<SW, 2>(c, P, d_counters);
         else if (minb == 3) launch_phase_a_v<SW, 3>(c, P, d_counters);
-        else launch_phase_a_v<SW, 4>(c, P, d_counters);
+        else if (minb == 4) launch_phase_a_v<SW, 4>(c, P, d_counters);
+        else launch_phase_a_v<SW, 5>(c, P, d_counters);
     } else {
         launch_phase_a_v<SW, 1>(c, P, d_counters);
     }
