@@ -143,7 +143,7 @@ void sage2gpu_destroy(sage2gpu_ctx *ctx)
     cudaStreamSynchronize(st);
     {
         sg::Context &c = ctx->c;
-        c.d_bases.release(); c.d_offsets.release(); c.up_d_bases.release(); c.up_d_offsets.release(); c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
+        c.d_bases.release(); c.d_offsets.release(); c.up_d_bases.release(); c.up_d_offsets.release(); c.raw.release(); c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
         c.slots.release(); c.entries.release(); c.extR.release(); c.extL.release(); c.flag5.release();
         c.cont_max.release(); c.explored.release(); c.edges.release();
     }

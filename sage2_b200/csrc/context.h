@@ -47,6 +47,7 @@ struct Context {
     bool up_open = false;
     cudaEvent_t up_event = nullptr;
 
+    DevBuf<u64> raw;            // [n_input*SW] packed canonical records in input order (step 1, before the sort)
     // unique reads, ids 1..U map to index 0..U-1
     DevBuf<u64> F, RC;          // [U*SWS] records (SW words used, stride SWS = storage_words(SW))
     DevBuf<uint16_t> len, freq; // [U]

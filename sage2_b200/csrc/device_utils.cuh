@@ -34,28 +34,31 @@ struct CudaError : public std::runtime_error {
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;      // n = elements in use, cap = elements allocated
     cudaStream_t s = nullptr;
     DevBuf() {}
     DevBuf(size_t count, cudaStream_t st) { alloc(count, st); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap), s(o.s) { o.p = nullptr; o.n = 0; o.cap = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept
     {
-        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; s = o.s; o.p = nullptr; o.n = 0; o.cap = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
+    // Grow-only: a buffer that is already large enough is kept (the long-lived buffers of a context are
+    // re-used run after run instead of cycling hundreds of MB through the pool).  Contents are undefined.
     void alloc(size_t count, cudaStream_t st)
     {
+        if (p && cap >= count && s == st) { n = count; return; }
         release();
-        s = st; n = count;
-        SG_CUDA(cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T), st));
+        s = st; n = count; cap = count ? count : 1;
+        SG_CUDA(cudaMallocAsync((void **)&p, cap * sizeof(T), st));
     }
     void release()
     {
-        if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; }
+        if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; cap = 0; }
     }
     size_t bytes() const { return n * sizeof(T); }
 };

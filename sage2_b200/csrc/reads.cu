@@ -29,49 +29,63 @@ __global__ void __launch_bounds__(K1_WARPS * 32) pack_kernel(const uint8_t *__re
                                                               u64 n, int k, int SW, u64 *__restrict__ rec,
                                                               unsigned long long *counters /*[0]=good,[1]=bp*/)
 {
+    // per warp: the read's characters (coalesced byte loads, zero padded to a multiple of 128), its packed
+    // forward words (written byte-wise, most significant byte first) and its reverse complement
+    __shared__ __align__(16) uint8_t sB[K1_WARPS][32 * kMaxWords];
     __shared__ u64 sF[K1_WARPS][kMaxWords], sR[K1_WARPS][kMaxWords];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 nwarps = (u64)gridDim.x * K1_WARPS;
     unsigned long long good = 0, bp = 0;
+    uint8_t *B = sB[warp];
+    uint8_t *Fb = reinterpret_cast<uint8_t *>(sF[warp]);
     for (u64 r = (u64)blockIdx.x * K1_WARPS + warp; r < n; r += nwarps) {
         const int64_t o = off[r];
         const int64_t len64 = off[r + 1] - o;
         const int max_ok = 32 * SW - 8;
         bool bad = len64 <= (int64_t)k || len64 > (int64_t)max_ok;
         const int len = bad ? 0 : (int)len64;
+        const int padded = (len + 127) & ~127;
+#pragma unroll 8
+        for (int p = lane; p < padded; p += 32) B[p] = p < len ? bases[o + p] : (uint8_t)'A';
+        if (lane < SW) sF[warp][lane] = 0;
+        __syncwarp();
+        // 4 characters -> 1 byte per lane and 128-base group: code = ((c >> 1) ^ (c >> 2)) & 3 (A0 C1 G2 T3, any case)
         bool invalid = false;
-        for (int w = 0; w < SW; ++w) {
-            const int p = 32 * w + lane;
-            u32 cf = 0, cr = 0;
-            if (p < len) {
-                const u32 a = bases[o + p], b = bases[o + len - 1 - p];
-                const u32 au = a & 0xDFu;
-                invalid |= !(au == 'A' || au == 'C' || au == 'G' || au == 'T');
-                cf = ((a >> 1) ^ (a >> 2)) & 3u;             // A0 C1 G2 T3, case-insensitive
-                cr = 3u - (((b >> 1) ^ (b >> 2)) & 3u);      // complement of the mirrored base
+        for (int g = 0; g < padded; g += 128) {
+            const u32 x = *reinterpret_cast<const u32 *>(B + g + 4 * lane);
+            const u32 up = x & 0xDFDFDFDFu;
+            const u32 eqA = up ^ 0x41414141u, eqC = up ^ 0x43434343u, eqG = up ^ 0x47474747u, eqT = up ^ 0x54545454u;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const u32 m = 0xFFu << (8 * t);
+                invalid |= (eqA & m) && (eqC & m) && (eqG & m) && (eqT & m);
             }
-            const int sh = 30 - 2 * (lane & 15);
-            const u32 fhi = __reduce_or_sync(0xffffffffu, lane < 16 ? cf << sh : 0u);
-            const u32 flo = __reduce_or_sync(0xffffffffu, lane >= 16 ? cf << sh : 0u);
-            const u32 rhi = __reduce_or_sync(0xffffffffu, lane < 16 ? cr << sh : 0u);
-            const u32 rlo = __reduce_or_sync(0xffffffffu, lane >= 16 ? cr << sh : 0u);
-            if (lane == 0) {
-                sF[warp][w] = ((u64)fhi << 32) | flo;
-                sR[warp][w] = ((u64)rhi << 32) | rlo;
-            }
+            const u32 c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+            const u32 byte = (c * 0x40100401u) >> 24;              // first character in the top two bits
+            const int bi = (g >> 2) + lane;                         // byte index in the big-endian 2-bit string
+            if (bi < 8 * SW) Fb[(bi & ~7) + 7 - (bi & 7)] = (uint8_t)byte;      // little-endian u64 words in shared memory
         }
         bad |= __any_sync(0xffffffffu, invalid);
         __syncwarp();
+        // padding 'A's packed as 0 bits already; reverse complement from the packed words (utils.cpp:73-91)
+        if (lane < SW) {
+            const int sh = 64 * SW - 2 * len, q = sh >> 6, rr = sh & 63;
+            const int i0 = lane + q, i1 = lane + q + 1;
+            const u64 a = i0 < SW ? rev2(~sF[warp][SW - 1 - i0]) : 0ull;
+            const u64 b2 = i1 < SW ? rev2(~sF[warp][SW - 1 - i1]) : 0ull;
+            sR[warp][lane] = rr == 0 ? a : ((a << rr) | (b2 >> (64 - rr)));
+        }
+        __syncwarp();
         // canonical orientation: keep the read iff read < revcomp (readLoader.cpp:195)
-        const u64 f = lane < SW ? sF[warp][lane] : 0ull, q = lane < SW ? sR[warp][lane] : 0ull;
-        const unsigned diff = __ballot_sync(0xffffffffu, f != q);
+        const u64 f = lane < SW ? sF[warp][lane] : 0ull, qv = lane < SW ? sR[warp][lane] : 0ull;
+        const unsigned diff = __ballot_sync(0xffffffffu, f != qv);
         bool use_rc = false;
         if (diff) {
             const int first = __ffs(diff) - 1;
-            use_rc = __shfl_sync(0xffffffffu, (int)(q < f), first) != 0;
+            use_rc = __shfl_sync(0xffffffffu, (int)(qv < f), first) != 0;
         }
         if (lane < SW) {
-            u64 v = use_rc ? q : f;
+            u64 v = use_rc ? qv : f;
             if (lane == SW - 1) v |= (u64)len;
             rec[r * SW + lane] = bad ? ~0ull : v;
         }
@@ -135,6 +149,8 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     const int64_t *d_o = offsets;
     if (!device_resident) {
         const int64_t total = offsets[n_reads];
+        // grow-only staging buffers, kept between calls: re-allocating ~0.5 GB per call made the stream-ordered
+        // pool map fresh memory every few calls (hundreds of ms)
         c.d_offsets.alloc((size_t)n_reads + 1, st);
         c.d_bases.alloc((size_t)total, st);
         SG_CUDA(cudaMemcpyAsync(c.d_offsets.p, offsets, ((size_t)n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -161,7 +177,8 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     }
 
     // K1
-    DevBuf<u64> rec((size_t)n_reads * c.SW, st);
+    c.raw.alloc((size_t)n_reads * c.SW, st);
+    DevBuf<u64> &rec = c.raw;
     DevBuf<unsigned long long> d_cnt(2, st);
     SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), st));
     unsigned gp = grid_for((u64)n_reads, 1, K1_WARPS);
@@ -174,9 +191,6 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     c.cnt.good_reads = h_cnt[0];
     c.cnt.total_bp = h_cnt[1];
     c.cnt.avg_len = h_cnt[0] ? h_cnt[1] / h_cnt[0] : 0;        // readLoader.cpp:161 integer division
-    c.F = std::move(rec);                                      // raw (unsorted, with bad reads) until organize
-    c.d_bases.release();
-    c.d_offsets.release();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -293,7 +307,7 @@ void stage_organize_reads(Context &c)
         c.have_reads = true;
         return;
     }
-    DevBuf<u64> rec = std::move(c.F);
+    DevBuf<u64> &rec = c.raw;      // packed canonical records in input order (bad reads all-ones)
     DevBuf<u64> ka(n_good, st), kb(n_good, st);
     DevBuf<u32> va(n_good, st), vb(n_good, st);
     {   // indices and first words of the good reads, input order
