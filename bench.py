@@ -105,8 +105,8 @@ def reference_run(reads, k, tmpdir: str, threads: int | None = None) -> dict:
     fq = os.path.join(tmpdir, "sample.fastq")
     synth.write_fastq(fq, reads)
     env = dict(os.environ)
-    if threads:
-        env["OMP_NUM_THREADS"] = str(threads)
+    # all host cores unless told otherwise (torchrun exports OMP_NUM_THREADS=1 to its ranks)
+    env["OMP_NUM_THREADS"] = str(threads or os.cpu_count() or 1)
     if os.access(oracle.REF_STEPS, os.X_OK):
         out = subprocess.run([oracle.REF_STEPS, fq, str(k)], env=env, check=True, capture_output=True, text=True).stdout
         d = json.loads(out.strip().splitlines()[-1])
@@ -147,7 +147,7 @@ def run_reference_arm(args):
     value = len(reads) / (ms / 1000.0)
     sample = f"cfg2-shaped sample: {cfg['genome_bp']} bp genome, {len(reads)} reads, steps 1-3 without FASTQ parse / text output"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "impl": "reference",
             "config": dict(cfg, workload=cfg["workload"], sample_reads=len(reads)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": last.get("threads"), "kind": last["kind"], "sample": sample},
@@ -210,9 +210,9 @@ def run_ours(args):
             gpu.load_reads_ptr(h_bases.data_ptr(), h_off.data_ptr(), n_reads, k, device=False)
             comm["h2d"] = int(bases.nbytes + offsets.nbytes)
         else:       # each rank moves 1/N of the input over PCIe, NVLink all-gather completes it
-            with torch.cuda.stream(stream):
-                tb, to, comm["h2d"] = multi.upload_partitioned(h_bases, h_off, rank, world, dev)
-            stream.synchronize()
+            # (on torch's own stream: pinned tensors must not be tied to the library's stream, which dies first)
+            tb, to, comm["h2d"] = multi.upload_partitioned(h_bases, h_off, rank, world, dev)
+            torch.cuda.current_stream(dev).synchronize()
             gpu.load_reads_ptr(tb.data_ptr(), to.data_ptr(), n_reads, k, device=True)
         gpu.build_hash_table()
         multi.build_overlap_graph(gpu, rank, world, dev)
@@ -262,10 +262,15 @@ def run_ours(args):
     e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_host, args.steps)
     n_edges = gpu.counters()["n_edges"]
 
-    if rank != 0:
-        gpu.close()
+    def teardown():
+        torch.cuda.synchronize()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
+        gpu.close()
+
+    if rank != 0:
+        teardown()
         return
 
     ms_per_step = dev_ms / args.steps
@@ -334,9 +339,7 @@ def run_ours(args):
                                                   "window_probes", "n_edges", "left_to_explore", "record_words")},
     }
     print(json.dumps(line), flush=True)
-    gpu.close()
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():
