@@ -183,3 +183,76 @@ def test_partitioned_phase_a_slices_compose(name, world):
         x = g.extensions()
         np.testing.assert_array_equal(x["explored"], o.explored_b[1:])
     assert total_calls == o.compare_calls
+
+
+def _decode(packed: np.ndarray, length: int) -> np.ndarray:
+    """reference byte layout (utils.cpp:96-119) -> base codes"""
+    bits = np.unpackbits(packed)
+    return (bits[0:2 * length:2] * 2 + bits[1:2 * length:2]).astype(np.uint8)
+
+
+def _check_edges_are_exact_overlaps(gpu, k, sample=3000, seed=5):
+    """Independent of the oracle: every sampled edge is an exact overlap of at least k bases of the kind its
+    type says (economyGraph.cpp:607-626), and its twin overhang is consistent (overlapGraph.cpp:147)."""
+    r, e = gpu.reads(), gpu.edges()
+    if len(e) == 0:
+        return 0
+    rng = np.random.default_rng(seed)
+    pick = rng.choice(len(e), size=min(sample, len(e)), replace=False)
+    off, ln = r["byte_off"].astype(np.int64), r["length"].astype(np.int64)
+    for x in e[pick]:
+        u, v, t, d = int(x["from"]) - 1, int(x["to"]) - 1, int(x["type"]), int(x["delta"])
+        lu, lv = int(ln[u]), int(ln[v])
+        ov = lv - d
+        assert k <= ov <= min(lu, lv), (x, ov)
+        uf = _decode(r["fwd"][off[u]:off[u + 1]], lu)
+        vs = _decode((r["rc"] if t in (1, 2) else r["fwd"])[off[v]:off[v + 1]], lv)
+        if t in (2, 3):       # v extends u to the right: prefix of v == suffix of u
+            assert np.array_equal(uf[lu - ov:], vs[:ov]), x
+        else:                 # v extends u to the left: suffix of v == prefix of u
+            assert np.array_equal(vs[lv - ov:], uf[:ov]), x
+        assert int(x["delta_twin"]) == lu - (lv - d)
+    return len(pick)
+
+
+@pytest.mark.parametrize("name", ["cfg3-40", "cfg3-60", "cfg3-90"])
+def test_cfg3_k_sweep_full_size(name):
+    """BASELINE config #3 (k = 40 / 60 / 90 on the cfg2 reads) at full size through size-independent properties."""
+    reads, k = _get(name)
+    b, off = synth.concat(reads)
+    gpu = api.Sage2Gpu(0)
+    gpu.run_steps123(b, off, k)
+    c = gpu.counters()
+    assert c["hash_len"] == min(k, 64) and c["good_reads"] == len(reads)
+    assert c["unique_reads"] == 2239082                      # k does not change the read set (all reads are longer than k)
+    assert c["window_probes"] == c["unique_reads"] * (150 - min(k, 64) + 1)
+    e = gpu.edges()
+    assert np.all(e["from"] < e["to"])
+    key = (e["from"].astype(np.uint64) << np.uint64(34)) | (e["to"].astype(np.uint64) << np.uint64(2)) | e["type"].astype(np.uint64)
+    assert np.all(np.diff(key.astype(np.int64)) > 0)
+    assert c["contained_ext"] + c["left_to_explore"] + c["contained_size"] == c["unique_reads"]
+    assert _check_edges_are_exact_overlaps(gpu, k) > 0
+
+
+def test_small_sets_edges_are_exact_overlaps():
+    for name in ("err", "varlen_err", "tandem", "hicopy"):
+        reads, k = _get(name)
+        b, off = synth.concat(reads)
+        gpu = api.Sage2Gpu(0)
+        gpu.run_steps123(b, off, k)
+        _check_edges_are_exact_overlaps(gpu, k, sample=1500)
+
+
+def test_streamed_upload_equals_one_shot():
+    reads, k = _get("mixed")
+    b, off = synth.concat(reads)
+    gpu = api.Sage2Gpu(0)
+    gpu.run_steps123(b, off, k)
+    e1, c1 = gpu.edges().copy(), gpu.counters()
+    gpu.load_reads_chunked(b, off, k, reads_per_chunk=3001)
+    gpu.build_hash_table()
+    gpu.build_overlap_graph()
+    c2 = gpu.counters()
+    np.testing.assert_array_equal(e1, gpu.edges())
+    for f in ("total_reads", "good_reads", "unique_reads", "total_bp", "compare_calls"):
+        assert c1[f] == c2[f], f
