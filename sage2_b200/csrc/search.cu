@@ -119,6 +119,30 @@ __device__ __forceinline__ bool t_overlap_equal(const u64 *X, int lenX, int star
     return acc == 0;
 }
 
+// The same test between two records in shared memory, restricted to t in [t0, ov) (bases before t0 are
+// known to agree): a real loop over the words that matter instead of SW predicated iterations.
+__device__ __forceinline__ bool overlap_equal_from(const u64 *X, int lenX, int start, const u64 *Y, int lenY, int t0)
+{
+    const int rem = lenX - start;
+    const int ov = lenY <= rem ? lenY : rem;
+    const int wb = ov >> 5;
+    const u64 bm = ~(~0ull >> ((ov & 31) * 2));
+    const unsigned s = (unsigned)(start & 31) * 2;
+    const bool upper = s >= 32;
+    const unsigned s5 = s & 31;
+    int w = t0 >> 5;
+    const u64 *Xp = X + (start >> 5) + w;
+    u64 acc = 0;
+    u64 a = Xp[0];
+    for (; w < wb; ++w) {
+        const u64 b = *++Xp;
+        acc |= funnel64(a, b, upper, s5) ^ Y[w];
+        a = b;
+    }
+    acc |= (funnel64(a, Xp[1], upper, s5) ^ Y[w]) & bm;       // w == wb (t0 <= ov)
+    return acc == 0;
+}
+
 // hashTableSearch (hashTable.cpp:193-231) on the sector index.  cnt == 0: absent (or masked).
 // `exact`: confirm every tag match by re-extracting the key from the bucket's first read (:203-220);
 // otherwise only masked keys are confirmed here and the caller proves the key in stage 2.
@@ -325,11 +349,13 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                         if (src >= 0) { prec = Qs + src * SWP; prevJ = pj; prevLen = plen; }
                         else if (right ? hasR : hasL) { prec = right ? prevR : prevL; prevJ = right ? fs.cJR : fs.cJL; prevLen = right ? fs.cLenR : fs.cLenL; }
                         if (prec) {
-                            bool c2, kb;
+                            // Both records agree with read i over its span (verified above), so only the bases past
+                            // read i's end can differ: right, Q[t] with t >= len1 - jj; left (records are oriented like
+                            // revcomp(read i)), prev[t] with t >= prevJ + h.
                             const u64 *mine = Qs + lane * SWP;
                             if (prevJ == jj) anomaly = true;                      // two hits of one side in one window
-                            else if (right) anomaly = !t_overlap_equal<SW>(prec, prevLen, jj - prevJ, mine, len2, 0ull, 0ull, c2, kb);   // :110-112
-                            else anomaly = !t_overlap_equal<SW>(mine, len2, jj - prevJ, prec, prevLen, 0ull, 0ull, c2, kb);             // :295-297
+                            else if (right) anomaly = !overlap_equal_from(prec, prevLen, jj - prevJ, mine, len2, len1 - jj);   // :110-112
+                            else anomaly = !overlap_equal_from(mine, len2, jj - prevJ, prec, prevLen, prevJ + P.h);           // :295-297
                         }
                     }
                     if (!__any_sync(FULL, anomaly)) {
