@@ -146,6 +146,7 @@ void sage2gpu_destroy(sage2gpu_ctx *ctx)
         c.d_bases.release(); c.d_offsets.release(); c.up_d_bases.release(); c.up_d_offsets.release(); c.raw.release(); c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
         c.slots.release(); c.entries.release(); c.extR.release(); c.extL.release(); c.flag5.release();
         c.cont_max.release(); c.explored.release(); c.edges.release();
+        c.arena.destroy();
     }
     cudaStreamSynchronize(st);
     if (ctx->c.up_event) cudaEventDestroy(ctx->c.up_event);
@@ -413,6 +414,7 @@ int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int gra
 {
     return guarded(ctx, [&](sg::Context &c) {
         SG_CHECK(gbps != nullptr, "null result pointer");
+        sg::ArenaScope arena_scope(c.arena, c.stream);
         *gbps = (double)sg::gather_bench(footprint_bytes, granule_bytes, n_loads, mode, c.stream);
     });
 }

@@ -28,6 +28,15 @@ struct Timers {   // milliseconds, CUDA events on the context stream
 };
 
 struct Context {
+    Context()
+    {
+        // everything a context keeps between stages is persistent; stage-local temporaries use `arena`
+        d_bases.persistent = d_offsets.persistent = up_d_bases.persistent = up_d_offsets.persistent = true;
+        raw.persistent = F.persistent = RC.persistent = len.persistent = freq.persistent = true;
+        slots.persistent = entries.persistent = true;
+        extR.persistent = extL.persistent = flag5.persistent = cont_max.persistent = explored.persistent = edges.persistent = true;
+    }
+    Arena arena;
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string last_error;

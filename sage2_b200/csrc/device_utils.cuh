@@ -4,8 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace sg {
 
@@ -30,35 +32,106 @@ struct CudaError : public std::runtime_error {
                                          std::to_string(__LINE__));                             \
     } while (0)
 
-// Stream-ordered device buffer (cudaMallocAsync pool: after warm-up an allocation is a pointer bump).
+// Workspace arena: the temporaries of one stage are bump-allocated from a few large grow-only blocks and the
+// arena is rewound when the stage ends.  (Cycling hundreds of MB .. GB of temporaries through the stream-ordered
+// pool every call made cudaMallocAsync map fresh memory at unpredictable times: stalls of 0.1 - 5 s at 33 M reads.)
+struct Arena {
+    struct Block { char *p; size_t cap; };
+    std::vector<Block> blocks;
+    size_t used = 0;            // bytes taken from the last block
+    size_t peak = 0;            // high-water mark of the current scope over all blocks
+    static size_t round(size_t b) { return (b + 255) & ~(size_t)255; }
+    size_t total() const { size_t t = 0; for (const Block &b : blocks) t += b.cap; return t; }
+    void *take(size_t bytes)
+    {
+        bytes = round(bytes ? bytes : 1);
+        if (blocks.empty() || used + bytes > blocks.back().cap) {
+            size_t cap = std::max<size_t>(bytes, std::max<size_t>((size_t)64 << 20, total() / 2));
+            char *p = nullptr;
+            SG_CUDA(cudaMalloc((void **)&p, cap));
+            blocks.push_back(Block{ p, cap });
+            used = 0;
+        }
+        void *r = blocks.back().p + used;
+        used += bytes;
+        return r;
+    }
+    void give_back(void *p, size_t bytes)      // only the most recent allocation is really returned
+    {
+        bytes = round(bytes ? bytes : 1);
+        if (!blocks.empty() && (char *)p + bytes == blocks.back().p + used) used -= bytes;
+    }
+    // end of a stage: rewind; several blocks (growth during this stage) are merged into one
+    void reset(cudaStream_t st)
+    {
+        if (blocks.size() > 1) {
+            const size_t want = total() + total() / 4;
+            cudaStreamSynchronize(st);
+            for (Block &b : blocks) cudaFree(b.p);
+            blocks.clear();
+            char *p = nullptr;
+            if (cudaMalloc((void **)&p, want) == cudaSuccess) blocks.push_back(Block{ p, want });
+            else cudaGetLastError();
+        }
+        used = 0;
+    }
+    void destroy()
+    {
+        for (Block &b : blocks) cudaFree(b.p);
+        blocks.clear();
+        used = 0;
+    }
+};
+
+inline Arena *&current_arena() { static thread_local Arena *a = nullptr; return a; }
+
+struct ArenaScope {
+    Arena *prev;
+    Arena &a;
+    cudaStream_t st;
+    ArenaScope(Arena &arena, cudaStream_t s) : prev(current_arena()), a(arena), st(s) { current_arena() = &a; }
+    ~ArenaScope() { current_arena() = prev; if (!prev) a.reset(st); }
+};
+
+// Device buffer.  Long-lived buffers of a context (`persistent`) come from the stream-ordered pool and are
+// grow-only; everything else comes from the arena of the running stage.
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0, cap = 0;      // n = elements in use, cap = elements allocated
     cudaStream_t s = nullptr;
+    bool persistent = false, from_arena = false;
     DevBuf() {}
     DevBuf(size_t count, cudaStream_t st) { alloc(count, st); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap), s(o.s) { o.p = nullptr; o.n = 0; o.cap = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap), s(o.s), persistent(o.persistent), from_arena(o.from_arena) { o.p = nullptr; o.n = 0; o.cap = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept
     {
-        if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; s = o.s; o.p = nullptr; o.n = 0; o.cap = 0; }
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; cap = o.cap; s = o.s; from_arena = o.from_arena;      // `persistent` is a property of the holder
+            o.p = nullptr; o.n = 0; o.cap = 0;
+        }
         return *this;
     }
     ~DevBuf() { release(); }
-    // Grow-only: a buffer that is already large enough is kept (the long-lived buffers of a context are
-    // re-used run after run instead of cycling hundreds of MB through the pool).  Contents are undefined.
+    // Contents are undefined.  A persistent buffer that is already large enough is kept.
     void alloc(size_t count, cudaStream_t st)
     {
-        if (p && cap >= count && s == st) { n = count; return; }
+        if (p && !from_arena && cap >= count && s == st) { n = count; return; }
         release();
         s = st; n = count; cap = count ? count : 1;
-        SG_CUDA(cudaMallocAsync((void **)&p, cap * sizeof(T), st));
+        Arena *a = persistent ? nullptr : current_arena();
+        if (a) { p = (T *)a->take(cap * sizeof(T)); from_arena = true; }
+        else { SG_CUDA(cudaMallocAsync((void **)&p, cap * sizeof(T), st)); from_arena = false; }
     }
     void release()
     {
-        if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; cap = 0; }
+        if (!p) return;
+        if (from_arena) { if (Arena *a = current_arena()) a->give_back(p, cap * sizeof(T)); }
+        else cudaFreeAsync(p, s);
+        p = nullptr; n = 0; cap = 0; from_arena = false;
     }
     size_t bytes() const { return n * sizeof(T); }
 };

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) gather_len_kernel(const u32 *__restrict__
 void stage_phase_b(Context &c)
 {
     cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
     const u64 U = c.cnt.unique_reads;
     c.explored.alloc(U, st);
     c.edges.alloc(4 * U + 2, st);
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(256) join_edges_kernel(const u64 *__restrict__
 void stage_phase_c_and_finalize(Context &c)
 {
     cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
     const u64 U = c.cnt.unique_reads;
     c.cnt.candidates_c = c.cnt.edges_inserted_c = c.cnt.transitive_removed = 0;
     c.cnt.n_edges = 0;

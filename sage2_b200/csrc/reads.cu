@@ -110,7 +110,9 @@ static void grow(DevBuf<T> &b, size_t used, size_t need, cudaStream_t st)
     if (need <= b.n) return;
     size_t cap = b.n ? b.n : (size_t)1 << 20;
     while (cap < need) cap += cap / 2 + 1;
-    DevBuf<T> nb(cap, st);
+    DevBuf<T> nb;
+    nb.persistent = true;       // moved into a context member below
+    nb.alloc(cap, st);
     if (used) SG_CUDA(cudaMemcpyAsync(nb.p, b.p, used * sizeof(T), cudaMemcpyDeviceToDevice, st));
     b = std::move(nb);
 }
@@ -118,6 +120,7 @@ static void grow(DevBuf<T> &b, size_t used, size_t need, cudaStream_t st)
 void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads)
 {
     cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
     const int64_t first = offsets[0], nb = offsets[n_reads] - first;
     SG_CHECK(nb >= 0, "offsets must be non-decreasing");
     SG_CHECK(c.up_reads + (u64)n_reads < 0x3FFFFFFFull, "at most 2^30-1 reads per context");
@@ -135,6 +138,7 @@ void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets
 void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident)
 {
     cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
     SG_CHECK(n_reads >= 0, "negative read count");
     SG_CHECK((u64)n_reads < 0x3FFFFFFFull, "at most 2^30-1 reads per context");
     c.n_input = (u64)n_reads;
@@ -299,6 +303,7 @@ __global__ void __launch_bounds__(256) tie_fix_kernel(const u64 *__restrict__ re
 void stage_organize_reads(Context &c)
 {
     cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
     const u64 n = c.n_input, n_good = c.cnt.good_reads;
     const int SW = c.SW;
     c.cnt.unique_reads = 0;

@@ -611,6 +611,7 @@ static SearchParams make_params(const Context &c)
 void stage_phase_a(Context &c, int rank, int world)
 {
     cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
     SG_CHECK(c.have_table, "build_hash_table must run before the overlap search");
     SG_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
     const u64 U = c.cnt.unique_reads;

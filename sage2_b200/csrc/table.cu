@@ -132,6 +132,7 @@ static unsigned big_grid(u64 n, unsigned block = 256)
 void stage_build_table(Context &c)
 {
     cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
     SG_CHECK(c.have_reads, "organize_reads must run before build_hash_table");
     const u64 U = c.cnt.unique_reads;
     const int SW = c.SW, h = c.h;
