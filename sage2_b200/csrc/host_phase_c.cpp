@@ -13,12 +13,12 @@
 
 #include <algorithm>
 #include <chrono>
-#include <unordered_map>
 
 namespace sg {
 namespace {
 
-struct HEdge { uint32_t id; uint8_t type, mark; uint32_t length; };
+struct HEdge { uint32_t id; uint32_t node; uint8_t type, mark; uint32_t length; };     // node = local index of `id`, kNone if not in play
+constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 inline uint32_t rev_type(uint32_t t) { return t == 0 ? 3u : (t == 3 ? 0u : t); }
 
@@ -30,9 +30,35 @@ inline bool by_length_desc(const HEdge &a, const HEdge &b)
     return a.type > b.type;
 }
 
+// read id -> local node index: open addressing on a power-of-two table (the walk does millions of lookups)
+struct IdMap {
+    std::vector<uint32_t> key, val;
+    uint32_t mask = 0;
+    void init(size_t expected)
+    {
+        size_t cap = 64;
+        while (cap < 2 * expected + 16) cap <<= 1;
+        key.assign(cap, 0); val.assign(cap, 0);
+        mask = (uint32_t)(cap - 1);
+    }
+    static uint32_t h(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+    uint32_t find(uint32_t id) const      // ids are >= 1; 0 marks an empty slot
+    {
+        for (uint32_t s = h(id) & mask;; s = (s + 1) & mask) {
+            if (key[s] == id) return val[s];
+            if (key[s] == 0) return kNone;
+        }
+    }
+    void put(uint32_t id, uint32_t v)
+    {
+        for (uint32_t s = h(id) & mask;; s = (s + 1) & mask)
+            if (key[s] == 0) { key[s] = id; val[s] = v; return; }
+    }
+};
+
 struct Walk {
     const PhaseCInput &in;
-    std::unordered_map<uint32_t, uint32_t> slot;   // read id (1-based) -> local node
+    IdMap slot;                                    // read id (1-based) -> local node
     std::vector<std::vector<HEdge>> adj;
     std::vector<uint8_t> state;                    // 0/1/2 for S nodes, 4 for everything else
     std::vector<uint8_t> marked;
@@ -43,10 +69,10 @@ struct Walk {
 
     uint32_t node(uint32_t id, uint8_t st, uint32_t len)
     {
-        auto it = slot.find(id);
-        if (it != slot.end()) return it->second;
+        const uint32_t f = slot.find(id);
+        if (f != kNone) return f;
         const uint32_t n = (uint32_t)adj.size();
-        slot.emplace(id, n);
+        slot.put(id, n);
         adj.emplace_back();
         state.push_back(st);
         marked.push_back(0);
@@ -61,8 +87,8 @@ struct Walk {
         const uint32_t u = node_id[nu], v = node_id[nv];
         const uint32_t lu = node_len[nu], lv = node_len[nv];
         const uint32_t delta2 = lu - (lv - delta);
-        adj[nu].push_back(HEdge{ v, (uint8_t)type, 0, delta & 0xFFFFFu });
-        adj[nv].push_back(HEdge{ u, (uint8_t)rev_type(type), 0, delta2 & 0xFFFFFu });
+        adj[nu].push_back(HEdge{ v, nv, (uint8_t)type, 0, delta & 0xFFFFFu });
+        adj[nv].push_back(HEdge{ u, nu, (uint8_t)rev_type(type), 0, delta2 & 0xFFFFFu });
     }
 
     // insertAllEdgesOfRead, economyGraph.cpp:580-638
@@ -74,8 +100,7 @@ struct Walk {
         uint64_t cnt = 0;
         for (uint32_t q = in.cand_off[s]; q < in.cand_off[s + 1]; ++q) {
             const uint64_t cw = in.cand[q];
-            const uint32_t read2 = (uint32_t)(cw >> 32);
-            const uint32_t n2 = slot.find(read2)->second;
+            const uint32_t n2 = slot.find((uint32_t)(cw >> 32));
             if (state[n2] != 0) continue;                                   // :605
             uint32_t delta = (uint32_t)(cw & 0xFFFFFu);
             if (delta & 0x80000u) delta |= 0xFFF00000u;                     // sign-extend the int32 overhang
@@ -90,22 +115,21 @@ struct Walk {
     void mark_transitive(uint32_t nf)
     {
         std::vector<HEdge> &lf = adj[nf];
-        for (auto &e : lf) marked[slot.find(e.id)->second] = 1;
+        for (auto &e : lf) marked[e.node] = 1;
         for (auto &e : lf) {
-            const uint32_t na = slot.find(e.id)->second;
+            const uint32_t na = e.node;
             if (marked[na] != 1) continue;
             for (auto &f : adj[na]) {
-                auto itb = slot.find(f.id);
-                if (itb == slot.end()) continue;      // not adjacent to any S read: cannot be in play
-                const uint32_t nb = itb->second;
+                const uint32_t nb = f.node;
+                if (nb == kNone) continue;            // not adjacent to any S read: cannot be in play
                 if (marked[nb] != 1) continue;
                 const uint32_t t1 = e.type, t2 = f.type;
                 if ((t1 == 0 || t1 == 2) && (t2 == 0 || t2 == 1)) marked[nb] = 2;
                 else if ((t1 == 1 || t1 == 3) && (t2 == 2 || t2 == 3)) marked[nb] = 2;
             }
         }
-        for (auto &e : lf) if (marked[slot.find(e.id)->second] == 2) e.mark = 1;
-        for (auto &e : lf) marked[slot.find(e.id)->second] = 0;
+        for (auto &e : lf) if (marked[e.node] == 2) e.mark = 1;
+        for (auto &e : lf) marked[e.node] = 0;
         marked[nf] = 0;
         state[nf] = 2;
     }
@@ -127,28 +151,28 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
 {
     const auto t0 = std::chrono::steady_clock::now();
     Walk w(in);
-    w.slot.reserve(in.nS * 4 + 16);
+    w.slot.init(in.nS + 2 * in.nB);
     for (uint64_t s = 0; s < in.nS; ++s) w.node(in.s_ids[s] + 1, 0, in.s_len[s]);
     const uint32_t nS = (uint32_t)in.nS;
 
     // phase-B neighbours of S, then every phase-B entry of every needed node
     for (uint64_t e = 0; e < in.nB; ++e) {
         const uint32_t a = (uint32_t)(in.edgesB[2 * e] >> 32), b = (uint32_t)in.edgesB[2 * e];
-        const auto ia = w.slot.find(a), ib = w.slot.find(b);
-        const bool a_in_s = ia != w.slot.end() && ia->second < nS;
-        const bool b_in_s = ib != w.slot.end() && ib->second < nS;
-        if (a_in_s && ib == w.slot.end()) w.node(b, 4, in.edgesB_len[e] >> 16);
-        if (b_in_s && ia == w.slot.end()) w.node(a, 4, in.edgesB_len[e] & 0xFFFFu);
+        const uint32_t ia = w.slot.find(a), ib = w.slot.find(b);
+        const bool a_in_s = ia != kNone && ia < nS;
+        const bool b_in_s = ib != kNone && ib < nS;
+        if (a_in_s && ib == kNone) w.node(b, 4, in.edgesB_len[e] >> 16);
+        if (b_in_s && ia == kNone) w.node(a, 4, in.edgesB_len[e] & 0xFFFFu);
     }
     for (uint64_t e = 0; e < in.nB; ++e) {
         const uint64_t w0 = in.edgesB[2 * e], w1 = in.edgesB[2 * e + 1];
         const uint32_t a = (uint32_t)(w0 >> 32), b = (uint32_t)w0;
         const uint32_t type = (uint32_t)(w1 >> 20) & 3u, length = (uint32_t)(w1 & 0xFFFFFu);
-        const auto ia = w.slot.find(a), ib = w.slot.find(b);
-        if (ia != w.slot.end()) w.adj[ia->second].push_back(HEdge{ b, (uint8_t)type, 0, length });
-        if (ib != w.slot.end()) {
+        const uint32_t ia = w.slot.find(a), ib = w.slot.find(b);
+        if (ia != kNone) w.adj[ia].push_back(HEdge{ b, ib, (uint8_t)type, 0, length });
+        if (ib != kNone) {
             const uint32_t la = in.edgesB_len[e] & 0xFFFFu, lb = in.edgesB_len[e] >> 16;
-            w.adj[ib->second].push_back(HEdge{ a, (uint8_t)rev_type(type), 0, (la - (lb - length)) & 0xFFFFFu });
+            w.adj[ib].push_back(HEdge{ a, ia, (uint8_t)rev_type(type), 0, (la - (lb - length)) & 0xFFFFFu });
         }
     }
 
@@ -166,17 +190,17 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
             if (w.adj[n1].empty()) continue;                                 // :525
             if (w.state[n1] == 1) {
                 for (size_t x = 0; x < w.adj[n1].size(); ++x) {
-                    const uint32_t n2 = w.slot.find(w.adj[n1][x].id)->second;
+                    const uint32_t n2 = w.adj[n1][x].node;
                     if (w.state[n2] == 0) { queue.push_back(n2); w.insert_all(n2); }
                 }
                 w.mark_transitive(n1);
             }
             if (w.state[n1] == 2) {
                 for (size_t x = 0; x < w.adj[n1].size(); ++x) {
-                    const uint32_t n2 = w.slot.find(w.adj[n1][x].id)->second;
+                    const uint32_t n2 = w.adj[n1][x].node;
                     if (w.state[n2] != 1) continue;
                     for (size_t y = 0; y < w.adj[n2].size(); ++y) {
-                        const uint32_t n3 = w.slot.find(w.adj[n2][y].id)->second;
+                        const uint32_t n3 = w.adj[n2][y].node;
                         if (w.state[n3] == 0) { queue.push_back(n3); w.insert_all(n3); }
                     }
                     w.mark_transitive(n2);
