@@ -159,6 +159,23 @@ __global__ void __launch_bounds__(256) split_edges_kernel(const u64 *__restrict_
         if (!flag || flag[e]) { const u64 p = flag ? idx[e] : e; w0[p] = edges[2 * e]; w1[p] = edges[2 * e + 1]; }
 }
 
+// runs of equal w0 = (from, to): sort the w1 = type << 20 | overhang words ascending (compareIdBased ties)
+__global__ void __launch_bounds__(256) order_pair_runs_kernel(const u64 *__restrict__ w0, u64 *__restrict__ w1, u64 n)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = w0[i];
+        if ((i > 0 && w0[i - 1] == k) || i + 1 >= n || w0[i + 1] != k) continue;      // not the head of a run of >= 2
+        u64 e = i + 2;
+        while (e < n && w0[e] == k) ++e;
+        for (u64 a = i + 1; a < e; ++a) {
+            const u64 x = w1[a];
+            u64 b = a;
+            while (b > i && w1[b - 1] > x) { w1[b] = w1[b - 1]; --b; }
+            w1[b] = x;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) flag_first_edge_kernel(const u64 *__restrict__ w0, const u64 *__restrict__ w1, u64 n, u32 *__restrict__ flag)
 {
     for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x)
@@ -303,9 +320,12 @@ void stage_phase_c_and_finalize(Context &c)
     // stable LSD passes, least significant field first; the bit ranges are known, no reduction / host round trip
     int id_bits = 1;
     while ((U >> id_bits) != 0) ++id_bits;                   // ids are 1..U
-    cur = radix_sort_bits(cols, cur, nAll, true, 0, 22, st);                 // w1: type << 20 | overhang
     cur = radix_sort_bits(cols, cur, nAll, false, 0, id_bits, st);           // w0: to
     cur = radix_sort_bits(cols, cur, nAll, false, 32, 32 + id_bits, st);     // w0: from
+    // several edges between one pair of reads are rare (tandem repeats, palindromes): order their
+    // (type, overhang) words in place instead of spending three more passes on every edge
+    order_pair_runs_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll);
+    SG_LAUNCHED();
     DevBuf<u32> fflag(nAll, st), fidx(nAll, st), d_ne(1, st);
     flag_first_edge_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll, fflag.p);
     SG_LAUNCHED();

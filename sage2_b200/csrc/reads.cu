@@ -198,9 +198,9 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: sort a permutation of the good reads by record (= Read::operator<), dedupe.  Eight stable 8-bit radix
-// passes on the first record word (32 bases) + an in-place fix of the short runs of equal first words by
-// the remaining words; inputs with very long runs fall back to LSD passes over every word.
+// K2: sort a permutation of the good reads by record (= Read::operator<), dedupe.  Six stable 8-bit radix
+// passes on the first 24 bases + an in-place fix of the short runs of equal 24-base prefixes by whole-record
+// compares; inputs with very long runs fall back to LSD passes over every word.
 // ------------------------------------------------------------------------------------------------
 __global__ void iota_kernel(u32 *v, u64 n)
 {
@@ -272,29 +272,30 @@ __global__ void compact_good_kernel(const u64 *__restrict__ rec, const u32 *__re
         if (flag[i]) { key[idx[i]] = rec[i * SW]; val[idx[i]] = (u32)i; }
 }
 
-// After the sort by the first word (32 bases): order every run of equal first words by the remaining words.
+// After the sort by the first 24 bases: order every run of equal 24-base prefixes by the whole records.
 // Runs are short (duplicate reads, shared 32-mers); a run longer than kTieLimit raises `overflow` and the
 // caller falls back to the full word-by-word LSD sort.
 constexpr int kTieLimit = 512;
-__device__ __forceinline__ bool rec_less_tail(const u64 *a, const u64 *b, int SW)
+constexpr int kSortSkipBits = 16;     // the radix passes cover the top 48 bits (24 bases) of the first word
+__device__ __forceinline__ bool rec_less(const u64 *a, const u64 *b, int SW)
 {
-    for (int w = 1; w < SW; ++w) { const u64 x = a[w], y = b[w]; if (x != y) return x < y; }
+    for (int w = 0; w < SW; ++w) { const u64 x = a[w], y = b[w]; if (x != y) return x < y; }
     return false;
 }
 __global__ void __launch_bounds__(256) tie_fix_kernel(const u64 *__restrict__ rec, const u64 *__restrict__ key, u32 *__restrict__ perm, u64 n, int SW,
                                                         u32 *__restrict__ overflow)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        const u64 k = key[i];
-        if ((i > 0 && key[i - 1] == k) || i + 1 >= n || key[i + 1] != k) continue;      // not the head of a run of >= 2
+        const u64 k = key[i] >> kSortSkipBits;
+        if ((i > 0 && (key[i - 1] >> kSortSkipBits) == k) || i + 1 >= n || (key[i + 1] >> kSortSkipBits) != k) continue;      // not the head of a run of >= 2
         u64 e = i + 2;
-        while (e < n && key[e] == k && e - i <= (u64)kTieLimit) ++e;
+        while (e < n && (key[e] >> kSortSkipBits) == k && e - i <= (u64)kTieLimit) ++e;
         if (e - i > (u64)kTieLimit) { *overflow = 1u; continue; }
         for (u64 a = i + 1; a < e; ++a) {
             const u32 x = perm[a];
             const u64 *rx = rec + (u64)x * SW;
             u64 b = a;
-            while (b > i && rec_less_tail(rx, rec + (u64)perm[b - 1] * SW, SW)) { perm[b] = perm[b - 1]; --b; }
+            while (b > i && rec_less(rx, rec + (u64)perm[b - 1] * SW, SW)) { perm[b] = perm[b - 1]; --b; }
             perm[b] = x;
         }
     }
@@ -325,10 +326,10 @@ void stage_organize_reads(Context &c)
     }
     SortCols cols;
     cols.a[0] = ka.p; cols.a[1] = kb.p; cols.b[0] = cols.b[1] = nullptr; cols.v[0] = va.p; cols.v[1] = vb.p;
-    int cur = radix_sort_bits(cols, 0, n_good, false, 0, 64, st);      // 8 passes on the first 32 bases
+    int cur = radix_sort_bits(cols, 0, n_good, false, kSortSkipBits, 64, st);      // 6 passes on the first 24 bases
     DevBuf<u32> d_flags(2, st);          // [0] tie-run overflow, [1] unique count
     SG_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(u32), st));
-    if (SW > 1) {
+    {
         tie_fix_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, cols.a[cur], cols.v[cur], n_good, SW, d_flags.p);
         SG_LAUNCHED();
     }
