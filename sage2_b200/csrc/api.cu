@@ -425,25 +425,12 @@ int sage2gpu_write_reads(sage2gpu_ctx *ctx, const char *path)
 {
     int io = 0;
     int rc = guarded(ctx, [&](sg::Context &c) {
-        HostReads h;
-        fetch_reads(c, h);
+        SG_CHECK(c.have_reads, "no reads loaded");
         FILE *f = fopen(path, "wb");
         if (!f) { io = 1; return; }
-        static const char T[4] = { 'A', 'C', 'G', 'T' };
-        const sg::u64 U = c.cnt.unique_reads;
-        fprintf(f, "%llu\n", (unsigned long long)U);
-        std::vector<char> line(2 * (size_t)(32 * c.SW) + 64);
-        for (sg::u64 i = 0; i < U; ++i) {
-            const int len = h.len[i];
-            int n = snprintf(line.data(), 64, "%u\t%u\t", (unsigned)h.freq[i], (unsigned)len);
-            for (int s = 0; s < 2; ++s) {
-                const sg::u64 *rec = (s ? h.RC.data() : h.F.data()) + i * c.SWS;
-                for (int p = 0; p < len; ++p) line[n++] = T[(rec[p >> 5] >> (62 - 2 * (p & 31))) & 3];
-                line[n++] = s ? '\n' : '\t';
-            }
-            fwrite(line.data(), 1, (size_t)n, f);
-        }
-        if (fclose(f) != 0) io = 1;
+        bool ok = false;
+        try { ok = sg::write_reads_text(c, f); } catch (...) { fclose(f); throw; }
+        if (fclose(f) != 0 || !ok) io = 1;
     });
     if (rc == 0 && io) { ctx->c.last_error = std::string("cannot write ") + path; return SAGE2GPU_ERR_IO; }
     return rc;
@@ -453,26 +440,12 @@ int sage2gpu_write_graph3(sage2gpu_ctx *ctx, const char *path)
 {
     int io = 0;
     int rc = guarded(ctx, [&](sg::Context &c) {
-        fetch_edges(c);
-        std::vector<uint16_t> len(c.cnt.unique_reads);
-        if (!len.empty()) {
-            SG_CUDA(cudaMemcpyAsync(len.data(), c.len.p, len.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
-            SG_CUDA(cudaStreamSynchronize(c.stream));
-        }
+        SG_CHECK(c.have_graph, "overlap graph not built");
         FILE *f = fopen(path, "wb");
         if (!f) { io = 1; return; }
-        // genomeSize (0 before step 5), numberOfReads, averageReadLength: overlapGraph.cpp:348-351
-        fprintf(f, "0\n%llu\n%llu\n", (unsigned long long)c.cnt.good_reads, (unsigned long long)c.cnt.avg_len);
-        const sg::u64 E = c.cnt.n_edges;
-        for (sg::u64 e = 0; e < E; ++e) {
-            const sg::u64 w0 = c.h_edges[2 * e], w1 = c.h_edges[2 * e + 1];
-            const unsigned long long a = w0 >> 32, b = w0 & 0xFFFFFFFFull;
-            const uint32_t type = (uint32_t)(w1 >> 20) & 3u, d = (uint32_t)(w1 & 0xFFFFFu);
-            const uint32_t dt = (uint32_t)len[a - 1] - ((uint32_t)len[b - 1] - d);
-            fprintf(f, "%llu\t%llu\t%u\t1\t%u\t0\t0\n\n%llu\t%llu\t%u\t1\t%u\t0\t0\n\n", a, b, type, d, b, a,
-                    sg::reverse_edge_type(type), dt);
-        }
-        if (fclose(f) != 0) io = 1;
+        bool ok = false;
+        try { ok = sg::write_graph3_text(c, f); } catch (...) { fclose(f); throw; }
+        if (fclose(f) != 0 || !ok) io = 1;
     });
     if (rc == 0 && io) { ctx->c.last_error = std::string("cannot write ") + path; return SAGE2GPU_ERR_IO; }
     return rc;

@@ -1,5 +1,6 @@
 // context.h -- device-resident state of one libsage2gpu context (one GPU, one stream).
 #pragma once
+#include <stdio.h>
 #include <string>
 #include <vector>
 #include "core.cuh"
@@ -88,5 +89,8 @@ void stage_build_table(Context &c);
 void stage_phase_a(Context &c, int rank = 0, int world = 1);   // rank's slice of the reads; arrays padded to world * chunk
 void stage_phase_b(Context &c);
 void stage_phase_c_and_finalize(Context &c);
+// device-side text formatters of the reference's -s files (format.cu); false = short write
+bool write_reads_text(Context &c, FILE *f);
+bool write_graph3_text(Context &c, FILE *f);
 
 }  // namespace sg
