@@ -24,7 +24,8 @@ extern "C" {
 
 typedef struct sage2gpu_ctx sage2gpu_ctx;
 
-enum { SAGE2GPU_OK = 0, SAGE2GPU_ERR_CUDA = 1, SAGE2GPU_ERR_ARG = 2, SAGE2GPU_ERR_STATE = 3, SAGE2GPU_ERR_IO = 4 };
+enum { SAGE2GPU_OK = 0, SAGE2GPU_ERR_CUDA = 1, SAGE2GPU_ERR_ARG = 2, SAGE2GPU_ERR_STATE = 3, SAGE2GPU_ERR_IO = 4,
+       SAGE2GPU_ERR_FORMAT = 5 /* sage2gpu_load_append_text: not the regular 4-line FASTQ / 2-line FASTA layout */ };
 
 /* Log counters of the reference (readLoader.cpp:164-169,257; hashTable.cpp:86,124;
  * economyGraph.cpp:485-487,569-571) plus the workload sizes the roofline needs. */
@@ -79,6 +80,20 @@ int sage2gpu_load_reads_device(sage2gpu_ctx *ctx, const uint8_t *d_bases, const 
 int sage2gpu_load_begin(sage2gpu_ctx *ctx, int min_overlap);
 int sage2gpu_load_append(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads);
 int sage2gpu_load_finish(sage2gpu_ctx *ctx);
+/* The same with the record splitting on the device (replaces the per-record work of FastAQReader::getNextRead,
+ * fastAQReader.cpp:16-45, for regular files): `text` is a piece of a FASTA / FASTQ file (already inflated if it was
+ * gzip) that starts at a record boundary.  Every complete record in it (at most max_records) is appended;
+ * *consumed tells how many bytes they took -- the caller prepends the rest to the next piece; is_final marks
+ * the last piece.  *marker is 0 before the first piece of a file and carries '@' / '>' afterwards.  Returns
+ * SAGE2GPU_ERR_FORMAT, with nothing appended, when the piece is not in the regular 4-line FASTQ / 2-line
+ * FASTA layout (multi-line records, blank lines, empty sequences, a truncated tail ...): the caller then
+ * parses that text sequentially and uses sage2gpu_load_append.  The buffer may be reused on return. */
+int sage2gpu_load_append_text(sage2gpu_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int is_final, int *marker,
+                              uint64_t max_records, uint64_t *consumed, uint64_t *n_records);
+/* Reads appended since sage2gpu_load_begin; removal of the appended reads [first, first + count) (the reference
+ * stops a two-file data set when the shorter mate file ends, inputReader.cpp:26-49). */
+int sage2gpu_load_count(sage2gpu_ctx *ctx, uint64_t *n_reads);
+int sage2gpu_load_remove(sage2gpu_ctx *ctx, uint64_t first, uint64_t count);
 /* Page-locked host memory for the buffers above (plain malloc'ed memory works too, synchronously). */
 void *sage2gpu_host_alloc(uint64_t n_bytes);
 void sage2gpu_host_free(void *p);

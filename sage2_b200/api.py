@@ -41,7 +41,8 @@ EDGE_DT = np.dtype([("from", "<u8"), ("to", "<u8"), ("type", "<u4"), ("delta", "
                     ("delta_twin", "<u4"), ("reserved", "<u4")])
 
 EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2gpu_load_reads",
-           "sage2gpu_load_begin", "sage2gpu_load_append", "sage2gpu_load_finish", "sage2gpu_host_alloc", "sage2gpu_host_free",
+           "sage2gpu_load_begin", "sage2gpu_load_append", "sage2gpu_load_append_text", "sage2gpu_load_count", "sage2gpu_load_remove",
+           "sage2gpu_load_finish", "sage2gpu_host_alloc", "sage2gpu_host_free",
            "sage2gpu_load_reads_device", "sage2gpu_build_hash_table", "sage2gpu_build_overlap_graph",
            "sage2gpu_phase_a_partition", "sage2gpu_phase_a_buffers", "sage2gpu_finish_graph",
            "sage2gpu_run_steps123", "sage2gpu_get_counters", "sage2gpu_get_timers", "sage2gpu_reads_bytes",
@@ -76,6 +77,9 @@ def load_library():
         lib.sage2gpu_load_reads_device.argtypes = [vp, vp, vp, i64, C.c_int]
         lib.sage2gpu_load_begin.argtypes = [vp, C.c_int]
         lib.sage2gpu_load_append.argtypes = [vp, vp, vp, i64]
+        lib.sage2gpu_load_append_text.argtypes = [vp, vp, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.c_uint64, u64p, u64p]
+        lib.sage2gpu_load_count.argtypes = [vp, u64p]
+        lib.sage2gpu_load_remove.argtypes = [vp, C.c_uint64, C.c_uint64]
         lib.sage2gpu_load_finish.argtypes = [vp]
         lib.sage2gpu_host_alloc.argtypes = [C.c_uint64]
         lib.sage2gpu_host_alloc.restype = vp

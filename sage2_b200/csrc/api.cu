@@ -191,6 +191,39 @@ int sage2gpu_load_append(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t 
     });
 }
 
+int sage2gpu_load_append_text(sage2gpu_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int is_final, int *marker,
+                              uint64_t max_records, uint64_t *consumed, uint64_t *n_records)
+{
+    bool regular = true;
+    int rc = guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.up_open, "sage2gpu_load_begin must be called first");
+        SG_CHECK(marker && consumed && n_records && (n_bytes == 0 || text), "null argument");
+        SG_CUDA(cudaEventSynchronize(c.up_event));
+        sg::u64 used = 0, nrec = 0;
+        regular = sg::stage_parse_text_chunk(c, text, n_bytes, is_final != 0, *marker, max_records, used, nrec);
+        *consumed = used; *n_records = nrec;
+    });
+    if (rc == 0 && !regular) { ctx->c.last_error = "text is not in the regular 4-line FASTQ / 2-line FASTA layout"; return SAGE2GPU_ERR_FORMAT; }
+    return rc;
+}
+
+int sage2gpu_load_count(sage2gpu_ctx *ctx, uint64_t *n_reads)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.up_open && n_reads, "sage2gpu_load_begin must be called first");
+        *n_reads = c.up_reads;
+    });
+}
+
+int sage2gpu_load_remove(sage2gpu_ctx *ctx, uint64_t first, uint64_t count)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.up_open, "sage2gpu_load_begin must be called first");
+        SG_CUDA(cudaEventSynchronize(c.up_event));
+        sg::stage_remove_uploaded(c, first, count);
+    });
+}
+
 int sage2gpu_load_finish(sage2gpu_ctx *ctx)
 {
     return guarded(ctx, [&](sg::Context &c) {

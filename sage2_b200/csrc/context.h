@@ -84,6 +84,9 @@ struct Context {
 // stages (each throws sg::CudaError)
 void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident);
 void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads);
+// parse.cu: record splitting of raw FASTA/FASTQ text on the device; false = irregular layout, nothing appended
+bool stage_parse_text_chunk(Context &c, const uint8_t *text, u64 n_bytes, bool final, int &marker, u64 max_records, u64 &consumed, u64 &n_records);
+void stage_remove_uploaded(Context &c, u64 first, u64 count);
 void stage_organize_reads(Context &c);
 void stage_build_table(Context &c);
 void stage_phase_a(Context &c, int rank = 0, int world = 1);   // rank's slice of the reads; arrays padded to world * chunk

@@ -1,6 +1,7 @@
 // fastaq.cpp -- see fastaq.h.
 #include "fastaq.h"
 
+#include <string.h>
 #include <zlib.h>
 #include <stdexcept>
 
@@ -11,6 +12,12 @@ FastAQStream::FastAQStream(const std::string &path) : buf_(1 << 20)
     gz_ = gzopen(path.c_str(), "r");
     if (!gz_) throw std::runtime_error("cannot open " + path);
     gzbuffer((gzFile)gz_, 1 << 20);
+}
+
+FastAQStream::FastAQStream(void *gz_handle, const uint8_t *pending, size_t n) : gz_(gz_handle), buf_(n > ((size_t)1 << 20) ? n : (size_t)1 << 20)
+{
+    if (n) memcpy(buf_.data(), pending, n);
+    pos_ = 0; end_ = n;
 }
 
 FastAQStream::~FastAQStream()

@@ -14,6 +14,8 @@ namespace sg_host {
 class FastAQStream {
 public:
     explicit FastAQStream(const std::string &path);     // throws std::runtime_error if the file cannot be opened
+    // continue on an already open zlib handle (ownership is taken) after `n` bytes that were read from it before
+    FastAQStream(void *gz_handle, const uint8_t *pending, size_t n);
     ~FastAQStream();
     FastAQStream(const FastAQStream &) = delete;
     FastAQStream &operator=(const FastAQStream &) = delete;

@@ -14,6 +14,7 @@
 // identical); <prefix>.hashTable is not written (the reference's slot order is an artefact of its own
 // hash function and is read by nothing but its -m 3 restart).  There is no CPU fallback: without a
 // CUDA device the program stops with an error, like the reference's printError (utils.cpp:36-40).
+#include <fcntl.h>
 #include <getopt.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -31,6 +32,8 @@
 #include <vector>
 
 #include "../../include/sage2gpu.h"
+#include <zlib.h>
+
 #include "fastaq.h"
 
 namespace {
@@ -173,6 +176,7 @@ public:
     ~Uploader()
     {
         for (Chunk &c : chunk_) release(c);
+        sage2gpu_host_free(text_);
     }
     void add(const uint8_t *seq, size_t len)
     {
@@ -193,8 +197,31 @@ public:
         flush();
         if (sage2gpu_load_finish(ctx_) != 0) printError("CUDA", sage2gpu_last_error(ctx_));
     }
+    // everything added so far is on the device after this
+    void sync()
+    {
+        if (!ctx_) return;
+        flush();
+        if (sage2gpu_load_append(ctx_, nullptr, nullptr, 0) != 0) printError("CUDA", sage2gpu_last_error(ctx_));
+    }
+    sage2gpu_ctx *ctx() const { return ctx_; }
+    uint64_t count()
+    {
+        uint64_t n = 0;
+        if (sage2gpu_load_count(ctx_, &n) != 0) printError("CUDA", sage2gpu_last_error(ctx_));
+        return n;
+    }
+    // pinned buffer for raw file text (device-side record splitting)
+    uint8_t *text(size_t &cap)
+    {
+        if (!text_) { text_ = (uint8_t *)sage2gpu_host_alloc(kTextCap); if (!text_) printError("MEM_ALLOC", "pinned text buffer"); }
+        cap = kTextCap;
+        return text_;
+    }
 
 private:
+    static constexpr size_t kTextCap = (size_t)32 << 20;
+    uint8_t *text_ = nullptr;
     void alloc(Chunk &c)
     {
         c.bases = (uint8_t *)sage2gpu_host_alloc(c.cap_bases);
@@ -240,6 +267,74 @@ struct ParseSink {
 };
 ParseSink *g_parse_sink = nullptr;
 
+// sequential parser (any layout the reference accepts) on `in`, at most max_records records
+uint64_t parseSequential(Uploader &up, sg_host::FastAQStream &in, uint64_t max_records)
+{
+    std::vector<uint8_t> seq;
+    uint64_t len = 0, n = 0;
+    while (n < max_records) {
+        seq.clear();
+        if (!in.next(seq, len)) break;
+        if (g_parse_sink) g_parse_sink->add(seq.data(), seq.size());
+        else up.add(seq.data(), seq.size());
+        ++n;
+    }
+    return n;
+}
+
+// One file: raw text goes to the device in 32 MB pieces and the records are split there
+// (sage2gpu_load_append_text); text that is not in the regular layout is parsed sequentially from that point on.
+uint64_t readFile(Uploader &up, const std::string &path, uint64_t max_records, bool &used_device_parser)
+{
+    used_device_parser = false;
+    if (!up.ctx()) {                       // --parse-only
+        sg_host::FastAQStream in(path);
+        return parseSequential(up, in, max_records);
+    }
+    // plain files are read with read(2) straight into the pinned buffer; gzip goes through zlib
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("cannot open " + path);
+    unsigned char magic[2] = { 0, 0 };
+    const bool is_gz = pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    gzFile gz = nullptr;
+    if (is_gz) {
+        gz = gzdopen(fd, "r");
+        if (!gz) { close(fd); throw std::runtime_error("cannot open " + path); }
+        gzbuffer(gz, 1 << 20);
+    }
+    size_t cap = 0, have = 0;
+    uint8_t *buf = up.text(cap);
+    int marker = 0;
+    bool eof = false;
+    uint64_t total = 0;
+    up.sync();                             // keep the upload order: everything added before is on the device
+    for (;;) {
+        while (have < cap && !eof) {
+            const long n = is_gz ? (long)gzread(gz, buf + have, (unsigned)(cap - have)) : (long)read(fd, buf + have, cap - have);
+            if (n <= 0) eof = true; else have += (size_t)n;
+        }
+        if (have == 0) break;
+        uint64_t consumed = 0, nrec = 0;
+        const int rc = sage2gpu_load_append_text(up.ctx(), buf, have, eof ? 1 : 0, &marker, max_records - total, &consumed, &nrec);
+        if (rc == SAGE2GPU_ERR_FORMAT || (rc == 0 && consumed == 0 && !eof)) {
+            if (!gz) gz = gzdopen(fd, "r");                   // transparent mode, continues at the descriptor's offset
+            if (!gz) { close(fd); throw std::runtime_error("cannot read " + path); }
+            sg_host::FastAQStream in(gz, buf, have);          // takes the handle; continues behind what the device consumed
+            total += parseSequential(up, in, max_records - total);
+            up.sync();
+            return total;
+        }
+        if (rc != 0) printError("CUDA", sage2gpu_last_error(up.ctx()));
+        used_device_parser = true;
+        total += nrec;
+        have -= (size_t)consumed;
+        if (have) memmove(buf, buf + consumed, have);
+        if (total >= max_records || (eof && have == 0)) break;
+    }
+    if (gz) gzclose(gz); else close(fd);
+    return total;
+}
+
 uint64_t readDataset(Uploader &up, const std::string &f1, const std::string &f2)      // readLoader.cpp:133-174
 {
     logStream << "In function readDatasetInBytes().\n";
@@ -247,16 +342,29 @@ uint64_t readDataset(Uploader &up, const std::string &f1, const std::string &f2)
     logStream.flush();
     uint64_t n = 0;
     try {
-        sg_host::MatePairStream in(f1, f2);
-        std::vector<uint8_t> seq;
-        uint64_t len = 0;
-        for (;;) {
-            seq.clear();
-            if (!in.next(seq, len)) break;
-            if (g_parse_sink) g_parse_sink->add(seq.data(), seq.size());
-            else up.add(seq.data(), seq.size());
-            ++n;
+        bool dev1 = false, dev2 = false;
+        if (f2.empty()) {
+            n = readFile(up, f1, UINT64_MAX, dev1);
+        } else if (!up.ctx()) {
+            sg_host::MatePairStream in(f1, f2);     // --parse-only keeps the reference's alternating order
+            std::vector<uint8_t> seq;
+            uint64_t len = 0;
+            for (;;) { seq.clear(); if (!in.next(seq, len)) break; g_parse_sink->add(seq.data(), seq.size()); ++n; }
+        } else {
+            // The reference alternates mate 1 / mate 2 and stops when a file ends (inputReader.cpp:26-49): with n1 and n2
+            // records it keeps min(n1, n2 + 1) of file 1 and min(n2, n1) of file 2.  Read ids are ranks in the sorted set,
+            // so the upload order is free: file 1, then file 2 capped at n1, then the surplus of file 1 is dropped.
+            const uint64_t start1 = up.count();
+            const uint64_t n1 = readFile(up, f1, UINT64_MAX, dev1);
+            const uint64_t n2 = readFile(up, f2, n1, dev2);
+            uint64_t keep1 = n1;
+            if (n1 > n2 + 1) {
+                keep1 = n2 + 1;
+                if (sage2gpu_load_remove(up.ctx(), start1 + keep1, n1 - keep1) != 0) printError("CUDA", sage2gpu_last_error(up.ctx()));
+            }
+            n = keep1 + n2;
         }
+        logStream << "\tRecords split on the device: " << ((dev1 || dev2) ? "yes" : "no (sequential parser)") << "\n";
     } catch (const std::runtime_error &e) {
         printError("OPEN_FILE", e.what());
     }

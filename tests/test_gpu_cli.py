@@ -77,3 +77,69 @@ def test_downstream_fasta_identical_through_reference_steps_4_to_7(tmp_path):
     assert fastas, "the reference wrote no FASTA"
     for f in fastas:
         assert open(ours / f, "rb").read() == open(ref / f, "rb").read(), f
+
+
+def _run_cli(args, out):
+    subprocess.run([BIN, *args, "-o", str(out), "-p", "g", "-M", "3"], check=True)
+    return _md5(out / "g.reads"), _md5(out / "g.graph3"), open(out / "g.log").read()
+
+
+def test_device_record_splitting_and_sequential_fallback(tmp_path):
+    """The same reads as regular FASTQ (records split on the device), 2-line FASTA, gzip, multi-line FASTA
+    (sequential parser) and a FASTQ whose irregular record sits in a later 32 MB piece (device first, then the
+    sequential parser from that point on): identical files every time."""
+    reads, k = _get("cfg1")                       # 400,000 reads, 88 MB of FASTQ: three pieces
+    gold = (GOLD["cfg1"]["reads_md5"], GOLD["cfg1"]["graph3_md5"])
+    fq = tmp_path / "a.fastq"
+    synth.write_fastq(str(fq), reads)
+    r, g, log = _run_cli(["-f", str(fq), "-k", str(k)], tmp_path / "o1")
+    assert (r, g) == gold and "Records split on the device: yes" in log
+
+    lst = synth.to_list(reads)
+    fa = tmp_path / "a.fa"
+    with open(fa, "wb") as f:
+        for i, s in enumerate(lst):
+            f.write(b">r%d\n%s\n" % (i, s))
+    r, g, log = _run_cli(["-f", str(fa), "-k", str(k)], tmp_path / "o2")
+    assert (r, g) == gold and "Records split on the device: yes" in log
+
+    gz = tmp_path / "a.fastq.gz"
+    with gzip.open(gz, "wb", compresslevel=1) as f:
+        f.write(open(fq, "rb").read())
+    r, g, log = _run_cli(["-f", str(gz), "-k", str(k)], tmp_path / "o3")
+    assert (r, g) == gold and "Records split on the device: yes" in log
+
+    ml = tmp_path / "multi.fa"
+    with open(ml, "wb") as f:
+        for i, s in enumerate(lst):
+            f.write(b">r%d\n%s\n%s\n" % (i, s[:60], s[60:]))
+    r, g, log = _run_cli(["-f", str(ml), "-k", str(k)], tmp_path / "o4")
+    assert (r, g) == gold and "Records split on the device: no" in log
+
+    mixed = tmp_path / "mixed.fastq"
+    with open(mixed, "wb") as f:
+        for i, s in enumerate(lst):
+            if i == 250_000:          # ~55 MB into the file: a record with its sequence and quality on two lines each
+                f.write(b"@r%d\n%s\n%s\n+\n%s\n%s\n" % (i, s[:50], s[50:], b"I" * 50, b"I" * (len(s) - 50)))
+            else:
+                f.write(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+    r, g, log = _run_cli(["-f", str(mixed), "-k", str(k)], tmp_path / "o5")
+    assert (r, g) == gold and "Records split on the device: yes" in log
+
+
+def test_two_mate_files_of_unequal_length(tmp_path):
+    """The reference alternates the mate files and stops when one ends (inputReader.cpp:26-49)."""
+    reads, k = _get("rep")
+    lst = synth.to_list(reads)
+    m1, m2 = lst[0::2], lst[1::2]
+    for name, (a, b) in {"long1": (m1, m2[:-700]), "long2": (m1[:-500], m2)}.items():
+        synth.write_fastq(str(tmp_path / f"{name}_1.fastq"), a)
+        synth.write_fastq(str(tmp_path / f"{name}_2.fastq"), b)
+        (tmp_path / f"{name}.list").write_text(f"f1={tmp_path}/{name}_1.fastq\nf2={tmp_path}/{name}_2.fastq\n")
+        n1, n2 = len(a), len(b)
+        kept = a[:min(n1, n2 + 1)] + b[:min(n2, n1)]
+        synth.write_fastq(str(tmp_path / f"{name}_expected.fastq"), kept)
+        got = _run_cli(["-l", str(tmp_path / f"{name}.list"), "-k", str(k)], tmp_path / f"{name}_o")
+        want = _run_cli(["-f", str(tmp_path / f"{name}_expected.fastq"), "-k", str(k)], tmp_path / f"{name}_w")
+        assert got[:2] == want[:2]
+        assert f"Good reads: {len(kept)}" in got[2].replace(",", "")
