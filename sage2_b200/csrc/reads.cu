@@ -2,6 +2,7 @@
 // frequencies + packed reverse complements (K2).  Restates ReadLoader::readDatasetInBytes /
 // insertReadIntoList / organizeReads (inputReader/readLoader.cpp:133-260) and the utils.cpp helpers
 // they call (isGoodRead :144, reverseComplement :73, charsToBytes :96).
+#include <stdlib.h>
 #include "context.h"
 
 namespace sg {
@@ -98,6 +99,86 @@ __global__ void __launch_bounds__(K1_WARPS * 32) pack_kernel(const uint8_t *__re
     }
 }
 
+// K1, thread per read.  A block stages the contiguous characters of its reads in shared memory with coalesced
+// loads (16 bytes per lane where the alignment allows), then every thread packs, reverse-complements and
+// orients ONE read: 32 reads per warp instruction instead of one (the warp-per-read kernel above is issue-bound
+// at ~400 instructions per read).  Used when a block's reads fit the staging buffer.
+constexpr int K1T_THREADS = 256;
+constexpr int K1T_STAGE = 40 * 1024;        // bytes of characters per block
+
+template <int SW>
+__global__ void __launch_bounds__(K1T_THREADS) pack_thread_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ off, u64 n, int k,
+                                                                    int rpb, u64 *__restrict__ rec, unsigned long long *counters)
+{
+    __shared__ __align__(16) uint8_t sB[K1T_STAGE + 32];
+    __shared__ unsigned long long sCnt[2];
+    if (threadIdx.x < 2) sCnt[threadIdx.x] = 0;
+    const u64 nblocks = (n + rpb - 1) / rpb;
+    unsigned long long good = 0, bp = 0;
+    for (u64 blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const u64 r0 = blk * (u64)rpb;
+        const int nr = (int)((n - r0) < (u64)rpb ? (n - r0) : (u64)rpb);
+        const int64_t start = off[r0], end = off[r0 + nr];
+        const int64_t a0 = start & ~(int64_t)15;                   // staging keeps the 16-byte phase of the global address
+        const int head = (int)(start - a0);
+        const int64_t span = end - start;
+        __syncthreads();                                           // previous batch fully consumed
+        if (span <= K1T_STAGE) {
+            const bool aligned = (((uintptr_t)bases) & 15) == 0;
+            const int64_t lo16 = (start + 15) & ~(int64_t)15, hi16 = end & ~(int64_t)15;
+            if (aligned && hi16 > lo16) {
+                for (int64_t g = lo16 + 16 * (int64_t)threadIdx.x; g < hi16; g += 16 * K1T_THREADS)
+                    *reinterpret_cast<uint4 *>(sB + (g - a0)) = __ldg(reinterpret_cast<const uint4 *>(bases + g));
+                for (int64_t g = start + threadIdx.x; g < lo16; g += K1T_THREADS) sB[g - a0] = bases[g];
+                for (int64_t g = hi16 + threadIdx.x; g < end; g += K1T_THREADS) sB[g - a0] = bases[g];
+            } else {
+                for (int64_t g = start + threadIdx.x; g < end; g += K1T_THREADS) sB[g - a0] = bases[g];
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nr) {
+            const u64 r = r0 + threadIdx.x;
+            const int64_t o = off[r];
+            const int64_t len64 = off[r + 1] - o;
+            const int max_ok = 32 * SW - 8;
+            bool bad = len64 <= (int64_t)k || len64 > (int64_t)max_ok;
+            const int len = bad ? 0 : (int)len64;
+            // (a block whose span does not fit -- only possible next to over-long, rejected reads -- reads global memory)
+            const uint8_t *B = span <= K1T_STAGE ? sB + head + (o - start) : bases + o;
+            u64 f[SW], q[SW];
+#pragma unroll
+            for (int w = 0; w < SW; ++w) f[w] = 0;
+            bool invalid = false;
+#pragma unroll
+            for (int w = 0; w < SW; ++w) {
+                if (32 * w < len) {
+                    u64 acc = 0;
+                    const int m = len - 32 * w < 32 ? len - 32 * w : 32;
+                    for (int t = 0; t < m; ++t) {
+                        const u32 ch = B[32 * w + t];
+                        const u32 up = ch & 0xDFu;
+                        invalid |= !(up == 'A' || up == 'C' || up == 'G' || up == 'T');
+                        acc |= (u64)(((ch >> 1) ^ (ch >> 2)) & 3u) << (62 - 2 * t);
+                    }
+                    f[w] = acc;
+                }
+            }
+            bad |= invalid;
+            revcomp_record(f, q, SW, len);          // q[SW-1] carries the length, f does not yet
+            f[SW - 1] |= (u64)len;
+            bool use_rc = false;                    // keep the read iff read < revcomp (readLoader.cpp:195)
+#pragma unroll
+            for (int w = SW - 1; w >= 0; --w) if (f[w] != q[w]) use_rc = q[w] < f[w];
+#pragma unroll
+            for (int w = 0; w < SW; ++w) rec[r * SW + w] = bad ? ~0ull : (use_rc ? q[w] : f[w]);
+            if (!bad) { good++; bp += (unsigned long long)len; }
+        }
+    }
+    if (good) { atomicAdd(&sCnt[0], good); atomicAdd(&sCnt[1], bp); }
+    __syncthreads();
+    if (threadIdx.x == 0 && sCnt[0]) { atomicAdd(&counters[0], sCnt[0]); atomicAdd(&counters[1], sCnt[1]); }
+}
+
 // One chunk of the streamed upload: append the bases, append the offsets rebased to the running total.
 __global__ void __launch_bounds__(256) rebase_offsets_kernel(const int64_t *__restrict__ in, int64_t n, int64_t delta, int64_t *__restrict__ out)
 {
@@ -185,9 +266,26 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     DevBuf<u64> &rec = c.raw;
     DevBuf<unsigned long long> d_cnt(2, st);
     SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), st));
-    unsigned gp = grid_for((u64)n_reads, 1, K1_WARPS);
-    if (gp > kSMs * 16) gp = kSMs * 16;
-    pack_kernel<<<gp, K1_WARPS * 32, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, c.SW, rec.p, d_cnt.p);
+    int rpb = K1T_STAGE / (max_len > 0 ? max_len : 1);           // reads per block of the thread-per-read kernel
+    if (rpb > K1T_THREADS) rpb = K1T_THREADS;
+    rpb &= ~31;
+    static const bool warp_per_read = getenv("SAGE2GPU_PACK_WARP") != nullptr;
+    if (rpb >= 32 && c.SW <= 8 && !warp_per_read) {
+        unsigned gp = grid_for((u64)n_reads, 1, (unsigned)rpb);
+        if (gp > kSMs * 8) gp = kSMs * 8;
+        switch (c.SW) {
+            case 2: pack_thread_kernel<2><<<gp, K1T_THREADS, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, rpb, rec.p, d_cnt.p); break;
+            case 3: pack_thread_kernel<3><<<gp, K1T_THREADS, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, rpb, rec.p, d_cnt.p); break;
+            case 4: pack_thread_kernel<4><<<gp, K1T_THREADS, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, rpb, rec.p, d_cnt.p); break;
+            case 5: pack_thread_kernel<5><<<gp, K1T_THREADS, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, rpb, rec.p, d_cnt.p); break;
+            case 6: pack_thread_kernel<6><<<gp, K1T_THREADS, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, rpb, rec.p, d_cnt.p); break;
+            default: pack_thread_kernel<8><<<gp, K1T_THREADS, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, rpb, rec.p, d_cnt.p); break;
+        }
+    } else {        // long reads: one warp per read
+        unsigned gp = grid_for((u64)n_reads, 1, K1_WARPS);
+        if (gp > kSMs * 16) gp = kSMs * 16;
+        pack_kernel<<<gp, K1_WARPS * 32, 0, st>>>(d_b, d_o, (u64)n_reads, c.min_overlap, c.SW, rec.p, d_cnt.p);
+    }
     SG_LAUNCHED();
     unsigned long long h_cnt[2];
     SG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
