@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 
 namespace sg {
 namespace {
@@ -111,31 +112,33 @@ struct Walk {
         inserted += 2 * cnt;
     }
 
-    // markTransitiveEdge, economyGraph.cpp:643-679
-    void mark_transitive(uint32_t nf)
+    // markTransitiveEdge, economyGraph.cpp:643-679.  The walk only records that nf's marking is due (its position in the
+    // traversal is what later pushes depend on); the marking itself is computed after the walk, see run_host_phase_c.
+    void mark_transitive(uint32_t nf) { state[nf] = 2; }
+
+    void compute_marks(uint32_t nf, std::vector<uint8_t> &scratch)      // scratch: one zeroed byte per node
     {
         std::vector<HEdge> &lf = adj[nf];
-        for (auto &e : lf) marked[e.node] = 1;
+        for (auto &e : lf) scratch[e.node] = 1;
         for (auto &e : lf) {
             const uint32_t na = e.node;
-            if (marked[na] != 1) continue;
+            if (scratch[na] != 1) continue;
             for (auto &f : adj[na]) {
                 const uint32_t nb = f.node;
                 if (nb == kNone) continue;            // not adjacent to any S read: cannot be in play
-                if (marked[nb] != 1) continue;
+                if (scratch[nb] != 1) continue;
                 const uint32_t t1 = e.type, t2 = f.type;
-                if ((t1 == 0 || t1 == 2) && (t2 == 0 || t2 == 1)) marked[nb] = 2;
-                else if ((t1 == 1 || t1 == 3) && (t2 == 2 || t2 == 3)) marked[nb] = 2;
+                if ((t1 == 0 || t1 == 2) && (t2 == 0 || t2 == 1)) scratch[nb] = 2;
+                else if ((t1 == 1 || t1 == 3) && (t2 == 2 || t2 == 3)) scratch[nb] = 2;
             }
         }
-        for (auto &e : lf) if (marked[e.node] == 2) e.mark = 1;
-        for (auto &e : lf) marked[e.node] = 0;
-        marked[nf] = 0;
-        state[nf] = 2;
+        for (auto &e : lf) if (scratch[e.node] == 2) e.mark = 1;
+        for (auto &e : lf) scratch[e.node] = 0;
+        scratch[nf] = 0;
     }
 
-    // removeTransitiveEdges, economyGraph.cpp:681-707
-    void remove_transitive(uint32_t n)
+    // removeTransitiveEdges, economyGraph.cpp:681-707 (after all marks are known)
+    void remove_marked(uint32_t n)
     {
         std::vector<HEdge> &l = adj[n];
         size_t w = 0;
@@ -205,9 +208,33 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
                     }
                     w.mark_transitive(n2);
                 }
-                w.remove_transitive(n1);
             }
         }
+    }
+
+    // Marking and removal, after the walk.  When the reference marks a node, every neighbour already has all its
+    // edges (insertAllEdgesOfRead ran for it and nothing is appended to an explored node's list), the node's own list
+    // was sorted at the end of its insertAllEdgesOfRead, and a node's marked edges are removed only after all its
+    // neighbours were marked: so the marks are a function of the complete lists alone and every node can be marked
+    // independently -- here on all host cores (the quadratic part of the phase: sum over nodes of degree^2).
+    {
+        std::vector<uint32_t> todo;
+        for (uint32_t i = 0; i < nS; ++i) if (w.state[i] == 2) todo.push_back(i);
+        unsigned T = std::thread::hardware_concurrency();
+        if (T > 32) T = 32;
+        if (T < 1 || todo.size() < 4096) T = 1;
+        const size_t n_nodes = w.adj.size();
+        auto work = [&](unsigned t) {
+            std::vector<uint8_t> scratch(n_nodes, 0);
+            for (size_t x = t; x < todo.size(); x += T) w.compute_marks(todo[x], scratch);
+        };
+        if (T == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < T; ++t) pool.emplace_back(work, t);
+            for (auto &th : pool) th.join();
+        }
+        for (uint32_t i : todo) w.remove_marked(i);
     }
 
     // what convertGraph consumes from the lists of S reads (overlapGraph.cpp:93-112)

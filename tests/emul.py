@@ -22,7 +22,7 @@ def lib():
     if _lib is None:
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
-            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO] + SRCS)
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-x", "c++", "-o", SO] + SRCS)
         _lib = C.CDLL(SO)
         _lib.hemu_run.restype = C.c_void_p
         _lib.hemu_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
