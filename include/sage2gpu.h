@@ -40,6 +40,7 @@ typedef struct {
     uint64_t slow_path_reads;   /* reads whose extension chain ran hit by hit (ambiguity / multi-hit windows) */
     uint64_t record_words;      /* 64-bit words per packed read record */
     uint64_t probe_restarts;    /* reads redone with verified probes after a tag collision */
+    uint64_t phase_c_on_device; /* 1 when phase C ran on the device (order-independent input), 0 for the host walk */
 } sage2gpu_counters;
 
 /* Stage times in milliseconds (CUDA events on the context's stream; host part by steady_clock). */

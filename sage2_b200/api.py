@@ -28,7 +28,7 @@ class Counters(C.Structure):
         "hash_len", "distinct_keys", "keys_over_threshold", "table_capacity",
         "contained_ext", "contained_size", "left_to_explore",
         "edges_phase_b", "candidates_c", "edges_inserted_c", "transitive_removed",
-        "n_edges", "compare_calls", "window_probes", "slow_path_reads", "record_words", "probe_restarts")]
+        "n_edges", "compare_calls", "window_probes", "slow_path_reads", "record_words", "probe_restarts", "phase_c_on_device")]
 
 
 class Timers(C.Structure):

@@ -340,6 +340,7 @@ int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *o)
     o->compare_calls = n.compare_calls; o->window_probes = n.window_probes; o->slow_path_reads = n.slow_path_reads;
     o->record_words = (uint64_t)ctx->c.SW;
     o->probe_restarts = n.probe_restarts;
+    o->phase_c_on_device = n.phase_c_on_device;
     return SAGE2GPU_OK;
 }
 

@@ -3,6 +3,7 @@
 // EconomyGraph::buildInitialOverlapGraph phase B (economyGraph/economyGraph.cpp:455-480),
 // sortEconomyGraph (:896-913) and the part of OverlapGraph::convertGraph that decides which entries
 // become edges (overlapGraph/overlapGraph.cpp:93-112).
+#include <stdlib.h>
 #include <algorithm>
 #include "context.h"
 #include "host_phase_c.h"
@@ -10,6 +11,9 @@
 namespace sg {
 
 void launch_phase_c_candidates(Context &c, const u32 *s_ids, u64 nS, u32 *counts, const u32 *offsets, u64 *cand, bool fill);
+// phase_c_device.cu
+bool device_phase_c(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand, u64 nC,
+                    const u64 *selB, const u32 *selLen, u64 nSel, DevBuf<u64> &out, u64 &n_out, u64 &removed);
 
 static unsigned big_grid(u64 n, unsigned block = 256)
 {
@@ -195,6 +199,7 @@ void stage_phase_c_and_finalize(Context &c)
     ArenaScope arena_scope(c.arena, st);
     const u64 U = c.cnt.unique_reads;
     c.cnt.candidates_c = c.cnt.edges_inserted_c = c.cnt.transitive_removed = 0;
+    c.cnt.phase_c_on_device = 0;
     c.cnt.n_edges = 0;
     c.h_edges.clear();
     if (U == 0) { c.have_graph = true; return; }
@@ -214,6 +219,9 @@ void stage_phase_c_and_finalize(Context &c)
 
     u64 nB = c.cnt.edges_phase_b;
     std::vector<u64> host_c_edges;     // records owned by state-0 reads after the walk
+    DevBuf<u64> dev_c_edges;           // the same when phase C ran on the device
+    u64 n_dev_c = 0;
+    bool c_on_device = false;
     float host_ms = 0.f;
     if (nS > 0) {
         DevBuf<u32> s_ids(nS, st), counts(nS, st), offs(nS, st), d_ctotal(1, st);
@@ -253,6 +261,17 @@ void stage_phase_c_and_finalize(Context &c)
                 SG_LAUNCHED();
             }
         }
+        // ---- phase C on the device when the traversal order cannot matter (phase_c_device.cu) -----------
+        const bool force_host = getenv("SAGE2GPU_PHASE_C_HOST") != nullptr;       // test knob: always take the walk
+        u64 removed_dev = 0;
+        if (!force_host)
+            c_on_device = device_phase_c(c, s_ids.p, idx.p, nS, counts.p, offs.p, cand.p, nC, selB.p, selLen.p, nSel, dev_c_edges, n_dev_c, removed_dev);
+        c.cnt.phase_c_on_device = c_on_device ? 1 : 0;
+        if (c_on_device) {
+            c.cnt.edges_inserted_c = nC;               // every overlap was found from both ends: 2 entries per pair
+            c.cnt.transitive_removed = removed_dev;
+            SG_CUDA(cudaEventRecord(ev1, st));
+        } else {
         PhaseCInput in;
         std::vector<u32> h_sids(nS), h_off((size_t)nS + 1), h_selLen(nSel);
         std::vector<u64> h_cand(nC), h_selB(2 * (u64)nSel);
@@ -275,12 +294,13 @@ void stage_phase_c_and_finalize(Context &c)
         c.cnt.edges_inserted_c = out.inserted;
         c.cnt.transitive_removed = out.removed;
         host_c_edges.swap(out.edges);
+        }
     } else {
         SG_CUDA(cudaEventRecord(ev1, st));
     }
 
     // ---- assemble the final record set on device --------------------------------------------------
-    const u64 nH = host_c_edges.size() / 2;
+    const u64 nH = c_on_device ? n_dev_c : host_c_edges.size() / 2;
     DevBuf<u32> eflag, eidx, d_keep(1, st);
     u64 nKeep = nB;
     if (nS > 0 && nB > 0) {
@@ -307,7 +327,10 @@ void stage_phase_c_and_finalize(Context &c)
         split_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, eflag.p, eidx.p, a0.p, b0.p);
         SG_LAUNCHED();
     }
-    if (nH) {
+    if (nH && c_on_device) {
+        split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(dev_c_edges.p, nH, nullptr, nullptr, a0.p + nKeep, b0.p + nKeep);
+        SG_LAUNCHED();
+    } else if (nH) {
         DevBuf<u64> tmp(2 * nH, st);
         SG_CUDA(cudaMemcpyAsync(tmp.p, host_c_edges.data(), 2 * nH * sizeof(u64), cudaMemcpyHostToDevice, st));
         split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(tmp.p, nH, nullptr, nullptr, a0.p + nKeep, b0.p + nKeep);

@@ -1,0 +1,241 @@
+// phase_c_device.cu -- EconomyGraph::buildOverlapGraphEconomy (economyGraph/economyGraph.cpp:495-707) without the
+// sequential walk, for the inputs where the walk's order cannot matter.
+//
+// What the walk does, read r by read r in breadth-first order: insertAllEdgesOfRead inserts r's overlaps with the reads
+// that are still unexplored (both directions, :605-631) and sorts r's list (:634); markTransitiveEdge(r) runs once all
+// of r's neighbours have their edges; removeTransitiveEdges(r) once all of r's neighbours are marked.  Hence
+//   * nothing is appended to a list after its read was explored, and the list is sorted then: at marking time every
+//     list involved is complete and in compareLengthBased order -- the marks are a function of the final lists only
+//     (host_phase_c.cpp already computes them after the traversal, checked against the oracle);
+//   * the final lists depend on the traversal order only through WHICH endpoint inserted an overlap.  If every
+//     candidate (a -> b, type, overhang) has its twin (b -> a, reverse type, twin overhang) in b's own candidate list,
+//     either endpoint inserts the same two entries and list[a] = a's own candidates + a's phase-B entries.
+// So: check that the candidate set is symmetric (it is not when a read contains another one -- variable read lengths --
+// or when one of the two h-mers of an overlap is a masked key); if it is, build, sort, mark and filter every list on the
+// device, one warp per read; if it is not (or a list exceeds the per-warp capacity) the caller falls back to the walk.
+#include "context.h"
+
+namespace sg {
+
+constexpr int PC_MAXD = 512;        // entries per list handled on the device
+constexpr int PC_HCAP = 1024;       // per-warp hash capacity (ids of one list)
+constexpr int PC_WARPS = 4;
+
+__device__ __forceinline__ u32 pc_rev(u32 t) { return t == 0 ? 3u : (t == 3 ? 0u : t); }
+__device__ __forceinline__ bool pc_rule(u32 t1, u32 t2)      // economyGraph.cpp:661-664
+{
+    return ((t1 == 0 || t1 == 2) && (t2 == 0 || t2 == 1)) || ((t1 == 1 || t1 == 3) && (t2 == 2 || t2 == 3));
+}
+
+// phase-B half edges: every selected record (from,to,type,len) as seen from both endpoints
+__global__ void __launch_bounds__(256) pc_half_edges_kernel(const u64 *__restrict__ selB, const u32 *__restrict__ selLen, u64 n,
+                                                             u64 *__restrict__ owner, u64 *__restrict__ rec)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        const u64 w0 = selB[2 * e], w1 = selB[2 * e + 1];
+        const u32 a = (u32)(w0 >> 32), b = (u32)w0, type = (u32)(w1 >> 20) & 3u, len = (u32)(w1 & 0xFFFFFu);
+        const u32 la = selLen[e] & 0xFFFFu, lb = selLen[e] >> 16;
+        owner[2 * e] = a;     rec[2 * e] = ((u64)b << 32) | ((u64)type << 20) | len;
+        owner[2 * e + 1] = b; rec[2 * e + 1] = ((u64)a << 32) | ((u64)pc_rev(type) << 20) | ((la - (lb - len)) & 0xFFFFFu);
+    }
+}
+
+__device__ __forceinline__ void pc_range(const u64 *owner, u64 n, u64 id, u64 &lo, u64 &hi)
+{
+    u64 a = 0, b = n;
+    while (a < b) { const u64 m = (a + b) >> 1; if (owner[m] < id) a = m + 1; else b = m; }
+    lo = a; b = n;
+    while (a < b) { const u64 m = (a + b) >> 1; if (owner[m] <= id) a = m + 1; else b = m; }
+    hi = a;
+}
+
+// every candidate must have its twin in the other read's list
+__global__ void __launch_bounds__(256) pc_symmetry_kernel(const u32 *__restrict__ s_ids, const u32 *__restrict__ sidx, u64 nS,
+                                                           const u32 *__restrict__ counts, const u32 *__restrict__ offs, const u64 *__restrict__ cand,
+                                                           const uint16_t *__restrict__ len, u32 *__restrict__ flags)
+{
+    const int lane = threadIdx.x & 31;
+    const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
+    bool bad = false;
+    for (u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nS; s += nwarps) {
+        const u32 a = s_ids[s] + 1, la = len[a - 1];
+        const u32 base = offs[s], m = counts[s];
+        for (u32 x = lane; x < m; x += 32) {
+            const u64 cw = cand[base + x];
+            const u32 b = (u32)(cw >> 32), t = (u32)(cw >> 20) & 3u;
+            u32 d = (u32)(cw & 0xFFFFFu);
+            if (d & 0x80000u) d |= 0xFFF00000u;
+            const u32 lb = len[b - 1];
+            const u64 want = ((u64)a << 32) | ((u64)pc_rev(t) << 20) | ((la - (lb - d)) & 0xFFFFFu);
+            const u32 sb = sidx[b - 1], bb = offs[sb], mb = counts[sb];
+            bool found = false;
+            for (u32 y = 0; y < mb && !found; ++y) found = cand[bb + y] == want;
+            bad |= !found;
+        }
+    }
+    if (bad) atomicOr(&flags[0], 1u);
+}
+
+struct PcHash {
+    u32 *id;
+    uint8_t *st;
+    __device__ __forceinline__ static u32 h(u32 x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+    __device__ __forceinline__ int find(u32 key) const
+    {
+        for (u32 s = h(key) & (PC_HCAP - 1);; s = (s + 1) & (PC_HCAP - 1)) {
+            const u32 k = id[s];
+            if (k == key) return (int)s;
+            if (k == 0) return -1;
+        }
+    }
+};
+
+// one warp per read of S: list = own candidates + phase-B half edges, sorted by compareLengthBased (:853-871), marked
+// like markTransitiveEdge, filtered like removeTransitiveEdges; survivors with id > read go to `out`
+__global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__restrict__ s_ids, const u32 *__restrict__ sidx, u64 nS,
+                                                                 const u32 *__restrict__ counts, const u32 *__restrict__ offs, const u64 *__restrict__ cand,
+                                                                 const uint8_t *__restrict__ explored, const u64 *__restrict__ pb_owner, const u64 *__restrict__ pb_rec, u64 n_pb,
+                                                                 u64 *__restrict__ out, unsigned long long *__restrict__ counters /*[0] out, [1] removed*/,
+                                                                 u32 *__restrict__ flags)
+{
+    __shared__ u64 sKey[PC_WARPS][PC_MAXD];
+    __shared__ u32 sHid[PC_WARPS][PC_HCAP];
+    __shared__ uint8_t sHst[PC_WARPS][PC_HCAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 *key = sKey[warp];
+    PcHash H{ sHid[warp], sHst[warp] };
+    const u64 nwarps = (u64)gridDim.x * PC_WARPS;
+    unsigned long long removed = 0;
+    for (u64 s = (u64)blockIdx.x * PC_WARPS + warp; s < nS; s += nwarps) {
+        const u32 n = s_ids[s] + 1;
+        const u32 cnt = counts[s], base = offs[s];
+        u64 plo, phi;
+        pc_range(pb_owner, n_pb, n, plo, phi);
+        const u32 d = cnt + (u32)(phi - plo);
+        if (d > (u32)PC_MAXD) { if (lane == 0) atomicOr(&flags[0], 2u); continue; }
+        if (d == 0) continue;
+        u32 P = 1;
+        while (P < d) P <<= 1;
+        __syncwarp();
+        for (u32 x = lane; x < P; x += 32) {
+            u64 cw = 0;
+            if (x < cnt) cw = cand[base + x];
+            else if (x < d) cw = pb_rec[plo + (x - cnt)];
+            // length desc, id desc, type desc  ==  one descending 54-bit key
+            key[x] = x < d ? (((cw & 0xFFFFFull) << 34) | ((cw >> 32) << 2) | ((cw >> 20) & 3ull)) : 0ull;
+        }
+        for (u32 x = lane; x < (u32)PC_HCAP; x += 32) { H.id[x] = 0; H.st[x] = 0; }
+        __syncwarp();
+        for (u32 k = 2; k <= P; k <<= 1)
+            for (u32 j = k >> 1; j > 0; j >>= 1) {
+                for (u32 i = lane; i < P; i += 32) {
+                    const u32 p = i ^ j;
+                    if (p > i) {
+                        const u64 a = key[i], b = key[p];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? a < b : a > b) { key[i] = b; key[p] = a; }
+                    }
+                }
+                __syncwarp();
+            }
+        for (u32 x = lane; x < d; x += 32) {
+            const u32 id = (u32)(key[x] >> 2);
+            for (u32 sl = PcHash::h(id) & (PC_HCAP - 1);; sl = (sl + 1) & (PC_HCAP - 1)) {
+                const u32 old = atomicCAS(&H.id[sl], 0u, id);
+                if (old == 0u || old == id) { H.st[sl] = 1; break; }
+            }
+        }
+        __syncwarp();
+        for (u32 x = 0; x < d; ++x) {
+            const u32 ida = (u32)(key[x] >> 2), t1 = (u32)key[x] & 3u;
+            const int sa = H.find(ida);
+            if (H.st[sa] == 1) {
+                if (explored[ida - 1] == 0) {
+                    const u32 sx = sidx[ida - 1], bx = offs[sx], mx = counts[sx];
+                    for (u32 y = lane; y < mx; y += 32) {
+                        const u64 cw = cand[bx + y];
+                        const int sf = H.find((u32)(cw >> 32));
+                        if (sf >= 0 && H.st[sf] == 1 && pc_rule(t1, (u32)(cw >> 20) & 3u)) H.st[sf] = 2;
+                    }
+                }
+                u64 qlo, qhi;
+                pc_range(pb_owner, n_pb, ida, qlo, qhi);
+                for (u64 y = qlo + lane; y < qhi; y += 32) {
+                    const u64 cw = pb_rec[y];
+                    const int sf = H.find((u32)(cw >> 32));
+                    if (sf >= 0 && H.st[sf] == 1 && pc_rule(t1, (u32)(cw >> 20) & 3u)) H.st[sf] = 2;
+                }
+            }
+            __syncwarp();
+        }
+        for (u32 x = lane; x < d; x += 32) {
+            const u64 kx = key[x];
+            const u32 id = (u32)(kx >> 2);
+            if (H.st[H.find(id)] == 2) { removed++; continue; }
+            if (id > n) {
+                const unsigned long long pos = atomicAdd(&counters[0], 1ull);
+                out[2 * pos] = ((u64)n << 32) | id;
+                out[2 * pos + 1] = ((kx & 3ull) << 20) | (kx >> 34);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    if (lane == 0 && removed) atomicAdd(&counters[1], removed);
+}
+
+static unsigned pc_grid(u64 n, unsigned per_block)
+{
+    u64 g = (n + per_block - 1) / per_block;
+    if (g > (u64)kSMs * 16) g = (u64)kSMs * 16;
+    if (g == 0) g = 1;
+    return (unsigned)g;
+}
+
+// true: `out` holds n_out (w0,w1) records owned by the S reads; false: not applicable, use the host walk
+bool device_phase_c(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand, u64 nC,
+                    const u64 *selB, const u32 *selLen, u64 nSel, DevBuf<u64> &out, u64 &n_out, u64 &removed)
+{
+    cudaStream_t st = c.stream;
+    const u64 U = c.cnt.unique_reads;
+    DevBuf<u32> flags(1, st);
+    SG_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(u32), st));
+    pc_symmetry_kernel<<<pc_grid(nS, 8), 256, 0, st>>>(s_ids, sidx, nS, counts, offs, cand, c.len.p, flags.p);
+    SG_LAUNCHED();
+    u32 h_flags = 0;
+    SG_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (h_flags) return false;
+
+    // phase-B half edges sorted by owner
+    const u64 n_pb = 2 * nSel;
+    DevBuf<u64> o0(n_pb, st), o1(n_pb, st), r0(n_pb, st), r1(n_pb, st);
+    const u64 *pb_owner = o0.p, *pb_rec = r0.p;
+    if (n_pb) {
+        pc_half_edges_kernel<<<pc_grid(nSel, 256), 256, 0, st>>>(selB, selLen, nSel, o0.p, r0.p);
+        SG_LAUNCHED();
+        SortCols cols;
+        cols.a[0] = o0.p; cols.a[1] = o1.p; cols.b[0] = r0.p; cols.b[1] = r1.p; cols.v[0] = cols.v[1] = nullptr;
+        int id_bits = 1;
+        while ((U >> id_bits) != 0) ++id_bits;
+        const int cur = radix_sort_bits(cols, 0, n_pb, false, 0, id_bits, st);
+        pb_owner = cols.a[cur]; pb_rec = cols.b[cur];
+    }
+    out.alloc(2 * (nC + n_pb) + 2, st);
+    DevBuf<unsigned long long> cnt(2, st);
+    SG_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(unsigned long long), st));
+    pc_node_kernel<<<pc_grid(nS, PC_WARPS), PC_WARPS * 32, 0, st>>>(s_ids, sidx, nS, counts, offs, cand, c.explored.p, pb_owner, pb_rec, n_pb,
+                                                                    out.p, cnt.p, flags.p);
+    SG_LAUNCHED();
+    unsigned long long h_cnt[2];
+    SG_CUDA(cudaMemcpyAsync(h_cnt, cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (h_flags) return false;           // a list longer than PC_MAXD
+    n_out = h_cnt[0];
+    removed = h_cnt[1];
+    return true;
+}
+
+}  // namespace sg

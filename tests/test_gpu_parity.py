@@ -256,3 +256,27 @@ def test_streamed_upload_equals_one_shot():
     np.testing.assert_array_equal(e1, gpu.edges())
     for f in ("total_reads", "good_reads", "unique_reads", "total_bp", "compare_calls"):
         assert c1[f] == c2[f], f
+
+
+@pytest.mark.parametrize("name,on_device", [("err", 1), ("rep", 1), ("tandem", 1), ("varlen_err", None), ("deep_varlen", None), ("hicopy", None), ("mixed", None)])
+def test_phase_c_device_and_host_walk_agree(name, on_device, monkeypatch):
+    """Phase C runs on the device when the candidate set is symmetric (fixed read length, no masked-key asymmetry) and
+    through the host walk otherwise; both must give the oracle's graph, and forcing the walk changes nothing."""
+    reads, k = _get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    gpu = api.Sage2Gpu(0)
+    gpu.run_steps123(b, off, k)
+    c = gpu.counters()
+    if on_device is not None:
+        assert c["phase_c_on_device"] == on_device
+    e1 = gpu.edges().copy()
+    assert (c["edges_inserted_c"], c["transitive_removed"]) == (o.edges_inserted_c, o.transitive_removed)
+    monkeypatch.setenv("SAGE2GPU_PHASE_C_HOST", "1")
+    gpu.run_steps123(b, off, k)
+    c2 = gpu.counters()
+    assert c2["phase_c_on_device"] == 0
+    np.testing.assert_array_equal(e1, gpu.edges())
+    assert (c2["edges_inserted_c"], c2["transitive_removed"]) == (o.edges_inserted_c, o.transitive_removed)
+    for f in ("from", "to", "type", "delta", "delta_twin"):
+        np.testing.assert_array_equal(e1[f], o.edges[f])
