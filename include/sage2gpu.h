@@ -121,6 +121,43 @@ int sage2gpu_phase_a_buffers(sage2gpu_ctx *ctx, void **right_ext, void **left_ex
                              uint64_t *reads_per_rank, uint64_t *unique_reads);
 int sage2gpu_finish_graph(sage2gpu_ctx *ctx);
 
+/* ---- The table sharded by key hash (north_star) ---------------------------------------------------
+ * The reads stay on every GPU; shard `rank` of `world` indexes only the keys whose hash it owns, so the table of a
+ * data set is spread over the GPUs of the box.  A window probe of HashTable::hashTableSearch (hashTable.cpp:193-231)
+ * becomes a query routed to the owner of its key (all-to-all between the ranks, e.g. NCCL through
+ * sage2_b200/multi.py; this library only fills and consumes the device buffers):
+ *
+ *   build_hash_table_shard                         replaces hashPrefixesAndSuffix (hashTable.cpp:70-128) for one shard
+ *   phase_a_sharded_begin                          this rank's slice [first, first+count) of the unique reads (0-based)
+ *   per batch of the slice:
+ *     route_begin(what=0, first, count, exact=0)   window keys of the batch bucketed by owner: `queries` = world
+ *                                                  contiguous streams (counts[g] queries for owner g; a query is one
+ *                                                  uint64 key hash, or two uint64 = the 128-bit key when exact)
+ *     [all-to-all]  shard_answer                   the owner's answers: one uint64 per received query, same order,
+ *                                                  + one stream of uint32 bucket entries per source (entry_counts[s])
+ *     [all-to-all]  route_finish                   answers back at the source, in the order the queries were sent;
+ *                                                  entry streams of owner 0, 1, .. back to back
+ *     phase_a_routed                               the phase-A kernel of buildInitialOverlapGraph (economyGraph.cpp:64-452)
+ *                                                  on the batch; *n_redo = reads that met a 24-bit tag collision
+ *   if any rank has such reads: route_begin(what=2, exact=1) .. phase_a_routed once more (verified probes,
+ *                                                  hashTable.cpp:203-220), then phase_a_sharded_end
+ *   exchange of the phase-A arrays (sage2gpu_phase_a_buffers), sage2gpu_phase_b,
+ *   route_begin(what=1, exact=1) .. route_finish for the reads left for phase C (insertAllEdgesOfRead,
+ *   economyGraph.cpp:580-638), sage2gpu_finish_graph.
+ * counts / entry_counts arrays have `world` elements (world <= 64); all buffers handed out are device memory owned by
+ * the context and stay valid until the next call of the same function. */
+int sage2gpu_build_hash_table_shard(sage2gpu_ctx *ctx, int rank, int world);
+int sage2gpu_phase_a_sharded_begin(sage2gpu_ctx *ctx, int rank, int world, uint64_t *first, uint64_t *count);
+int sage2gpu_route_begin(sage2gpu_ctx *ctx, int what, uint64_t first, uint64_t count, int exact, int world, void **queries,
+                         uint64_t *counts, uint64_t *n_reads);
+int sage2gpu_shard_answer(sage2gpu_ctx *ctx, const void *queries, const uint64_t *counts_per_source, int exact, int world,
+                          void **responses, void **entries, uint64_t *entry_counts);
+int sage2gpu_route_finish(sage2gpu_ctx *ctx, const void *responses, const void *entries, const uint64_t *entry_counts);
+int sage2gpu_phase_a_routed(sage2gpu_ctx *ctx, uint64_t *n_redo);
+int sage2gpu_phase_a_sharded_end(sage2gpu_ctx *ctx);
+/* Phase B alone (economyGraph.cpp:455-480); sage2gpu_finish_graph skips it when it already ran. */
+int sage2gpu_phase_b(sage2gpu_ctx *ctx);
+
 /* All three steps back to back (main.cpp:37-132 without the file I/O). */
 int sage2gpu_run_steps123(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
                           int64_t n_reads, int min_overlap);

@@ -47,7 +47,9 @@ EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2g
            "sage2gpu_phase_a_partition", "sage2gpu_phase_a_buffers", "sage2gpu_finish_graph",
            "sage2gpu_run_steps123", "sage2gpu_get_counters", "sage2gpu_get_timers", "sage2gpu_reads_bytes",
            "sage2gpu_get_reads", "sage2gpu_get_extensions", "sage2gpu_get_edges", "sage2gpu_get_edges_packed", "sage2gpu_write_reads",
-           "sage2gpu_write_graph3", "sage2gpu_kernel_launches", "sage2gpu_stream", "sage2gpu_measure_gather"]
+           "sage2gpu_write_graph3", "sage2gpu_kernel_launches", "sage2gpu_stream", "sage2gpu_measure_gather",
+           "sage2gpu_build_hash_table_shard", "sage2gpu_phase_a_sharded_begin", "sage2gpu_route_begin", "sage2gpu_shard_answer",
+           "sage2gpu_route_finish", "sage2gpu_phase_a_routed", "sage2gpu_phase_a_sharded_end", "sage2gpu_phase_b"]
 
 _lib = None
 
@@ -90,6 +92,14 @@ def load_library():
         lib.sage2gpu_phase_a_partition.argtypes = [vp, C.c_int, C.c_int]
         lib.sage2gpu_phase_a_buffers.argtypes = [vp] + [C.POINTER(vp)] * 4 + [u64p, u64p]
         lib.sage2gpu_finish_graph.argtypes = [vp]
+        lib.sage2gpu_build_hash_table_shard.argtypes = [vp, C.c_int, C.c_int]
+        lib.sage2gpu_phase_a_sharded_begin.argtypes = [vp, C.c_int, C.c_int, u64p, u64p]
+        lib.sage2gpu_route_begin.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp), u64p, u64p]
+        lib.sage2gpu_shard_answer.argtypes = [vp, vp, u64p, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), u64p]
+        lib.sage2gpu_route_finish.argtypes = [vp, vp, vp, u64p]
+        lib.sage2gpu_phase_a_routed.argtypes = [vp, u64p]
+        lib.sage2gpu_phase_a_sharded_end.argtypes = [vp]
+        lib.sage2gpu_phase_b.argtypes = [vp]
         lib.sage2gpu_run_steps123.argtypes = [vp, vp, vp, i64, C.c_int]
         lib.sage2gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
         lib.sage2gpu_get_timers.argtypes = [vp, C.POINTER(Timers)]
@@ -187,6 +197,51 @@ class Sage2Gpu:
 
     def finish_graph(self):
         self._check(self._lib.sage2gpu_finish_graph(self._h), "finish_graph")
+
+    # ---- sharded table (include/sage2gpu.h, "The table sharded by key hash") ----------------------------------
+    def build_hash_table_shard(self, rank: int, world: int):
+        self._check(self._lib.sage2gpu_build_hash_table_shard(self._h, int(rank), int(world)), "build_hash_table_shard")
+
+    def phase_a_sharded_begin(self, rank: int, world: int) -> tuple:
+        """(first, count): this rank's slice of the unique reads (0-based indices)."""
+        first, count = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sage2gpu_phase_a_sharded_begin(self._h, int(rank), int(world), C.byref(first), C.byref(count)),
+                    "phase_a_sharded_begin")
+        return int(first.value), int(count.value)
+
+    def route_begin(self, what: int, first: int, count: int, exact: bool, world: int) -> dict:
+        """-> {"ptr": device pointer of the query streams, "counts": queries per owner, "words": uint64 per query,
+        "n_reads": reads in the batch}."""
+        q = C.c_void_p()
+        counts = (C.c_uint64 * world)()
+        n = C.c_uint64()
+        self._check(self._lib.sage2gpu_route_begin(self._h, int(what), int(first), int(count), int(bool(exact)), int(world),
+                                                   C.byref(q), counts, C.byref(n)), "route_begin")
+        return {"ptr": q.value or 0, "counts": [int(x) for x in counts], "words": 2 if exact else 1, "n_reads": int(n.value)}
+
+    def shard_answer(self, queries_ptr: int, counts_per_source, exact: bool, world: int) -> dict:
+        """-> {"resp": device pointer (uint64 per query), "entries": device pointer (uint32), "entry_counts": per source}."""
+        cps = (C.c_uint64 * world)(*[int(x) for x in counts_per_source])
+        resp, ent = C.c_void_p(), C.c_void_p()
+        ecnt = (C.c_uint64 * world)()
+        self._check(self._lib.sage2gpu_shard_answer(self._h, queries_ptr or None, cps, int(bool(exact)), int(world), C.byref(resp),
+                                                    C.byref(ent), ecnt), "shard_answer")
+        return {"resp": resp.value or 0, "entries": ent.value or 0, "entry_counts": [int(x) for x in ecnt]}
+
+    def route_finish(self, resp_ptr: int, entries_ptr: int, entry_counts):
+        ec = (C.c_uint64 * len(entry_counts))(*[int(x) for x in entry_counts])
+        self._check(self._lib.sage2gpu_route_finish(self._h, resp_ptr or None, entries_ptr or None, ec), "route_finish")
+
+    def phase_a_routed(self) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.sage2gpu_phase_a_routed(self._h, C.byref(n)), "phase_a_routed")
+        return int(n.value)
+
+    def phase_a_sharded_end(self):
+        self._check(self._lib.sage2gpu_phase_a_sharded_end(self._h), "phase_a_sharded_end")
+
+    def phase_b(self):
+        self._check(self._lib.sage2gpu_phase_b(self._h), "phase_b")
 
     def run_steps123(self, bases, offsets, min_overlap: int):
         self.load_reads(bases, offsets, min_overlap)

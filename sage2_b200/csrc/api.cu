@@ -265,12 +265,13 @@ int sage2gpu_build_hash_table(sage2gpu_ctx *ctx)
 static void finish_graph(sg::Context &c)
 {
     SG_CHECK(c.have_phase_a, "phase A must run first");
-    {
+    if (!c.have_phase_b) {      // (a sharded build ran it already: the reads left for phase C had to be routed first)
         StageTimer t(c.stream);
         sg::stage_phase_b(c);
         c.tm.phase_b = t.stop();
     }
     sg::stage_phase_c_and_finalize(c);
+    c.have_phase_b = false;
     c.tm.total_device = c.tm.ingest + c.tm.sort_reads + c.tm.build_table + c.tm.phase_a + c.tm.phase_b +
                         c.tm.phase_c_dev + c.tm.phase_c_host + c.tm.sort_edges;
 }
@@ -302,6 +303,84 @@ int sage2gpu_phase_a_buffers(sage2gpu_ctx *ctx, void **right_ext, void **left_ex
 int sage2gpu_finish_graph(sage2gpu_ctx *ctx)
 {
     return guarded(ctx, [&](sg::Context &c) { finish_graph(c); });
+}
+
+// ---- sharded table -----------------------------------------------------------------------------------
+int sage2gpu_build_hash_table_shard(sage2gpu_ctx *ctx, int rank, int world)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_build_table(c, rank, world);
+        c.tm.build_table = t.stop();
+    });
+}
+
+int sage2gpu_phase_a_sharded_begin(sage2gpu_ctx *ctx, int rank, int world, uint64_t *first, uint64_t *count)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        sg::stage_phase_a_sharded_begin(c, rank, world);
+        c.tm.phase_a = 0;
+        if (first) *first = c.pa_lo;
+        if (count) *count = c.pa_hi - c.pa_lo;
+    });
+}
+
+int sage2gpu_route_begin(sage2gpu_ctx *ctx, int what, uint64_t first, uint64_t count, int exact, int world, void **queries,
+                         uint64_t *counts, uint64_t *n_reads)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(counts != nullptr, "null counts");
+        StageTimer t(c.stream);
+        sg::stage_route_begin(c, what, first, count, exact, world, queries, counts);
+        if (n_reads) *n_reads = c.rt_n;
+        (what == 1 ? c.tm.phase_c_dev : c.tm.phase_a) += t.stop();
+    });
+}
+
+int sage2gpu_shard_answer(sage2gpu_ctx *ctx, const void *queries, const uint64_t *counts_per_source, int exact, int world, void **responses,
+                          void **entries, uint64_t *entry_counts)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(counts_per_source && responses && entries && entry_counts, "null argument");
+        StageTimer t(c.stream);
+        sg::stage_shard_answer(c, queries, counts_per_source, exact, world, responses, entries, entry_counts);
+        c.tm.phase_a += t.stop();
+    });
+}
+
+int sage2gpu_route_finish(sage2gpu_ctx *ctx, const void *responses, const void *entries, const uint64_t *entry_counts)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(entry_counts != nullptr, "null entry counts");
+        StageTimer t(c.stream);
+        sg::stage_route_finish(c, responses, entries, entry_counts);
+        (c.rt_what == 1 ? c.tm.phase_c_dev : c.tm.phase_a) += t.stop();
+    });
+}
+
+int sage2gpu_phase_a_routed(sage2gpu_ctx *ctx, uint64_t *n_redo)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        const sg::u64 r = sg::stage_phase_a_routed(c);
+        if (n_redo) *n_redo = r;
+        c.tm.phase_a += t.stop();
+    });
+}
+
+int sage2gpu_phase_a_sharded_end(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) { sg::stage_phase_a_sharded_end(c); });
+}
+
+int sage2gpu_phase_b(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.have_phase_a, "phase A must run first");
+        StageTimer t(c.stream);
+        sg::stage_phase_b(c);
+        c.tm.phase_b = t.stop();
+    });
 }
 
 int sage2gpu_build_overlap_graph(sage2gpu_ctx *ctx)

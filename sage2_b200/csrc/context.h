@@ -37,6 +37,8 @@ struct Context {
         raw.persistent = F.persistent = RC.persistent = len.persistent = freq.persistent = true;
         slots.persistent = entries.persistent = true;
         extR.persistent = extL.persistent = flag5.persistent = cont_max.persistent = explored.persistent = edges.persistent = true;
+        rt_queries.persistent = rt_qmap.persistent = rt_wslot.persistent = rt_wentries.persistent = rt_ids.persistent = true;
+        rt_redo.persistent = an_resp.persistent = an_entries.persistent = true;
     }
     Arena arena;
     int device = 0;
@@ -67,6 +69,7 @@ struct Context {
     DevBuf<u64> slots;          // [cap]
     DevBuf<u32> entries;        // [4U]
     u64 cap = 0;
+    int tb_rank = 0, tb_world = 1;   // which key-hash shard the table holds (0 / 1: all keys)
 
     // phase A output
     DevBuf<u64> extR, extL;     // [U] ext_pack
@@ -77,9 +80,25 @@ struct Context {
     // edges
     DevBuf<u64> edges;          // [2*n_edges] (w0,w1) pairs, canonical sorted after finalize
     std::vector<u64> h_edges;   // host copy of final edges (w0,w1 interleaved)
-    bool have_reads = false, have_table = false, have_phase_a = false, have_graph = false;
+    bool have_reads = false, have_table = false, have_phase_a = false, have_phase_b = false, have_graph = false;
     u64 pa_chunk = 0;           // reads per rank in the last phase-A call (partition_chunk)
     int pa_world = 1;
+    u64 pa_lo = 0, pa_hi = 0;   // this rank's slice of the reads (sharded phase A)
+
+    // routed probes (shard.cu).  Source side: the current batch
+    DevBuf<u64> rt_queries;     // [Q] key hashes or [2Q] keys, one contiguous stream per owner
+    DevBuf<u32> rt_qmap;        // [Q] send position -> s * rt_wstride + window
+    DevBuf<u64> rt_wslot;       // [rt_n * rt_wstride] answer word of every window of the batch
+    DevBuf<u32> rt_wentries;    // entry streams of all owners back to back
+    DevBuf<u32> rt_ids;         // list batches: 0-based read indices, ascending
+    DevBuf<uint8_t> rt_redo;    // [pa_chunk] reads of the slice that met a tag collision
+    u64 rt_n = 0, rt_first = 0, rt_Q = 0, rt_counts[kMaxWorld] = {};
+    u32 rt_wstride = 0;
+    int rt_what = 0, rt_world = 1, rt_state = 0;     // state: 0 idle, 1 queries out, 2 answers in
+    bool rt_is_list = false, rt_exact = false, rt_for_c = false;
+    // owner side: the answers of the last sage2gpu_shard_answer
+    DevBuf<u64> an_resp;
+    DevBuf<u32> an_entries;
 };
 
 // stages (each throws sg::CudaError)
@@ -89,8 +108,16 @@ void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets
 bool stage_parse_text_chunk(Context &c, const uint8_t *text, u64 n_bytes, bool final, int &marker, u64 max_records, u64 &consumed, u64 &n_records);
 void stage_remove_uploaded(Context &c, u64 first, u64 count);
 void stage_organize_reads(Context &c);
-void stage_build_table(Context &c);
+void stage_build_table(Context &c, int rank = 0, int world = 1);   // key-hash shard `rank` of `world`
 void stage_phase_a(Context &c, int rank = 0, int world = 1);   // rank's slice of the reads; arrays padded to world * chunk
+// sharded table (shard.cu, search.cu)
+void stage_phase_a_sharded_begin(Context &c, int rank, int world);
+void stage_route_begin(Context &c, int what, u64 first, u64 count, int exact, int world, void **queries, u64 *counts);
+void stage_shard_answer(Context &c, const void *queries, const u64 *counts_per_source, int exact, int world, void **responses, void **entries,
+                        u64 *entry_counts);
+void stage_route_finish(Context &c, const void *responses, const void *entries, const u64 *entry_counts);
+u64 stage_phase_a_routed(Context &c);
+void stage_phase_a_sharded_end(Context &c);
 void stage_phase_b(Context &c);
 void stage_phase_c_and_finalize(Context &c);
 // device-side text formatters of the reference's -s files (format.cu); false = short write

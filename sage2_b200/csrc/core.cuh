@@ -261,6 +261,15 @@ SG_HD u64 candidate_record(int type, int j, int h, int len1, int len2, u32 rid2_
 // ---- multi-GPU: reads (as query sources) are block-partitioned by id, the last rank's slice may be short ----
 SG_HD u64 partition_chunk(u64 U, int world) { return world <= 1 ? U : (U + (u64)world - 1) / (u64)world; }
 
+// ---- multi-GPU, sharded table: shard g owns the keys with key_owner(hash) == g.  The owner comes
+// from hash bits 24..33: disjoint from the slot tag (bits 0..23) and from the bits home_sector() consumes.
+constexpr int kMaxWorld = 64;
+SG_HD int key_owner(u64 hsh, int world) { return world <= 1 ? 0 : (int)(((hsh >> 24) & 0x3FFull) % (u64)world); }
+// Answer of an owner to one routed window probe = a slot word without its tag: count << 33 | payload, payload =
+// the only entry (count 1), a representative entry (count >= 100, tag probes only) or the offset of the bucket's
+// run in the entry stream the owner returns alongside.  0 = absent.
+SG_HD u64 answer_encode(u32 count, u64 payload) { return ((u64)(count > 127 ? 127u : count) << 33) | payload; }
+
 // ---- phase B (economyGraph.cpp:455-480) ---------------------------------------------------------------
 // State after phase A.  The reference writes 6 from any thread (:735) and 5 from the owner (:444); a
 // 1-thread run resolves that race by time order, reproduced here: the containing scan with the largest

@@ -127,6 +127,7 @@ void stage_phase_b(Context &c)
     c.edges.alloc(4 * U + 2, st);
     c.cnt.contained_ext = c.cnt.contained_size = 0;
     c.cnt.left_to_explore = 0; c.cnt.edges_phase_b = 0;
+    c.have_phase_b = true;
     if (U == 0) return;
     DevBuf<unsigned long long> d_cnt(3, st);
     SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 3 * sizeof(unsigned long long), st));
@@ -202,7 +203,7 @@ void stage_phase_c_and_finalize(Context &c)
     c.cnt.phase_c_on_device = 0;
     c.cnt.n_edges = 0;
     c.h_edges.clear();
-    if (U == 0) { c.have_graph = true; return; }
+    if (U == 0) { c.have_graph = true; c.rt_for_c = false; return; }
 
     cudaEvent_t ev0, ev1, ev2;
     SG_CUDA(cudaEventCreate(&ev0)); SG_CUDA(cudaEventCreate(&ev1)); SG_CUDA(cudaEventCreate(&ev2));
@@ -317,7 +318,7 @@ void stage_phase_c_and_finalize(Context &c)
     if (nAll == 0) {
         SG_CUDA(cudaEventRecord(ev2, st));
         SG_CUDA(cudaEventSynchronize(ev2));
-        c.have_graph = true;
+        c.have_graph = true; c.rt_for_c = false;
         c.tm.phase_c_host = host_ms;
         cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
         return;
@@ -369,7 +370,7 @@ void stage_phase_c_and_finalize(Context &c)
     c.tm.phase_c_host = host_ms;
     c.tm.sort_edges = ms12 - host_ms > 0 ? ms12 - host_ms : 0;
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
-    c.have_graph = true;
+    c.have_graph = true; c.rt_for_c = false;
 }
 
 }  // namespace sg

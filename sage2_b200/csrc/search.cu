@@ -32,6 +32,16 @@ struct SearchParams {
     u64 nsec, U;
     u64 lo, hi;         // phase A handles read indices [lo, hi)
     int h, k;
+    // ROUTED kernels (sharded table, shard.cu): the probes of a batch of reads were answered by the shards that
+    // own their keys.  The batch is ids[0..n) (0-based read indices) or lo + [0..n); the answer word of window j
+    // of the s-th read is wslot[s * wstride + j] (core.cuh answer_encode) and `entries` is the batch's own entry
+    // stream.  Untrusted answers (tag probes) are proven in the kernel; a collision sets redo[s] and skips the read.
+    const u64 *wslot;
+    const u32 *ids;
+    uint8_t *redo;
+    u64 n;
+    u32 wstride;
+    int trusted;
 };
 
 // 256-bit read-only load: one 32-byte sector per lane and instruction (LDG.E.256 on sm_100a)
@@ -197,7 +207,7 @@ __device__ __forceinline__ u64 make_item(int jj, bool first, bool inl, u64 paylo
 // ------------------------------------------------------------------------------------------------
 // K4: phase A
 // ------------------------------------------------------------------------------------------------
-template <int SW, int MINB>
+template <int SW, int MINB, bool ROUTED>
 __global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32, MINB)
 phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, uint8_t *__restrict__ flag5,
                u32 *__restrict__ cont_max, unsigned long long *__restrict__ counters)
@@ -218,7 +228,9 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
     unsigned calls = 0, probes = 0, n_exact = 0, n_restart = 0;      // per warp: far below 2^32
     if (lane == 0) { Xf[SW] = 0; Xr[SW] = 0; prevR[SW] = 0; prevL[SW] = 0; }
 
-    for (u64 i = P.lo + (u64)blockIdx.x * WARPS + warp; i < P.hi; i += nwarps) {
+    const u64 n_batch = ROUTED ? P.n : P.hi - P.lo;
+    for (u64 sb = (u64)blockIdx.x * WARPS + warp; sb < n_batch; sb += nwarps) {
+        const u64 i = (ROUTED && P.ids) ? (u64)P.ids[sb] : P.lo + sb;
         if (lane < SW) { Xf[lane] = P.F[i * SWS + lane]; Xr[lane] = P.RC[i * SWS + lane]; }
         __syncwarp();
         const int len1 = (int)(Xf[SW - 1] & 0xFFFF);
@@ -240,7 +252,31 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
             u64 payload = 0;
             u32 cnt = 0;
             const int j = base + lane;
-            if (j < W) {
+            if (ROUTED) {
+                bool bad = false;
+                if (j < W) {
+                    const u64 w = __ldg(&P.wslot[sb * P.wstride + j]);
+                    cnt = slot_get_count(w); payload = slot_get_payload(w);
+                    if (cnt >= (u32)kHashThreshold) {       // masked key (tag probes only): proven through its
+                        if (!P.trusted) {                   // representative, then it reads as absent (hashTable.cpp:203)
+                            u64 v0, v1, w0, w1;
+                            t_extract_key<SW>(Xf, j, P.h, v0, v1);
+                            const u32 ent = (u32)payload;
+                            const u64 *X = ((ent & 2) ? P.RC : P.F) + (u64)(ent >> 2) * SWS;
+                            const int l = (int)(__ldg(&X[SW - 1]) & 0xFFFF);
+                            t_extract_key<SW>(X, (ent & 1) ? l - P.h : 0, P.h, w0, w1);
+                            bad = w0 != v0 || w1 != v1;
+                        }
+                        cnt = 0; payload = 0;
+                    }
+                }
+                if (__any_sync(FULL, bad)) {
+                    if (lane == 0) P.redo[sb] = 1;
+                    n_restart++;
+                    __syncwarp();
+                    goto next_read;
+                }
+            } else if (j < W) {
                 u64 v0, v1;
                 t_extract_key<SW>(Xf, j, P.h, v0, v1);
                 probe_window<SW>(P, v0, v1, exact_probe, payload, cnt);
@@ -327,9 +363,10 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                     }
                 }
                 if (__any_sync(FULL, fp)) {          // tag collision: redo this read with verified probes
-                    exact_probe = true;
                     n_restart++;
                     __syncwarp();
+                    if (ROUTED) { if (lane == 0) P.redo[sb] = 1; goto next_read; }
+                    exact_probe = true;
                     goto restart;
                 }
                 unsigned hm = __ballot_sync(FULL, hit);
@@ -452,6 +489,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
             }
         }
         calls += my_calls; probes += my_probes;
+    next_read:
         __syncwarp();
     }
 #pragma unroll
@@ -473,7 +511,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
 // skipped at :605 and never returns to 0).  Pass 1 counts, pass 2 fills.
 // candidate = read2(1-based) << 32 | edgeType << 20 | (overhang & 0xFFFFF)
 // ------------------------------------------------------------------------------------------------
-template <int SW, bool FILL>
+template <int SW, bool FILL, bool ROUTED>
 __global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32)
 phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint8_t *__restrict__ explored,
                u32 *__restrict__ counts, const u32 *__restrict__ offsets, u64 *__restrict__ cand)
@@ -496,7 +534,12 @@ phase_c_kernel(SearchParams P, const u32 *__restrict__ s_ids, u64 nS, const uint
             const int j = base + lane;
             u64 payload = 0;
             u32 cnt = 0;
-            if (j < W) {
+            if (ROUTED) {          // verified answers of the owning shards, s_ids is the routed batch
+                if (j < W) {
+                    const u64 w = __ldg(&P.wslot[s * P.wstride + j]);
+                    cnt = slot_get_count(w); payload = slot_get_payload(w);
+                }
+            } else if (j < W) {
                 u64 v0, v1;
                 t_extract_key<SW>(Xf, j, P.h, v0, v1);
                 probe_window<SW>(P, v0, v1, true, payload, cnt);
@@ -550,16 +593,17 @@ static unsigned search_grid(u64 n_reads, int warps, int blocks_per_sm)
     return (unsigned)g;
 }
 
-template <int SW, int MINB>
+template <int SW, int MINB, bool ROUTED>
 static void launch_phase_a_v(Context &c, const SearchParams &P, unsigned long long *d_counters)
 {
     constexpr int WARPS = SearchCfg<SW>::WARPS;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_kernel<SW, MINB>, WARPS * 32, 0));
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_kernel<SW, MINB, ROUTED>, WARPS * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    phase_a_kernel<SW, MINB><<<search_grid(P.hi - P.lo, WARPS, blocks_per_sm), WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters);
+    const u64 n = ROUTED ? P.n : P.hi - P.lo;
+    phase_a_kernel<SW, MINB, ROUTED><<<search_grid(n, WARPS, blocks_per_sm), WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters);
 }
 
 // MINB = resident blocks per SM the register budget is cut for (occupancy against spills).
@@ -568,13 +612,20 @@ static void launch_phase_a(Context &c, const SearchParams &P, unsigned long long
 {
     if constexpr (SW <= 8) {
         static const int minb = [] { const char *e = getenv("SAGE2GPU_PA_MINB"); return e ? atoi(e) : 4; }();
-        if (minb <= 2) launch_phase_a_v<SW, 2>(c, P, d_counters);
-        else if (minb == 3) launch_phase_a_v<SW, 3>(c, P, d_counters);
-        else if (minb == 4) launch_phase_a_v<SW, 4>(c, P, d_counters);
-        else launch_phase_a_v<SW, 5>(c, P, d_counters);
+        if (minb <= 2) launch_phase_a_v<SW, 2, false>(c, P, d_counters);
+        else if (minb == 3) launch_phase_a_v<SW, 3, false>(c, P, d_counters);
+        else if (minb == 4) launch_phase_a_v<SW, 4, false>(c, P, d_counters);
+        else launch_phase_a_v<SW, 5, false>(c, P, d_counters);
     } else {
-        launch_phase_a_v<SW, 1>(c, P, d_counters);
+        launch_phase_a_v<SW, 1, false>(c, P, d_counters);
     }
+}
+
+template <int SW>
+static void launch_phase_a_routed(Context &c, const SearchParams &P, unsigned long long *d_counters)
+{
+    if constexpr (SW <= 8) launch_phase_a_v<SW, 4, true>(c, P, d_counters);
+    else launch_phase_a_v<SW, 1, true>(c, P, d_counters);
 }
 
 template <int SW>
@@ -582,8 +633,13 @@ static void launch_phase_c(Context &c, const SearchParams &P, const u32 *s_ids, 
 {
     constexpr int WARPS = SearchCfg<SW>::WARPS;
     const unsigned g = search_grid(nS, WARPS, 8);
-    if (fill) phase_c_kernel<SW, true><<<g, WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
-    else phase_c_kernel<SW, false><<<g, WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
+    if (P.wslot) {
+        if (fill) phase_c_kernel<SW, true, true><<<g, WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
+        else phase_c_kernel<SW, false, true><<<g, WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
+    } else {
+        if (fill) phase_c_kernel<SW, true, false><<<g, WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
+        else phase_c_kernel<SW, false, false><<<g, WARPS * 32, 0, c.stream>>>(P, s_ids, nS, c.explored.p, counts, offsets, cand);
+    }
 }
 
 #define SG_DISPATCH_SW(SWV, CALL)                                                       \
@@ -605,7 +661,17 @@ static SearchParams make_params(const Context &c)
     SearchParams P;
     P.F = c.F.p; P.RC = c.RC.p; P.slots = c.slots.p; P.entries = c.entries.p;
     P.nsec = c.cap / kSlotsPerSector; P.U = c.cnt.unique_reads; P.lo = 0; P.hi = P.U; P.h = c.h; P.k = c.min_overlap;
+    P.wslot = nullptr; P.ids = nullptr; P.redo = nullptr; P.n = 0; P.wstride = 0; P.trusted = 0;
     return P;
+}
+
+// the answers of the routed batch (shard.cu) instead of the local table
+static void use_routed_batch(const Context &c, SearchParams &P)
+{
+    P.slots = nullptr; P.nsec = 0;
+    P.wslot = c.rt_wslot.p; P.entries = c.rt_wentries.p; P.wstride = c.rt_wstride; P.n = c.rt_n;
+    P.ids = c.rt_is_list ? c.rt_ids.p : nullptr; P.lo = c.rt_first; P.hi = c.rt_first + c.rt_n;
+    P.trusted = c.rt_exact ? 1 : 0;
 }
 
 void stage_phase_a(Context &c, int rank, int world)
@@ -613,11 +679,12 @@ void stage_phase_a(Context &c, int rank, int world)
     cudaStream_t st = c.stream;
     ArenaScope arena_scope(c.arena, st);
     SG_CHECK(c.have_table, "build_hash_table must run before the overlap search");
+    SG_CHECK(c.tb_world == 1, "this context holds one shard of the table: use the routed search (sage2gpu_route_*)");
     SG_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
     const u64 U = c.cnt.unique_reads;
     const u64 chunk = partition_chunk(U, world), padded = chunk * (u64)world;
     c.pa_chunk = chunk; c.pa_world = world;
-    c.have_phase_a = false; c.have_graph = false;
+    c.have_phase_a = false; c.have_phase_b = false; c.have_graph = false;
     c.extR.alloc(padded, st); c.extL.alloc(padded, st); c.flag5.alloc(padded, st); c.cont_max.alloc(padded, st);
     c.cnt.compare_calls = 0; c.cnt.window_probes = 0; c.cnt.slow_path_reads = 0; c.cnt.probe_restarts = 0;
     if (U == 0) { c.have_phase_a = true; return; }
@@ -652,10 +719,81 @@ void stage_phase_a(Context &c, int rank, int world)
     c.have_phase_a = true;
 }
 
+// ---- phase A over a sharded table: begin (allocate the slice's arrays) / one routed batch / end ------------------
+void stage_phase_a_sharded_begin(Context &c, int rank, int world)
+{
+    cudaStream_t st = c.stream;
+    SG_CHECK(c.have_table, "build_hash_table[_shard] must run before the overlap search");
+    SG_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+    const u64 U = c.cnt.unique_reads;
+    const u64 chunk = partition_chunk(U, world), padded = chunk * (u64)world;
+    c.pa_chunk = chunk; c.pa_world = world;
+    c.pa_lo = (u64)rank * chunk < U ? (u64)rank * chunk : U;
+    c.pa_hi = c.pa_lo + chunk < U ? c.pa_lo + chunk : U;
+    c.have_phase_a = false; c.have_phase_b = false; c.have_graph = false;
+    c.extR.alloc(padded, st); c.extL.alloc(padded, st); c.flag5.alloc(padded, st); c.cont_max.alloc(padded, st);
+    c.rt_redo.alloc(chunk, st);
+    c.cnt.compare_calls = 0; c.cnt.window_probes = 0; c.cnt.slow_path_reads = 0; c.cnt.probe_restarts = 0;
+    c.tm.phase_a_kernel = 0;
+    if (U == 0) return;
+    SG_CUDA(cudaMemsetAsync(c.extR.p, 0, padded * sizeof(u64), st));
+    SG_CUDA(cudaMemsetAsync(c.extL.p, 0, padded * sizeof(u64), st));
+    SG_CUDA(cudaMemsetAsync(c.flag5.p, 0, padded, st));
+    SG_CUDA(cudaMemsetAsync(c.cont_max.p, 0, padded * sizeof(u32), st));
+    SG_CUDA(cudaMemsetAsync(c.rt_redo.p, 0, chunk, st));
+}
+
+// K4 on the routed batch (route_begin .. route_finish); returns the reads of the batch flagged for the redo pass
+u64 stage_phase_a_routed(Context &c)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    SG_CHECK(c.rt_state == 2, "route_finish must precede the routed search");
+    SG_CHECK(c.rt_what == 0 || c.rt_what == 2, "the routed batch is not a phase-A batch");
+    c.rt_state = 0;
+    if (c.rt_n == 0) return 0;
+    SearchParams P = make_params(c);
+    use_routed_batch(c, P);
+    // redo flags: by position in the slice for range batches; a private array for the redo list itself
+    DevBuf<uint8_t> redo2;
+    if (c.rt_is_list) { redo2.alloc(c.rt_n, st); SG_CUDA(cudaMemsetAsync(redo2.p, 0, c.rt_n, st)); P.redo = redo2.p; }
+    else P.redo = c.rt_redo.p + (c.rt_first - c.pa_lo);
+    DevBuf<unsigned long long> d_counters(4, st);
+    SG_CUDA(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+    cudaEvent_t e0, e1;
+    SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
+    SG_CUDA(cudaEventRecord(e0, st));
+    SG_DISPATCH_SW(c.SW, launch_phase_a_routed<SWC>(c, P, d_counters.p));
+    SG_LAUNCHED();
+    SG_CUDA(cudaEventRecord(e1, st));
+    unsigned long long h[4];
+    SG_CUDA(cudaMemcpyAsync(h, d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.cnt.compare_calls += h[0];
+    c.cnt.window_probes += h[1];
+    c.cnt.slow_path_reads += h[2];
+    if (!c.rt_exact) c.cnt.probe_restarts += h[3];
+    else SG_CHECK(h[3] == 0, "a verified answer failed its proof in the search kernel");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c.tm.phase_a_kernel += ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return h[3];
+}
+
+void stage_phase_a_sharded_end(Context &c)
+{
+    c.have_phase_a = true;
+}
+
 // used by graph.cu
 void launch_phase_c_candidates(Context &c, const u32 *s_ids, u64 nS, u32 *counts, const u32 *offsets, u64 *cand, bool fill)
 {
-    const SearchParams P = make_params(c);
+    SearchParams P = make_params(c);
+    if (c.tb_world > 1 || c.rt_for_c) {      // sharded table: the state-0 reads were routed (what = 1) before finish_graph
+        SG_CHECK(c.rt_for_c && c.rt_n == nS, "the reads left for phase C must be routed before finish_graph");
+        use_routed_batch(c, P);
+    }
     SG_DISPATCH_SW(c.SW, launch_phase_c<SWC>(c, P, s_ids, nS, counts, offsets, cand, fill));
     SG_LAUNCHED();
 }

@@ -1,0 +1,365 @@
+// shard.cu -- the prefix/suffix table sharded by key hash over the GPUs of one box (north_star):
+// shard g (table.cu, stage_build_table(rank, world)) indexes the keys with key_owner(hash) == g; the reads stay
+// replicated.  A window probe of HashTable::hashTableSearch (hashTable.cpp:193-231) becomes a routed query:
+//
+//   source  route_begin   the window keys of a batch of reads (a slice of phase A, the redo list, or the reads left
+//                         for phase C) are derived (utils.cpp:171-207) and bucketed by owner: one contiguous
+//                         stream of queries per owner + the map send position -> (read of the batch, window).
+//                         A query is the 64-bit key hash (tag probes) or the 128-bit key (verified probes).
+//           [all-to-all of the query streams: NCCL over NVLink, sage2_b200/multi.py]
+//   owner   shard_answer  one thread per received query probes the shard's sector index and answers with a slot
+//                         word without its tag (count | inline entry / run offset); the entry runs of the
+//                         2..99-entry buckets are copied into one stream per source, in query order.
+//           [all-to-all of the answer words and of the entry streams]
+//   source  route_finish  answers are scattered to wslot[read of the batch][window] (run offsets rebased into the
+//                         concatenated entry streams): a direct-indexed table of exactly the probes the batch needs.
+//
+// The search kernels then run unchanged except for stage 1 (search.cu, ROUTED): a coalesced load of wslot instead
+// of a random sector probe.  Tag probes are proven by the search kernel itself (first entry of every bucket /
+// representative of a masked key); a 24-bit tag collision flags the read, and the flagged reads are routed again
+// with verified probes (the owner confirms the key from its copy of the reads, hashTable.cpp:203-220).
+#include <stdlib.h>
+#include "context.h"
+
+namespace sg {
+
+constexpr int RT_WARPS = 8;
+
+__device__ __forceinline__ void ldg256s(const u64 *p, u64 (&v)[4])
+{
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+
+// ---- source: keys of a batch, bucketed by owner ------------------------------------------------------------
+// WRITE = false: g_count[g] += queries for owner g.  WRITE = true: g_count[g] is the cursor of owner g's stream
+// (initialised to the stream's base); a tile of RT_WARPS reads reserves its share with one atomic per owner.
+template <bool WRITE>
+__global__ void __launch_bounds__(RT_WARPS * 32) route_kernel(const u64 *__restrict__ F, int SW, int SWS, int h, const u32 *__restrict__ ids, u64 first,
+                                                              u64 n, u32 wstride, int world, int exact, unsigned long long *__restrict__ g_count,
+                                                              u64 *__restrict__ queries, u32 *__restrict__ qmap)
+{
+    __shared__ u64 sX[RT_WARPS][kMaxWords];
+    __shared__ unsigned int tcount[kMaxWorld];
+    __shared__ unsigned long long tbase[kMaxWorld];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    u64 *X = sX[warp];
+    if (threadIdx.x < kMaxWorld) tcount[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 ntiles = (n + RT_WARPS - 1) / RT_WARPS;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u64 s = tile * RT_WARPS + warp;
+        const bool active = s < n;
+        int W = 0;
+        if (active) {
+            const u64 i = ids ? (u64)ids[s] : first + s;
+            for (int w = lane; w < SW; w += 32) X[w] = F[i * SWS + w];
+            __syncwarp();
+            W = rec_len(X, SW) - h + 1;
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < (WRITE ? 2 : 1); ++pass) {
+            for (int base = 0; base < W; base += 32) {
+                const int j = base + lane;
+                int g = -1;
+                u64 v0 = 0, v1 = 0, hsh = 0;
+                if (j < W) {
+                    extract_key(X, SW, j, h, v0, v1);
+                    hsh = hash_key(v0, v1);
+                    g = key_owner(hsh, world);
+                }
+                const unsigned same = __match_any_sync(0xffffffffu, g);
+                const int leader = __ffs(same) - 1;
+                unsigned off = 0;
+                if (g >= 0 && lane == leader) off = atomicAdd(&tcount[g], (unsigned)__popc(same));
+                if (WRITE && pass == 1) {
+                    off = __shfl_sync(0xffffffffu, off, leader);
+                    if (g >= 0) {
+                        const u64 pos = tbase[g] + off + (unsigned)__popc(same & lt_mask);
+                        if (exact) { queries[2 * pos] = v0; queries[2 * pos + 1] = v1; }
+                        else queries[pos] = hsh;
+                        qmap[pos] = (u32)(s * wstride + (u64)j);
+                    }
+                }
+            }
+            if (WRITE && pass == 0) {
+                __syncthreads();
+                if (threadIdx.x < world) {
+                    tbase[threadIdx.x] = atomicAdd(&g_count[threadIdx.x], (unsigned long long)tcount[threadIdx.x]);
+                    tcount[threadIdx.x] = 0;
+                }
+                __syncthreads();
+            }
+        }
+        if (WRITE) {
+            __syncthreads();
+            if (threadIdx.x < world) tcount[threadIdx.x] = 0;
+            __syncthreads();
+        }
+    }
+    if (!WRITE) {
+        __syncthreads();
+        if (threadIdx.x < world && tcount[threadIdx.x]) atomicAdd(&g_count[threadIdx.x], (unsigned long long)tcount[threadIdx.x]);
+    }
+}
+
+// ---- owner: answers -------------------------------------------------------------------------------------------
+// hashTableSearch on this shard's sector index.  Tag probes take the first slot whose 24-bit tag matches (proven by
+// the source's search kernel); verified probes confirm the key from the bucket's first read and skip masked keys.
+// fake_mask (test knob SAGE2GPU_FAKE_TAG_COLLISIONS): tag probes whose hash has none of these bits take the first
+// occupied slot they see, i.e. behave like a tag collision.
+__global__ void __launch_bounds__(256) answer_kernel(const u64 *__restrict__ queries, u64 nq, int exact, const u64 *__restrict__ slots, u64 nsec,
+                                                     const u32 *__restrict__ entries, const u64 *__restrict__ F, const u64 *__restrict__ RC,
+                                                     const uint16_t *__restrict__ len, int SW, int SWS, int h, u64 fake_mask,
+                                                     u64 *__restrict__ resp, u32 *__restrict__ runlen)
+{
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
+        u64 v0 = 0, v1 = 0, hsh;
+        if (exact) { v0 = queries[2 * p]; v1 = queries[2 * p + 1]; hsh = hash_key(v0, v1); }
+        else hsh = queries[p];
+        const u64 tag = slot_tag(hsh);
+        const bool fake = !exact && fake_mask != 0 && (hsh & fake_mask) == 0;
+        u64 answer = 0;
+        u32 run = 0;
+        bool done = nsec == 0;
+        u64 sec = done ? 0 : home_sector(hsh, nsec);
+        while (!done) {
+            u64 s[4];
+            ldg256s(slots + kSlotsPerSector * sec, s);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (done) continue;
+                const u64 slot = s[t];
+                if (slot == 0) { done = true; continue; }
+                if (slot_get_tag(slot) != tag && !fake) continue;
+                const u32 c = slot_get_count(slot);
+                const u64 pay = slot_get_payload(slot);
+                if (exact) {
+                    const u32 ent = (c == 1 || c >= (u32)kHashThreshold) ? (u32)pay : __ldg(&entries[pay]);
+                    const u64 rid = ent >> 2;
+                    u64 w0, w1;
+                    entry_key(F + rid * SWS, RC + rid * SWS, SW, len[rid], h, (int)(ent & 3), w0, w1);
+                    if (w0 != v0 || w1 != v1) continue;                     // tag collision: keep probing
+                    if (c >= (u32)kHashThreshold) { done = true; continue; }   // masked key reads as absent (hashTable.cpp:203)
+                }
+                answer = answer_encode(c, pay);
+                if (c >= 2 && c < (u32)kHashThreshold) run = c;
+                done = true;
+            }
+            sec = (sec + 1 == nsec) ? 0 : sec + 1;
+        }
+        resp[p] = answer;
+        runlen[p] = run;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) runlen[nq] = 0;     // sentinel: off[nq] = total after the scan
+}
+
+// entry runs -> the stream of the query's source, answer payload := offset inside that stream
+__global__ void __launch_bounds__(256) answer_runs_kernel(u64 *__restrict__ resp, const u32 *__restrict__ runlen, const u32 *__restrict__ off, u64 nq,
+                                                          const u64 *__restrict__ seg_start /*[world+1]*/, int world,
+                                                          const u32 *__restrict__ entries, u32 *__restrict__ out)
+{
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
+        const u32 c = runlen[p];
+        if (c == 0) continue;
+        int s = 0;
+        while (s + 1 < world && seg_start[s + 1] <= p) ++s;
+        const u32 rel = off[p] - off[seg_start[s]];
+        const u64 src = slot_get_payload(resp[p]);
+        for (u32 e = 0; e < c; ++e) out[off[p] + e] = entries[src + e];
+        resp[p] = answer_encode(c, rel);
+    }
+}
+
+__global__ void seg_totals_kernel(const u32 *__restrict__ off, const u64 *__restrict__ seg_start, int world, u64 *__restrict__ out)
+{
+    const int s = threadIdx.x;
+    if (s < world) out[s] = (u64)(off[seg_start[s + 1]] - off[seg_start[s]]);
+}
+
+// ---- source: answers -> wslot ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) route_finish_kernel(const u64 *__restrict__ resp, const u32 *__restrict__ qmap, u64 Q,
+                                                           const u64 *__restrict__ qbase /*[world+1]*/, const u64 *__restrict__ ebase /*[world]*/,
+                                                           int world, u64 *__restrict__ wslot)
+{
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < Q; p += (u64)gridDim.x * blockDim.x) {
+        u64 w = resp[p];
+        const u32 c = slot_get_count(w);
+        if (c >= 2 && c < (u32)kHashThreshold) {
+            int g = 0;
+            while (g + 1 < world && qbase[g + 1] <= p) ++g;
+            w += ebase[g];
+        }
+        wslot[qmap[p]] = w;
+    }
+}
+
+// ---- id lists ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flag_equal_kernel(const uint8_t *__restrict__ a, u64 n, uint8_t value, u32 *__restrict__ flag)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) flag[i] = a[i] == value;
+}
+__global__ void __launch_bounds__(256) compact_list_kernel(const u32 *__restrict__ flag, const u32 *__restrict__ idx, u64 n, u32 base, u32 *__restrict__ out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if (flag[i]) out[idx[i]] = base + (u32)i;
+}
+
+static unsigned sm_grid(u64 n, unsigned per_block, unsigned blocks_per_sm)
+{
+    u64 g = (n + per_block - 1) / per_block;
+    const u64 cap = (u64)kSMs * blocks_per_sm;
+    if (g > cap) g = cap;
+    return g ? (unsigned)g : 1u;
+}
+
+// ascending list of base + i for the i in [0, n) with a[i] == value -> c.rt_ids; returns its length
+static u64 build_id_list(Context &c, const uint8_t *a, u64 n, uint8_t value, u32 base)
+{
+    cudaStream_t st = c.stream;
+    if (n == 0) { c.rt_ids.alloc(0, st); return 0; }
+    DevBuf<u32> flag(n, st), idx(n, st), d_total(1, st);
+    flag_equal_kernel<<<sm_grid(n, 1024, 8), 256, 0, st>>>(a, n, value, flag.p);
+    SG_LAUNCHED();
+    exclusive_scan_u32(flag.p, idx.p, n, d_total.p, st);
+    u32 cnt = 0;
+    SG_CUDA(cudaMemcpyAsync(&cnt, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.rt_ids.alloc(cnt, st);
+    if (cnt) {
+        compact_list_kernel<<<sm_grid(n, 1024, 8), 256, 0, st>>>(flag.p, idx.p, n, base, c.rt_ids.p);
+        SG_LAUNCHED();
+    }
+    return cnt;
+}
+
+// what = 0: reads [first, first + count) (0-based indices);  1: the reads in state 0 after phase B (phase C);
+//        2: the reads of this rank's phase-A slice flagged for the redo pass.
+void stage_route_begin(Context &c, int what, u64 first, u64 count, int exact, int world, void **queries, u64 *counts)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    SG_CHECK(c.have_reads, "organize_reads must run first");
+    SG_CHECK(world >= 1 && world <= kMaxWorld, "bad world size");
+    SG_CHECK(what >= 0 && what <= 2, "bad batch kind");
+    const u64 U = c.cnt.unique_reads;
+    c.rt_state = 0; c.rt_for_c = false;
+    c.rt_what = what; c.rt_exact = exact != 0; c.rt_world = world;
+    c.rt_is_list = what != 0;
+    if (what == 0) {
+        SG_CHECK(first <= U && count <= U - first, "batch outside the reads");
+        SG_CHECK(count == 0 || (first >= c.pa_lo && first + count <= c.pa_hi), "batch outside this rank's phase-A slice");
+        c.rt_first = first; c.rt_n = count;
+    } else if (what == 1) {
+        SG_CHECK(c.have_phase_b, "phase B must run before the phase-C reads are routed");
+        SG_CHECK(exact, "phase C needs verified probes");
+        c.rt_first = 0; c.rt_n = build_id_list(c, c.explored.p, U, 0, 0);
+    } else {
+        SG_CHECK(exact, "the redo pass needs verified probes");
+        c.rt_first = 0; c.rt_n = build_id_list(c, c.rt_redo.p, c.pa_hi - c.pa_lo, 1, (u32)c.pa_lo);
+    }
+    const int wstride = c.max_len - c.h + 1 > 1 ? c.max_len - c.h + 1 : 1;
+    c.rt_wstride = (u32)wstride;
+    const u64 n = c.rt_n;
+    SG_CHECK(n * (u64)wstride < 0xFFFFFFFFull, "routed batch too large: at most 2^32 windows per batch");
+    for (int g = 0; g < kMaxWorld; ++g) c.rt_counts[g] = 0;
+    c.rt_Q = 0;
+    if (n > 0) {
+        DevBuf<unsigned long long> d_cnt(world, st);
+        SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, world * sizeof(unsigned long long), st));
+        const u32 *ids = c.rt_is_list ? c.rt_ids.p : nullptr;
+        const unsigned grid = sm_grid(n, RT_WARPS, 8);
+        route_kernel<false><<<grid, RT_WARPS * 32, 0, st>>>(c.F.p, c.SW, c.SWS, c.h, ids, c.rt_first, n, c.rt_wstride, world, exact, d_cnt.p, nullptr, nullptr);
+        SG_LAUNCHED();
+        unsigned long long h_cnt[kMaxWorld], h_base[kMaxWorld];
+        SG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        u64 Q = 0;
+        for (int g = 0; g < world; ++g) { h_base[g] = Q; c.rt_counts[g] = h_cnt[g]; Q += h_cnt[g]; }
+        c.rt_Q = Q;
+        c.rt_queries.alloc(Q * (exact ? 2 : 1), st);
+        c.rt_qmap.alloc(Q, st);
+        c.rt_wslot.alloc(n * (u64)wstride, st);
+        SG_CUDA(cudaMemcpyAsync(d_cnt.p, h_base, world * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        route_kernel<true><<<grid, RT_WARPS * 32, 0, st>>>(c.F.p, c.SW, c.SWS, c.h, ids, c.rt_first, n, c.rt_wstride, world, exact, d_cnt.p, c.rt_queries.p, c.rt_qmap.p);
+        SG_LAUNCHED();
+        SG_CUDA(cudaStreamSynchronize(st));      // h_base is a stack array; the caller reads the queries from another stream
+    }
+    if (queries) *queries = c.rt_Q ? (void *)c.rt_queries.p : nullptr;
+    if (counts) for (int g = 0; g < world; ++g) counts[g] = c.rt_counts[g];
+    c.rt_state = 1;
+}
+
+// Owner side.  `queries` (device): the streams received from source 0, 1, .. world-1 back to back,
+// counts_per_source[s] queries each.  Answers in the same order; entry stream of source s = entry_counts[s] words.
+void stage_shard_answer(Context &c, const void *queries, const u64 *counts_per_source, int exact, int world, void **responses, void **entries,
+                        u64 *entry_counts)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    SG_CHECK(c.have_table, "build_hash_table[_shard] must run first");
+    SG_CHECK(world == c.tb_world, "world size differs from the one the table shard was built for");
+    u64 nq = 0;
+    u64 h_seg[kMaxWorld + 1];
+    for (int s = 0; s < world; ++s) { h_seg[s] = nq; nq += counts_per_source[s]; }
+    h_seg[world] = nq;
+    for (int s = 0; s < world; ++s) entry_counts[s] = 0;
+    *responses = nullptr; *entries = nullptr;
+    if (nq == 0) return;
+    SG_CHECK(queries != nullptr, "null query buffer");
+    const char *fake_env = getenv("SAGE2GPU_FAKE_TAG_COLLISIONS");
+    const u64 fake_mask = fake_env ? strtoull(fake_env, nullptr, 0) : 0ull;
+    c.an_resp.alloc(nq, st);
+    DevBuf<u32> runlen(nq + 1, st), off(nq + 1, st), d_total(1, st);
+    DevBuf<u64> d_seg(world + 1, st), d_ecnt(world, st);
+    SG_CUDA(cudaMemcpyAsync(d_seg.p, h_seg, (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+    answer_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>((const u64 *)queries, nq, exact, c.slots.p, c.cap / kSlotsPerSector, c.entries.p, c.F.p, c.RC.p,
+                                                        c.len.p, c.SW, c.SWS, c.h, fake_mask, c.an_resp.p, runlen.p);
+    SG_LAUNCHED();
+    exclusive_scan_u32(runlen.p, off.p, nq + 1, d_total.p, st);
+    seg_totals_kernel<<<1, kMaxWorld, 0, st>>>(off.p, d_seg.p, world, d_ecnt.p);
+    SG_LAUNCHED();
+    u32 total = 0;
+    u64 h_ecnt[kMaxWorld];
+    SG_CUDA(cudaMemcpyAsync(&total, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(h_ecnt, d_ecnt.p, world * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.an_entries.alloc(total, st);
+    if (total) {
+        answer_runs_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>(c.an_resp.p, runlen.p, off.p, nq, d_seg.p, world, c.entries.p, c.an_entries.p);
+        SG_LAUNCHED();
+    }
+    SG_CUDA(cudaStreamSynchronize(st));
+    for (int s = 0; s < world; ++s) entry_counts[s] = h_ecnt[s];
+    *responses = c.an_resp.p;
+    *entries = total ? (void *)c.an_entries.p : nullptr;
+}
+
+// Source side.  `responses`: one word per query in the order of route_begin's streams; `entries`: the entry
+// streams of owner 0, 1, .. back to back (entry_counts[g] words each).  Both device pointers.
+void stage_route_finish(Context &c, const void *responses, const void *entries, const u64 *entry_counts)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    SG_CHECK(c.rt_state == 1, "route_begin must precede route_finish");
+    const int world = c.rt_world;
+    u64 h_qbase[kMaxWorld + 1], h_ebase[kMaxWorld], E = 0, Q = 0;
+    for (int g = 0; g < world; ++g) { h_qbase[g] = Q; Q += c.rt_counts[g]; h_ebase[g] = E; E += entry_counts[g]; }
+    h_qbase[world] = Q;
+    SG_CHECK(E < (1ull << 32), "entry streams too long for one batch");
+    c.rt_wentries.alloc(E, st);
+    if (E) SG_CUDA(cudaMemcpyAsync(c.rt_wentries.p, entries, E * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    if (Q) {
+        SG_CHECK(responses != nullptr, "null answer buffer");
+        DevBuf<u64> d_qbase(world + 1, st), d_ebase(world, st);
+        SG_CUDA(cudaMemcpyAsync(d_qbase.p, h_qbase, (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(d_ebase.p, h_ebase, world * sizeof(u64), cudaMemcpyHostToDevice, st));
+        route_finish_kernel<<<sm_grid(Q, 1024, 8), 256, 0, st>>>((const u64 *)responses, c.rt_qmap.p, Q, d_qbase.p, d_ebase.p, world, c.rt_wslot.p);
+        SG_LAUNCHED();
+    }
+    SG_CUDA(cudaStreamSynchronize(st));       // the caller's buffers may be reused on return
+    c.rt_state = 2;
+    c.rt_for_c = c.rt_what == 1;
+}
+
+}  // namespace sg

@@ -24,12 +24,14 @@
 namespace sg {
 
 constexpr u64 kCountOne = 1ull << 33;
+constexpr u32 kNotOwned = 0xFFFFFFFFu;      // where[] of an entry whose key belongs to another shard
 
 __device__ __forceinline__ u64 load_slot(const u64 *p) { return *reinterpret_cast<const volatile u64 *>(p); }
 
 __global__ void __launch_bounds__(256) table_insert_kernel(const u64 *__restrict__ F, const u64 *__restrict__ RC,
                                                             const uint16_t *__restrict__ len, u64 U, int SW, int SWS, int h,
-                                                            u64 *__restrict__ slots, u64 nsec, u32 *__restrict__ where)
+                                                            u64 *__restrict__ slots, u64 nsec, u32 *__restrict__ where,
+                                                            int rank, int world, u32 *__restrict__ overflow)
 {
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < 4 * U; t += (u64)gridDim.x * blockDim.x) {
         const u64 rid = t >> 2;
@@ -37,9 +39,11 @@ __global__ void __launch_bounds__(256) table_insert_kernel(const u64 *__restrict
         u64 v0, v1;
         entry_key(F + rid * SWS, RC + rid * SWS, SW, len[rid], h, type, v0, v1);
         const u64 hsh = hash_key(v0, v1);
+        if (key_owner(hsh, world) != rank) { where[t] = kNotOwned; continue; }      // another shard's key
         const u64 tag = slot_tag(hsh);
         u64 sec = home_sector(hsh, nsec);
         bool done = false;
+        u64 tries = 0;
         while (!done) {
             for (int q = 0; q < kSlotsPerSector && !done; ++q) {
                 u64 *sp = slots + kSlotsPerSector * sec + q;
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(256) table_insert_kernel(const u64 *__restrict
                 done = true;
             }
             sec = (sec + 1 == nsec) ? 0 : sec + 1;
+            if (++tries > nsec) { *overflow = 1; where[t] = kNotOwned; break; }      // index full: reported, never silent
         }
     }
 }
@@ -97,6 +102,7 @@ __global__ void __launch_bounds__(256) table_fill_kernel(const u64 *__restrict__
                                                           u32 *__restrict__ cursor, u32 *__restrict__ entries)
 {
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
+        if (where[t] == kNotOwned) continue;
         const u64 v = slots[where[t]];
         const u32 c = slot_get_count(v);
         if (c < 2 || c >= (u32)kHashThreshold) continue;
@@ -129,11 +135,15 @@ static unsigned big_grid(u64 n, unsigned block = 256)
     return g > kSMs * 16u ? kSMs * 16u : g;
 }
 
-void stage_build_table(Context &c)
+// rank / world: the key-hash shard this context holds (0 / 1 = the whole table).  A shard indexes only the keys
+// with key_owner(hash) == rank; every context still streams all 4U entries (the reads are replicated).
+void stage_build_table(Context &c, int rank, int world)
 {
     cudaStream_t st = c.stream;
     ArenaScope arena_scope(c.arena, st);
     SG_CHECK(c.have_reads, "organize_reads must run before build_hash_table");
+    SG_CHECK(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad rank / world");
+    c.tb_rank = rank; c.tb_world = world;
     const u64 U = c.cnt.unique_reads;
     const int SW = c.SW, h = c.h;
     c.cnt.distinct_keys = 0; c.cnt.keys_over_threshold = 0; c.cap = 0; c.cnt.table_capacity = 0;
@@ -143,15 +153,18 @@ void stage_build_table(Context &c)
     SG_CHECK(n < 0xFFFFFFFFull, "at most 2^30-1 unique reads per context");
 
     // load factor <= 2/3 even if all 4U keys are distinct (typically ~0.5)
+    // (a shard expects 1/world of the keys; 10 % head room for the imbalance of the split)
     u64 nsec = (n + n / 2 + kSlotsPerSector - 1) / kSlotsPerSector;
+    if (world > 1) nsec = nsec / (u64)world + nsec / (10 * (u64)world) + 1;
     if (nsec < 256) nsec = 256;
     const u64 cap = nsec * kSlotsPerSector;
     SG_CHECK(cap < 0xFFFFFFFFull, "slot index too large for one context");
     c.slots.alloc(cap, st);
     SG_CUDA(cudaMemsetAsync(c.slots.p, 0, cap * sizeof(u64), st));
 
-    DevBuf<u32> where(n, st);
-    table_insert_kernel<<<big_grid(n), 256, 0, st>>>(c.F.p, c.RC.p, c.len.p, U, SW, c.SWS, h, c.slots.p, nsec, where.p);
+    DevBuf<u32> where(n, st), d_overflow(1, st);
+    SG_CUDA(cudaMemsetAsync(d_overflow.p, 0, sizeof(u32), st));
+    table_insert_kernel<<<big_grid(n), 256, 0, st>>>(c.F.p, c.RC.p, c.len.p, U, SW, c.SWS, h, c.slots.p, nsec, where.p, rank, world, d_overflow.p);
     SG_LAUNCHED();
 
     DevBuf<u32> run(cap, st), off(cap, st), d_total(1, st);
@@ -162,9 +175,12 @@ void stage_build_table(Context &c)
     exclusive_scan_u32(run.p, off.p, cap, d_total.p, st);
     u32 M = 0;
     unsigned long long h_cnt[2];
+    u32 h_overflow = 0;
+    SG_CUDA(cudaMemcpyAsync(&h_overflow, d_overflow.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(&M, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
+    SG_CHECK(h_overflow == 0, "slot index of this table shard is full (key split too uneven)");
 
     c.entries.alloc(M, st);
     if (M) {

@@ -90,3 +90,190 @@ def upload_partitioned(h_bases: torch.Tensor, h_offsets: torch.Tensor, rank: int
         dist.all_gather_into_tensor(full, mine)
         out.append(full[:n])
     return out[0], out[1], moved
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The table sharded by key hash (north_star): shard r holds the keys it owns, the window probes of
+# a batch of reads travel to their owners and the answers travel back -- NCCL all-to-all over NVLink / NVSwitch.
+# The library (include/sage2gpu.h, csrc/shard.cu) fills and consumes the device buffers; this module moves them.
+#
+# The steps of one rank are written once, as a generator that yields its exchange requests:
+#     ("counts", send_counts)                     -> counts received from every rank       (all-to-all of one int each)
+#     ("a2a", tensor, send_counts, recv_counts)   -> the elements received, by source rank (all-to-all, variable splits)
+#     ("max", value)                              -> the maximum over the ranks
+#     ("phase_a", bufs)                           -> exchange_phase_a on the arrays of sage2gpu_phase_a_buffers
+# run_dist() serves them with torch.distributed (one process per GPU); run_local() drives several contexts of ONE
+# process in lockstep (tests on one GPU, and the CPU emulation).
+# ---------------------------------------------------------------------------------------------------------------
+
+def host_view(ptr: int, n: int, typestr: str) -> torch.Tensor:
+    """Zero-copy torch view of host memory (the CPU emulation's buffers)."""
+    import ctypes
+    import numpy as np
+    dt = np.dtype(typestr)
+    if n == 0 or not ptr:
+        return torch.zeros(0, dtype=torch.from_numpy(np.zeros(0, dt)).dtype)
+    buf = (ctypes.c_char * (n * dt.itemsize)).from_address(ptr)
+    return torch.from_numpy(np.frombuffer(buf, dtype=dt, count=n))
+
+
+def device_view_fn(device):
+    def view(ptr: int, n: int, typestr: str) -> torch.Tensor:
+        if n == 0 or not ptr:
+            return torch.zeros(0, dtype={"<i8": torch.int64, "<i4": torch.int32, "|u1": torch.uint8}[typestr], device=device)
+        return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+    return view
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr() if t.numel() else 0
+
+
+def _route(gpu, what: int, first: int, count: int, exact: bool, world: int, view, begun=None):
+    """One routed batch: queries to their owners, answers and bucket entries back (csrc/shard.cu)."""
+    rb = begun if begun is not None else gpu.route_begin(what, first, count, exact, world)
+    qw, send_counts = rb["words"], rb["counts"]
+    recv_counts = yield ("counts", send_counts)
+    queries = view(rb["ptr"], sum(send_counts) * qw, "<i8")
+    recv_q = yield ("a2a", queries, [c * qw for c in send_counts], [c * qw for c in recv_counts])
+    ans = gpu.shard_answer(_ptr(recv_q), recv_counts, exact, world)
+    recv_resp = yield ("a2a", view(ans["resp"], sum(recv_counts), "<i8"), recv_counts, send_counts)
+    ecs = ans["entry_counts"]
+    recv_ecs = yield ("counts", ecs)
+    recv_ent = yield ("a2a", view(ans["entries"], sum(ecs), "<i4"), ecs, recv_ecs)
+    gpu.route_finish(_ptr(recv_resp), _ptr(recv_ent), recv_ecs)
+
+
+def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 << 19):
+    """Generator: sage2gpu_build_overlap_graph with the table sharded over `world` ranks.  Reads loaded on every rank
+    and sage2gpu_build_hash_table_shard(rank, world) done."""
+    first, count = gpu.phase_a_sharded_begin(rank, world)
+    U = gpu.counters()["unique_reads"]
+    chunk = -(-U // world) if U else 0
+    n_batches = -(-chunk // batch_reads) if chunk else 0          # the same on every rank: collectives stay in lockstep
+    redo = 0
+    for b in range(n_batches):
+        lo = min(first + b * batch_reads, first + count)
+        n = min(batch_reads, first + count - lo)
+        yield from _route(gpu, 0, lo, n, False, world, view)
+        redo += gpu.phase_a_routed()
+    if (yield ("max", redo)):
+        # 24-bit tag collisions (about U*W / 2^24 reads): those reads once more, with probes the owners verify
+        yield from _route(gpu, 2, 0, 0, True, world, view)
+        left = gpu.phase_a_routed()
+        if left:
+            raise RuntimeError(f"{left} reads still unresolved after the verified pass")
+    gpu.phase_a_sharded_end()
+    yield ("phase_a", gpu.phase_a_buffers())
+    gpu.phase_b()
+    rb = gpu.route_begin(1, 0, 0, True, world)          # reads left for phase C: identical list on every rank
+    if rb["n_reads"]:
+        yield from _route(gpu, 1, 0, 0, True, world, view, begun=rb)
+    gpu.finish_graph()
+
+
+def run_dist(gen, rank: int, world: int, device) -> int:
+    """Serve one rank's requests with torch.distributed (NCCL for CUDA tensors, gloo on the CPU).  Returns bytes sent."""
+    sent = 0
+    cuda = torch.device(device).type == "cuda"
+    try:
+        req = next(gen)
+        while True:
+            kind = req[0]
+            if kind == "counts":
+                t = torch.tensor(req[1], dtype=torch.int64, device=device)
+                out = torch.empty_like(t)
+                dist.all_to_all_single(out, t)
+                val = out.tolist()
+                sent += 8 * (world - 1)
+            elif kind == "a2a":
+                send, sc, rc = req[1], req[2], req[3]
+                out = torch.empty(sum(rc), dtype=send.dtype, device=send.device)
+                dist.all_to_all_single(out, send, rc, sc)
+                if cuda:
+                    torch.cuda.current_stream(device).synchronize()       # the library reads it on its own stream
+                sent += (sum(sc) - sc[rank]) * send.element_size()
+                val = out
+            elif kind == "max":
+                t = torch.tensor([req[1]], dtype=torch.int64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                val = int(t.item())
+            elif kind == "phase_a":
+                bufs = req[1]
+                views = req[2] if len(req) > 2 else device_views(bufs, world, device)
+                sent += exchange_phase_a(views, bufs["chunk"], rank, world)
+                if cuda:
+                    torch.cuda.current_stream(device).synchronize()
+                val = None
+            else:
+                raise ValueError(kind)
+            req = gen.send(val)
+    except StopIteration:
+        pass
+    return sent
+
+
+def run_local(gens: list, views_of=None) -> None:
+    """Drive the generators of all ranks of ONE process in lockstep, doing the exchanges in memory.
+    views_of(rank, bufs) -> the dict of torch views exchange_phase_a works on (default: device views on cuda:current)."""
+    world = len(gens)
+    reqs = [next(g) for g in gens]
+    while True:
+        kinds = {r[0] for r in reqs}
+        assert len(kinds) == 1, f"ranks out of step: {kinds}"
+        kind = kinds.pop()
+        if kind == "counts":
+            vals = [[reqs[s][1][r] for s in range(world)] for r in range(world)]
+        elif kind == "a2a":
+            vals = []
+            for r in range(world):
+                parts = []
+                for s in range(world):
+                    send, sc = reqs[s][1], reqs[s][2]
+                    assert reqs[r][3][s] == sc[r]
+                    o = sum(sc[:r])
+                    parts.append(send[o:o + sc[r]])
+                vals.append(torch.cat(parts).clone())
+            if vals[0].is_cuda:
+                torch.cuda.synchronize()
+        elif kind == "max":
+            vals = [max(r[1] for r in reqs)] * world
+        elif kind == "phase_a":
+            views = []
+            for r in range(world):
+                bufs = reqs[r][1]
+                views.append(views_of(r, bufs) if views_of else device_views(bufs, world, torch.device("cuda", torch.cuda.current_device())))
+            chunk = reqs[0][1]["chunk"]
+            if chunk:
+                for key in ("right", "left", "over_limit"):
+                    for s in range(world):
+                        mine = views[s][key][s * chunk:(s + 1) * chunk].clone()
+                        for r in range(world):
+                            views[r][key][s * chunk:(s + 1) * chunk] = mine
+                m = views[0]["contained_by"].clone()
+                for r in range(1, world):
+                    m = torch.maximum(m, views[r]["contained_by"])
+                for r in range(world):
+                    views[r]["contained_by"].copy_(m)
+                if m.is_cuda:
+                    torch.cuda.synchronize()
+            vals = [None] * world
+        else:
+            raise ValueError(kind)
+        nxt = []
+        done = 0
+        for g, v in zip(gens, vals):
+            try:
+                nxt.append(g.send(v))
+            except StopIteration:
+                done += 1
+        if done:
+            assert done == world, "ranks finished at different steps"
+            return
+        reqs = nxt
+
+
+def build_overlap_graph_sharded(gpu, rank: int, world: int, device=None, batch_reads: int = 1 << 19) -> int:
+    """One process per GPU (torchrun): the sharded-table build on this rank; returns the bytes this rank sent."""
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return run_dist(sharded_graph_steps(gpu, rank, world, device_view_fn(device), batch_reads), rank, world, device)

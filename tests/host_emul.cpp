@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <vector>
 #include "../sage2_b200/csrc/core.cuh"
@@ -28,7 +29,21 @@ struct Emu {
     std::vector<uint8_t> flag5;
     std::vector<u32> cont_max;
     u64 over = 0, distinct = 0, compare_calls = 0, inserted = 0, removed = 0, contained = 0, contained_size = 0, slow_reads = 0;
+    // ---- the sharded table (emulation of csrc/shard.cu: same buffers, same wire format) ----
+    int max_len = 1, tb_rank = 0, tb_world = 1;
+    std::map<u64, std::pair<u64, u64>> by_hash;      // owned keys by their 64-bit hash (what a tag probe can see)
+    u64 pa_lo = 0, pa_hi = 0, restarts = 0;
+    std::vector<u64> rt_queries, rt_wslot, an_resp;
+    std::vector<u32> rt_qmap, rt_wentries, rt_ids, an_entries;
+    std::vector<uint8_t> rt_redo;
+    u64 rt_n = 0, rt_first = 0, rt_counts[kMaxWorld] = {};
+    int rt_wstride = 1, rt_what = 0, rt_world = 1, rt_state = 0;
+    bool rt_exact = false, rt_is_list = false, rt_for_c = false, have_phase_b = false;
 };
+
+// table lookup of one window of one read of a scan: number of bucket entries (0: absent or masked) through `ents`,
+// or -1 when the answer failed its proof (tag collision; routed tag probes only).  s = position in the scanned batch.
+typedef std::function<int(u64 s, const u64 *Xf, int j, u64 v0, u64 v1, const u32 *&ents)> Lookup;
 
 int code_of(uint8_t c) { return ((c >> 1) ^ (c >> 2)) & 3; }
 bool valid_char(uint8_t c) { c &= 0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
@@ -49,6 +64,7 @@ void prepare(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
     const int h = e.h;
     int max_len = 1;
     for (int64_t r = 0; r < n; ++r) max_len = std::max<int64_t>(max_len, std::min<int64_t>(off[r + 1] - off[r], 32 * kMaxWords - 8));
+    e.max_len = max_len;
     int SW = words_for_len(max_len);
     static const int kStrides[] = { 2, 3, 4, 5, 6, 8, 12, 16, 32 };
     for (int s : kStrides) if (s >= SW) { SW = s; break; }
@@ -96,20 +112,35 @@ void prepare(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
 
 }
 
-// rank's slice of the reads (sage2gpu_phase_a_partition); arrays padded to world * chunk
-void phase_a(Emu &e, int rank, int world)
+Lookup local_table(Emu &e)
+{
+    return [&e](u64, const u64 *, int, u64 v0, u64 v1, const u32 *&ents) -> int {
+        auto it = e.table.find(std::make_pair(v0, v1));
+        if (it == e.table.end() || it->second.size() >= (size_t)kHashThreshold) return 0;
+        ents = it->second.data();
+        return (int)it->second.size();
+    };
+}
+
+void alloc_phase_a(Emu &e, int rank, int world)
+{
+    const u64 U = e.U;
+    const u64 chunk = partition_chunk(U, world), padded = chunk * (u64)world;
+    e.pa_lo = std::min<u64>(U, (u64)rank * chunk); e.pa_hi = std::min<u64>(U, e.pa_lo + chunk);
+    e.extR.assign(padded, 0); e.extL.assign(padded, 0);
+    e.flag5.assign(padded, 0); e.cont_max.assign(padded, 0);
+    e.rt_redo.assign(chunk, 0);
+    e.compare_calls = 0; e.slow_reads = 0; e.restarts = 0;
+}
+
+// Phase A of the reads ids[0..n) (or first + [0..n)); redo[s] is set, and the read skipped, when a lookup fails its proof
+void scan_reads(Emu &e, const u32 *ids, u64 first, u64 n, const Lookup &lookup, uint8_t *redo)
 {
     const int SW = e.SW, k = e.k, h = e.h;
-    const u64 U = e.U;
-    auto &table = e.table;
-    const u64 chunk = partition_chunk(U, world), padded = chunk * (u64)world;
-    const u64 lo = std::min<u64>(U, (u64)rank * chunk), hi = std::min<u64>(U, lo + chunk);
     // K4 phase A: the kernel's round structure (search.cu): the (window, bucket entry) items of a read are
     // consumed 32 at a time; a round is evaluated in FAST mode (every hit checked against the previous hit
     // of its side only) until the first anomaly, then converted to the reference's sequential chain.
     // With SAGE2_EMUL_EXACT_ONLY set the plain sequential chain runs instead (cross-check of the hybrid).
-    e.extR.assign(padded, 0); e.extL.assign(padded, 0);
-    e.flag5.assign(padded, 0); e.cont_max.assign(padded, 0);
     auto &flag5 = e.flag5;
     auto &cont_max = e.cont_max;
     std::vector<u64> prevR(SW), prevL(SW);
@@ -118,17 +149,21 @@ void phase_a(Emu &e, int rank, int world)
     struct Hit { int jj; bool right; u32 rid2; int type; int len2; const u64 *Q; };
     std::vector<Item> items;
     std::vector<Hit> hits;
-    for (u64 i = lo; i < hi; ++i) {
+    for (u64 sb = 0; sb < n; ++sb) {
+        const u64 i = ids ? (u64)ids[sb] : first + sb;
         const u64 *Xf = &e.F[i * SW], *Xr = &e.RC[i * SW];
         const int len1 = e.len[i];
         items.clear();
-        for (int j = 0; j <= len1 - h; ++j) {
+        bool collision = false;
+        for (int j = 0; j <= len1 - h && !collision; ++j) {
             u64 v0, v1;
             extract_key(Xf, SW, j, h, v0, v1);
-            auto it = table.find(std::make_pair(v0, v1));
-            if (it == table.end() || it->second.size() >= (size_t)kHashThreshold) continue;
-            for (u32 ent : it->second) items.push_back(Item{ j, ent });
+            const u32 *ents = nullptr;
+            const int cnt = lookup(sb, Xf, j, v0, v1, ents);
+            if (cnt < 0) { collision = true; break; }
+            for (int x = 0; x < cnt; ++x) items.push_back(Item{ j, ents[x] });
         }
+        if (collision) { redo[sb] = 1; e.restarts++; continue; }
         ExtState st;
         ext_init(st);
         bool exact = exact_only, hasR = false, hasL = false;
@@ -212,13 +247,165 @@ void phase_a(Emu &e, int rank, int world)
     }
 }
 
+// rank's slice of the reads (sage2gpu_phase_a_partition); arrays padded to world * chunk
+void phase_a(Emu &e, int rank, int world)
+{
+    alloc_phase_a(e, rank, world);
+    std::vector<uint8_t> redo(e.pa_hi - e.pa_lo + 1, 0);
+    scan_reads(e, nullptr, e.pa_lo, e.pa_hi - e.pa_lo, local_table(e), redo.data());
+}
+
+// ---- the sharded table: csrc/shard.cu on the CPU ---------------------------------------------------------------
+void shard_build(Emu &e, int rank, int world)
+{
+    e.tb_rank = rank; e.tb_world = world;
+    e.by_hash.clear();
+    for (auto it = e.table.begin(); it != e.table.end();) {
+        const u64 hsh = hash_key(it->first.first, it->first.second);
+        if (key_owner(hsh, world) != rank) it = e.table.erase(it);
+        else { e.by_hash[hsh] = it->first; ++it; }
+    }
+    e.distinct = e.table.size(); e.over = 0;
+    for (auto &kv : e.table) if (kv.second.size() >= (size_t)kHashThreshold) e.over++;
+}
+
+void route_begin(Emu &e, int what, u64 first, u64 count, int exact, int world)
+{
+    e.rt_what = what; e.rt_exact = exact != 0; e.rt_world = world; e.rt_is_list = what != 0; e.rt_for_c = false;
+    e.rt_ids.clear();
+    if (what == 0) { e.rt_first = first; e.rt_n = count; }
+    else if (what == 1) { for (u64 i = 0; i < e.U; ++i) if (e.explored_b[i] == 0) e.rt_ids.push_back((u32)i); e.rt_first = 0; e.rt_n = e.rt_ids.size(); }
+    else { for (u64 i = 0; i < e.pa_hi - e.pa_lo; ++i) if (e.rt_redo[i]) e.rt_ids.push_back((u32)(e.pa_lo + i)); e.rt_first = 0; e.rt_n = e.rt_ids.size(); }
+    e.rt_wstride = std::max(1, e.max_len - e.h + 1);
+    const int qw = exact ? 2 : 1;
+    std::vector<std::vector<u64>> q(world);
+    std::vector<std::vector<u32>> m(world);
+    for (u64 s = 0; s < e.rt_n; ++s) {
+        const u64 i = e.rt_is_list ? (u64)e.rt_ids[s] : e.rt_first + s;
+        const u64 *Xf = &e.F[i * e.SW];
+        for (int j = 0; j <= (int)e.len[i] - e.h; ++j) {
+            u64 v0, v1;
+            extract_key(Xf, e.SW, j, e.h, v0, v1);
+            const u64 hsh = hash_key(v0, v1);
+            const int g = key_owner(hsh, world);
+            if (exact) { q[g].push_back(v0); q[g].push_back(v1); } else q[g].push_back(hsh);
+            m[g].push_back((u32)(s * (u64)e.rt_wstride + (u64)j));
+        }
+    }
+    e.rt_queries.clear(); e.rt_qmap.clear();
+    for (int g = 0; g < world; ++g) {
+        e.rt_counts[g] = m[g].size();
+        e.rt_queries.insert(e.rt_queries.end(), q[g].begin(), q[g].end());
+        e.rt_qmap.insert(e.rt_qmap.end(), m[g].begin(), m[g].end());
+    }
+    (void)qw;
+    e.rt_wslot.assign(e.rt_n * (u64)e.rt_wstride, 0);
+    e.rt_state = 1;
+}
+
+void shard_answer(Emu &e, const u64 *queries, const u64 *counts_per_source, int exact, int world, u64 *entry_counts)
+{
+    const char *fe = getenv("SAGE2_EMUL_FAKE_TAG_COLLISIONS");
+    const u64 fake_mask = fe ? strtoull(fe, nullptr, 0) : 0ull;
+    e.an_resp.clear(); e.an_entries.clear();
+    u64 p = 0;
+    for (int s = 0; s < world; ++s) {
+        const u64 ebase = e.an_entries.size();
+        for (u64 x = 0; x < counts_per_source[s]; ++x, ++p) {
+            const std::vector<u32> *bucket = nullptr;
+            if (exact) {
+                auto it = e.table.find(std::make_pair(queries[2 * p], queries[2 * p + 1]));
+                if (it != e.table.end() && it->second.size() < (size_t)kHashThreshold) bucket = &it->second;
+            } else {
+                const u64 hsh = queries[p];
+                if (fake_mask && (hsh & fake_mask) == 0 && !e.table.empty()) bucket = &e.table.begin()->second;   // a wrong bucket, like a tag collision
+                else {
+                    auto it = e.by_hash.find(hsh);
+                    if (it != e.by_hash.end()) bucket = &e.table[it->second];
+                }
+            }
+            u64 answer = 0;
+            if (bucket) {
+                const size_t c = bucket->size();
+                if (c == 1 || c >= (size_t)kHashThreshold) answer = answer_encode((u32)c, (*bucket)[0]);
+                else {
+                    answer = answer_encode((u32)c, e.an_entries.size() - ebase);
+                    e.an_entries.insert(e.an_entries.end(), bucket->begin(), bucket->end());
+                }
+            }
+            e.an_resp.push_back(answer);
+        }
+        entry_counts[s] = e.an_entries.size() - ebase;
+    }
+}
+
+void route_finish(Emu &e, const u64 *resp, const u32 *entries, const u64 *entry_counts)
+{
+    u64 E = 0, p = 0;
+    for (int g = 0; g < e.rt_world; ++g) {
+        for (u64 x = 0; x < e.rt_counts[g]; ++x, ++p) {
+            u64 w = resp[p];
+            const u32 c = slot_get_count(w);
+            if (c >= 2 && c < (u32)kHashThreshold) w += E;
+            e.rt_wslot[e.rt_qmap[p]] = w;
+        }
+        E += entry_counts[g];
+    }
+    e.rt_wentries.assign(entries, entries + E);
+    e.rt_state = 2;
+    e.rt_for_c = e.rt_what == 1;
+}
+
+// the routed batch as a lookup; untrusted answers are proven like search.cu does (first entry of the bucket /
+// representative of a masked key against the window's key)
+Lookup routed_table(Emu &e)
+{
+    return [&e](u64 s, const u64 *, int j, u64 v0, u64 v1, const u32 *&ents) -> int {
+        const u64 w = e.rt_wslot[s * (u64)e.rt_wstride + (u64)j];
+        const u32 c = slot_get_count(w);
+        if (c == 0) return 0;
+        static thread_local u32 single;
+        const u32 *first_entry;
+        if (c == 1 || c >= (u32)kHashThreshold) { single = (u32)slot_get_payload(w); first_entry = &single; }
+        else first_entry = &e.rt_wentries[slot_get_payload(w)];
+        if (!e.rt_exact) {
+            const u64 r = *first_entry >> 2;
+            u64 w0, w1;
+            entry_key(&e.F[r * e.SW], &e.RC[r * e.SW], e.SW, e.len[r], e.h, (int)(*first_entry & 3), w0, w1);
+            if (w0 != v0 || w1 != v1) return -1;
+        }
+        if (c >= (u32)kHashThreshold) return 0;
+        ents = first_entry;
+        return (int)c;
+    };
+}
+
+u64 phase_a_routed(Emu &e)
+{
+    const u64 before = e.restarts;
+    std::vector<uint8_t> redo2(e.rt_n + 1, 0);
+    uint8_t *redo = e.rt_is_list ? redo2.data() : e.rt_redo.data() + (e.rt_first - e.pa_lo);
+    scan_reads(e, e.rt_is_list ? e.rt_ids.data() : nullptr, e.rt_first, e.rt_n, routed_table(e), redo);
+    e.rt_state = 0;
+    return e.restarts - before;
+}
+
+void phase_b(Emu &e);
+void finish_after_b(Emu &e);
 void finish(Emu &e)
 {
-    const int SW = e.SW, k = e.k, h = e.h;
+    if (!e.have_phase_b) phase_b(e);
+    finish_after_b(e);
+    e.have_phase_b = false;
+}
+
+void phase_b(Emu &e)
+{
     const u64 U = e.U;
-    auto &table = e.table;
     auto &flag5 = e.flag5;
     auto &cont_max = e.cont_max;
+    e.have_phase_b = true;
+    e.contained = e.contained_size = 0;
     // phase B
     e.explored_a.resize(U); e.explored_b.resize(U);
     for (u64 i = 0; i < U; ++i) {
@@ -228,6 +415,13 @@ void finish(Emu &e)
         else e.contained_size++;
         e.explored_b[i] = s;
     }
+}
+
+void finish_after_b(Emu &e)
+{
+    const int SW = e.SW, k = e.k, h = e.h;
+    const u64 U = e.U;
+    const Lookup lookup = (e.tb_world > 1 || e.rt_for_c) ? routed_table(e) : local_table(e);
     std::vector<u64> edgesB;
     for (u64 i = 0; i < U; ++i) {
         EdgeRec r[2];
@@ -239,6 +433,7 @@ void finish(Emu &e)
     std::vector<u64> cand;
     for (u64 i = 0; i < U; ++i) {
         if (e.explored_b[i] != 0) continue;
+        const u64 sb = s_ids.size();
         s_ids.push_back((u32)i);
         cand_off.push_back((u32)cand.size());
         const u64 *Xf = &e.F[i * SW], *Xr = &e.RC[i * SW];
@@ -246,9 +441,10 @@ void finish(Emu &e)
         for (int j = 0; j <= len1 - h; ++j) {
             u64 v0, v1;
             extract_key(Xf, SW, j, h, v0, v1);
-            auto it = table.find(std::make_pair(v0, v1));
-            if (it == table.end() || it->second.size() >= (size_t)kHashThreshold) continue;
-            for (u32 ent : it->second) {
+            const u32 *ents = nullptr;
+            const int cnt = lookup(sb, Xf, j, v0, v1, ents);
+            for (int x = 0; x < cnt; ++x) {
+                const u32 ent = ents[x];
                 const u32 rid2 = ent >> 2;
                 const int type = (int)(ent & 3);
                 const bool right = !(type & 1);
@@ -330,6 +526,31 @@ uint64_t hemu_phase_a_arrays(void *p, uint64_t **extR, uint64_t **extL, uint8_t 
     return e->extR.size();
 }
 void hemu_finish(void *p) { finish(*(Emu *)p); }
+// the sharded table: the entry points of include/sage2gpu.h with host buffers
+void hemu_shard_build(void *p, int rank, int world) { shard_build(*(Emu *)p, rank, world); }
+void hemu_phase_a_sharded_begin(void *p, int rank, int world, uint64_t *first, uint64_t *count)
+{
+    Emu *e = (Emu *)p;
+    alloc_phase_a(*e, rank, world);
+    *first = e->pa_lo; *count = e->pa_hi - e->pa_lo;
+}
+void hemu_route_begin(void *p, int what, uint64_t first, uint64_t count, int exact, int world, uint64_t **queries, uint64_t *counts, uint64_t *n_reads)
+{
+    Emu *e = (Emu *)p;
+    route_begin(*e, what, first, count, exact, world);
+    *queries = e->rt_queries.data(); *n_reads = e->rt_n;
+    for (int g = 0; g < world; ++g) counts[g] = e->rt_counts[g];
+}
+void hemu_shard_answer(void *p, const uint64_t *queries, const uint64_t *counts_per_source, int exact, int world, uint64_t **resp,
+                       uint32_t **entries, uint64_t *entry_counts)
+{
+    Emu *e = (Emu *)p;
+    shard_answer(*e, queries, counts_per_source, exact, world, entry_counts);
+    *resp = e->an_resp.data(); *entries = e->an_entries.data();
+}
+void hemu_route_finish(void *p, const uint64_t *resp, const uint32_t *entries, const uint64_t *entry_counts) { route_finish(*(Emu *)p, resp, entries, entry_counts); }
+uint64_t hemu_phase_a_routed(void *p) { return phase_a_routed(*(Emu *)p); }
+void hemu_phase_b(void *p) { phase_b(*(Emu *)p); }
 void hemu_free(void *p) { delete (Emu *)p; }
 // sizes: [0]=U [1]=SW [2]=good [3]=total_bp [4]=n_edges [5]=over [6]=distinct [7]=compare_calls [8]=inserted
 //        [9]=removed [10]=contained [11]=contained_size [12]=reads that left the fast mode

@@ -1,0 +1,109 @@
+"""GPU parity of the sharded-table build (include/sage2gpu.h "The table sharded by key hash"):
+`world` contexts on ONE GPU hold one key-hash shard each, the exchanges of sage2_b200/multi.py are done in memory
+(run_local), and every rank must end with the oracle's state: extension records, explored states, counters and
+the edge list.  The same steps over NCCL on two real GPUs are in test_gpu_multi.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import datasets
+from oracle import oracle
+from sage2_b200 import api, multi, synth
+from test_gpu_parity import _compare
+
+pytestmark = pytest.mark.gpu
+
+
+def _sharded(name, world, batch_reads=1 << 19):
+    reads, k = datasets.get(name) if name in datasets.DATASETS else synth.config(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    dev = torch.device("cuda", 0)
+    gpus = []
+    for r in range(world):
+        g = api.Sage2Gpu(0)
+        g.load_reads(b, off, k)
+        g.build_hash_table_shard(r, world)
+        gpus.append(g)
+    view = multi.device_view_fn(dev)
+    multi.run_local([multi.sharded_graph_steps(g, r, world, view, batch_reads) for r, g in enumerate(gpus)])
+    return o, gpus
+
+
+@pytest.mark.parametrize("name,world", [("clean", 1), ("rep", 2), ("k70", 3), ("hicopy", 2), ("deep", 2), ("varlen_err", 3),
+                                        ("deep_varlen", 2), ("tandem", 2), ("mixed", 4), ("err", 8), ("k31", 2),
+                                        ("empty", 2), ("allbad", 2), ("single", 3)])
+def test_sharded_table_equals_oracle(name, world):
+    o, gpus = _sharded(name, world)
+    calls = sum(g.counters()["compare_calls"] for g in gpus)
+    keys = sum(g.counters()["distinct_keys"] for g in gpus)
+    over = sum(g.counters()["keys_over_threshold"] for g in gpus)
+    assert (calls, keys, over) == (o.compare_calls, o.distinct_keys, o.keys_over_threshold)
+    for g in gpus:
+        c = g.counters()
+        c0 = dict(c)
+        # per-rank counters that are sums over the ranks are checked above; patch them so _compare can check the rest
+        g.counters = lambda c0=c0: {**c0, "compare_calls": o.compare_calls, "distinct_keys": o.distinct_keys,
+                                    "keys_over_threshold": o.keys_over_threshold}
+        _compare(o, g)
+
+
+def test_small_batches_and_uneven_slices():
+    o, gpus = _sharded("rep", 3, batch_reads=1000)
+    for g in gpus:
+        e = g.edges()
+        assert len(e) == o.n_edges
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], o.edges[f])
+
+
+def test_tag_collisions_take_the_verified_pass(monkeypatch):
+    # test knob of csrc/shard.cu: tag probes whose key hash has none of the mask bits behave like a tag collision
+    monkeypatch.setenv("SAGE2GPU_FAKE_TAG_COLLISIONS", "0x3f00000000")
+    o, gpus = _sharded("varlen_err", 2)
+    assert sum(g.counters()["probe_restarts"] for g in gpus) > 0
+    assert sum(g.counters()["compare_calls"] for g in gpus) == o.compare_calls
+    for g in gpus:
+        e = g.edges()
+        assert len(e) == o.n_edges
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], o.edges[f])
+        np.testing.assert_array_equal(g.extensions()["explored"], o.explored_b[1:])
+
+
+def test_sharded_context_refuses_the_local_search():
+    reads, k = datasets.get("clean")
+    b, off = synth.concat(reads)
+    g = api.Sage2Gpu(0)
+    g.load_reads(b, off, k)
+    g.build_hash_table_shard(1, 2)
+    with pytest.raises(api.Sage2GpuError):
+        g.build_overlap_graph()
+
+
+def test_cfg2_sharded_full_size():
+    """cfg2 at full size over 4 shards on one GPU: the edge list equals the single-table build's."""
+    reads, k = synth.config("cfg2")
+    b, off = synth.concat(reads)
+    ref = api.Sage2Gpu(0)
+    ref.run_steps123(b, off, k)
+    want = ref.edges()
+    want_calls = ref.counters()["compare_calls"]
+    del ref
+    world = 4
+    gpus = []
+    for r in range(world):
+        g = api.Sage2Gpu(0)
+        g.load_reads(b, off, k)
+        g.build_hash_table_shard(r, world)
+        gpus.append(g)
+    view = multi.device_view_fn(torch.device("cuda", 0))
+    multi.run_local([multi.sharded_graph_steps(g, r, world, view) for r, g in enumerate(gpus)])
+    assert sum(g.counters()["compare_calls"] for g in gpus) == want_calls
+    for g in gpus[:2]:
+        e = g.edges()
+        assert len(e) == len(want)
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], want[f])
