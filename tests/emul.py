@@ -33,6 +33,15 @@ def lib():
         _lib.hemu_phase_a_arrays.restype = C.c_uint64
         _lib.hemu_phase_a_arrays.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
         _lib.hemu_finish.argtypes = [C.c_void_p]
+        u64p, vpp = C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)
+        _lib.hemu_shard_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _lib.hemu_phase_a_sharded_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p]
+        _lib.hemu_route_begin.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vpp, u64p, u64p]
+        _lib.hemu_shard_answer.argtypes = [C.c_void_p, C.c_void_p, u64p, C.c_int, C.c_int, vpp, vpp, u64p]
+        _lib.hemu_route_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64p]
+        _lib.hemu_phase_a_routed.restype = C.c_uint64
+        _lib.hemu_phase_a_routed.argtypes = [C.c_void_p]
+        _lib.hemu_phase_b.argtypes = [C.c_void_p]
         _lib.hemu_sizes.argtypes = [C.c_void_p, C.c_void_p]
         _lib.hemu_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 9
         _lib.hemu_get_bases.restype = C.c_uint64
@@ -80,6 +89,98 @@ class EmuRun:
                                                   self.explored_a, self.explored_b, self.edges)))
         L.hemu_free(h)
         self.F = self.F.reshape(U, SW); self.RC = self.RC.reshape(U, SW)
+
+
+class EmuShard:
+    """One rank of the sharded-table build on the CPU: the methods sage2_b200/multi.py's sharded_graph_steps calls on
+    api.Sage2Gpu, with host buffers (tests/host_emul.cpp restates csrc/shard.cu)."""
+
+    def __init__(self, bases, offsets, k):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.L = lib()
+        self.h = self.L.hemu_prepare(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k)
+        self.redone = 0
+
+    def close(self):
+        if self.h:
+            self.L.hemu_free(self.h)
+            self.h = None
+
+    def _sizes(self):
+        sz = np.zeros(13, dtype=np.uint64)
+        self.L.hemu_sizes(self.h, sz.ctypes.data)
+        return [int(x) for x in sz]
+
+    def counters(self):
+        sz = self._sizes()
+        return {"unique_reads": sz[0], "n_edges": sz[4], "compare_calls": sz[7], "distinct_keys": sz[6], "probe_restarts": self.redone}
+
+    def build_hash_table_shard(self, rank, world):
+        self.L.hemu_shard_build(self.h, rank, world)
+
+    def phase_a_sharded_begin(self, rank, world):
+        first, count = C.c_uint64(), C.c_uint64()
+        self.L.hemu_phase_a_sharded_begin(self.h, rank, world, C.byref(first), C.byref(count))
+        self.world = world
+        return int(first.value), int(count.value)
+
+    def route_begin(self, what, first, count, exact, world):
+        q, n = C.c_void_p(), C.c_uint64()
+        counts = (C.c_uint64 * world)()
+        self.L.hemu_route_begin(self.h, what, first, count, int(bool(exact)), world, C.byref(q), counts, C.byref(n))
+        return {"ptr": q.value or 0, "counts": [int(x) for x in counts], "words": 2 if exact else 1, "n_reads": int(n.value)}
+
+    def shard_answer(self, queries_ptr, counts_per_source, exact, world):
+        cps = (C.c_uint64 * world)(*[int(x) for x in counts_per_source])
+        resp, ent = C.c_void_p(), C.c_void_p()
+        ecnt = (C.c_uint64 * world)()
+        self.L.hemu_shard_answer(self.h, queries_ptr or None, cps, int(bool(exact)), world, C.byref(resp), C.byref(ent), ecnt)
+        return {"resp": resp.value or 0, "entries": ent.value or 0, "entry_counts": [int(x) for x in ecnt]}
+
+    def route_finish(self, resp_ptr, entries_ptr, entry_counts):
+        ec = (C.c_uint64 * len(entry_counts))(*[int(x) for x in entry_counts])
+        self.L.hemu_route_finish(self.h, resp_ptr or None, entries_ptr or None, ec)
+
+    def phase_a_routed(self):
+        n = int(self.L.hemu_phase_a_routed(self.h))
+        self.redone += n
+        return n
+
+    def phase_a_sharded_end(self):
+        pass
+
+    def phase_a_buffers(self):
+        p = [C.c_void_p() for _ in range(4)]
+        n = int(self.L.hemu_phase_a_arrays(self.h, *(C.byref(x) for x in p)))
+        return {"right": p[0].value or 0, "left": p[1].value or 0, "over_limit": p[2].value or 0, "contained_by": p[3].value or 0,
+                "chunk": n // self.world, "unique_reads": self._sizes()[0]}
+
+    def phase_b(self):
+        self.L.hemu_phase_b(self.h)
+
+    def finish_graph(self):
+        self.L.hemu_finish(self.h)
+
+    def edges(self):
+        E = self._sizes()[4]
+        w = np.zeros(2 * E, np.uint64)
+        self.L.hemu_copy(self.h, None, None, None, None, None, None, None, None, w.ctypes.data)
+        return w
+
+    def extensions(self):
+        U = self._sizes()[0]
+        r, l = np.zeros(U, np.uint64), np.zeros(U, np.uint64)
+        self.L.hemu_copy(self.h, None, None, None, None, r.ctypes.data, l.ctypes.data, None, None, None)
+        return r, l
+
+
+def host_phase_a_views(bufs, world):
+    """torch views (sharing memory) of an EmuShard's padded phase-A arrays, as multi.exchange_phase_a wants them."""
+    from sage2_b200 import multi
+    n = bufs["chunk"] * world
+    return {"right": multi.host_view(bufs["right"], n, "<i8"), "left": multi.host_view(bufs["left"], n, "<i8"),
+            "over_limit": multi.host_view(bufs["over_limit"], n, "|u1"), "contained_by": multi.host_view(bufs["contained_by"], n, "<i4")}
 
 
 def records_to_bytes(rec: np.ndarray, lens: np.ndarray) -> np.ndarray:
