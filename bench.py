@@ -197,10 +197,19 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     comm = {"sent": 0, "h2d": 0}
 
+    layout = {"sharded": args.table == "sharded"}
+    xstats = {}
+
+    def build_graph():
+        if layout["sharded"]:       # key-hash shard per GPU, window probes routed to their owners by NCCL all-to-all
+            gpu.build_hash_table_shard(rank, world)
+            return multi.build_overlap_graph_sharded(gpu, rank, world, dev, batch_reads=args.batch_reads, stats=xstats)
+        gpu.build_hash_table()
+        return multi.build_overlap_graph(gpu, rank, world, dev)
+
     def step_device():
         gpu.load_reads_ptr(d_bases.data_ptr(), d_off.data_ptr(), n_reads, k, device=True)
-        gpu.build_hash_table()
-        comm["sent"] = multi.build_overlap_graph(gpu, rank, world, dev)
+        comm["sent"] = build_graph()
 
     h_edges = {"buf": None}
 
@@ -214,8 +223,7 @@ def run_ours(args):
             tb, to, comm["h2d"] = multi.upload_partitioned(h_bases, h_off, rank, world, dev)
             torch.cuda.current_stream(dev).synchronize()
             gpu.load_reads_ptr(tb.data_ptr(), to.data_ptr(), n_reads, k, device=True)
-        gpu.build_hash_table()
-        multi.build_overlap_graph(gpu, rank, world, dev)
+        build_graph()
         if h_edges["buf"] is None:
             h_edges["buf"] = torch.empty(2 * max(1, gpu.counters()["n_edges"]), dtype=torch.int64).pin_memory()
         gpu.edges_packed_into(h_edges["buf"].data_ptr(), h_edges["buf"].numel() // 2)
@@ -261,6 +269,24 @@ def run_ours(args):
     step_host()
     e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_host, args.steps)
     n_edges = gpu.counters()["n_edges"]
+    sharded = layout["sharded"]
+    main_sent = comm["sent"]
+
+    # N > 1: the other table layout on the same reads, device-resident, reported next to the headline
+    alt = None
+    if world > 1 and not args.no_alt_table:
+        layout["sharded"] = not sharded
+        xstats.clear()
+        for _ in range(3):
+            step_device()
+        xstats.clear()
+        a_ms, _, a_launches, a_stage = timed(step_device, args.steps)
+        alt = {"table": "sharded" if layout["sharded"] else "replicated", "ms_per_step": a_ms / args.steps,
+               "value": n_reads / (a_ms / args.steps / 1000.0), "unit": UNIT, "sent_bytes_per_rank_and_step": comm["sent"],
+               "gpu_launches": a_launches, "stage_ms": a_stage,
+               "exchange_wall_ms_per_step": {kk: (vv / args.steps) for kk, vv in xstats.items()}}
+        layout["sharded"] = sharded
+        comm["sent"] = main_sent
 
     def teardown():
         torch.cuda.synchronize()
@@ -320,9 +346,14 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": dict(cfg, parallelism=("single GPU" if world == 1 else
-                                         f"{world} GPUs: reads + table replicated, phase A partitioned by read id, "
-                                         f"one NCCL exchange (all-gather + all-reduce MAX, {comm['sent']} B sent per rank)"),
+        "config": dict(cfg, parallelism=(
+                           (f"{world} GPU(s): reads replicated, table sharded by key hash, window probes routed to their owners by "
+                            f"NCCL all-to-all in batches of {args.batch_reads} reads, phase A partitioned by read id "
+                            f"({comm['sent']} B sent per rank and step)") if sharded else
+                           "single GPU" if world == 1 else
+                           f"{world} GPUs: reads + table replicated, phase A partitioned by read id, "
+                           f"one NCCL exchange (all-gather + all-reduce MAX, {comm['sent']} B sent per rank)"),
+                       table=args.table,
                        reads_per_step=n_reads, l2_policy="inputs (460 MB ASCII + working set) larger than the 126 MB L2",
                        timing="CUDA events on the library stream around all steps, max over ranks"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(comm["h2d"]) * world,
@@ -334,6 +365,7 @@ def run_ours(args):
         "edges_per_sec": counters["n_edges"] / (ms_per_step / 1000.0),
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms": stage,
+        "alt_table": alt,
         "per_step_ms": {"device_resident": per_step[0], "e2e": per_step[1]},
         "counters": {kk: counters[kk] for kk in ("good_reads", "unique_reads", "distinct_keys", "compare_calls",
                                                   "window_probes", "n_edges", "left_to_explore", "record_words")},
@@ -350,6 +382,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table", default="replicated", choices=["replicated", "sharded"],
+                    help="N > 1: every GPU holds the whole table, or one key-hash shard of it with routed probes (SURVEY 8(e))")
+    ap.add_argument("--no-alt-table", action="store_true", help="N > 1: do not also time the other table layout")
+    ap.add_argument("--batch-reads", type=int, default=1 << 19, help="reads per routed batch (--table sharded)")
     ap.add_argument("--no-gather", action="store_true", help="skip the random-gather ceiling microbenchmark")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -183,6 +183,15 @@ int sage2gpu_reads_bytes(const sage2gpu_ctx *ctx, uint64_t *n_bytes);
 int sage2gpu_get_reads(sage2gpu_ctx *ctx, uint16_t *length, uint16_t *frequency, uint64_t *byte_off,
                        uint8_t *fwd, uint8_t *rc);
 
+/* replaces: ReadLoader::getIdOfRead (readLoader.cpp:319-353) for a whole batch of reads, as step 6 uses it behind
+ * isGoodRead (MatePair::processMatePairs, matePair.cpp:176-181).  Input like sage2gpu_load_reads (host buffers, or
+ * device buffers when on_device != 0).  ids[r] (host) = +id when read r itself is the stored orientation, -id when
+ * its reverse complement is (a read equal to its reverse complement gives -id, readLoader.cpp:325-334), 0 when it is
+ * not among the unique reads; good[r] (host, may be NULL) = isGoodRead(read r, min_overlap) -- the reference never
+ * looks a bad read up, its id is reported as 0.  *kernel_ms (may be NULL) = the lookup kernel alone. */
+int sage2gpu_map_reads(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int on_device,
+                       int64_t *ids, uint8_t *good, float *kernel_ms);
+
 /* Phase A / B state for inspection: packed extension records (id | type<<32 | overhang<<33) of
  * rightExtension / leftExtension (economyGraph.cpp:46-47) and exploredReads after phase B. */
 int sage2gpu_get_extensions(sage2gpu_ctx *ctx, uint64_t *right_ext, uint64_t *left_ext, uint8_t *explored);

@@ -69,6 +69,8 @@ def lib():
         _lib.sgo_get64.restype = C.c_uint64
         _lib.sgo_string_compare.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _lib.sgo_string_compare.restype = C.c_int
+        _lib.sgo_map_reads.argtypes = [C.POINTER(Result), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.sgo_map_reads.restype = C.c_int
     return _lib
 
 
@@ -116,6 +118,16 @@ class OracleRun:
             self.edges = a.view(EDGE_DT)
         else:
             self.edges = np.zeros(0, dtype=EDGE_DT)
+
+    def map_reads(self, bases: np.ndarray, offsets: np.ndarray, k: int):
+        """getIdOfRead of every read (readLoader.cpp:319-353): (signed ids int64, isGoodRead uint8)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        ids, good = np.zeros(n, np.int64), np.zeros(n, np.uint8)
+        if lib().sgo_map_reads(C.byref(self._r), bases.ctypes.data, offsets.ctypes.data, n, k, ids.ctypes.data, good.ctypes.data) != 0:
+            raise RuntimeError("sgo_map_reads failed")
+        return ids, good
 
     def write_reads(self, path: str) -> None:
         if lib().sgo_write_reads(C.byref(self._r), path.encode()) != 0:

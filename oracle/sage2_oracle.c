@@ -723,3 +723,41 @@ int sgo_write_graph3(const sgo_result *r, const char *path)
     }
     return fclose(f);
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* step 6 mapping of mates to read ids: ReadLoader::getIdOfRead (readLoader.cpp:319-353) behind  */
+/* the gate of MatePair::processMatePairs (matePair.cpp:176-179).                                */
+/* ids[r] = +id when the read itself is the stored orientation (read < revcomp, strictly),       */
+/*          -id when its reverse complement is (ties included), 0 when it is not in the list;    */
+/* good[r] = isGoodRead (a bad read is never looked up: ids[r] = 0).                             */
+/* ------------------------------------------------------------------------------------------- */
+int sgo_map_reads(const sgo_result *r, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
+                  int min_overlap, int64_t *ids, uint8_t *good)
+{
+    for (int64_t q = 0; q < n_reads; q++) {
+        const int len = (int)(offsets[q + 1] - offsets[q]);
+        ids[q] = 0;
+        if (good) good[q] = 0;
+        char *s = (char *)malloc((size_t)2 * (size_t)(len > 0 ? len : 1) + 2);
+        uint8_t *b = (uint8_t *)calloc((size_t)(len + 3) / 4 + 2, 1);
+        if (!s || !b) { free(s); free(b); return 1; }
+        memcpy(s, bases + offsets[q], (size_t)len);
+        if (is_good_read(s, len, min_overlap)) {
+            if (good) good[q] = 1;
+            char *rcs = s + len;
+            reverse_complement(s, len, rcs);
+            int flag;
+            if (strncmp(s, rcs, (size_t)len) < 0) { sgo_chars_to_bytes((const uint8_t *)s, len, b); flag = 1; }      /* :325-329 */
+            else { sgo_chars_to_bytes((const uint8_t *)rcs, len, b); flag = -1; }                                      /* :330-334 */
+            int64_t lb = 1, ub = (int64_t)r->unique_reads;
+            while (lb <= ub) {                                                                                        /* :335-348 */
+                const int64_t mid = (ub + lb) >> 1;
+                const int c = sgo_string_compare(b, len, r->fwd + r->byte_off[mid], r->length[mid]);
+                if (c == 0) { ids[q] = mid * flag; break; }
+                if (c > 0) lb = mid + 1; else ub = mid - 1;
+            }
+        }
+        free(s); free(b);
+    }
+    return 0;
+}

@@ -59,6 +59,12 @@ void sgo_free(sgo_result *r);
 int  sgo_write_reads(const sgo_result *r, const char *path);
 int  sgo_write_graph3(const sgo_result *r, const char *path);
 
+/* Step-6 mapping of reads to ids (ReadLoader::getIdOfRead, readLoader.cpp:319-353, gated by isGoodRead as in
+ * matePair.cpp:176-179): ids[r] = +/- id or 0, good[r] (may be NULL) = isGoodRead.  Pinned against the reference's
+ * own getIdOfRead (oracle/ref_mapids.cpp -> tests/golden/mapids.json). */
+int  sgo_map_reads(const sgo_result *r, const uint8_t *bases, const int64_t *offsets, int64_t n_reads,
+                   int min_overlap, int64_t *ids, uint8_t *good);
+
 /* Small known-answer entry points for unit tests (utils.cpp restatements). */
 void     sgo_chars_to_bytes(const uint8_t *s, int len, uint8_t *out);
 uint64_t sgo_get64(const uint8_t *read, int start, int length);

@@ -49,7 +49,8 @@ EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2g
            "sage2gpu_get_reads", "sage2gpu_get_extensions", "sage2gpu_get_edges", "sage2gpu_get_edges_packed", "sage2gpu_write_reads",
            "sage2gpu_write_graph3", "sage2gpu_kernel_launches", "sage2gpu_stream", "sage2gpu_measure_gather",
            "sage2gpu_build_hash_table_shard", "sage2gpu_phase_a_sharded_begin", "sage2gpu_route_begin", "sage2gpu_shard_answer",
-           "sage2gpu_route_finish", "sage2gpu_phase_a_routed", "sage2gpu_phase_a_sharded_end", "sage2gpu_phase_b"]
+           "sage2gpu_route_finish", "sage2gpu_phase_a_routed", "sage2gpu_phase_a_sharded_end", "sage2gpu_phase_b",
+           "sage2gpu_map_reads"]
 
 _lib = None
 
@@ -100,6 +101,7 @@ def load_library():
         lib.sage2gpu_phase_a_routed.argtypes = [vp, u64p]
         lib.sage2gpu_phase_a_sharded_end.argtypes = [vp]
         lib.sage2gpu_phase_b.argtypes = [vp]
+        lib.sage2gpu_map_reads.argtypes = [vp, vp, vp, i64, C.c_int, vp, vp, C.POINTER(C.c_float)]
         lib.sage2gpu_run_steps123.argtypes = [vp, vp, vp, i64, C.c_int]
         lib.sage2gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
         lib.sage2gpu_get_timers.argtypes = [vp, C.POINTER(Timers)]
@@ -243,6 +245,22 @@ class Sage2Gpu:
     def phase_b(self):
         self._check(self._lib.sage2gpu_phase_b(self._h), "phase_b")
 
+    def map_reads(self, bases: np.ndarray, offsets: np.ndarray):
+        """getIdOfRead of every read (readLoader.cpp:319-353): (signed ids int64, isGoodRead uint8, kernel ms)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        ids, good, ms = np.zeros(n, np.int64), np.zeros(n, np.uint8), C.c_float()
+        self._check(self._lib.sage2gpu_map_reads(self._h, bases.ctypes.data, offsets.ctypes.data, n, 0, ids.ctypes.data,
+                                                 good.ctypes.data, C.byref(ms)), "map_reads")
+        return ids, good, float(ms.value)
+
+    def map_reads_ptr(self, bases_ptr: int, offsets_ptr: int, n: int, ids_ptr: int, good_ptr: int, device: bool) -> float:
+        ms = C.c_float()
+        self._check(self._lib.sage2gpu_map_reads(self._h, bases_ptr, offsets_ptr, int(n), int(bool(device)), ids_ptr, good_ptr or None,
+                                                 C.byref(ms)), "map_reads")
+        return float(ms.value)
+
     def run_steps123(self, bases, offsets, min_overlap: int):
         self.load_reads(bases, offsets, min_overlap)
         self.build_hash_table()
@@ -334,6 +352,12 @@ class ReadLoader:
 
     def saveReadsInFile(self, path: str):
         self.gpu.write_reads(path)
+
+    def getIdOfRead(self, reads):
+        """readLoader.cpp:319-353 for a batch: signed ids (0 = absent; bad reads, which step 6 never looks up, give 0)."""
+        from . import synth
+        b, off = synth.concat(reads)
+        return self.gpu.map_reads(b, off)[0]
 
 
 class HashTable:

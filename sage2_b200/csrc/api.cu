@@ -373,6 +373,15 @@ int sage2gpu_phase_a_sharded_end(sage2gpu_ctx *ctx)
     return guarded(ctx, [&](sg::Context &c) { sg::stage_phase_a_sharded_end(c); });
 }
 
+int sage2gpu_map_reads(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int on_device, int64_t *ids,
+                       uint8_t *good, float *kernel_ms)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        const float ms = sg::stage_map_reads(c, bases, offsets, n_reads, on_device != 0, ids, good);
+        if (kernel_ms) *kernel_ms = ms;
+    });
+}
+
 int sage2gpu_phase_b(sage2gpu_ctx *ctx)
 {
     return guarded(ctx, [&](sg::Context &c) {

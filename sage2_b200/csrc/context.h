@@ -118,6 +118,8 @@ void stage_shard_answer(Context &c, const void *queries, const u64 *counts_per_s
 void stage_route_finish(Context &c, const void *responses, const void *entries, const u64 *entry_counts);
 u64 stage_phase_a_routed(Context &c);
 void stage_phase_a_sharded_end(Context &c);
+// mapids.cu: step-6 mapping of reads to ids (getIdOfRead, readLoader.cpp:319-353); returns the kernel milliseconds
+float stage_map_reads(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident, int64_t *ids, uint8_t *good);
 void stage_phase_b(Context &c);
 void stage_phase_c_and_finalize(Context &c);
 // device-side text formatters of the reference's -s files (format.cu); false = short write

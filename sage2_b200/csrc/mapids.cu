@@ -1,0 +1,118 @@
+// mapids.cu -- step-6 mapping of reads to read ids: ReadLoader::getIdOfRead
+// (inputReader/readLoader.cpp:319-353) for a whole batch of reads, behind the isGoodRead gate of
+// MatePair::processMatePairs (matePair/matePair.cpp:176-179).
+//
+// One warp per query read.  The ASCII bases are read coalesced and packed straight into registers: lane w holds
+// word w of the forward record and of the reverse-complement record (core.cuh layout, so an unsigned word-wise
+// compare is Read::operator< / stringCompareInBytes).  The orientation the reference would look up is the smaller
+// one (ties -> reverse complement, flag -1, readLoader.cpp:325-334); the binary search over the sorted unique
+// reads F (readLoader.cpp:335-348) compares whole records with one coalesced load + ballot per step.
+#include "context.h"
+
+namespace sg {
+
+constexpr int MP_WARPS = 8;
+
+__device__ __forceinline__ int base_code(uint8_t c) { return ((c >> 1) ^ (c >> 2)) & 3; }       // A0 C1 G2 T3 (either case)
+__device__ __forceinline__ bool base_valid(uint8_t c) { c &= 0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+__global__ void __launch_bounds__(MP_WARPS * 32) map_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ off, u64 n, int k,
+                                                                  const u64 *__restrict__ F, u64 U, int SW, int SWS,
+                                                                  long long *__restrict__ ids, uint8_t *__restrict__ good)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const u64 warp = (u64)blockIdx.x * MP_WARPS + (threadIdx.x >> 5), nwarps = (u64)gridDim.x * MP_WARPS;
+    for (u64 q = warp; q < n; q += nwarps) {
+        const int64_t o0 = off[q];
+        const int64_t len64 = off[q + 1] - o0;
+        const uint8_t *s = bases + o0;
+        const bool fits = len64 <= (int64_t)(32 * SW - 8);
+        const int len = fits ? (int)len64 : 0;
+        bool ok = len64 > (int64_t)k;                       // utils.cpp:146
+        u64 myF = 0, myR = 0;
+        if (ok && fits) {
+            const int nw = (len + 31) >> 5;
+            for (int w = 0; w < nw; ++w) {
+                const int p = 32 * w + lane;
+                uint8_t cf = 'A', cr = 'T';
+                if (p < len) { cf = s[p]; cr = s[len - 1 - p]; }
+                ok = ok && base_valid(cf);
+                const unsigned f = p < len ? (unsigned)base_code(cf) : 0u, r = p < len ? 3u - (unsigned)base_code(cr) : 0u;
+                const int sh = 30 - 2 * (lane & 15);
+                const unsigned fh = __reduce_or_sync(FULL, lane < 16 ? f << sh : 0u), fl = __reduce_or_sync(FULL, lane >= 16 ? f << sh : 0u);
+                const unsigned rh = __reduce_or_sync(FULL, lane < 16 ? r << sh : 0u), rl = __reduce_or_sync(FULL, lane >= 16 ? r << sh : 0u);
+                if (lane == w) { myF = ((u64)fh << 32) | fl; myR = ((u64)rh << 32) | rl; }
+            }
+            if (lane == SW - 1) { myF |= (u64)len; myR |= (u64)len; }
+        } else if (ok) {                                    // longer than any read of the set: good or not, never present
+            for (int64_t p = lane; p < len64; p += 32) ok = ok && base_valid(s[p]);
+        }
+        ok = __all_sync(FULL, ok);
+        long long id = 0;
+        if (ok && fits && U > 0) {
+            // read.compare(read_r) < 0 (readLoader.cpp:325): the codes order like the characters
+            const unsigned dm = __ballot_sync(FULL, lane < SW && myF != myR);
+            bool fwd_smaller = false;
+            if (dm) {
+                const int d = __ffs(dm) - 1;
+                fwd_smaller = __shfl_sync(FULL, myF, d) < __shfl_sync(FULL, myR, d);
+            }
+            const u64 Q = fwd_smaller ? myF : myR;
+            long long lb = 0, ub = (long long)U - 1;
+            while (lb <= ub) {
+                const long long mid = (lb + ub) >> 1;
+                const u64 X = lane < SW ? __ldg(&F[(u64)mid * SWS + lane]) : 0ull;
+                const unsigned ne = __ballot_sync(FULL, lane < SW && X != Q);
+                if (ne == 0) { id = fwd_smaller ? mid + 1 : -(mid + 1); break; }
+                const int d = __ffs(ne) - 1;
+                if (__shfl_sync(FULL, Q, d) > __shfl_sync(FULL, X, d)) lb = mid + 1; else ub = mid - 1;
+            }
+        }
+        if (lane == 0) { ids[q] = id; if (good) good[q] = ok ? 1 : 0; }
+    }
+}
+
+// bases / offsets: host (uploaded here) or device buffers; ids / good: host buffers.  Returns the kernel milliseconds.
+float stage_map_reads(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident,
+                      int64_t *ids, uint8_t *good)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    SG_CHECK(c.have_reads, "organize_reads must run first");
+    SG_CHECK(n_reads >= 0 && ids != nullptr, "bad arguments");
+    if (n_reads == 0) return 0.f;
+    SG_CHECK(bases != nullptr && offsets != nullptr, "null input");
+    const u64 n = (u64)n_reads;
+    DevBuf<int64_t> d_off;
+    DevBuf<uint8_t> d_bases, d_good(n, st);
+    DevBuf<long long> d_ids(n, st);
+    const uint8_t *pb = bases;
+    const int64_t *po = offsets;
+    if (!device_resident) {
+        const int64_t first = offsets[0], total = offsets[n] - first;      // offsets are relative to `bases`
+        SG_CHECK(total >= 0, "offsets must ascend");
+        d_off.alloc(n + 1, st);
+        d_bases.alloc((size_t)total + 1, st);
+        SG_CUDA(cudaMemcpyAsync(d_off.p, offsets, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (total) SG_CUDA(cudaMemcpyAsync(d_bases.p, bases + first, (size_t)total, cudaMemcpyHostToDevice, st));
+        pb = d_bases.p - first; po = d_off.p;
+    }
+    cudaEvent_t e0, e1;
+    SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
+    SG_CUDA(cudaEventRecord(e0, st));
+    u64 g = (n + MP_WARPS - 1) / MP_WARPS;
+    if (g > (u64)kSMs * 16) g = (u64)kSMs * 16;
+    map_reads_kernel<<<(unsigned)g, MP_WARPS * 32, 0, st>>>(pb, po, n, c.min_overlap, c.F.p, c.cnt.unique_reads, c.SW, c.SWS, d_ids.p, d_good.p);
+    SG_LAUNCHED();
+    SG_CUDA(cudaEventRecord(e1, st));
+    SG_CUDA(cudaMemcpyAsync(ids, d_ids.p, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (good) SG_CUDA(cudaMemcpyAsync(good, d_good.p, n, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
+}
+
+}  // namespace sg

@@ -172,14 +172,17 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
     gpu.finish_graph()
 
 
-def run_dist(gen, rank: int, world: int, device) -> int:
-    """Serve one rank's requests with torch.distributed (NCCL for CUDA tensors, gloo on the CPU).  Returns bytes sent."""
+def run_dist(gen, rank: int, world: int, device, stats: dict | None = None) -> int:
+    """Serve one rank's requests with torch.distributed (NCCL for CUDA tensors, gloo on the CPU).  Returns bytes sent.
+    stats (optional): wall milliseconds spent in the exchanges, by request kind, are added to it."""
+    import time
     sent = 0
     cuda = torch.device(device).type == "cuda"
     try:
         req = next(gen)
         while True:
             kind = req[0]
+            t0 = time.perf_counter()
             if kind == "counts":
                 t = torch.tensor(req[1], dtype=torch.int64, device=device)
                 out = torch.empty_like(t)
@@ -207,6 +210,9 @@ def run_dist(gen, rank: int, world: int, device) -> int:
                 val = None
             else:
                 raise ValueError(kind)
+            if stats is not None:
+                stats[kind] = stats.get(kind, 0.0) + (time.perf_counter() - t0) * 1e3
+                stats["n_" + kind] = stats.get("n_" + kind, 0) + 1
             req = gen.send(val)
     except StopIteration:
         pass
@@ -273,7 +279,11 @@ def run_local(gens: list, views_of=None) -> None:
         reqs = nxt
 
 
-def build_overlap_graph_sharded(gpu, rank: int, world: int, device=None, batch_reads: int = 1 << 19) -> int:
+def build_overlap_graph_sharded(gpu, rank: int, world: int, device=None, batch_reads: int = 1 << 19, stats: dict | None = None) -> int:
     """One process per GPU (torchrun): the sharded-table build on this rank; returns the bytes this rank sent."""
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    return run_dist(sharded_graph_steps(gpu, rank, world, device_view_fn(device), batch_reads), rank, world, device)
+    steps = sharded_graph_steps(gpu, rank, world, device_view_fn(device), batch_reads)
+    if world == 1:          # one shard = the whole table: the same steps, the exchanges are copies
+        run_local([steps])
+        return 0
+    return run_dist(steps, rank, world, device, stats)

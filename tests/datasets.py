@@ -145,3 +145,40 @@ NO_REFERENCE = {"empty", "allbad", "single"}
 
 def get(name: str):
     return DATASETS[name]()
+
+
+def map_queries(name: str, n: int = 4000, seed: int = 777):
+    """Query reads for the step-6 mapping (ReadLoader::getIdOfRead, readLoader.cpp:319-353) against dataset `name`:
+    reads of the data set as they are, reverse-complemented, lower-cased, with one substitution (mostly absent),
+    truncated / extended (absent or bad), with an N (bad), palindromes, and reads longer than any in the set."""
+    reads, k = get(name)
+    reads = synth.to_list(reads) if not isinstance(reads, list) else reads
+    rng = np.random.default_rng(seed)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65, 97: 116, 99: 103, 103: 99, 116: 97, 78: 78}
+    out = []
+    for _ in range(n):
+        r = reads[int(rng.integers(0, len(reads)))] if reads else b"ACGT" * 30
+        x = rng.random()
+        if x < 0.30:
+            pass
+        elif x < 0.55:
+            r = bytes(comp.get(c, 78) for c in reversed(r))
+        elif x < 0.62:
+            r = r.lower()
+        elif x < 0.77 and len(r) > 0:
+            p = int(rng.integers(0, len(r)))
+            r = r[:p] + bytes([b"ACGT"[(b"ACGT".find(r[p:p + 1].upper()) + 1) % 4]]) + r[p + 1:]
+        elif x < 0.82:
+            r = r[: int(rng.integers(1, max(2, len(r))))]
+        elif x < 0.87:
+            r = r + bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(1, 40))).astype(np.uint8))
+        elif x < 0.92 and len(r) > 0:
+            p = int(rng.integers(0, len(r)))
+            r = r[:p] + b"N" + r[p + 1:]
+        elif x < 0.96:
+            half = r[: max(1, len(r) // 2)].upper()
+            r = half + bytes(comp.get(c, 78) for c in reversed(half))
+        else:
+            r = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(1, 400))).astype(np.uint8))
+        out.append(r)
+    return out, k

@@ -61,3 +61,26 @@ def test_oracle_degenerate_inputs(name):
     r = _run(name)
     assert r.n_edges == 0
     assert r.U == (1 if name == "single" else 0)
+
+
+MAPIDS = json.load(open(os.path.join(HERE, "golden", "mapids.json")))
+
+
+@pytest.mark.parametrize("name", sorted(MAPIDS))
+def test_map_reads_equals_reference_getIdOfRead(name):
+    """oracle sgo_map_reads (restating readLoader.cpp:319-353 + the isGoodRead gate of matePair.cpp:176-179) against
+    the ids the UNMODIFIED reference's ReadLoader::getIdOfRead printed for the same queries (make_mapids_golden.py)."""
+    import hashlib
+    g = MAPIDS[name]
+    reads, k = datasets.get(name)
+    queries, _ = datasets.map_queries(name)
+    assert k == g["k"] and len(queries) == g["n_queries"]
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    qb, qoff = synth.concat(queries)
+    ids, good = o.map_reads(qb, qoff, k)
+    text = ["bad" if not gd else str(int(i)) for i, gd in zip(ids, good)]
+    assert text[:64] == g["first"]
+    assert hashlib.md5("\n".join(text).encode()).hexdigest() == g["md5"]
+    assert (int((ids > 0).sum()), int((ids < 0).sum()), int(((ids == 0) & (good == 1)).sum()), int((good == 0).sum())) == \
+        (g["positive"], g["negative"], g["absent"], g["bad"])
