@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--table", default="replicated", choices=["replicated", "sharded"],
                     help="N > 1: every GPU holds the whole table, or one key-hash shard of it with routed probes (SURVEY 8(e))")
     ap.add_argument("--no-alt-table", action="store_true", help="N > 1: do not also time the other table layout")
-    ap.add_argument("--batch-reads", type=int, default=1 << 19, help="reads per routed batch (--table sharded)")
+    ap.add_argument("--batch-reads", type=int, default=1 << 20, help="reads per routed batch (--table sharded)")
     ap.add_argument("--no-gather", action="store_true", help="skip the random-gather ceiling microbenchmark")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -144,7 +144,7 @@ def _route(gpu, what: int, first: int, count: int, exact: bool, world: int, view
     gpu.route_finish(_ptr(recv_resp), _ptr(recv_ent), recv_ecs)
 
 
-def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 << 19):
+def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 << 20):
     """Generator: sage2gpu_build_overlap_graph with the table sharded over `world` ranks.  Reads loaded on every rank
     and sage2gpu_build_hash_table_shard(rank, world) done."""
     first, count = gpu.phase_a_sharded_begin(rank, world)
@@ -279,7 +279,7 @@ def run_local(gens: list, views_of=None) -> None:
         reqs = nxt
 
 
-def build_overlap_graph_sharded(gpu, rank: int, world: int, device=None, batch_reads: int = 1 << 19, stats: dict | None = None) -> int:
+def build_overlap_graph_sharded(gpu, rank: int, world: int, device=None, batch_reads: int = 1 << 20, stats: dict | None = None) -> int:
     """One process per GPU (torchrun): the sharded-table build on this rank; returns the bytes this rank sent."""
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     steps = sharded_graph_steps(gpu, rank, world, device_view_fn(device), batch_reads)
