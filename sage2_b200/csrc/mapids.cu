@@ -2,11 +2,11 @@
 // (inputReader/readLoader.cpp:319-353) for a whole batch of reads, behind the isGoodRead gate of
 // MatePair::processMatePairs (matePair/matePair.cpp:176-179).
 //
-// One warp per query read.  The ASCII bases are read coalesced and packed straight into registers: lane w holds
-// word w of the forward record and of the reverse-complement record (core.cuh layout, so an unsigned word-wise
-// compare is Read::operator< / stringCompareInBytes).  The orientation the reference would look up is the smaller
-// one (ties -> reverse complement, flag -1, readLoader.cpp:325-334); the binary search over the sorted unique
-// reads F (readLoader.cpp:335-348) compares whole records with one coalesced load + ballot per step.
+// Pass 1, one warp per query read: the ASCII bases are read coalesced and packed in registers (lane w holds word w of
+// the forward and of the reverse-complement record; core.cuh layout, so an unsigned word-wise compare is
+// Read::operator< / stringCompareInBytes).  The orientation the reference would look up is the smaller one (ties ->
+// reverse complement, flag -1, readLoader.cpp:325-334).  Pass 2, one thread per query: the binary search over the
+// sorted unique reads F (readLoader.cpp:335-348), 32 independent random lines in flight per warp.
 #include "context.h"
 
 namespace sg {
@@ -16,90 +16,76 @@ constexpr int MP_WARPS = 8;
 __device__ __forceinline__ int base_code(uint8_t c) { return ((c >> 1) ^ (c >> 2)) & 3; }       // A0 C1 G2 T3 (either case)
 __device__ __forceinline__ bool base_valid(uint8_t c) { c &= 0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
-constexpr int MP_QPW = 4;      // queries a warp searches in lock step (independent loads in flight)
-
-__global__ void __launch_bounds__(MP_WARPS * 32) map_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ off, u64 n, int k,
-                                                                  const u64 *__restrict__ F, u64 U, int SW, int SWS,
-                                                                  long long *__restrict__ ids, uint8_t *__restrict__ good)
+// pass 1: one warp per query packs it (coalesced byte loads) and writes the record to look up + its flags
+//   meta bit 0: isGoodRead, bit 1: the read itself is the smaller orientation (flag +1), bit 2: worth searching
+__global__ void __launch_bounds__(MP_WARPS * 32) map_pack_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ off, u64 n, int k,
+                                                                 u64 U, int SW, u64 *__restrict__ qrec, uint8_t *__restrict__ meta)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const u64 warp = (u64)blockIdx.x * MP_WARPS + (threadIdx.x >> 5), nwarps = (u64)gridDim.x * MP_WARPS;
-    for (u64 q0 = warp * MP_QPW; q0 < n; q0 += nwarps * MP_QPW) {
-        u64 Q[MP_QPW];
-        long long lb[MP_QPW], ub[MP_QPW], id[MP_QPW];
-        bool fwd_smaller[MP_QPW], okq[MP_QPW];
-#pragma unroll
-        for (int t = 0; t < MP_QPW; ++t) {
-            const u64 q = q0 + t;
-            Q[t] = 0; lb[t] = 0; ub[t] = -1; id[t] = 0; fwd_smaller[t] = false; okq[t] = false;
-            if (q >= n) continue;
-            const int64_t o0 = off[q];
-            const int64_t len64 = off[q + 1] - o0;
-            const uint8_t *s = bases + o0;
-            const bool fits = len64 <= (int64_t)(32 * SW - 8);
-            const int len = fits ? (int)len64 : 0;
-            bool ok = len64 > (int64_t)k;                       // utils.cpp:146
-            u64 myF = 0, myR = 0;
-            if (ok && fits) {
-                const int nw = (len + 31) >> 5;
-                for (int w = 0; w < nw; ++w) {
-                    const int p = 32 * w + lane;
-                    uint8_t cf = 'A', cr = 'T';
-                    if (p < len) { cf = s[p]; cr = s[len - 1 - p]; }
-                    ok = ok && base_valid(cf);
-                    const unsigned f = p < len ? (unsigned)base_code(cf) : 0u, r = p < len ? 3u - (unsigned)base_code(cr) : 0u;
-                    const int sh = 30 - 2 * (lane & 15);
-                    const unsigned fh = __reduce_or_sync(FULL, lane < 16 ? f << sh : 0u), fl = __reduce_or_sync(FULL, lane >= 16 ? f << sh : 0u);
-                    const unsigned rh = __reduce_or_sync(FULL, lane < 16 ? r << sh : 0u), rl = __reduce_or_sync(FULL, lane >= 16 ? r << sh : 0u);
-                    if (lane == w) { myF = ((u64)fh << 32) | fl; myR = ((u64)rh << 32) | rl; }
-                }
-                if (lane == SW - 1) { myF |= (u64)len; myR |= (u64)len; }
-            } else if (ok) {                                    // longer than any read of the set: good or not, never present
-                for (int64_t p = lane; p < len64; p += 32) ok = ok && base_valid(s[p]);
+    for (u64 q = warp; q < n; q += nwarps) {
+        const int64_t o0 = off[q];
+        const int64_t len64 = off[q + 1] - o0;
+        const uint8_t *s = bases + o0;
+        const bool fits = len64 <= (int64_t)(32 * SW - 8);
+        const int len = fits ? (int)len64 : 0;
+        bool ok = len64 > (int64_t)k;                       // utils.cpp:146
+        u64 myF = 0, myR = 0;
+        if (ok && fits) {
+            const int nw = (len + 31) >> 5;
+            for (int w = 0; w < nw; ++w) {
+                const int p = 32 * w + lane;
+                uint8_t cf = 'A', cr = 'T';
+                if (p < len) { cf = s[p]; cr = s[len - 1 - p]; }
+                ok = ok && base_valid(cf);
+                const unsigned f = p < len ? (unsigned)base_code(cf) : 0u, r = p < len ? 3u - (unsigned)base_code(cr) : 0u;
+                const int sh = 30 - 2 * (lane & 15);
+                const unsigned fh = __reduce_or_sync(FULL, lane < 16 ? f << sh : 0u), fl = __reduce_or_sync(FULL, lane >= 16 ? f << sh : 0u);
+                const unsigned rh = __reduce_or_sync(FULL, lane < 16 ? r << sh : 0u), rl = __reduce_or_sync(FULL, lane >= 16 ? r << sh : 0u);
+                if (lane == w) { myF = ((u64)fh << 32) | fl; myR = ((u64)rh << 32) | rl; }
             }
-            ok = __all_sync(FULL, ok);
-            okq[t] = ok;
-            if (ok && fits && U > 0) {
-                // read.compare(read_r) < 0 (readLoader.cpp:325): the codes order like the characters
-                const unsigned dm = __ballot_sync(FULL, lane < SW && myF != myR);
-                if (dm) {
-                    const int d = __ffs(dm) - 1;
-                    fwd_smaller[t] = __shfl_sync(FULL, myF, d) < __shfl_sync(FULL, myR, d);
-                }
-                Q[t] = fwd_smaller[t] ? myF : myR;
-                ub[t] = (long long)U - 1;
+            if (lane == SW - 1) { myF |= (u64)len; myR |= (u64)len; }
+        } else if (ok) {                                    // longer than any read of the set: good or not, never present
+            for (int64_t p = lane; p < len64; p += 32) ok = ok && base_valid(s[p]);
+        }
+        ok = __all_sync(FULL, ok);
+        // read.compare(read_r) < 0 (readLoader.cpp:325): the codes order like the characters; ties look the revcomp up
+        const unsigned dm = __ballot_sync(FULL, lane < SW && myF != myR);
+        bool fwd_smaller = false;
+        if (dm) {
+            const int d = __ffs(dm) - 1;
+            fwd_smaller = __shfl_sync(FULL, myF, d) < __shfl_sync(FULL, myR, d);
+        }
+        if (lane < SW) qrec[q * SW + lane] = fwd_smaller ? myF : myR;
+        if (lane == 0) meta[q] = (uint8_t)((ok ? 1 : 0) | (fwd_smaller ? 2 : 0) | ((ok && fits && U > 0) ? 4 : 0));
+    }
+}
+
+// pass 2: one THREAD per query walks the binary search of readLoader.cpp:335-348 over the sorted unique reads: a warp
+// keeps 32 independent random lines in flight; words after the first differing one are never read
+__global__ void __launch_bounds__(256) map_search_kernel(const u64 *__restrict__ qrec, const uint8_t *__restrict__ meta, u64 n,
+                                                         const u64 *__restrict__ F, u64 U, int SW, int SWS,
+                                                         long long *__restrict__ ids, uint8_t *__restrict__ good)
+{
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x) {
+        const uint8_t m = meta[q];
+        long long id = 0;
+        if (m & 4) {
+            const u64 *Q = qrec + q * SW;
+            const u64 q0 = Q[0];
+            long long lb = 0, ub = (long long)U - 1;
+            while (lb <= ub) {
+                const long long mid = (lb + ub) >> 1;
+                const u64 *X = F + (u64)mid * SWS;
+                u64 x = __ldg(&X[0]), y = q0;
+                for (int w = 1; x == y && w < SW; ++w) { x = __ldg(&X[w]); y = Q[w]; }
+                if (x == y) { id = (m & 2) ? mid + 1 : -(mid + 1); break; }
+                if (y > x) lb = mid + 1; else ub = mid - 1;
             }
         }
-        // readLoader.cpp:335-348, MP_QPW searches in lock step
-        for (;;) {
-            bool any = false;
-            u64 X[MP_QPW];
-            long long mid[MP_QPW];
-#pragma unroll
-            for (int t = 0; t < MP_QPW; ++t) {
-                mid[t] = (lb[t] + ub[t]) >> 1;
-                X[t] = 0;
-                if (lb[t] <= ub[t]) { any = true; if (lane < SW) X[t] = __ldg(&F[(u64)mid[t] * SWS + lane]); }
-            }
-            if (!any) break;
-#pragma unroll
-            for (int t = 0; t < MP_QPW; ++t) {
-                if (lb[t] > ub[t]) continue;
-                const unsigned ne = __ballot_sync(FULL, lane < SW && X[t] != Q[t]);
-                if (ne == 0) { id[t] = fwd_smaller[t] ? mid[t] + 1 : -(mid[t] + 1); ub[t] = lb[t] - 1; continue; }
-                const int d = __ffs(ne) - 1;
-                if (__shfl_sync(FULL, Q[t], d) > __shfl_sync(FULL, X[t], d)) lb[t] = mid[t] + 1; else ub[t] = mid[t] - 1;
-            }
-        }
-        if (lane < MP_QPW && q0 + lane < n) {
-            long long v = 0;
-            bool g = false;
-#pragma unroll
-            for (int t = 0; t < MP_QPW; ++t) if (lane == t) { v = id[t]; g = okq[t]; }
-            ids[q0 + lane] = v;
-            if (good) good[q0 + lane] = g ? 1 : 0;
-        }
+        ids[q] = id;
+        if (good) good[q] = m & 1;
     }
 }
 
@@ -131,9 +117,15 @@ float stage_map_reads(Context &c, const uint8_t *bases, const int64_t *offsets, 
     cudaEvent_t e0, e1;
     SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
     SG_CUDA(cudaEventRecord(e0, st));
-    u64 g = (n + MP_WARPS * MP_QPW - 1) / (MP_WARPS * MP_QPW);
+    DevBuf<u64> qrec(n * (u64)c.SW, st);
+    DevBuf<uint8_t> meta(n, st);
+    u64 g = (n + MP_WARPS - 1) / MP_WARPS;
     if (g > (u64)kSMs * 16) g = (u64)kSMs * 16;
-    map_reads_kernel<<<(unsigned)g, MP_WARPS * 32, 0, st>>>(pb, po, n, c.min_overlap, c.F.p, c.cnt.unique_reads, c.SW, c.SWS, d_ids.p, d_good.p);
+    map_pack_kernel<<<(unsigned)g, MP_WARPS * 32, 0, st>>>(pb, po, n, c.min_overlap, c.cnt.unique_reads, c.SW, qrec.p, meta.p);
+    SG_LAUNCHED();
+    g = (n + 255) / 256;
+    if (g > (u64)kSMs * 8) g = (u64)kSMs * 8;
+    map_search_kernel<<<(unsigned)g, 256, 0, st>>>(qrec.p, meta.p, n, c.F.p, c.cnt.unique_reads, c.SW, c.SWS, d_ids.p, d_good.p);
     SG_LAUNCHED();
     SG_CUDA(cudaEventRecord(e1, st));
     SG_CUDA(cudaMemcpyAsync(ids, d_ids.p, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
