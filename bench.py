@@ -203,7 +203,9 @@ def run_ours(args):
     def build_graph():
         if layout["sharded"]:       # key-hash shard per GPU, window probes routed to their owners by NCCL all-to-all
             gpu.build_hash_table_shard(rank, world)
-            return multi.build_overlap_graph_sharded(gpu, rank, world, dev, batch_reads=args.batch_reads, stats=xstats)
+            p2p = args.exchange == "p2p"      # peer-memory mailboxes (NVLink P2P stores) or NCCL all-to-all
+            return multi.build_overlap_graph_sharded(gpu, rank, world, dev, batch_reads=min(args.batch_reads, 1 << 19) if p2p else args.batch_reads,
+                                                     stats=xstats, p2p=p2p)
         gpu.build_hash_table()
         return multi.build_overlap_graph(gpu, rank, world, dev)
 
@@ -281,7 +283,8 @@ def run_ours(args):
             step_device()
         xstats.clear()
         a_ms, _, a_launches, a_stage = timed(step_device, args.steps)
-        alt = {"table": "sharded" if layout["sharded"] else "replicated", "ms_per_step": a_ms / args.steps,
+        alt = {"table": "sharded" if layout["sharded"] else "replicated", "exchange": args.exchange if layout["sharded"] else "nccl",
+               "ms_per_step": a_ms / args.steps,
                "value": n_reads / (a_ms / args.steps / 1000.0), "unit": UNIT, "sent_bytes_per_rank_and_step": comm["sent"],
                "gpu_launches": a_launches, "stage_ms": a_stage,
                "exchange_wall_ms_per_step": {kk: (vv / args.steps) for kk, vv in xstats.items()}}
@@ -347,9 +350,9 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
         "config": dict(cfg, parallelism=(
-                           (f"{world} GPU(s): reads replicated, table sharded by key hash, window probes routed to their owners by "
-                            f"NCCL all-to-all in batches of {args.batch_reads} reads, phase A partitioned by read id "
-                            f"({comm['sent']} B sent per rank and step)") if sharded else
+                           (f"{world} GPU(s): reads replicated, table sharded by key hash, window probes routed to their owners "
+                            f"({'kernel stores into peer-memory mailboxes over NVLink' if args.exchange == 'p2p' else 'NCCL all-to-all'}), "
+                            f"phase A partitioned by read id ({comm['sent']} B sent per rank and step)") if sharded else
                            "single GPU" if world == 1 else
                            f"{world} GPUs: reads + table replicated, phase A partitioned by read id, "
                            f"one NCCL exchange (all-gather + all-reduce MAX, {comm['sent']} B sent per rank)"),
@@ -384,6 +387,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table", default="replicated", choices=["replicated", "sharded"],
                     help="N > 1: every GPU holds the whole table, or one key-hash shard of it with routed probes (SURVEY 8(e))")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="--table sharded: routed probes through peer-memory mailboxes (kernel stores over NVLink) or NCCL all-to-all")
     ap.add_argument("--no-alt-table", action="store_true", help="N > 1: do not also time the other table layout")
     ap.add_argument("--batch-reads", type=int, default=1 << 20, help="reads per routed batch (--table sharded)")
     ap.add_argument("--no-gather", action="store_true", help="skip the random-gather ceiling microbenchmark")

@@ -155,6 +155,22 @@ int sage2gpu_shard_answer(sage2gpu_ctx *ctx, const void *queries, const uint64_t
 int sage2gpu_route_finish(sage2gpu_ctx *ctx, const void *responses, const void *entries, const uint64_t *entry_counts);
 int sage2gpu_phase_a_routed(sage2gpu_ctx *ctx, uint64_t *n_redo);
 int sage2gpu_phase_a_sharded_end(sage2gpu_ctx *ctx);
+/* The same exchange over PEER MEMORY (NVLink / NVSwitch P2P) instead of an all-to-all of the host: every rank owns a
+ * "mailbox" in its device memory which the other ranks map (CUDA IPC between processes: hand the 64-byte
+ * ipc_handle_out of mailbox_create to the other ranks and pass it to their mailbox_open; inside one process pass
+ * *local_ptr instead).  The mailbox holds, per peer, room for the windows of max_reads_per_batch reads.
+ *   route_post     = route_begin, but the routing kernel stores every query straight into its owner's mailbox
+ *   [barrier between the ranks]
+ *   answer_post    = shard_answer out of the own mailbox; answers and bucket entries are copied into the sources' mailboxes
+ *   [barrier between the ranks]
+ *   route_collect  = route_finish out of the own mailbox
+ * No sizes travel ahead of the data and the host moves nothing.  *bytes_sent = bytes this rank put into other ranks' memory. */
+int sage2gpu_mailbox_create(sage2gpu_ctx *ctx, int rank, int world, uint64_t max_reads_per_batch, void *ipc_handle_out, void **local_ptr);
+int sage2gpu_mailbox_open(sage2gpu_ctx *ctx, int peer_rank, const void *ipc_handle, void *ptr);
+int sage2gpu_route_post(sage2gpu_ctx *ctx, int what, uint64_t first, uint64_t count, int exact, uint64_t *n_reads, uint64_t *bytes_sent);
+int sage2gpu_answer_post(sage2gpu_ctx *ctx, int exact, uint64_t *bytes_sent);
+int sage2gpu_route_collect(sage2gpu_ctx *ctx);
+
 /* Phase B alone (economyGraph.cpp:455-480); sage2gpu_finish_graph skips it when it already ran. */
 int sage2gpu_phase_b(sage2gpu_ctx *ctx);
 

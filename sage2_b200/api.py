@@ -50,7 +50,8 @@ EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2g
            "sage2gpu_write_graph3", "sage2gpu_kernel_launches", "sage2gpu_stream", "sage2gpu_measure_gather",
            "sage2gpu_build_hash_table_shard", "sage2gpu_phase_a_sharded_begin", "sage2gpu_route_begin", "sage2gpu_shard_answer",
            "sage2gpu_route_finish", "sage2gpu_phase_a_routed", "sage2gpu_phase_a_sharded_end", "sage2gpu_phase_b",
-           "sage2gpu_map_reads"]
+           "sage2gpu_map_reads", "sage2gpu_mailbox_create", "sage2gpu_mailbox_open", "sage2gpu_route_post", "sage2gpu_answer_post",
+           "sage2gpu_route_collect"]
 
 _lib = None
 
@@ -101,6 +102,11 @@ def load_library():
         lib.sage2gpu_phase_a_routed.argtypes = [vp, u64p]
         lib.sage2gpu_phase_a_sharded_end.argtypes = [vp]
         lib.sage2gpu_phase_b.argtypes = [vp]
+        lib.sage2gpu_mailbox_create.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, vp, C.POINTER(vp)]
+        lib.sage2gpu_mailbox_open.argtypes = [vp, C.c_int, vp, vp]
+        lib.sage2gpu_route_post.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, u64p, u64p]
+        lib.sage2gpu_answer_post.argtypes = [vp, C.c_int, u64p]
+        lib.sage2gpu_route_collect.argtypes = [vp]
         lib.sage2gpu_map_reads.argtypes = [vp, vp, vp, i64, C.c_int, vp, vp, C.POINTER(C.c_float)]
         lib.sage2gpu_run_steps123.argtypes = [vp, vp, vp, i64, C.c_int]
         lib.sage2gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
@@ -233,6 +239,32 @@ class Sage2Gpu:
     def route_finish(self, resp_ptr: int, entries_ptr: int, entry_counts):
         ec = (C.c_uint64 * len(entry_counts))(*[int(x) for x in entry_counts])
         self._check(self._lib.sage2gpu_route_finish(self._h, resp_ptr or None, entries_ptr or None, ec), "route_finish")
+
+    # ---- the same exchange over peer memory (mailboxes) ------------------------------------------------------------
+    def mailbox_create(self, rank: int, world: int, max_reads_per_batch: int) -> dict:
+        """-> {"handle": the 64-byte CUDA IPC handle (bytes), "ptr": the mailbox's device pointer (same-process peers)}."""
+        h = (C.c_char * 64)()
+        p = C.c_void_p()
+        self._check(self._lib.sage2gpu_mailbox_create(self._h, int(rank), int(world), int(max_reads_per_batch), h, C.byref(p)), "mailbox_create")
+        self.mailbox_batch_reads = int(max_reads_per_batch)
+        return {"handle": bytes(h.raw), "ptr": p.value or 0}
+
+    def mailbox_open(self, peer_rank: int, handle: bytes | None = None, ptr: int = 0):
+        self._check(self._lib.sage2gpu_mailbox_open(self._h, int(peer_rank), handle if handle else None, ptr or None), "mailbox_open")
+
+    def route_post(self, what: int, first: int, count: int, exact: bool) -> tuple:
+        """-> (reads in the batch, bytes stored into other ranks' mailboxes)."""
+        n, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sage2gpu_route_post(self._h, int(what), int(first), int(count), int(bool(exact)), C.byref(n), C.byref(b)), "route_post")
+        return int(n.value), int(b.value)
+
+    def answer_post(self, exact: bool) -> int:
+        b = C.c_uint64()
+        self._check(self._lib.sage2gpu_answer_post(self._h, int(bool(exact)), C.byref(b)), "answer_post")
+        return int(b.value)
+
+    def route_collect(self):
+        self._check(self._lib.sage2gpu_route_collect(self._h), "route_collect")
 
     def phase_a_routed(self) -> int:
         n = C.c_uint64()

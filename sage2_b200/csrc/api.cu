@@ -146,6 +146,7 @@ void sage2gpu_destroy(sage2gpu_ctx *ctx)
         c.d_bases.release(); c.d_offsets.release(); c.up_d_bases.release(); c.up_d_offsets.release(); c.raw.release(); c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
         c.slots.release(); c.entries.release(); c.extR.release(); c.extL.release(); c.flag5.release();
         c.cont_max.release(); c.explored.release(); c.edges.release();
+        sg::stage_mailbox_destroy(c);
         c.arena.destroy();
     }
     cudaStreamSynchronize(st);
@@ -354,6 +355,51 @@ int sage2gpu_route_finish(sage2gpu_ctx *ctx, const void *responses, const void *
         SG_CHECK(entry_counts != nullptr, "null entry counts");
         StageTimer t(c.stream);
         sg::stage_route_finish(c, responses, entries, entry_counts);
+        (c.rt_what == 1 ? c.tm.phase_c_dev : c.tm.phase_a) += t.stop();
+    });
+}
+
+int sage2gpu_mailbox_create(sage2gpu_ctx *ctx, int rank, int world, uint64_t max_reads_per_batch, void *ipc_handle_out, void **local_ptr)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.have_reads, "load the reads first: the mailbox is sized for their window count");
+        const int wstride = c.max_len - c.h + 1 > 1 ? c.max_len - c.h + 1 : 1;
+        sg::stage_mailbox_create(c, rank, world, (max_reads_per_batch ? max_reads_per_batch : 1) * (sg::u64)wstride, ipc_handle_out, local_ptr);
+    });
+}
+
+int sage2gpu_mailbox_open(sage2gpu_ctx *ctx, int peer_rank, const void *ipc_handle, void *ptr)
+{
+    return guarded(ctx, [&](sg::Context &c) { sg::stage_mailbox_open(c, peer_rank, ipc_handle, ptr); });
+}
+
+int sage2gpu_route_post(sage2gpu_ctx *ctx, int what, uint64_t first, uint64_t count, int exact, uint64_t *n_reads, uint64_t *bytes_sent)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_route_post(c, what, first, count, exact, n_reads);
+        if (bytes_sent) {
+            *bytes_sent = 0;
+            for (int g = 0; g < c.mb.world; ++g) if (g != c.mb.rank) *bytes_sent += c.rt_counts[g] * (exact ? 16 : 8);
+        }
+        (what == 1 ? c.tm.phase_c_dev : c.tm.phase_a) += t.stop();
+    });
+}
+
+int sage2gpu_answer_post(sage2gpu_ctx *ctx, int exact, uint64_t *bytes_sent)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_answer_post(c, exact, bytes_sent);
+        c.tm.phase_a += t.stop();
+    });
+}
+
+int sage2gpu_route_collect(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_route_collect(c);
         (c.rt_what == 1 ? c.tm.phase_c_dev : c.tm.phase_a) += t.stop();
     });
 }

@@ -29,6 +29,16 @@ struct Timers {   // milliseconds, CUDA events on the context stream
           phase_c_dev = 0, phase_c_host = 0, sort_edges = 0, total_device = 0, phase_a_kernel = 0;
 };
 
+// peer-memory exchange of the routed probes (shard.cu): this rank's mailbox + the mapped mailboxes of the others
+struct Mailbox {
+    char *base = nullptr;
+    size_t bytes = 0;
+    int world = 0, rank = -1;
+    u64 cap = 0, ecap = 0;              // windows / entries per (source, owner) segment
+    char *peer[kMaxWorld] = {};
+    bool ipc[kMaxWorld] = {};
+};
+
 struct Context {
     Context()
     {
@@ -95,7 +105,9 @@ struct Context {
     u64 rt_n = 0, rt_first = 0, rt_Q = 0, rt_counts[kMaxWorld] = {};
     u32 rt_wstride = 0;
     int rt_what = 0, rt_world = 1, rt_state = 0;     // state: 0 idle, 1 queries out, 2 answers in
-    bool rt_is_list = false, rt_exact = false, rt_for_c = false;
+    bool rt_is_list = false, rt_exact = false, rt_for_c = false, rt_mailbox = false;
+    const u32 *rt_entries_view = nullptr;   // the batch's entry streams: rt_wentries, or the mailbox region read in place
+    Mailbox mb;
     // owner side: the answers of the last sage2gpu_shard_answer
     DevBuf<u64> an_resp;
     DevBuf<u32> an_entries;
@@ -117,6 +129,13 @@ void stage_shard_answer(Context &c, const void *queries, const u64 *counts_per_s
                         u64 *entry_counts);
 void stage_route_finish(Context &c, const void *responses, const void *entries, const u64 *entry_counts);
 u64 stage_phase_a_routed(Context &c);
+// ... and the same exchange over peer memory (NVLink P2P stores / copies into the ranks' mailboxes)
+void stage_mailbox_create(Context &c, int rank, int world, u64 cap_windows, void *ipc_handle_out, void **local_ptr);
+void stage_mailbox_open(Context &c, int peer_rank, const void *ipc_handle, void *ptr);
+void stage_mailbox_destroy(Context &c);
+void stage_route_post(Context &c, int what, u64 first, u64 count, int exact, u64 *n_reads);
+void stage_answer_post(Context &c, int exact, u64 *bytes_sent);
+void stage_route_collect(Context &c);
 void stage_phase_a_sharded_end(Context &c);
 // mapids.cu: step-6 mapping of reads to ids (getIdOfRead, readLoader.cpp:319-353); returns the kernel milliseconds
 float stage_map_reads(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident, int64_t *ids, uint8_t *good);

@@ -669,7 +669,7 @@ static SearchParams make_params(const Context &c)
 static void use_routed_batch(const Context &c, SearchParams &P)
 {
     P.slots = nullptr; P.nsec = 0;
-    P.wslot = c.rt_wslot.p; P.entries = c.rt_wentries.p; P.wstride = c.rt_wstride; P.n = c.rt_n;
+    P.wslot = c.rt_wslot.p; P.entries = c.rt_entries_view; P.wstride = c.rt_wstride; P.n = c.rt_n;
     P.ids = c.rt_is_list ? c.rt_ids.p : nullptr; P.lo = c.rt_first; P.hi = c.rt_first + c.rt_n;
     P.trusted = c.rt_exact ? 1 : 0;
 }

@@ -19,6 +19,7 @@
 // representative of a masked key); a 24-bit tag collision flags the read, and the flagged reads are routed again
 // with verified probes (the owner confirms the key from its copy of the reads, hashTable.cpp:203-220).
 #include <stdlib.h>
+#include <string.h>
 #include "context.h"
 
 namespace sg {
@@ -31,12 +32,20 @@ __device__ __forceinline__ void ldg256s(const u64 *p, u64 (&v)[4])
 }
 
 // ---- source: keys of a batch, bucketed by owner ------------------------------------------------------------
+// Where the stream of every owner goes: dst[g] = first query word of owner g's stream -- local memory (NCCL
+// exchange) or the owner's mailbox in PEER memory (the stores then travel over NVLink while the kernel runs);
+// qoff[g] = position of the stream in the local send-order map qmap.
+struct RouteDst {
+    u64 *dst[kMaxWorld];
+    u64 qoff[kMaxWorld];
+};
+
 // WRITE = false: g_count[g] += queries for owner g.  WRITE = true: g_count[g] is the cursor of owner g's stream
-// (initialised to the stream's base); a tile of RT_WARPS reads reserves its share with one atomic per owner.
+// (starts at 0); a tile of RT_WARPS reads reserves its share with one atomic per owner.
 template <bool WRITE>
 __global__ void __launch_bounds__(RT_WARPS * 32) route_kernel(const u64 *__restrict__ F, int SW, int SWS, int h, const u32 *__restrict__ ids, u64 first,
                                                               u64 n, u32 wstride, int world, int exact, unsigned long long *__restrict__ g_count,
-                                                              u64 *__restrict__ queries, u32 *__restrict__ qmap)
+                                                              const __grid_constant__ RouteDst D, u32 *__restrict__ qmap)
 {
     __shared__ u64 sX[RT_WARPS][kMaxWords];
     __shared__ unsigned int tcount[kMaxWorld];
@@ -76,9 +85,10 @@ __global__ void __launch_bounds__(RT_WARPS * 32) route_kernel(const u64 *__restr
                     off = __shfl_sync(0xffffffffu, off, leader);
                     if (g >= 0) {
                         const u64 pos = tbase[g] + off + (unsigned)__popc(same & lt_mask);
-                        if (exact) { queries[2 * pos] = v0; queries[2 * pos + 1] = v1; }
-                        else queries[pos] = hsh;
-                        qmap[pos] = (u32)(s * wstride + (u64)j);
+                        u64 *q = D.dst[g];
+                        if (exact) { q[2 * pos] = v0; q[2 * pos + 1] = v1; }
+                        else q[pos] = hsh;
+                        qmap[D.qoff[g] + pos] = (u32)(s * wstride + (u64)j);
                     }
                 }
             }
@@ -235,10 +245,8 @@ static u64 build_id_list(Context &c, const uint8_t *a, u64 n, uint8_t value, u32
 
 // what = 0: reads [first, first + count) (0-based indices);  1: the reads in state 0 after phase B (phase C);
 //        2: the reads of this rank's phase-A slice flagged for the redo pass.
-void stage_route_begin(Context &c, int what, u64 first, u64 count, int exact, int world, void **queries, u64 *counts)
+static void select_batch(Context &c, int what, u64 first, u64 count, int exact, int world)
 {
-    cudaStream_t st = c.stream;
-    ArenaScope arena_scope(c.arena, st);
     SG_CHECK(c.have_reads, "organize_reads must run first");
     SG_CHECK(world >= 1 && world <= kMaxWorld, "bad world size");
     SG_CHECK(what >= 0 && what <= 2, "bad batch kind");
@@ -260,18 +268,29 @@ void stage_route_begin(Context &c, int what, u64 first, u64 count, int exact, in
     }
     const int wstride = c.max_len - c.h + 1 > 1 ? c.max_len - c.h + 1 : 1;
     c.rt_wstride = (u32)wstride;
-    const u64 n = c.rt_n;
-    SG_CHECK(n * (u64)wstride < 0xFFFFFFFFull, "routed batch too large: at most 2^32 windows per batch");
+    SG_CHECK(c.rt_n * (u64)wstride < 0xFFFFFFFFull, "routed batch too large: at most 2^32 windows per batch");
     for (int g = 0; g < kMaxWorld; ++g) c.rt_counts[g] = 0;
     c.rt_Q = 0;
+}
+
+void stage_route_begin(Context &c, int what, u64 first, u64 count, int exact, int world, void **queries, u64 *counts)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    select_batch(c, what, first, count, exact, world);
+    const u64 n = c.rt_n;
+    const int wstride = (int)c.rt_wstride;
+    c.rt_mailbox = false;
     if (n > 0) {
         DevBuf<unsigned long long> d_cnt(world, st);
         SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, world * sizeof(unsigned long long), st));
         const u32 *ids = c.rt_is_list ? c.rt_ids.p : nullptr;
         const unsigned grid = sm_grid(n, RT_WARPS, 8);
-        route_kernel<false><<<grid, RT_WARPS * 32, 0, st>>>(c.F.p, c.SW, c.SWS, c.h, ids, c.rt_first, n, c.rt_wstride, world, exact, d_cnt.p, nullptr, nullptr);
+        RouteDst D = {};
+        route_kernel<false><<<grid, RT_WARPS * 32, 0, st>>>(c.F.p, c.SW, c.SWS, c.h, ids, c.rt_first, n, c.rt_wstride, world, exact, d_cnt.p, D, nullptr);
         SG_LAUNCHED();
-        unsigned long long h_cnt[kMaxWorld], h_base[kMaxWorld];
+        unsigned long long h_cnt[kMaxWorld];
+        u64 h_base[kMaxWorld];
         SG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaStreamSynchronize(st));
         u64 Q = 0;
@@ -280,10 +299,11 @@ void stage_route_begin(Context &c, int what, u64 first, u64 count, int exact, in
         c.rt_queries.alloc(Q * (exact ? 2 : 1), st);
         c.rt_qmap.alloc(Q, st);
         c.rt_wslot.alloc(n * (u64)wstride, st);
-        SG_CUDA(cudaMemcpyAsync(d_cnt.p, h_base, world * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-        route_kernel<true><<<grid, RT_WARPS * 32, 0, st>>>(c.F.p, c.SW, c.SWS, c.h, ids, c.rt_first, n, c.rt_wstride, world, exact, d_cnt.p, c.rt_queries.p, c.rt_qmap.p);
+        SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, world * sizeof(unsigned long long), st));
+        for (int g = 0; g < world; ++g) { D.dst[g] = c.rt_queries.p + h_base[g] * (exact ? 2 : 1); D.qoff[g] = h_base[g]; }
+        route_kernel<true><<<grid, RT_WARPS * 32, 0, st>>>(c.F.p, c.SW, c.SWS, c.h, ids, c.rt_first, n, c.rt_wstride, world, exact, d_cnt.p, D, c.rt_qmap.p);
         SG_LAUNCHED();
-        SG_CUDA(cudaStreamSynchronize(st));      // h_base is a stack array; the caller reads the queries from another stream
+        SG_CUDA(cudaStreamSynchronize(st));      // the caller reads the queries from another stream
     }
     if (queries) *queries = c.rt_Q ? (void *)c.rt_queries.p : nullptr;
     if (counts) for (int g = 0; g < world; ++g) counts[g] = c.rt_counts[g];
@@ -358,6 +378,229 @@ void stage_route_finish(Context &c, const void *responses, const void *entries, 
         SG_LAUNCHED();
     }
     SG_CUDA(cudaStreamSynchronize(st));       // the caller's buffers may be reused on return
+    c.rt_entries_view = c.rt_wentries.p;
+    c.rt_state = 2;
+    c.rt_for_c = c.rt_what == 1;
+}
+
+
+// =====================================================================================================================
+// The same exchange over PEER MEMORY (NVLink / NVSwitch P2P) instead of NCCL.  Every rank owns one "mailbox" (one
+// cudaMalloc block, opened by the other ranks through CUDA IPC, or plain pointers inside one process):
+//
+//   counts   [world]            u64   queries source s sent me in this batch
+//   queries  [world][cap][2]    u64   stream of source s (key hashes, or 128-bit keys)      -- I answer these as OWNER
+//   answers  [world][cap]       u64   answers of owner g to the queries I sent it           -- I consume these as SOURCE
+//   entries  [world][ecap]      u32   entry stream of owner g for my queries
+//
+// route_post    the routing kernel stores every query straight into its owner's mailbox (the all-to-all "dispatch" is
+//               the kernel's own store traffic, tile by tile) and publishes the counts;   [barrier between the ranks]
+// answer_post   the owner answers out of its mailbox and copies answers + entries into the sources' mailboxes over
+//               NVLink ("combine");                                                     [barrier between the ranks]
+// route_collect the source scatters the answers from its own mailbox into wslot; the search kernel reads the entry
+//               streams in place.  Segments have a fixed capacity, so no sizes travel ahead of the data.
+// =====================================================================================================================
+static size_t mb_align(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t mb_off_counts() { return 0; }
+static size_t mb_off_queries(int world) { return mb_align((size_t)world * 8); }
+static size_t mb_off_answers(int world, u64 cap) { return mb_off_queries(world) + mb_align((size_t)world * cap * 16); }
+static size_t mb_off_entries(int world, u64 cap) { return mb_off_answers(world, cap) + mb_align((size_t)world * cap * 8); }
+static size_t mb_bytes(int world, u64 cap, u64 ecap) { return mb_off_entries(world, cap) + mb_align((size_t)world * ecap * 4); }
+
+void stage_mailbox_create(Context &c, int rank, int world, u64 cap_windows, void *ipc_handle_out, void **local_ptr)
+{
+    SG_CHECK(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad rank / world");
+    SG_CHECK(cap_windows >= 1 && cap_windows < 0xFFFFFFFFull, "bad mailbox capacity");
+    stage_mailbox_destroy(c);
+    Mailbox &m = c.mb;
+    m.world = world; m.rank = rank; m.cap = cap_windows; m.ecap = cap_windows;
+    m.bytes = mb_bytes(world, m.cap, m.ecap);
+    SG_CUDA(cudaMalloc((void **)&m.base, m.bytes));          // plain cudaMalloc: pool memory cannot be exported through IPC
+    SG_CUDA(cudaMemset(m.base, 0, mb_off_queries(world)));
+    for (int r = 0; r < kMaxWorld; ++r) { m.peer[r] = nullptr; m.ipc[r] = false; }
+    m.peer[rank] = m.base;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t hnd;
+        SG_CUDA(cudaIpcGetMemHandle(&hnd, m.base));
+        static_assert(sizeof(hnd) == 64, "CUDA IPC handles are 64 bytes");
+        memcpy(ipc_handle_out, &hnd, sizeof(hnd));
+    }
+    if (local_ptr) *local_ptr = m.base;
+}
+
+// the mailbox of `peer_rank`: an IPC handle exported by another process, or (same process) its pointer
+void stage_mailbox_open(Context &c, int peer_rank, const void *ipc_handle, void *ptr)
+{
+    Mailbox &m = c.mb;
+    SG_CHECK(m.base != nullptr, "mailbox_create must run first");
+    SG_CHECK(peer_rank >= 0 && peer_rank < m.world, "bad peer rank");
+    if (peer_rank == m.rank) return;
+    if (ipc_handle) {
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, ipc_handle, sizeof(hnd));
+        void *p = nullptr;
+        SG_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        m.peer[peer_rank] = (char *)p; m.ipc[peer_rank] = true;
+    } else {
+        SG_CHECK(ptr != nullptr, "null peer pointer");
+        m.peer[peer_rank] = (char *)ptr; m.ipc[peer_rank] = false;
+    }
+}
+
+void stage_mailbox_destroy(Context &c)
+{
+    Mailbox &m = c.mb;
+    if (!m.base) return;
+    cudaStreamSynchronize(c.stream);
+    for (int r = 0; r < m.world; ++r) if (r != m.rank && m.peer[r] && m.ipc[r]) cudaIpcCloseMemHandle(m.peer[r]);
+    cudaFree(m.base);
+    m = Mailbox();
+}
+
+__global__ void publish_counts_kernel(const unsigned long long *__restrict__ cnt, const __grid_constant__ RouteDst D, int world)
+{
+    const int g = threadIdx.x;
+    if (g < world) *D.dst[g] = cnt[g];        // counts[rank] in owner g's mailbox
+}
+
+void stage_route_post(Context &c, int what, u64 first, u64 count, int exact, u64 *n_reads)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    Mailbox &m = c.mb;
+    SG_CHECK(m.base != nullptr, "mailbox_create must run first");
+    const int world = m.world, rank = m.rank;
+    for (int g = 0; g < world; ++g) SG_CHECK(m.peer[g] != nullptr, "a peer mailbox has not been opened");
+    select_batch(c, what, first, count, exact, world);
+    c.rt_mailbox = true;
+    const u64 n = c.rt_n;
+    SG_CHECK(n * (u64)c.rt_wstride <= m.cap, "routed batch larger than the mailbox capacity");
+    if (n_reads) *n_reads = n;
+    DevBuf<unsigned long long> d_cnt(world, st);
+    SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, world * sizeof(unsigned long long), st));
+    RouteDst D = {}, C = {};
+    const int qw = exact ? 2 : 1;
+    for (int g = 0; g < world; ++g) {
+        D.dst[g] = (u64 *)(m.peer[g] + mb_off_queries(world)) + (u64)rank * m.cap * 2;      // my segment in owner g's mailbox
+        D.qoff[g] = (u64)g * m.cap;
+        C.dst[g] = (u64 *)(m.peer[g] + mb_off_counts()) + rank;
+    }
+    (void)qw;
+    if (n > 0) {
+        c.rt_qmap.alloc((u64)world * m.cap, st);
+        c.rt_wslot.alloc(n * (u64)c.rt_wstride, st);
+        const u32 *ids = c.rt_is_list ? c.rt_ids.p : nullptr;
+        route_kernel<true><<<sm_grid(n, RT_WARPS, 8), RT_WARPS * 32, 0, st>>>(c.F.p, c.SW, c.SWS, c.h, ids, c.rt_first, n, c.rt_wstride, world, exact,
+                                                                            d_cnt.p, D, c.rt_qmap.p);
+        SG_LAUNCHED();
+    }
+    publish_counts_kernel<<<1, kMaxWorld, 0, st>>>(d_cnt.p, C, world);
+    SG_LAUNCHED();
+    unsigned long long h_cnt[kMaxWorld];
+    SG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));       // every store to the peers has landed when the caller enters the barrier
+    u64 Q = 0;
+    for (int g = 0; g < world; ++g) { c.rt_counts[g] = h_cnt[g]; Q += h_cnt[g]; }
+    c.rt_Q = Q;
+    c.rt_state = 1;
+}
+
+// owner: answer what the sources posted (after the barrier that follows route_post on every rank)
+void stage_answer_post(Context &c, int exact, u64 *bytes_sent)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    Mailbox &m = c.mb;
+    SG_CHECK(m.base != nullptr, "mailbox_create must run first");
+    SG_CHECK(c.have_table, "build_hash_table[_shard] must run first");
+    const int world = m.world, rank = m.rank;
+    SG_CHECK(world == c.tb_world && rank == c.tb_rank, "the mailbox and the table shard disagree about rank / world");
+    u64 h_cnt[kMaxWorld], h_seg[kMaxWorld + 1], nq = 0;
+    SG_CUDA(cudaMemcpyAsync(h_cnt, m.base + mb_off_counts(), world * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    for (int s = 0; s < world; ++s) { SG_CHECK(h_cnt[s] <= m.cap, "posted count exceeds the mailbox capacity"); h_seg[s] = nq; nq += h_cnt[s]; }
+    h_seg[world] = nq;
+    if (bytes_sent) *bytes_sent = 0;
+    if (nq == 0) return;
+    SG_CHECK(nq < 0xFFFFFFFFull, "too many queries for one batch");
+    const char *fake_env = getenv("SAGE2GPU_FAKE_TAG_COLLISIONS");
+    const u64 fake_mask = fake_env ? strtoull(fake_env, nullptr, 0) : 0ull;
+    c.an_resp.alloc(nq, st);
+    DevBuf<u32> runlen(nq + 1, st), off(nq + 1, st), d_total(1, st);
+    DevBuf<u64> d_seg(world + 1, st), d_ecnt(world, st);
+    SG_CUDA(cudaMemcpyAsync(d_seg.p, h_seg, (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+    const u64 *qin = (const u64 *)(m.base + mb_off_queries(world));
+    for (int s = 0; s < world; ++s) {
+        if (h_cnt[s] == 0) continue;
+        answer_kernel<<<sm_grid(h_cnt[s], 256, 8), 256, 0, st>>>(qin + (u64)s * m.cap * 2, h_cnt[s], exact, c.slots.p, c.cap / kSlotsPerSector, c.entries.p,
+                                                                   c.F.p, c.RC.p, c.len.p, c.SW, c.SWS, c.h, fake_mask, c.an_resp.p + h_seg[s],
+                                                                   runlen.p + h_seg[s]);
+        SG_LAUNCHED();       // (each launch also zeroes runlen[h_seg[s] + count]: the next segment's launch, queued after it, overwrites that)
+    }
+    exclusive_scan_u32(runlen.p, off.p, nq + 1, d_total.p, st);
+    seg_totals_kernel<<<1, kMaxWorld, 0, st>>>(off.p, d_seg.p, world, d_ecnt.p);
+    SG_LAUNCHED();
+    u32 total = 0;
+    u64 h_ecnt[kMaxWorld], h_eoff[kMaxWorld];
+    SG_CUDA(cudaMemcpyAsync(&total, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(h_ecnt, d_ecnt.p, world * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.an_entries.alloc(total, st);
+    if (total) {
+        answer_runs_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>(c.an_resp.p, runlen.p, off.p, nq, d_seg.p, world, c.entries.p, c.an_entries.p);
+        SG_LAUNCHED();
+    }
+    // "combine": my answers and entry streams into the sources' mailboxes (segment `rank` there)
+    u64 eo = 0, sent = 0;
+    for (int s = 0; s < world; ++s) { h_eoff[s] = eo; eo += h_ecnt[s]; SG_CHECK(h_ecnt[s] <= m.ecap, "entry stream exceeds the mailbox capacity"); }
+    for (int s = 0; s < world; ++s) {
+        if (h_cnt[s] == 0) continue;
+        u64 *ans = (u64 *)(m.peer[s] + mb_off_answers(world, m.cap)) + (u64)rank * m.cap;
+        SG_CUDA(cudaMemcpyAsync(ans, c.an_resp.p + h_seg[s], h_cnt[s] * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        if (h_ecnt[s]) {
+            u32 *ent = (u32 *)(m.peer[s] + mb_off_entries(world, m.cap)) + (u64)rank * m.ecap;
+            SG_CUDA(cudaMemcpyAsync(ent, c.an_entries.p + h_eoff[s], h_ecnt[s] * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        }
+        if (s != rank) sent += h_cnt[s] * 8 + h_ecnt[s] * 4;
+    }
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (bytes_sent) *bytes_sent = sent;
+}
+
+__global__ void __launch_bounds__(256) route_collect_kernel(const u64 *__restrict__ answers, const u32 *__restrict__ qmap, u64 cap, u64 ecap,
+                                                            const __grid_constant__ RouteDst N /* qoff[g] = my queries to owner g */, int world,
+                                                            u64 *__restrict__ wslot)
+{
+    for (int g = 0; g < world; ++g) {
+        const u64 cnt = N.qoff[g];
+        const u64 *a = answers + (u64)g * cap;
+        const u32 *qm = qmap + (u64)g * cap;
+        for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < cnt; p += (u64)gridDim.x * blockDim.x) {
+            u64 w = a[p];
+            const u32 c = slot_get_count(w);
+            if (c >= 2 && c < (u32)kHashThreshold) w += (u64)g * ecap;
+            wslot[qm[p]] = w;
+        }
+    }
+}
+
+// source: after the barrier that follows answer_post on every rank
+void stage_route_collect(Context &c)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    Mailbox &m = c.mb;
+    SG_CHECK(c.rt_state == 1 && c.rt_mailbox, "route_post must precede route_collect");
+    const int world = m.world;
+    if (c.rt_Q) {
+        RouteDst N = {};
+        for (int g = 0; g < world; ++g) N.qoff[g] = c.rt_counts[g];
+        route_collect_kernel<<<sm_grid(c.rt_Q, 1024, 8), 256, 0, st>>>((const u64 *)(m.base + mb_off_answers(world, m.cap)), c.rt_qmap.p, m.cap, m.ecap, N,
+                                                                       world, c.rt_wslot.p);
+        SG_LAUNCHED();
+        SG_CUDA(cudaStreamSynchronize(st));
+    }
+    c.rt_entries_view = (const u32 *)(m.base + mb_off_entries(world, m.cap));
     c.rt_state = 2;
     c.rt_for_c = c.rt_what == 1;
 }

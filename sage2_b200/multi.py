@@ -144,9 +144,38 @@ def _route(gpu, what: int, first: int, count: int, exact: bool, world: int, view
     gpu.route_finish(_ptr(recv_resp), _ptr(recv_ent), recv_ecs)
 
 
-def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 << 20):
+def _route_p2p(gpu, what: int, first: int, count: int, exact: bool, sent: list, posted=None):
+    """One routed batch over peer memory: the kernels store / copy into the other ranks' mailboxes, the host only
+    separates the three steps with barriers (csrc/shard.cu, second half)."""
+    if posted is None:
+        posted = gpu.route_post(what, first, count, exact)
+    sent[0] += posted[1]
+    yield ("barrier",)
+    sent[0] += gpu.answer_post(exact)
+    yield ("barrier",)
+    gpu.route_collect()
+
+
+def mailbox_steps(gpu, rank: int, world: int, batch_reads: int):
+    """Generator: create this rank's mailbox and map everybody else's (once per context; the reads must be loaded)."""
+    mine = gpu.mailbox_create(rank, world, batch_reads)
+    boxes = yield ("mailboxes", mine)
+    for r, b in enumerate(boxes):
+        if r != rank:
+            gpu.mailbox_open(r, handle=b.get("handle"), ptr=b.get("ptr", 0))
+    yield ("barrier",)
+
+
+def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 << 20, p2p: bool = False, sent: list | None = None):
     """Generator: sage2gpu_build_overlap_graph with the table sharded over `world` ranks.  Reads loaded on every rank
-    and sage2gpu_build_hash_table_shard(rank, world) done."""
+    and sage2gpu_build_hash_table_shard(rank, world) done.  p2p: exchange through the ranks' mailboxes (mailbox_steps
+    done, batch_reads <= the mailbox's) instead of all-to-all requests; sent[0] accumulates the bytes stored remotely."""
+    sent = sent if sent is not None else [0]
+    if p2p:
+        def _route(gpu, what, first, count, exact, world, view, begun=None):      # noqa: F811 (same protocol, other transport)
+            return _route_p2p(gpu, what, first, count, exact, sent, posted=begun)
+    else:
+        _route = globals()["_route"]
     first, count = gpu.phase_a_sharded_begin(rank, world)
     U = gpu.counters()["unique_reads"]
     chunk = -(-U // world) if U else 0
@@ -166,9 +195,14 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
     gpu.phase_a_sharded_end()
     yield ("phase_a", gpu.phase_a_buffers())
     gpu.phase_b()
-    rb = gpu.route_begin(1, 0, 0, True, world)          # reads left for phase C: identical list on every rank
-    if rb["n_reads"]:
-        yield from _route(gpu, 1, 0, 0, True, world, view, begun=rb)
+    if p2p:
+        posted = gpu.route_post(1, 0, 0, True)          # reads left for phase C: identical list on every rank
+        if posted[0]:
+            yield from _route(gpu, 1, 0, 0, True, world, view, begun=posted)
+    else:
+        rb = gpu.route_begin(1, 0, 0, True, world)
+        if rb["n_reads"]:
+            yield from _route(gpu, 1, 0, 0, True, world, view, begun=rb)
     gpu.finish_graph()
 
 
@@ -201,6 +235,14 @@ def run_dist(gen, rank: int, world: int, device, stats: dict | None = None) -> i
                 t = torch.tensor([req[1]], dtype=torch.int64, device=device)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 val = int(t.item())
+            elif kind == "barrier":           # every rank's library call before it has returned (= its stream is drained)
+                t = torch.zeros(1, dtype=torch.int32, device=device)
+                dist.all_reduce(t)
+                val = int(t.item())
+            elif kind == "mailboxes":         # CUDA IPC handles of all ranks (other processes cannot use the pointer)
+                boxes = [None] * world
+                dist.all_gather_object(boxes, {"handle": req[1]["handle"]})
+                val = boxes
             elif kind == "phase_a":
                 bufs = req[1]
                 views = req[2] if len(req) > 2 else device_views(bufs, world, device)
@@ -244,6 +286,10 @@ def run_local(gens: list, views_of=None) -> None:
                 torch.cuda.synchronize()
         elif kind == "max":
             vals = [max(r[1] for r in reqs)] * world
+        elif kind == "barrier":
+            vals = [0] * world
+        elif kind == "mailboxes":             # one process: plain pointers
+            vals = [[{"ptr": r[1]["ptr"]} for r in reqs]] * world
         elif kind == "phase_a":
             views = []
             for r in range(world):
@@ -279,11 +325,15 @@ def run_local(gens: list, views_of=None) -> None:
         reqs = nxt
 
 
-def build_overlap_graph_sharded(gpu, rank: int, world: int, device=None, batch_reads: int = 1 << 20, stats: dict | None = None) -> int:
-    """One process per GPU (torchrun): the sharded-table build on this rank; returns the bytes this rank sent."""
+def build_overlap_graph_sharded(gpu, rank: int, world: int, device=None, batch_reads: int = 1 << 20, stats: dict | None = None,
+                                p2p: bool = False) -> int:
+    """One process per GPU (torchrun): the sharded-table build on this rank; returns the bytes this rank sent.
+    p2p: the routed probes travel through peer-memory mailboxes (set up on first use) instead of NCCL all-to-all."""
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    steps = sharded_graph_steps(gpu, rank, world, device_view_fn(device), batch_reads)
-    if world == 1:          # one shard = the whole table: the same steps, the exchanges are copies
-        run_local([steps])
-        return 0
-    return run_dist(steps, rank, world, device, stats)
+    drive = (lambda g: run_local([g])) if world == 1 else (lambda g: run_dist(g, rank, world, device, stats))
+    sent = [0]
+    if p2p and getattr(gpu, "mailbox_batch_reads", 0) < batch_reads:
+        drive(mailbox_steps(gpu, rank, world, batch_reads))
+    steps = sharded_graph_steps(gpu, rank, world, device_view_fn(device), batch_reads, p2p=p2p, sent=sent)
+    other = drive(steps)
+    return sent[0] + (other or 0)

@@ -95,6 +95,8 @@ class EmuShard:
     """One rank of the sharded-table build on the CPU: the methods sage2_b200/multi.py's sharded_graph_steps calls on
     api.Sage2Gpu, with host buffers (tests/host_emul.cpp restates csrc/shard.cu)."""
 
+    _registry = {}
+
     def __init__(self, bases, offsets, k):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -141,6 +143,52 @@ class EmuShard:
     def route_finish(self, resp_ptr, entries_ptr, entry_counts):
         ec = (C.c_uint64 * len(entry_counts))(*[int(x) for x in entry_counts])
         self.L.hemu_route_finish(self.h, resp_ptr or None, entries_ptr or None, ec)
+
+    # the peer-memory transport of multi.sharded_graph_steps(p2p=True), in ONE process: a "mailbox" is the peer object
+    def mailbox_create(self, rank, world, max_reads_per_batch):
+        self.rank, self.world, self.peers, self.mailbox_batch_reads = rank, world, {}, max_reads_per_batch
+        EmuShard._registry[id(self)] = self
+        return {"handle": None, "ptr": id(self)}
+
+    def mailbox_open(self, peer_rank, handle=None, ptr=0):
+        self.peers[peer_rank] = EmuShard._registry[ptr]
+
+    def route_post(self, what, first, count, exact):
+        rb = self.route_begin(what, first, count, exact, self.world)
+        q = np.ctypeslib.as_array(C.cast(rb["ptr"], C.POINTER(C.c_uint64)), shape=(max(1, sum(rb["counts"]) * rb["words"]),)).copy() \
+            if sum(rb["counts"]) else np.zeros(0, np.uint64)
+        self.posted, o = {}, 0
+        for g, c in enumerate(rb["counts"]):
+            self.posted[g] = q[o:o + c * rb["words"]]
+            o += c * rb["words"]
+        self.inbox = {}
+        return rb["n_reads"], int(sum(c for g, c in enumerate(rb["counts"]) if g != self.rank)) * 8 * rb["words"]
+
+    def answer_post(self, exact):
+        peers = dict(self.peers)
+        peers[self.rank] = self
+        words = 2 if exact else 1
+        segs = [peers[s].posted[self.rank] for s in range(self.world)]
+        counts = [len(x) // words for x in segs]
+        q = np.ascontiguousarray(np.concatenate(segs)) if sum(counts) else np.zeros(1, np.uint64)
+        ans = self.shard_answer(q.ctypes.data, counts, exact, self.world)
+        resp = np.ctypeslib.as_array(C.cast(ans["resp"], C.POINTER(C.c_uint64)), shape=(max(1, sum(counts)),)).copy() if sum(counts) else np.zeros(0, np.uint64)
+        ne = sum(ans["entry_counts"])
+        ent = np.ctypeslib.as_array(C.cast(ans["entries"], C.POINTER(C.c_uint32)), shape=(max(1, ne),)).copy() if ne else np.zeros(0, np.uint32)
+        o = eo = sent = 0
+        for s in range(self.world):
+            peers[s].inbox[self.rank] = (resp[o:o + counts[s]], ent[eo:eo + ans["entry_counts"][s]])
+            if s != self.rank:
+                sent += counts[s] * 8 + ans["entry_counts"][s] * 4
+            o += counts[s]
+            eo += ans["entry_counts"][s]
+        return sent
+
+    def route_collect(self):
+        resp = np.ascontiguousarray(np.concatenate([self.inbox[g][0] for g in range(self.world)]).astype(np.uint64))
+        ent = np.ascontiguousarray(np.concatenate([self.inbox[g][1] for g in range(self.world)]).astype(np.uint32))
+        ecs = [len(self.inbox[g][1]) for g in range(self.world)]
+        self.route_finish(resp.ctypes.data if len(resp) else 0, ent.ctypes.data if len(ent) else 0, ecs)
 
     def phase_a_routed(self):
         n = int(self.L.hemu_phase_a_routed(self.h))

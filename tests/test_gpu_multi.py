@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, out, sharded=False):
+def _worker(rank, world, port, name, out, sharded=False, p2p=False):
     import torch.distributed as dist
     from sage2_b200 import api, multi
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -39,7 +39,7 @@ def _worker(rank, world, port, name, out, sharded=False):
         g.load_reads_ptr(tb.data_ptr(), to.data_ptr(), len(off) - 1, k, device=True)
         if sharded:      # key-hash shard per GPU, probes routed by NCCL all-to-all
             g.build_hash_table_shard(rank, world)
-            multi.build_overlap_graph_sharded(g, rank, world, dev, batch_reads=20000)
+            multi.build_overlap_graph_sharded(g, rank, world, dev, batch_reads=20000, p2p=p2p)
         else:
             g.build_hash_table()
             multi.build_overlap_graph(g, rank, world, dev)
@@ -68,6 +68,22 @@ def test_two_gpus_one_graph(name, tmp_path):
 def test_two_gpus_sharded_table(name, tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), name, str(tmp_path), True), nprocs=2, join=True)
+    reads, k = datasets.get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    for r in range(2):
+        e = np.load(tmp_path / f"edges{r}.npy")
+        assert len(e) == o.n_edges
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], o.edges[f])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("name", ["rep", "varlen_err", "hicopy"])
+def test_two_gpus_sharded_table_over_peer_memory(name, tmp_path):
+    """Two processes, CUDA IPC mailboxes: the routing kernel stores into the other GPU's memory over NVLink."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), name, str(tmp_path), True, True), nprocs=2, join=True)
     reads, k = datasets.get(name)
     b, off = synth.concat(reads)
     o = oracle.OracleRun(b, off, k)

@@ -16,7 +16,7 @@ from test_gpu_parity import _compare
 pytestmark = pytest.mark.gpu
 
 
-def _sharded(name, world, batch_reads=1 << 19):
+def _sharded(name, world, batch_reads=1 << 19, p2p=False):
     reads, k = datasets.get(name) if name in datasets.DATASETS else synth.config(name)
     b, off = synth.concat(reads)
     o = oracle.OracleRun(b, off, k)
@@ -28,8 +28,36 @@ def _sharded(name, world, batch_reads=1 << 19):
         g.build_hash_table_shard(r, world)
         gpus.append(g)
     view = multi.device_view_fn(dev)
-    multi.run_local([multi.sharded_graph_steps(g, r, world, view, batch_reads) for r, g in enumerate(gpus)])
+    if p2p:      # mailboxes of the other contexts: plain device pointers inside one process
+        batch_reads = min(batch_reads, 1 << 14)
+        multi.run_local([multi.mailbox_steps(g, r, world, batch_reads) for r, g in enumerate(gpus)])
+    multi.run_local([multi.sharded_graph_steps(g, r, world, view, batch_reads, p2p=p2p) for r, g in enumerate(gpus)])
     return o, gpus
+
+
+@pytest.mark.parametrize("name,world", [("clean", 1), ("rep", 2), ("hicopy", 3), ("deep", 2), ("varlen_err", 3), ("mixed", 4),
+                                        ("tandem", 2), ("empty", 2), ("single", 3)])
+def test_sharded_table_over_mailboxes_equals_oracle(name, world):
+    """The peer-memory transport: queries stored by the routing kernel into the owners' mailboxes, answers copied back."""
+    o, gpus = _sharded(name, world, p2p=True)
+    assert sum(g.counters()["compare_calls"] for g in gpus) == o.compare_calls
+    for g in gpus:
+        e = g.edges()
+        assert len(e) == o.n_edges
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], o.edges[f])
+        np.testing.assert_array_equal(g.extensions()["explored"], o.explored_b[1:])
+
+
+def test_mailbox_tag_collisions(monkeypatch):
+    monkeypatch.setenv("SAGE2GPU_FAKE_TAG_COLLISIONS", "0x3f00000000")
+    o, gpus = _sharded("varlen_err", 2, p2p=True)
+    assert sum(g.counters()["probe_restarts"] for g in gpus) > 0
+    for g in gpus:
+        e = g.edges()
+        assert len(e) == o.n_edges
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], o.edges[f])
 
 
 @pytest.mark.parametrize("name,world", [("clean", 1), ("rep", 2), ("k70", 3), ("hicopy", 2), ("deep", 2), ("varlen_err", 3),

@@ -55,6 +55,29 @@ def test_sharded_steps_in_one_process(name, world):
         s.close()
 
 
+@pytest.mark.parametrize("name,world", [("rep", 2), ("varlen_err", 3), ("hicopy", 2)])
+def test_sharded_steps_over_mailboxes(name, world, monkeypatch):
+    """The peer-memory transport (route_post / answer_post / route_collect between barriers) of the same steps."""
+    if name == "varlen_err":
+        monkeypatch.setenv("SAGE2_EMUL_FAKE_TAG_COLLISIONS", "0x3f00000000")
+    reads, k = datasets.get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    shards = []
+    for r in range(world):
+        s = emul.EmuShard(b, off, k)
+        s.build_hash_table_shard(r, world)
+        shards.append(s)
+    multi.run_local([multi.mailbox_steps(s, r, world, 3000) for r, s in enumerate(shards)])
+    sent = [[0] for _ in shards]
+    multi.run_local([multi.sharded_graph_steps(s, r, world, multi.host_view, 3000, p2p=True, sent=sent[r]) for r, s in enumerate(shards)],
+                    views_of=lambda r, bufs: emul.host_phase_a_views(bufs, world))
+    assert sum(s.counters()["compare_calls"] for s in shards) == o.compare_calls
+    assert all(x[0] > 0 for x in sent)
+    for s in shards:
+        _check(s.edges(), o)
+
+
 def test_small_batches(monkeypatch):
     o, shards = _local("rep", 3, batch_reads=700)
     for s in shards:
