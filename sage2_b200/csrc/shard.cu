@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(RT_WARPS * 32) route_kernel(const u64 *__restr
             __syncwarp();
             W = rec_len(X, SW) - h + 1;
         }
+        u64 hc0 = 0, hc1 = 0, hc2 = 0, hc3 = 0;        // key hashes of the first four chunks, computed once for both passes
 #pragma unroll 1
         for (int pass = 0; pass < (WRITE ? 2 : 1); ++pass) {
             for (int base = 0; base < W; base += 32) {
@@ -73,8 +74,14 @@ __global__ void __launch_bounds__(RT_WARPS * 32) route_kernel(const u64 *__restr
                 int g = -1;
                 u64 v0 = 0, v1 = 0, hsh = 0;
                 if (j < W) {
-                    extract_key(X, SW, j, h, v0, v1);
-                    hsh = hash_key(v0, v1);
+                    const int ch = base >> 5;
+                    const bool cached = WRITE && !exact && pass == 1 && ch < 4;
+                    if (cached) hsh = ch == 0 ? hc0 : ch == 1 ? hc1 : ch == 2 ? hc2 : hc3;
+                    else {
+                        extract_key(X, SW, j, h, v0, v1);
+                        hsh = hash_key(v0, v1);
+                        if (WRITE && pass == 0) { if (ch == 0) hc0 = hsh; else if (ch == 1) hc1 = hsh; else if (ch == 2) hc2 = hsh; else if (ch == 3) hc3 = hsh; }
+                    }
                     g = key_owner(hsh, world);
                 }
                 const unsigned same = __match_any_sync(0xffffffffu, g);
@@ -118,19 +125,34 @@ __global__ void __launch_bounds__(RT_WARPS * 32) route_kernel(const u64 *__restr
 // the source's search kernel); verified probes confirm the key from the bucket's first read and skip masked keys.
 // fake_mask (test knob SAGE2GPU_FAKE_TAG_COLLISIONS): tag probes whose hash has none of these bits take the first
 // occupied slot they see, i.e. behave like a tag collision.
-__global__ void __launch_bounds__(256) answer_kernel(const u64 *__restrict__ queries, u64 nq, int exact, const u64 *__restrict__ slots, u64 nsec,
-                                                     const u32 *__restrict__ entries, const u64 *__restrict__ F, const u64 *__restrict__ RC,
-                                                     const uint16_t *__restrict__ len, int SW, int SWS, int h, u64 fake_mask,
-                                                     u64 *__restrict__ resp, u32 *__restrict__ runlen)
+constexpr u32 kEntryChunk = 1024;     // entries a warp of answer_fused_kernel reserves at a time (one atomic per ~1000 entries)
+
+struct ShardView {
+    const u64 *slots;
+    u64 nsec;
+    const u32 *entries;
+    const u64 *F, *RC;
+    const uint16_t *len;
+    int SW, SWS, h;
+    u64 fake_mask;
+};
+
+// answer word of query p (payload = OWNER-side offset for a 2..99-entry bucket, whose length comes back in `run`)
+__device__ __forceinline__ u64 answer_one(const ShardView &T, const u64 *__restrict__ queries, u64 p, int exact, u32 &run)
 {
-    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
+    const u64 *slots = T.slots, *F = T.F, *RC = T.RC;
+    const u32 *entries = T.entries;
+    const uint16_t *len = T.len;
+    const u64 nsec = T.nsec, fake_mask = T.fake_mask;
+    const int SW = T.SW, SWS = T.SWS, h = T.h;
+    {
         u64 v0 = 0, v1 = 0, hsh;
         if (exact) { v0 = queries[2 * p]; v1 = queries[2 * p + 1]; hsh = hash_key(v0, v1); }
         else hsh = queries[p];
         const u64 tag = slot_tag(hsh);
         const bool fake = !exact && fake_mask != 0 && (hsh & fake_mask) == 0;
         u64 answer = 0;
-        u32 run = 0;
+        run = 0;
         bool done = nsec == 0;
         u64 sec = done ? 0 : home_sector(hsh, nsec);
         while (!done) {
@@ -158,10 +180,60 @@ __global__ void __launch_bounds__(256) answer_kernel(const u64 *__restrict__ que
             }
             sec = (sec + 1 == nsec) ? 0 : sec + 1;
         }
-        resp[p] = answer;
+        return answer;
+    }
+}
+
+__global__ void __launch_bounds__(256) answer_kernel(const u64 *__restrict__ queries, u64 nq, int exact, const __grid_constant__ ShardView T,
+                                                     u64 *__restrict__ resp, u32 *__restrict__ runlen)
+{
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
+        u32 run;
+        resp[p] = answer_one(T, queries, p, exact, run);
         runlen[p] = run;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) runlen[nq] = 0;     // sentinel: off[nq] = total after the scan
+}
+
+// The mailbox form, one launch per source: the finished answer word goes straight into the source's mailbox
+// (`resp` is PEER memory: coalesced 8-byte stores over NVLink), the entry runs into a local stream in chunks a warp
+// reserves with one atomic (no scan, no second pass; the answers carry explicit offsets, so the unused tail of a chunk
+// may stay a hole); the stream is copied to the source afterwards.
+__global__ void __launch_bounds__(256) answer_fused_kernel(const u64 *__restrict__ queries, u64 nq, int exact, const __grid_constant__ ShardView T,
+                                                           u64 *__restrict__ resp, u32 *__restrict__ ent_out, u64 ecap,
+                                                           unsigned long long *__restrict__ cursor)
+{
+    const int lane = threadIdx.x & 31;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    unsigned long long wbase = 0;
+    u32 wleft = 0;
+    for (u64 p0 = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); p0 < nq; p0 += stride) {      // warp-uniform trip count
+        const u64 p = p0 + lane;
+        u32 run = 0;
+        u64 answer = 0;
+        if (p < nq) answer = answer_one(T, queries, p, exact, run);
+        u32 incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > wleft) {          // a fresh chunk of the stream for this warp (what is left of the old one stays a hole)
+            const u32 take = total > kEntryChunk ? total : kEntryChunk;
+            if (lane == 31) wbase = atomicAdd(cursor, (unsigned long long)take);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            wleft = take;
+        }
+        const unsigned long long base = wbase;
+        wbase += total; wleft -= total;
+        if (run) {
+            const u64 at = base + incl - run;
+            if (at + run <= ecap) {                       // (an overflow is reported by the host from the cursor)
+                const u32 *src = T.entries + slot_get_payload(answer);
+                for (u32 e = 0; e < run; ++e) ent_out[at + e] = src[e];
+            }
+            answer = answer_encode(run, at);
+        }
+        if (p < nq) resp[p] = answer;
+    }
 }
 
 // entry runs -> the stream of the query's source, answer payload := offset inside that stream
@@ -213,6 +285,14 @@ __global__ void __launch_bounds__(256) compact_list_kernel(const u32 *__restrict
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
         if (flag[i]) out[idx[i]] = base + (u32)i;
+}
+
+static ShardView shard_view(const Context &c, u64 fake_mask)
+{
+    ShardView T;
+    T.slots = c.slots.p; T.nsec = c.cap / kSlotsPerSector; T.entries = c.entries.p; T.F = c.F.p; T.RC = c.RC.p; T.len = c.len.p;
+    T.SW = c.SW; T.SWS = c.SWS; T.h = c.h; T.fake_mask = fake_mask;
+    return T;
 }
 
 static unsigned sm_grid(u64 n, unsigned per_block, unsigned blocks_per_sm)
@@ -333,8 +413,8 @@ void stage_shard_answer(Context &c, const void *queries, const u64 *counts_per_s
     DevBuf<u32> runlen(nq + 1, st), off(nq + 1, st), d_total(1, st);
     DevBuf<u64> d_seg(world + 1, st), d_ecnt(world, st);
     SG_CUDA(cudaMemcpyAsync(d_seg.p, h_seg, (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
-    answer_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>((const u64 *)queries, nq, exact, c.slots.p, c.cap / kSlotsPerSector, c.entries.p, c.F.p, c.RC.p,
-                                                        c.len.p, c.SW, c.SWS, c.h, fake_mask, c.an_resp.p, runlen.p);
+    const ShardView T = shard_view(c, fake_mask);
+    answer_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>((const u64 *)queries, nq, exact, T, c.an_resp.p, runlen.p);
     SG_LAUNCHED();
     exclusive_scan_u32(runlen.p, off.p, nq + 1, d_total.p, st);
     seg_totals_kernel<<<1, kMaxWorld, 0, st>>>(off.p, d_seg.p, world, d_ecnt.p);
@@ -410,10 +490,13 @@ static size_t mb_bytes(int world, u64 cap, u64 ecap) { return mb_off_entries(wor
 void stage_mailbox_create(Context &c, int rank, int world, u64 cap_windows, void *ipc_handle_out, void **local_ptr)
 {
     SG_CHECK(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad rank / world");
-    SG_CHECK(cap_windows >= 1 && cap_windows < 0xFFFFFFFFull, "bad mailbox capacity");
+    SG_CHECK(cap_windows >= 1 && cap_windows < 0xFFFFFFFFull && (u64)world * cap_windows < (1ull << 33), "bad mailbox capacity");
     stage_mailbox_destroy(c);
     Mailbox &m = c.mb;
-    m.world = world; m.rank = rank; m.cap = cap_windows; m.ecap = cap_windows;
+    // entry segments: every bucket entry of every window in the worst case + the holes the chunked reservation of
+    // answer_fused_kernel can leave (one chunk per warp of its grid)
+    m.world = world; m.rank = rank; m.cap = cap_windows; m.ecap = cap_windows + (u64)kSMs * 8 * 8 * kEntryChunk;
+    SG_CHECK((u64)world * m.ecap < (1ull << 33), "mailbox too large for the 33-bit answer payload");
     m.bytes = mb_bytes(world, m.cap, m.ecap);
     SG_CUDA(cudaMalloc((void **)&m.base, m.bytes));          // plain cudaMalloc: pool memory cannot be exported through IPC
     SG_CUDA(cudaMemset(m.base, 0, mb_off_queries(world)));
@@ -515,51 +598,37 @@ void stage_answer_post(Context &c, int exact, u64 *bytes_sent)
     SG_CHECK(c.have_table, "build_hash_table[_shard] must run first");
     const int world = m.world, rank = m.rank;
     SG_CHECK(world == c.tb_world && rank == c.tb_rank, "the mailbox and the table shard disagree about rank / world");
-    u64 h_cnt[kMaxWorld], h_seg[kMaxWorld + 1], nq = 0;
+    u64 h_cnt[kMaxWorld], nq = 0;
     SG_CUDA(cudaMemcpyAsync(h_cnt, m.base + mb_off_counts(), world * sizeof(u64), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
-    for (int s = 0; s < world; ++s) { SG_CHECK(h_cnt[s] <= m.cap, "posted count exceeds the mailbox capacity"); h_seg[s] = nq; nq += h_cnt[s]; }
-    h_seg[world] = nq;
+    for (int s = 0; s < world; ++s) { SG_CHECK(h_cnt[s] <= m.cap, "posted count exceeds the mailbox capacity"); nq += h_cnt[s]; }
     if (bytes_sent) *bytes_sent = 0;
     if (nq == 0) return;
     SG_CHECK(nq < 0xFFFFFFFFull, "too many queries for one batch");
     const char *fake_env = getenv("SAGE2GPU_FAKE_TAG_COLLISIONS");
     const u64 fake_mask = fake_env ? strtoull(fake_env, nullptr, 0) : 0ull;
-    c.an_resp.alloc(nq, st);
-    DevBuf<u32> runlen(nq + 1, st), off(nq + 1, st), d_total(1, st);
-    DevBuf<u64> d_seg(world + 1, st), d_ecnt(world, st);
-    SG_CUDA(cudaMemcpyAsync(d_seg.p, h_seg, (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+    // one fused launch per source: answers land in the source's mailbox while the kernel runs ("combine")
+    const ShardView T = shard_view(c, fake_mask);
+    DevBuf<unsigned long long> d_cur(world, st);
+    SG_CUDA(cudaMemsetAsync(d_cur.p, 0, world * sizeof(unsigned long long), st));
+    c.an_entries.alloc((u64)world * m.ecap, st);
     const u64 *qin = (const u64 *)(m.base + mb_off_queries(world));
     for (int s = 0; s < world; ++s) {
         if (h_cnt[s] == 0) continue;
-        answer_kernel<<<sm_grid(h_cnt[s], 256, 8), 256, 0, st>>>(qin + (u64)s * m.cap * 2, h_cnt[s], exact, c.slots.p, c.cap / kSlotsPerSector, c.entries.p,
-                                                                   c.F.p, c.RC.p, c.len.p, c.SW, c.SWS, c.h, fake_mask, c.an_resp.p + h_seg[s],
-                                                                   runlen.p + h_seg[s]);
-        SG_LAUNCHED();       // (each launch also zeroes runlen[h_seg[s] + count]: the next segment's launch, queued after it, overwrites that)
-    }
-    exclusive_scan_u32(runlen.p, off.p, nq + 1, d_total.p, st);
-    seg_totals_kernel<<<1, kMaxWorld, 0, st>>>(off.p, d_seg.p, world, d_ecnt.p);
-    SG_LAUNCHED();
-    u32 total = 0;
-    u64 h_ecnt[kMaxWorld], h_eoff[kMaxWorld];
-    SG_CUDA(cudaMemcpyAsync(&total, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaMemcpyAsync(h_ecnt, d_ecnt.p, world * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
-    c.an_entries.alloc(total, st);
-    if (total) {
-        answer_runs_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>(c.an_resp.p, runlen.p, off.p, nq, d_seg.p, world, c.entries.p, c.an_entries.p);
+        u64 *ans = (u64 *)(m.peer[s] + mb_off_answers(world, m.cap)) + (u64)rank * m.cap;
+        answer_fused_kernel<<<sm_grid(h_cnt[s], 256, 8), 256, 0, st>>>(qin + (u64)s * m.cap * 2, h_cnt[s], exact, T, ans, c.an_entries.p + (u64)s * m.ecap,
+                                                                         m.ecap, d_cur.p + s);
         SG_LAUNCHED();
     }
-    // "combine": my answers and entry streams into the sources' mailboxes (segment `rank` there)
-    u64 eo = 0, sent = 0;
-    for (int s = 0; s < world; ++s) { h_eoff[s] = eo; eo += h_ecnt[s]; SG_CHECK(h_ecnt[s] <= m.ecap, "entry stream exceeds the mailbox capacity"); }
+    unsigned long long h_ecnt[kMaxWorld];
+    SG_CUDA(cudaMemcpyAsync(h_ecnt, d_cur.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    u64 sent = 0;
     for (int s = 0; s < world; ++s) {
-        if (h_cnt[s] == 0) continue;
-        u64 *ans = (u64 *)(m.peer[s] + mb_off_answers(world, m.cap)) + (u64)rank * m.cap;
-        SG_CUDA(cudaMemcpyAsync(ans, c.an_resp.p + h_seg[s], h_cnt[s] * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        SG_CHECK(h_ecnt[s] <= m.ecap, "entry stream exceeds the mailbox capacity");
         if (h_ecnt[s]) {
             u32 *ent = (u32 *)(m.peer[s] + mb_off_entries(world, m.cap)) + (u64)rank * m.ecap;
-            SG_CUDA(cudaMemcpyAsync(ent, c.an_entries.p + h_eoff[s], h_ecnt[s] * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+            SG_CUDA(cudaMemcpyAsync(ent, c.an_entries.p + (u64)s * m.ecap, h_ecnt[s] * sizeof(u32), cudaMemcpyDeviceToDevice, st));
         }
         if (s != rank) sent += h_cnt[s] * 8 + h_ecnt[s] * 4;
     }
