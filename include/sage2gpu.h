@@ -167,6 +167,9 @@ int sage2gpu_phase_a_sharded_end(sage2gpu_ctx *ctx);
  * No sizes travel ahead of the data and the host moves nothing.  *bytes_sent = bytes this rank put into other ranks' memory. */
 int sage2gpu_mailbox_create(sage2gpu_ctx *ctx, int rank, int world, uint64_t max_reads_per_batch, void *ipc_handle_out, void **local_ptr);
 int sage2gpu_mailbox_open(sage2gpu_ctx *ctx, int peer_rank, const void *ipc_handle, void *ptr);
+/* The barrier between the three steps, on the device: every rank stores its barrier count into the peers' mailboxes and
+ * waits for theirs (all ranks must call it the same number of times; gives up with an error after a few seconds). */
+int sage2gpu_mailbox_barrier(sage2gpu_ctx *ctx);
 int sage2gpu_route_post(sage2gpu_ctx *ctx, int what, uint64_t first, uint64_t count, int exact, uint64_t *n_reads, uint64_t *bytes_sent);
 int sage2gpu_answer_post(sage2gpu_ctx *ctx, int exact, uint64_t *bytes_sent);
 int sage2gpu_route_collect(sage2gpu_ctx *ctx);

@@ -51,7 +51,7 @@ EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2g
            "sage2gpu_build_hash_table_shard", "sage2gpu_phase_a_sharded_begin", "sage2gpu_route_begin", "sage2gpu_shard_answer",
            "sage2gpu_route_finish", "sage2gpu_phase_a_routed", "sage2gpu_phase_a_sharded_end", "sage2gpu_phase_b",
            "sage2gpu_map_reads", "sage2gpu_mailbox_create", "sage2gpu_mailbox_open", "sage2gpu_route_post", "sage2gpu_answer_post",
-           "sage2gpu_route_collect"]
+           "sage2gpu_route_collect", "sage2gpu_mailbox_barrier"]
 
 _lib = None
 
@@ -107,6 +107,7 @@ def load_library():
         lib.sage2gpu_route_post.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, u64p, u64p]
         lib.sage2gpu_answer_post.argtypes = [vp, C.c_int, u64p]
         lib.sage2gpu_route_collect.argtypes = [vp]
+        lib.sage2gpu_mailbox_barrier.argtypes = [vp]
         lib.sage2gpu_map_reads.argtypes = [vp, vp, vp, i64, C.c_int, vp, vp, C.POINTER(C.c_float)]
         lib.sage2gpu_run_steps123.argtypes = [vp, vp, vp, i64, C.c_int]
         lib.sage2gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
@@ -262,6 +263,9 @@ class Sage2Gpu:
         b = C.c_uint64()
         self._check(self._lib.sage2gpu_answer_post(self._h, int(bool(exact)), C.byref(b)), "answer_post")
         return int(b.value)
+
+    def mailbox_barrier(self):
+        self._check(self._lib.sage2gpu_mailbox_barrier(self._h), "mailbox_barrier")
 
     def route_collect(self):
         self._check(self._lib.sage2gpu_route_collect(self._h), "route_collect")

@@ -373,6 +373,11 @@ int sage2gpu_mailbox_open(sage2gpu_ctx *ctx, int peer_rank, const void *ipc_hand
     return guarded(ctx, [&](sg::Context &c) { sg::stage_mailbox_open(c, peer_rank, ipc_handle, ptr); });
 }
 
+int sage2gpu_mailbox_barrier(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) { sg::stage_mailbox_barrier(c); });
+}
+
 int sage2gpu_route_post(sage2gpu_ctx *ctx, int what, uint64_t first, uint64_t count, int exact, uint64_t *n_reads, uint64_t *bytes_sent)
 {
     return guarded(ctx, [&](sg::Context &c) {

@@ -35,6 +35,7 @@ struct Mailbox {
     size_t bytes = 0;
     int world = 0, rank = -1;
     u64 cap = 0, ecap = 0;              // windows / entries per (source, owner) segment
+    u64 epoch = 0;                      // barriers passed so far (mailbox_barrier)
     char *peer[kMaxWorld] = {};
     bool ipc[kMaxWorld] = {};
 };
@@ -133,6 +134,7 @@ u64 stage_phase_a_routed(Context &c);
 void stage_mailbox_create(Context &c, int rank, int world, u64 cap_windows, void *ipc_handle_out, void **local_ptr);
 void stage_mailbox_open(Context &c, int peer_rank, const void *ipc_handle, void *ptr);
 void stage_mailbox_destroy(Context &c);
+void stage_mailbox_barrier(Context &c);
 void stage_route_post(Context &c, int what, u64 first, u64 count, int exact, u64 *n_reads);
 void stage_answer_post(Context &c, int exact, u64 *bytes_sent);
 void stage_route_collect(Context &c);

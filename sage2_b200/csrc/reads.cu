@@ -371,9 +371,9 @@ __global__ void compact_good_kernel(const u64 *__restrict__ rec, const u32 *__re
 }
 
 // After the sort by the first 24 bases: order every run of equal 24-base prefixes by the whole records.
-// Runs are short (duplicate reads, shared 32-mers); a run longer than kTieLimit raises `overflow` and the
-// caller falls back to the full word-by-word LSD sort.
-constexpr int kTieLimit = 512;
+// Runs are short (duplicate reads, shared 24-mers); a run longer than kTieLimit (an insertion sort by one thread would
+// be the tail of the kernel) raises `overflow` and is left to refine_long_runs.
+constexpr int kTieLimit = 32;
 constexpr int kSortSkipBits = 16;     // the radix passes cover the top 48 bits (24 bases) of the first word
 __device__ __forceinline__ bool rec_less(const u64 *a, const u64 *b, int SW)
 {
@@ -397,6 +397,73 @@ __global__ void __launch_bounds__(256) tie_fix_kernel(const u64 *__restrict__ re
             perm[b] = x;
         }
     }
+}
+
+// ---- runs longer than kTieLimit (reads inside high-copy repeats, low-complexity sequence) ---------------------------
+// Only their members are sorted again, by (run, rest of the record): LSD radix passes over a compacted copy, written
+// back to the positions the run occupies.  Everything else keeps the order the first-word sort + tie_fix gave it.
+__global__ void __launch_bounds__(256) run_boundary_kernel(const u64 *__restrict__ key, u64 n, u32 *__restrict__ flag)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        flag[i] = (i == 0 || (key[i] >> kSortSkipBits) != (key[i - 1] >> kSortSkipBits)) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) run_count_kernel(const u32 *__restrict__ flag, const u32 *__restrict__ excl, u64 n, u32 *__restrict__ cnt)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[excl[i] + flag[i] - 1], 1u);
+}
+__global__ void __launch_bounds__(256) run_long_flag_kernel(const u32 *__restrict__ flag, const u32 *__restrict__ excl, const u32 *__restrict__ cnt, u64 n,
+                                                            u32 *__restrict__ lflag)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        lflag[i] = cnt[excl[i] + flag[i] - 1] > (u32)kTieLimit ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) run_compact_kernel(const u32 *__restrict__ lflag, const u32 *__restrict__ lidx, const u32 *__restrict__ flag,
+                                                          const u32 *__restrict__ excl, const u32 *__restrict__ perm, u64 n,
+                                                          u32 *__restrict__ pos, u32 *__restrict__ val, u64 *__restrict__ run)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if (lflag[i]) { const u32 j = lidx[i]; pos[j] = (u32)i; val[j] = perm[i]; run[j] = (u64)(excl[i] + flag[i] - 1); }
+}
+__global__ void __launch_bounds__(256) run_scatter_kernel(const u32 *__restrict__ pos, const u32 *__restrict__ val, u64 m, u32 *__restrict__ perm)
+{
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (u64)gridDim.x * blockDim.x) perm[pos[j]] = val[j];
+}
+
+static void refine_long_runs(Context &c, const u64 *rec, const u64 *key, u32 *perm, u64 n, int SW)
+{
+    cudaStream_t st = c.stream;
+    DevBuf<u32> flag(n, st), excl(n, st), cnt(n, st), lflag(n, st), lidx(n, st), d_m(1, st);
+    run_boundary_kernel<<<big_grid(n), 256, 0, st>>>(key, n, flag.p);
+    SG_LAUNCHED();
+    exclusive_scan_u32(flag.p, excl.p, n, nullptr, st);
+    SG_CUDA(cudaMemsetAsync(cnt.p, 0, n * sizeof(u32), st));
+    run_count_kernel<<<big_grid(n), 256, 0, st>>>(flag.p, excl.p, n, cnt.p);
+    SG_LAUNCHED();
+    run_long_flag_kernel<<<big_grid(n), 256, 0, st>>>(flag.p, excl.p, cnt.p, n, lflag.p);
+    SG_LAUNCHED();
+    exclusive_scan_u32(lflag.p, lidx.p, n, d_m.p, st);
+    u32 m = 0;
+    SG_CUDA(cudaMemcpyAsync(&m, d_m.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (m == 0) return;
+    DevBuf<u32> pos(m, st), v0(m, st), v1(m, st);
+    DevBuf<u64> a0(m, st), a1(m, st), b0(m, st), b1(m, st);
+    run_compact_kernel<<<big_grid(n), 256, 0, st>>>(lflag.p, lidx.p, flag.p, excl.p, perm, n, pos.p, v0.p, b0.p);
+    SG_LAUNCHED();
+    SortCols cols;
+    cols.a[0] = a0.p; cols.a[1] = a1.p; cols.b[0] = b0.p; cols.b[1] = b1.p; cols.v[0] = v0.p; cols.v[1] = v1.p;
+    int cur = 0;
+    for (int w = SW - 1; w >= 0; --w) {      // least significant word first; of the first word only the bits the first sort skipped
+        gather_word_kernel<<<big_grid(m), 256, 0, st>>>(rec, cols.v[cur], m, SW, w, cols.a[cur]);
+        SG_LAUNCHED();
+        cur = radix_sort_bits(cols, cur, m, false, 0, w == 0 ? kSortSkipBits : 64, st);
+    }
+    int id_bits = 1;
+    while ((n >> id_bits) != 0) ++id_bits;
+    cur = radix_sort_bits(cols, cur, m, true, 0, id_bits, st);      // ... and the run last: members return to their run's positions
+    run_scatter_kernel<<<big_grid(m), 256, 0, st>>>(pos.p, cols.v[cur], m, perm);
+    SG_LAUNCHED();
 }
 
 void stage_organize_reads(Context &c)
@@ -440,14 +507,10 @@ void stage_organize_reads(Context &c)
         SG_CUDA(cudaMemcpyAsync(h_flags, d_flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaStreamSynchronize(st));
         if (!h_flags[0] || attempt == 1) break;
-        // a run of more than kTieLimit equal first words (low-complexity input): sort by every remaining word,
-        // last word first (stable LSD passes; the first word is already the most significant key)
+        // runs of more than kTieLimit equal 24-base prefixes (high-copy repeats, low-complexity input): their members
+        // alone are sorted again by the rest of the record
         SG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(u32), st));
-        for (int w = SW - 1; w >= 0; --w) {
-            gather_word_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, cols.v[cur], n_good, SW, w, cols.a[cur]);
-            SG_LAUNCHED();
-            cur = radix_sort_varying(cols, cur, n_good, false, st);
-        }
+        refine_long_runs(c, rec.p, cols.a[cur], cols.v[cur], n_good, SW);
     }
     const u32 *perm = cols.v[cur];
     const u32 U = h_flags[1];

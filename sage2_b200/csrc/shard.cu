@@ -469,6 +469,7 @@ void stage_route_finish(Context &c, const void *responses, const void *entries, 
 // cudaMalloc block, opened by the other ranks through CUDA IPC, or plain pointers inside one process):
 //
 //   counts   [world]            u64   queries source s sent me in this batch
+//   flags    [world]            u64   barrier epochs: peer r has arrived at barrier number flags[r]
 //   queries  [world][cap][2]    u64   stream of source s (key hashes, or 128-bit keys)      -- I answer these as OWNER
 //   answers  [world][cap]       u64   answers of owner g to the queries I sent it           -- I consume these as SOURCE
 //   entries  [world][ecap]      u32   entry stream of owner g for my queries
@@ -482,7 +483,8 @@ void stage_route_finish(Context &c, const void *responses, const void *entries, 
 // =====================================================================================================================
 static size_t mb_align(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t mb_off_counts() { return 0; }
-static size_t mb_off_queries(int world) { return mb_align((size_t)world * 8); }
+static size_t mb_off_flags(int world) { return mb_align((size_t)world * 8); }                // barrier epochs, one per peer
+static size_t mb_off_queries(int world) { return mb_off_flags(world) + mb_align((size_t)world * 8); }
 static size_t mb_off_answers(int world, u64 cap) { return mb_off_queries(world) + mb_align((size_t)world * cap * 16); }
 static size_t mb_off_entries(int world, u64 cap) { return mb_off_answers(world, cap) + mb_align((size_t)world * cap * 8); }
 static size_t mb_bytes(int world, u64 cap, u64 ecap) { return mb_off_entries(world, cap) + mb_align((size_t)world * ecap * 4); }
@@ -544,6 +546,48 @@ __global__ void publish_counts_kernel(const unsigned long long *__restrict__ cnt
 {
     const int g = threadIdx.x;
     if (g < world) *D.dst[g] = cnt[g];        // counts[rank] in owner g's mailbox
+}
+
+// Barrier between the ranks ON THE DEVICE: one thread per peer stores this rank's epoch into the peer's mailbox (after a
+// system-scope fence: everything this rank stored into peer memory before is visible first) and then waits until the
+// peer's epoch has arrived here.  Stream-ordered, no host round trip through a collective.  A peer that never arrives
+// (a dead rank) ends the wait after ~4 s with an error instead of hanging the GPU.
+__global__ void mailbox_barrier_kernel(const __grid_constant__ RouteDst D /* dst[g] = flags[rank] in peer g's mailbox */,
+                                       const volatile u64 *__restrict__ my_flags, u64 epoch, int world, int rank, u32 *__restrict__ timed_out)
+{
+    const int g = threadIdx.x;
+    if (g >= world || g == rank) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile u64 *>(D.dst[g]) = epoch;
+    const long long t0 = clock64();
+    while (my_flags[g] < epoch) {
+        __nanosleep(200);
+        if (clock64() - t0 > 8000000000ll) { *timed_out = 1; break; }
+    }
+    __threadfence_system();
+}
+
+void stage_mailbox_barrier(Context &c)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    Mailbox &m = c.mb;
+    SG_CHECK(m.base != nullptr, "mailbox_create must run first");
+    if (m.world == 1) return;
+    RouteDst D = {};
+    for (int g = 0; g < m.world; ++g) {
+        SG_CHECK(m.peer[g] != nullptr, "a peer mailbox has not been opened");
+        D.dst[g] = (u64 *)(m.peer[g] + mb_off_flags(m.world)) + m.rank;
+    }
+    DevBuf<u32> d_to(1, st);
+    SG_CUDA(cudaMemsetAsync(d_to.p, 0, sizeof(u32), st));
+    ++m.epoch;
+    mailbox_barrier_kernel<<<1, kMaxWorld, 0, st>>>(D, (const volatile u64 *)(m.base + mb_off_flags(m.world)), m.epoch, m.world, m.rank, d_to.p);
+    SG_LAUNCHED();
+    u32 h_to = 0;
+    SG_CUDA(cudaMemcpyAsync(&h_to, d_to.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    SG_CHECK(h_to == 0, "mailbox barrier timed out: a peer rank never arrived");
 }
 
 void stage_route_post(Context &c, int what, u64 first, u64 count, int exact, u64 *n_reads)

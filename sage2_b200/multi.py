@@ -150,9 +150,9 @@ def _route_p2p(gpu, what: int, first: int, count: int, exact: bool, sent: list, 
     if posted is None:
         posted = gpu.route_post(what, first, count, exact)
     sent[0] += posted[1]
-    yield ("barrier",)
+    yield ("device_barrier", gpu)
     sent[0] += gpu.answer_post(exact)
-    yield ("barrier",)
+    yield ("device_barrier", gpu)
     gpu.route_collect()
 
 
@@ -239,6 +239,9 @@ def run_dist(gen, rank: int, world: int, device, stats: dict | None = None) -> i
                 t = torch.zeros(1, dtype=torch.int32, device=device)
                 dist.all_reduce(t)
                 val = int(t.item())
+            elif kind == "device_barrier":    # flags in the peers' mailboxes, written and awaited by a kernel (csrc/shard.cu)
+                req[1].mailbox_barrier()
+                val = 0
             elif kind == "mailboxes":         # CUDA IPC handles of all ranks (other processes cannot use the pointer)
                 boxes = [None] * world
                 dist.all_gather_object(boxes, {"handle": req[1]["handle"]})
@@ -286,7 +289,7 @@ def run_local(gens: list, views_of=None) -> None:
                 torch.cuda.synchronize()
         elif kind == "max":
             vals = [max(r[1] for r in reqs)] * world
-        elif kind == "barrier":
+        elif kind in ("barrier", "device_barrier"):      # one process drives the ranks in turn: nothing to wait for
             vals = [0] * world
         elif kind == "mailboxes":             # one process: plain pointers
             vals = [[{"ptr": r[1]["ptr"]} for r in reqs]] * world
