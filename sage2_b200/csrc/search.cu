@@ -49,6 +49,16 @@ __device__ __forceinline__ void ldg256(const u64 *p, u64 (&v)[4])
 {
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
 }
+// the same with an L2 eviction priority: the slot index is re-read by every read (keep: evict_last), a partner record
+// is needed once per overlap and should not push the index out (evict_first)
+__device__ __forceinline__ void ldg256_keep(const u64 *p, u64 (&v)[4])
+{
+    asm volatile("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256_stream(const u64 *p, u64 (&v)[4])
+{
+    asm volatile("ld.global.nc.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
 
 // FAST-mode scan state of one read (warp-uniform): first right hit, last left hit, last hit of each side
 struct FastState {
@@ -165,7 +175,7 @@ __device__ __forceinline__ void probe_window(const SearchParams &P, u64 v0, u64 
     u64 sec = home_sector(hsh, P.nsec);
     for (;;) {
         u64 s[4];
-        ldg256(P.slots + kSlotsPerSector * sec, s);
+        ldg256_keep(P.slots + kSlotsPerSector * sec, s);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const u64 slot = s[t];
@@ -342,7 +352,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
                     const bool fetch = __shfl_sync(FULL, (int)load, src) != 0 && 4 * part < SW;
                     if (fetch) {
                         u64 v[4];
-                        ldg256(base + 4 * part, v);
+                        ldg256_stream(base + 4 * part, v);
 #pragma unroll
                         for (int w = 0; w < 4; ++w) Qs[src * SWP + 4 * part + w] = v[w];
                     }
