@@ -171,11 +171,12 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
     and sage2gpu_build_hash_table_shard(rank, world) done.  p2p: exchange through the ranks' mailboxes (mailbox_steps
     done, batch_reads <= the mailbox's) instead of all-to-all requests; sent[0] accumulates the bytes stored remotely."""
     sent = sent if sent is not None else [0]
-    if p2p:
-        def _route(gpu, what, first, count, exact, world, view, begun=None):      # noqa: F811 (same protocol, other transport)
+
+    def route(what, first, count, exact, begun=None):      # one batch through the chosen transport
+        if p2p:
             return _route_p2p(gpu, what, first, count, exact, sent, posted=begun)
-    else:
-        _route = globals()["_route"]
+        return _route(gpu, what, first, count, exact, world, view, begun=begun)
+
     first, count = gpu.phase_a_sharded_begin(rank, world)
     U = gpu.counters()["unique_reads"]
     chunk = -(-U // world) if U else 0
@@ -184,11 +185,11 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
     for b in range(n_batches):
         lo = min(first + b * batch_reads, first + count)
         n = min(batch_reads, first + count - lo)
-        yield from _route(gpu, 0, lo, n, False, world, view)
+        yield from route(0, lo, n, False)
         redo += gpu.phase_a_routed()
     if (yield ("max", redo)):
         # 24-bit tag collisions (about U*W / 2^24 reads): those reads once more, with probes the owners verify
-        yield from _route(gpu, 2, 0, 0, True, world, view)
+        yield from route(2, 0, 0, True)
         left = gpu.phase_a_routed()
         if left:
             raise RuntimeError(f"{left} reads still unresolved after the verified pass")
@@ -198,11 +199,11 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
     if p2p:
         posted = gpu.route_post(1, 0, 0, True)          # reads left for phase C: identical list on every rank
         if posted[0]:
-            yield from _route(gpu, 1, 0, 0, True, world, view, begun=posted)
+            yield from route(1, 0, 0, True, begun=posted)
     else:
         rb = gpu.route_begin(1, 0, 0, True, world)
         if rb["n_reads"]:
-            yield from _route(gpu, 1, 0, 0, True, world, view, begun=rb)
+            yield from route(1, 0, 0, True, begun=rb)
     gpu.finish_graph()
 
 
