@@ -297,7 +297,7 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
 
 // ------------------------------------------------------------------------------------------------
 // K2: sort a permutation of the good reads by record (= Read::operator<), dedupe.  Six stable 8-bit radix
-// passes on the first 24 bases + an in-place fix of the short runs of equal 24-base prefixes by whole-record
+// passes on the leading 16..24 bases + an in-place fix of the short runs of equal prefixes by whole-record
 // compares; inputs with very long runs fall back to LSD passes over every word.
 // ------------------------------------------------------------------------------------------------
 __global__ void iota_kernel(u32 *v, u64 n)
@@ -370,18 +370,29 @@ __global__ void compact_good_kernel(const u64 *__restrict__ rec, const u32 *__re
         if (flag[i]) { key[idx[i]] = rec[i * SW]; val[idx[i]] = (u32)i; }
 }
 
-// After the sort by the first 24 bases: order every run of equal 24-base prefixes by the whole records.
+// After the sort by the leading bases: order every run of equal prefixes by the whole records.
 // Runs are short (duplicate reads, shared 24-mers); a run longer than kTieLimit (an insertion sort by one thread would
 // be the tail of the kernel) raises `overflow` and is left to refine_long_runs.
 constexpr int kTieLimit = 32;
-constexpr int kSortSkipBits = 16;     // the radix passes cover the top 48 bits (24 bases) of the first word
+// The radix passes cover the top 64 - skip bits of the first word: enough bits that runs of equal prefixes stay short
+// for the number of reads at hand (n reads spread over 2^(64-skip) prefixes), in whole 8-bit passes: 32 bits (16 bases,
+// 4 passes) up to 134 M reads, 40 bits up to 2^35, never more than 48.
+static int sort_skip_bits(u64 n)
+{
+    int lg = 0;
+    while (lg < 63 && (1ull << lg) < n) ++lg;
+    int bits = ((lg + 5 + 7) / 8) * 8;
+    if (bits < 32) bits = 32;
+    if (bits > 48) bits = 48;
+    return 64 - bits;
+}
 __device__ __forceinline__ bool rec_less(const u64 *a, const u64 *b, int SW)
 {
     for (int w = 0; w < SW; ++w) { const u64 x = a[w], y = b[w]; if (x != y) return x < y; }
     return false;
 }
 __global__ void __launch_bounds__(256) tie_fix_kernel(const u64 *__restrict__ rec, const u64 *__restrict__ key, u32 *__restrict__ perm, u64 n, int SW,
-                                                        u32 *__restrict__ overflow)
+                                                        int kSortSkipBits, u32 *__restrict__ overflow)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const u64 k = key[i] >> kSortSkipBits;
@@ -402,7 +413,7 @@ __global__ void __launch_bounds__(256) tie_fix_kernel(const u64 *__restrict__ re
 // ---- runs longer than kTieLimit (reads inside high-copy repeats, low-complexity sequence) ---------------------------
 // Only their members are sorted again, by (run, rest of the record): LSD radix passes over a compacted copy, written
 // back to the positions the run occupies.  Everything else keeps the order the first-word sort + tie_fix gave it.
-__global__ void __launch_bounds__(256) run_boundary_kernel(const u64 *__restrict__ key, u64 n, u32 *__restrict__ flag)
+__global__ void __launch_bounds__(256) run_boundary_kernel(const u64 *__restrict__ key, u64 n, int kSortSkipBits, u32 *__restrict__ flag)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
         flag[i] = (i == 0 || (key[i] >> kSortSkipBits) != (key[i - 1] >> kSortSkipBits)) ? 1u : 0u;
@@ -430,11 +441,11 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(const u32 *__restrict_
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (u64)gridDim.x * blockDim.x) perm[pos[j]] = val[j];
 }
 
-static void refine_long_runs(Context &c, const u64 *rec, const u64 *key, u32 *perm, u64 n, int SW)
+static void refine_long_runs(Context &c, const u64 *rec, const u64 *key, u32 *perm, u64 n, int SW, int kSortSkipBits)
 {
     cudaStream_t st = c.stream;
     DevBuf<u32> flag(n, st), excl(n, st), cnt(n, st), lflag(n, st), lidx(n, st), d_m(1, st);
-    run_boundary_kernel<<<big_grid(n), 256, 0, st>>>(key, n, flag.p);
+    run_boundary_kernel<<<big_grid(n), 256, 0, st>>>(key, n, kSortSkipBits, flag.p);
     SG_LAUNCHED();
     exclusive_scan_u32(flag.p, excl.p, n, nullptr, st);
     SG_CUDA(cudaMemsetAsync(cnt.p, 0, n * sizeof(u32), st));
@@ -491,11 +502,12 @@ void stage_organize_reads(Context &c)
     }
     SortCols cols;
     cols.a[0] = ka.p; cols.a[1] = kb.p; cols.b[0] = cols.b[1] = nullptr; cols.v[0] = va.p; cols.v[1] = vb.p;
-    int cur = radix_sort_bits(cols, 0, n_good, false, kSortSkipBits, 64, st);      // 6 passes on the first 24 bases
+    const int kSortSkipBits = sort_skip_bits(n_good);
+    int cur = radix_sort_bits(cols, 0, n_good, false, kSortSkipBits, 64, st);      // 4 .. 6 passes on the leading bases
     DevBuf<u32> d_flags(2, st);          // [0] tie-run overflow, [1] unique count
     SG_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(u32), st));
     {
-        tie_fix_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, cols.a[cur], cols.v[cur], n_good, SW, d_flags.p);
+        tie_fix_kernel<<<big_grid(n_good), 256, 0, st>>>(rec.p, cols.a[cur], cols.v[cur], n_good, SW, kSortSkipBits, d_flags.p);
         SG_LAUNCHED();
     }
     DevBuf<u32> flag(n_good, st), uidx(n_good, st);
@@ -507,10 +519,10 @@ void stage_organize_reads(Context &c)
         SG_CUDA(cudaMemcpyAsync(h_flags, d_flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaStreamSynchronize(st));
         if (!h_flags[0] || attempt == 1) break;
-        // runs of more than kTieLimit equal 24-base prefixes (high-copy repeats, low-complexity input): their members
+        // runs of more than kTieLimit equal prefixes (high-copy repeats, low-complexity input): their members
         // alone are sorted again by the rest of the record
         SG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(u32), st));
-        refine_long_runs(c, rec.p, cols.a[cur], cols.v[cur], n_good, SW);
+        refine_long_runs(c, rec.p, cols.a[cur], cols.v[cur], n_good, SW, kSortSkipBits);
     }
     const u32 *perm = cols.v[cur];
     const u32 U = h_flags[1];
