@@ -149,18 +149,52 @@ __global__ void __launch_bounds__(K1T_THREADS) pack_thread_kernel(const uint8_t 
 #pragma unroll
             for (int w = 0; w < SW; ++w) f[w] = 0;
             bool invalid = false;
+            if (span <= K1T_STAGE) {
+                // four characters per step out of the staging buffer: two aligned 32-bit words funnel-shifted to the read's
+                // byte phase; codes of the four bytes at once ((c >> 1) ^ (c >> 2)) & 3; validity by rebuilding the
+                // upper-case character each code stands for (A 0x41, C +2, G +6, T +0x13) and comparing; the four 2-bit
+                // codes gathered into one byte by a multiply
+                const u32 *Bw = reinterpret_cast<const u32 *>(reinterpret_cast<uintptr_t>(B) & ~(uintptr_t)3);
+                const unsigned ph = (unsigned)(reinterpret_cast<uintptr_t>(B) & 3) * 8;
+                u32 lo = Bw[0], bad_bits = 0;
 #pragma unroll
-            for (int w = 0; w < SW; ++w) {
-                if (32 * w < len) {
+                for (int w = 0; w < SW; ++w) {
                     u64 acc = 0;
-                    const int m = len - 32 * w < 32 ? len - 32 * w : 32;
-                    for (int t = 0; t < m; ++t) {
-                        const u32 ch = B[32 * w + t];
-                        const u32 up = ch & 0xDFu;
-                        invalid |= !(up == 'A' || up == 'C' || up == 'G' || up == 'T');
-                        acc |= (u64)(((ch >> 1) ^ (ch >> 2)) & 3u) << (62 - 2 * t);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int c4 = 8 * w + q;
+                        if (4 * c4 < len) {
+                            const u32 hi = Bw[c4 + 1];
+                            u32 x = __funnelshift_r(lo, hi, ph);
+                            lo = hi;
+                            const int left = len - 4 * c4;
+                            if (left < 4) { const u32 keep = 0xFFFFFFFFu >> (8 * (4 - left)); x = (x & keep) | (0x41414141u & ~keep); }
+                            const u32 c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+                            const u32 c0 = c & 0x01010101u, c1 = (c >> 1) & 0x01010101u;
+                            const u32 expect = 0x41414141u + (c0 & ~c1) * 2u + (c1 & ~c0) * 6u + (c1 & c0) * 0x13u;
+                            bad_bits |= expect ^ (x & 0xDFDFDFDFu);
+                            u32 byte = (c * 0x40100401u) >> 24;
+                            if (left < 4) byte &= 0xFFu << (2 * (4 - left));      // padding characters are not bases
+                            acc |= (u64)byte << (56 - 8 * q);
+                        }
                     }
                     f[w] = acc;
+                }
+                invalid = bad_bits != 0;
+            } else {
+#pragma unroll
+                for (int w = 0; w < SW; ++w) {
+                    if (32 * w < len) {
+                        u64 acc = 0;
+                        const int m = len - 32 * w < 32 ? len - 32 * w : 32;
+                        for (int t = 0; t < m; ++t) {
+                            const u32 ch = B[32 * w + t];
+                            const u32 up = ch & 0xDFu;
+                            invalid |= !(up == 'A' || up == 'C' || up == 'G' || up == 'T');
+                            acc |= (u64)(((ch >> 1) ^ (ch >> 2)) & 3u) << (62 - 2 * t);
+                        }
+                        f[w] = acc;
+                    }
                 }
             }
             bad |= invalid;
