@@ -16,7 +16,89 @@ constexpr int MP_WARPS = 8;
 __device__ __forceinline__ int base_code(uint8_t c) { return ((c >> 1) ^ (c >> 2)) & 3; }       // A0 C1 G2 T3 (either case)
 __device__ __forceinline__ bool base_valid(uint8_t c) { c &= 0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
-// pass 1: one warp per query packs it (coalesced byte loads) and writes the record to look up + its flags
+// Packing of one read by ONE thread, four characters per step: two aligned 32-bit words funnel-shifted to the read's
+// byte phase, the codes of four bytes at once, validity by rebuilding the upper-case character each code stands for, the
+// four 2-bit codes gathered into one byte by a multiply (the same arithmetic as reads.cu's pack_thread_kernel).
+// f[] receives the forward record without its length.  Returns false on a non-ACGT character.
+template <int SW>
+__device__ __forceinline__ bool pack_read_simd(const uint8_t *__restrict__ s, int len, u64 (&f)[SW])
+{
+    const u32 *Bw = reinterpret_cast<const u32 *>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+    const unsigned ph = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
+    u32 lo = __ldg(Bw), bad_bits = 0;
+#pragma unroll
+    for (int w = 0; w < SW; ++w) {
+        u64 acc = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int c4 = 8 * w + q;
+            if (4 * c4 < len) {
+                const int left = len - 4 * c4;
+                // the second word is needed only when the four characters reach into it (never read past the read's last byte's word)
+                const u32 hi = (ph != 0 && (int)(ph >> 3) + left > 4) || (ph == 0 && left > 4) ? __ldg(Bw + c4 + 1) : 0u;
+                u32 x = __funnelshift_r(lo, hi, ph);
+                lo = hi;
+                if (left < 4) { const u32 keep = 0xFFFFFFFFu >> (8 * (4 - left)); x = (x & keep) | (0x41414141u & ~keep); }
+                const u32 c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+                const u32 c0 = c & 0x01010101u, c1 = (c >> 1) & 0x01010101u;
+                const u32 expect = 0x41414141u + (c0 & ~c1) * 2u + (c1 & ~c0) * 6u + (c1 & c0) * 0x13u;
+                bad_bits |= expect ^ (x & 0xDFDFDFDFu);
+                acc |= (u64)((c * 0x40100401u) >> 24) << (56 - 8 * q);
+            }
+        }
+        f[w] = acc;
+    }
+    return bad_bits == 0;
+}
+
+// One thread per query: pack (above), reverse complement, pick the orientation the reference looks up, binary search of
+// readLoader.cpp:335-348 over the sorted unique reads -- a warp keeps 32 independent random lines in flight; words after
+// the first differing one are never read.
+template <int SW>
+__global__ void __launch_bounds__(256) map_reads_thread_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ off, u64 n, int k,
+                                                               const u64 *__restrict__ F, u64 U, int SWS,
+                                                               long long *__restrict__ ids, uint8_t *__restrict__ good)
+{
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x) {
+        const int64_t o0 = off[q];
+        const int64_t len64 = off[q + 1] - o0;
+        const uint8_t *s = bases + o0;
+        const bool fits = len64 <= (int64_t)(32 * SW - 8);
+        bool ok = len64 > (int64_t)k;                       // utils.cpp:146
+        long long id = 0;
+        if (ok && fits) {
+            const int len = (int)len64;
+            u64 f[SW], r[SW];
+            ok = pack_read_simd<SW>(s, len, f);
+            if (ok && U > 0) {
+                revcomp_record(f, r, SW, len);              // r carries the length
+                f[SW - 1] |= (u64)len;
+                bool fwd_smaller = false;                   // read.compare(read_r) < 0 (readLoader.cpp:325); ties look the revcomp up
+#pragma unroll
+                for (int w = SW - 1; w >= 0; --w) if (f[w] != r[w]) fwd_smaller = f[w] < r[w];
+#pragma unroll
+                for (int w = 0; w < SW; ++w) f[w] = fwd_smaller ? f[w] : r[w];
+                long long lb = 0, ub = (long long)U - 1;
+                while (lb <= ub) {
+                    const long long mid = (lb + ub) >> 1;
+                    const u64 *X = F + (u64)mid * SWS;
+                    u64 x = __ldg(&X[0]), y = f[0];
+#pragma unroll
+                    for (int w = 1; w < SW; ++w) if (x == y) { x = __ldg(&X[w]); y = f[w]; }
+                    if (x == y) { id = fwd_smaller ? mid + 1 : -(mid + 1); break; }
+                    if (y > x) lb = mid + 1; else ub = mid - 1;
+                }
+            }
+        } else if (ok) {                                    // longer than any read of the set: good or not, never present
+            for (int64_t p = 0; p < len64; ++p) ok = ok && base_valid(s[p]);
+        }
+        ids[q] = id;
+        if (good) good[q] = ok ? 1 : 0;
+    }
+}
+
+// records of more than 8 words (reads longer than 248 bases): one warp per query packs it (coalesced byte loads) and writes
+// the record to look up + its flags
 //   meta bit 0: isGoodRead, bit 1: the read itself is the smaller orientation (flag +1), bit 2: worth searching
 __global__ void __launch_bounds__(MP_WARPS * 32) map_pack_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ off, u64 n, int k,
                                                                  u64 U, int SW, u64 *__restrict__ qrec, uint8_t *__restrict__ meta)
@@ -117,16 +199,29 @@ float stage_map_reads(Context &c, const uint8_t *bases, const int64_t *offsets, 
     cudaEvent_t e0, e1;
     SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
     SG_CUDA(cudaEventRecord(e0, st));
-    DevBuf<u64> qrec(n * (u64)c.SW, st);
-    DevBuf<uint8_t> meta(n, st);
-    u64 g = (n + MP_WARPS - 1) / MP_WARPS;
-    if (g > (u64)kSMs * 16) g = (u64)kSMs * 16;
-    map_pack_kernel<<<(unsigned)g, MP_WARPS * 32, 0, st>>>(pb, po, n, c.min_overlap, c.cnt.unique_reads, c.SW, qrec.p, meta.p);
-    SG_LAUNCHED();
-    g = (n + 255) / 256;
+    u64 g = (n + 255) / 256;
     if (g > (u64)kSMs * 8) g = (u64)kSMs * 8;
-    map_search_kernel<<<(unsigned)g, 256, 0, st>>>(qrec.p, meta.p, n, c.F.p, c.cnt.unique_reads, c.SW, c.SWS, d_ids.p, d_good.p);
-    SG_LAUNCHED();
+    const u64 U = c.cnt.unique_reads;
+    if (c.SW <= 8) {      // one fused thread-per-read kernel
+        switch (c.SW) {
+            case 2: map_reads_thread_kernel<2><<<(unsigned)g, 256, 0, st>>>(pb, po, n, c.min_overlap, c.F.p, U, c.SWS, d_ids.p, d_good.p); break;
+            case 3: map_reads_thread_kernel<3><<<(unsigned)g, 256, 0, st>>>(pb, po, n, c.min_overlap, c.F.p, U, c.SWS, d_ids.p, d_good.p); break;
+            case 4: map_reads_thread_kernel<4><<<(unsigned)g, 256, 0, st>>>(pb, po, n, c.min_overlap, c.F.p, U, c.SWS, d_ids.p, d_good.p); break;
+            case 5: map_reads_thread_kernel<5><<<(unsigned)g, 256, 0, st>>>(pb, po, n, c.min_overlap, c.F.p, U, c.SWS, d_ids.p, d_good.p); break;
+            case 6: map_reads_thread_kernel<6><<<(unsigned)g, 256, 0, st>>>(pb, po, n, c.min_overlap, c.F.p, U, c.SWS, d_ids.p, d_good.p); break;
+            default: map_reads_thread_kernel<8><<<(unsigned)g, 256, 0, st>>>(pb, po, n, c.min_overlap, c.F.p, U, c.SWS, d_ids.p, d_good.p); break;
+        }
+        SG_LAUNCHED();
+    } else {              // long reads: warp-per-read pack, then the thread-per-read search
+        DevBuf<u64> qrec(n * (u64)c.SW, st);
+        DevBuf<uint8_t> meta(n, st);
+        u64 gp = (n + MP_WARPS - 1) / MP_WARPS;
+        if (gp > (u64)kSMs * 16) gp = (u64)kSMs * 16;
+        map_pack_kernel<<<(unsigned)gp, MP_WARPS * 32, 0, st>>>(pb, po, n, c.min_overlap, U, c.SW, qrec.p, meta.p);
+        SG_LAUNCHED();
+        map_search_kernel<<<(unsigned)g, 256, 0, st>>>(qrec.p, meta.p, n, c.F.p, U, c.SW, c.SWS, d_ids.p, d_good.p);
+        SG_LAUNCHED();
+    }
     SG_CUDA(cudaEventRecord(e1, st));
     SG_CUDA(cudaMemcpyAsync(ids, d_ids.p, n * sizeof(long long), cudaMemcpyDeviceToHost, st));
     if (good) SG_CUDA(cudaMemcpyAsync(good, d_good.p, n, cudaMemcpyDeviceToHost, st));
