@@ -16,9 +16,12 @@ config #2 (4.6 Mbp random genome, 150 bp paired-end, 100x, -k 63): 3,066,666 inp
             built from /root/reference in the build container) on the box's host cores, on a bounded
             cfg2-shaped sample.
 
-N > 1 (torchrun, one rank per GPU): ONE cfg2 read set for the whole job; reads and table are
-replicated, phase A is partitioned by read id and followed by one NCCL exchange (sage2_b200/multi.py);
-total work is fixed, so scaling is "strong".
+N > 1 (torchrun, one rank per GPU): ONE cfg2 read set for the whole job, total work fixed, so scaling is
+"strong".  Two layouts, the headline is the faster one at this size:
+  --table replicated (default): reads and table on every GPU, phase A partitioned by read id, one NCCL exchange;
+  --table sharded: every GPU holds one key-hash shard of the table, the window probes are routed to their owners
+            through peer-memory mailboxes (--exchange p2p: kernel stores over NVLink) or NCCL all-to-all.
+The other layout is timed on the same reads and reported as `alt_table`.
 """
 from __future__ import annotations
 
@@ -197,13 +200,19 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     comm = {"sent": 0, "h2d": 0}
 
+    # the mailbox transport needs peer access between all GPUs of the job (NVLink / NVSwitch box); otherwise NCCL
+    peers_ok = all(torch.cuda.can_device_access_peer(local, d) for d in range(world) if d != local) if world > 1 else True
+    if world > 1:
+        t_ok = torch.tensor([1 if peers_ok else 0], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        peers_ok = bool(t_ok.item())
     layout = {"sharded": args.table == "sharded"}
     xstats = {}
 
     def build_graph():
         if layout["sharded"]:       # key-hash shard per GPU, window probes routed to their owners by NCCL all-to-all
             gpu.build_hash_table_shard(rank, world)
-            p2p = args.exchange == "p2p"      # peer-memory mailboxes (NVLink P2P stores) or NCCL all-to-all
+            p2p = args.exchange == "p2p" and peers_ok      # peer-memory mailboxes (NVLink P2P stores) or NCCL all-to-all
             return multi.build_overlap_graph_sharded(gpu, rank, world, dev, batch_reads=min(args.batch_reads, 1 << 19) if p2p else args.batch_reads,
                                                      stats=xstats, p2p=p2p)
         gpu.build_hash_table()
@@ -283,7 +292,8 @@ def run_ours(args):
             step_device()
         xstats.clear()
         a_ms, _, a_launches, a_stage = timed(step_device, args.steps)
-        alt = {"table": "sharded" if layout["sharded"] else "replicated", "exchange": args.exchange if layout["sharded"] else "nccl",
+        alt = {"table": "sharded" if layout["sharded"] else "replicated",
+               "exchange": (args.exchange if peers_ok else "nccl") if layout["sharded"] else "nccl",
                "ms_per_step": a_ms / args.steps,
                "value": n_reads / (a_ms / args.steps / 1000.0), "unit": UNIT, "sent_bytes_per_rank_and_step": comm["sent"],
                "gpu_launches": a_launches, "stage_ms": a_stage,
