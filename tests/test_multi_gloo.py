@@ -65,3 +65,29 @@ def test_partitioned_phase_a_with_exchange_equals_oracle(name, world, tmp_path):
         U = int(sent[-1])
         chunk = -(-U // world)
         assert int(sent[0]) == chunk * (8 + 8 + 1) + chunk * world * 4
+
+
+def _upload_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        reads, _ = datasets.get("varlen")
+        b, off = synth.concat(reads)
+        tb, to, moved = multi.upload_partitioned(torch.from_numpy(b), torch.from_numpy(off), rank, world, torch.device("cpu"))
+        np.save(os.path.join(out, f"up{rank}.npy"), np.array([int((tb.numpy() == b).all()), int((to.numpy() == off).all()), moved]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_upload_reassembles_the_input(world, tmp_path):
+    """Every rank copies only its 1/world share of the input; the all-gather must give every rank the whole of it."""
+    mp.spawn(_upload_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    reads, _ = datasets.get("varlen")
+    b, off = synth.concat(reads)
+    total = 0
+    for r in range(world):
+        ok_b, ok_o, moved = np.load(tmp_path / f"up{r}.npy")
+        assert ok_b == 1 and ok_o == 1
+        total += int(moved)
+    assert total == b.nbytes + off.nbytes
