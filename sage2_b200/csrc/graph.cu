@@ -5,6 +5,7 @@
 // become edges (overlapGraph/overlapGraph.cpp:93-112).
 #include <stdlib.h>
 #include <algorithm>
+#include <stdio.h>
 #include "context.h"
 #include "host_phase_c.h"
 
@@ -292,6 +293,17 @@ void stage_phase_c_and_finalize(Context &c)
         in.cand = h_cand.data(); in.nB = nSel; in.edgesB = h_selB.data(); in.edgesB_len = h_selLen.data();
         PhaseCOutput out;
         host_ms = run_host_phase_c(in, out);
+        if (const char *dump = getenv("SAGE2GPU_DUMP_PHASE_C")) {      // test knob: the walk's input and output, for tools/phase_c_bench
+            if (FILE *f = fopen(dump, "wb")) {
+                const u64 hdr[6] = { nS, nC, nSel, out.edges.size(), out.inserted, out.removed };
+                fwrite(hdr, sizeof(u64), 6, f);
+                fwrite(h_sids.data(), sizeof(u32), nS, f); fwrite(h_slen.data(), sizeof(uint16_t), nS, f);
+                fwrite(h_off.data(), sizeof(u32), (size_t)nS + 1, f); fwrite(h_cand.data(), sizeof(u64), nC, f);
+                fwrite(h_selB.data(), sizeof(u64), 2 * (size_t)nSel, f); fwrite(h_selLen.data(), sizeof(u32), nSel, f);
+                fwrite(out.edges.data(), sizeof(u64), out.edges.size(), f);
+                fclose(f);
+            }
+        }
         c.cnt.edges_inserted_c = out.inserted;
         c.cnt.transitive_removed = out.removed;
         host_c_edges.swap(out.edges);

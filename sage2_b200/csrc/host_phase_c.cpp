@@ -11,6 +11,7 @@
 // with id > a after the walk, i.e. exactly what convertGraph would consume (overlapGraph.cpp:103).
 #include "host_phase_c.h"
 
+#include <stdlib.h>
 #include <algorithm>
 #include <chrono>
 #include <thread>
@@ -57,12 +58,34 @@ struct IdMap {
     }
 };
 
+// Adjacency lists live in ONE pool: list n is pool[start[n] .. start[n] + size[n]) with room for every entry it can ever
+// receive (its own candidates, the candidates of others that name it, its phase-B records), so the walk never allocates.
+// The big buffers survive between calls (grow-only, one set per calling thread): a fresh 50 MB block per call costs more in
+// page faults than the walk itself.
+struct Workspace {
+    HEdge *pool = nullptr;
+    size_t pool_cap = 0;
+    std::vector<uint32_t> cnode, room, eb_a, eb_b;
+    HEdge *get_pool(size_t n)
+    {
+        if (n > pool_cap) {
+            free(pool);
+            pool_cap = n + n / 4 + 1024;
+            pool = (HEdge *)malloc(pool_cap * sizeof(HEdge));       // entries are always written before they are read
+        }
+        return pool;
+    }
+    ~Workspace() { free(pool); }
+};
+
 struct Walk {
     const PhaseCInput &in;
     IdMap slot;                                    // read id (1-based) -> local node
-    std::vector<std::vector<HEdge>> adj;
+    HEdge *pool = nullptr;
+    std::vector<uint64_t> start;
+    std::vector<uint32_t> size;
+    const uint32_t *cnode = nullptr;               // candidate q -> local node of its read2 (resolved by all cores before the walk)
     std::vector<uint8_t> state;                    // 0/1/2 for S nodes, 4 for everything else
-    std::vector<uint8_t> marked;
     std::vector<uint32_t> node_id, node_len;
     uint64_t inserted = 0, removed = 0;
 
@@ -72,15 +95,15 @@ struct Walk {
     {
         const uint32_t f = slot.find(id);
         if (f != kNone) return f;
-        const uint32_t n = (uint32_t)adj.size();
+        const uint32_t n = (uint32_t)state.size();
         slot.put(id, n);
-        adj.emplace_back();
         state.push_back(st);
-        marked.push_back(0);
         node_id.push_back(id);
         node_len.push_back(len);
         return n;
     }
+    HEdge *list(uint32_t n) { return pool + start[n]; }
+    void push(uint32_t n, const HEdge &e) { pool[start[n] + size[n]++] = e; }
 
     // insertEdgeEconomy, economyGraph.cpp:813-849 (both endpoints are S nodes here)
     void insert_edge(uint32_t nu, uint32_t nv, uint32_t delta, uint32_t type)
@@ -88,8 +111,8 @@ struct Walk {
         const uint32_t u = node_id[nu], v = node_id[nv];
         const uint32_t lu = node_len[nu], lv = node_len[nv];
         const uint32_t delta2 = lu - (lv - delta);
-        adj[nu].push_back(HEdge{ v, nv, (uint8_t)type, 0, delta & 0xFFFFFu });
-        adj[nv].push_back(HEdge{ u, nu, (uint8_t)rev_type(type), 0, delta2 & 0xFFFFFu });
+        push(nu, HEdge{ v, nv, (uint8_t)type, 0, delta & 0xFFFFFu });
+        push(nv, HEdge{ u, nu, (uint8_t)rev_type(type), 0, delta2 & 0xFFFFFu });
     }
 
     // insertAllEdgesOfRead, economyGraph.cpp:580-638
@@ -100,15 +123,15 @@ struct Walk {
         const uint32_t s = n1;    // S nodes occupy local slots 0..nS-1 in s_ids order
         uint64_t cnt = 0;
         for (uint32_t q = in.cand_off[s]; q < in.cand_off[s + 1]; ++q) {
+            const uint32_t n2 = cnode[q];
+            if (n2 == kNone || state[n2] != 0) continue;                    // :605
             const uint64_t cw = in.cand[q];
-            const uint32_t n2 = slot.find((uint32_t)(cw >> 32));
-            if (state[n2] != 0) continue;                                   // :605
             uint32_t delta = (uint32_t)(cw & 0xFFFFFu);
             if (delta & 0x80000u) delta |= 0xFFF00000u;                     // sign-extend the int32 overhang
             insert_edge(n1, n2, delta, (uint32_t)((cw >> 20) & 3u));
             cnt++;
         }
-        if (adj[n1].size() > 1) std::sort(adj[n1].begin(), adj[n1].end(), by_length_desc);   // :634
+        if (size[n1] > 1) std::sort(list(n1), list(n1) + size[n1], by_length_desc);   // :634
         inserted += 2 * cnt;
     }
 
@@ -118,12 +141,17 @@ struct Walk {
 
     void compute_marks(uint32_t nf, std::vector<uint8_t> &scratch)      // scratch: one zeroed byte per node
     {
-        std::vector<HEdge> &lf = adj[nf];
-        for (auto &e : lf) scratch[e.node] = 1;
-        for (auto &e : lf) {
+        HEdge *lf = list(nf);
+        const uint32_t nfe = size[nf];
+        for (uint32_t x = 0; x < nfe; ++x) scratch[lf[x].node] = 1;
+        for (uint32_t x = 0; x < nfe; ++x) {
+            const HEdge &e = lf[x];
             const uint32_t na = e.node;
             if (scratch[na] != 1) continue;
-            for (auto &f : adj[na]) {
+            const HEdge *la = list(na);
+            const uint32_t nae = size[na];
+            for (uint32_t y = 0; y < nae; ++y) {
+                const HEdge &f = la[y];
                 const uint32_t nb = f.node;
                 if (nb == kNone) continue;            // not adjacent to any S read: cannot be in play
                 if (scratch[nb] != 1) continue;
@@ -132,21 +160,34 @@ struct Walk {
                 else if ((t1 == 1 || t1 == 3) && (t2 == 2 || t2 == 3)) scratch[nb] = 2;
             }
         }
-        for (auto &e : lf) if (scratch[e.node] == 2) e.mark = 1;
-        for (auto &e : lf) scratch[e.node] = 0;
+        for (uint32_t x = 0; x < nfe; ++x) if (scratch[lf[x].node] == 2) lf[x].mark = 1;
+        for (uint32_t x = 0; x < nfe; ++x) scratch[lf[x].node] = 0;
         scratch[nf] = 0;
     }
 
     // removeTransitiveEdges, economyGraph.cpp:681-707 (after all marks are known)
     void remove_marked(uint32_t n)
     {
-        std::vector<HEdge> &l = adj[n];
-        size_t w = 0;
-        for (size_t r = 0; r < l.size(); ++r) if (!l[r].mark) l[w++] = l[r];
-        removed += l.size() - w;
-        l.resize(w);
+        HEdge *l = list(n);
+        uint32_t w = 0;
+        for (uint32_t r = 0; r < size[n]; ++r) if (!l[r].mark) l[w++] = l[r];
+        removed += size[n] - w;
+        size[n] = w;
     }
 };
+
+// fn(t, T) on T host threads (T = 1 for small inputs)
+template <typename Fn>
+void on_all_cores(size_t work_items, Fn fn)
+{
+    unsigned T = std::thread::hardware_concurrency();
+    if (T > 32) T = 32;
+    if (T < 1 || work_items < 4096) T = 1;
+    if (T == 1) { fn(0u, 1u); return; }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; ++t) pool.emplace_back(fn, t, T);
+    for (auto &th : pool) th.join();
+}
 
 }  // namespace
 
@@ -155,10 +196,12 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
     const auto t0 = std::chrono::steady_clock::now();
     Walk w(in);
     w.slot.init(in.nS + 2 * in.nB);
+    w.state.reserve(in.nS + 2 * in.nB); w.node_id.reserve(in.nS + 2 * in.nB); w.node_len.reserve(in.nS + 2 * in.nB);
     for (uint64_t s = 0; s < in.nS; ++s) w.node(in.s_ids[s] + 1, 0, in.s_len[s]);
     const uint32_t nS = (uint32_t)in.nS;
+    const uint64_t nC = in.nS ? in.cand_off[in.nS] : 0;
 
-    // phase-B neighbours of S, then every phase-B entry of every needed node
+    // phase-B neighbours of S
     for (uint64_t e = 0; e < in.nB; ++e) {
         const uint32_t a = (uint32_t)(in.edgesB[2 * e] >> 32), b = (uint32_t)in.edgesB[2 * e];
         const uint32_t ia = w.slot.find(a), ib = w.slot.find(b);
@@ -167,15 +210,49 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
         if (a_in_s && ib == kNone) w.node(b, 4, in.edgesB_len[e] >> 16);
         if (b_in_s && ia == kNone) w.node(a, 4, in.edgesB_len[e] & 0xFFFFu);
     }
+    const size_t n_nodes = w.state.size();
+
+    static thread_local Workspace ws;
+
+    // candidate -> node of its read2, on all cores (the id map is read-only from here on)
+    ws.cnode.resize(nC);
+    uint32_t *cnode = ws.cnode.data();
+    w.cnode = cnode;
+    on_all_cores(nC, [&](unsigned t, unsigned T) {
+        const uint64_t lo = nC * t / T, hi = nC * (t + 1) / T;
+        for (uint64_t q = lo; q < hi; ++q) cnode[q] = w.slot.find((uint32_t)(in.cand[q] >> 32));
+    });
+
+    // room of every list: own candidates + candidates naming the node + phase-B records
+    std::vector<uint32_t> &room = ws.room, &eb_a = ws.eb_a, &eb_b = ws.eb_b;
+    room.assign(n_nodes, 0);
+    for (uint32_t s = 0; s < nS; ++s) room[s] = in.cand_off[s + 1] - in.cand_off[s];
+    for (uint64_t q = 0; q < nC; ++q) if (cnode[q] != kNone) room[cnode[q]]++;
+    eb_a.resize(in.nB); eb_b.resize(in.nB);
+    for (uint64_t e = 0; e < in.nB; ++e) {
+        eb_a[e] = w.slot.find((uint32_t)(in.edgesB[2 * e] >> 32));
+        eb_b[e] = w.slot.find((uint32_t)in.edgesB[2 * e]);
+        if (eb_a[e] != kNone) room[eb_a[e]]++;
+        if (eb_b[e] != kNone) room[eb_b[e]]++;
+    }
+    w.start.resize(n_nodes + 1);
+    w.size.assign(n_nodes, 0);
+    uint64_t total = 0;
+    for (size_t n = 0; n < n_nodes; ++n) { w.start[n] = total; total += room[n]; }
+    w.start[n_nodes] = total;
+    w.pool = ws.get_pool(total);
+    if (total && !w.pool) return -1.f;
+
+    // every phase-B entry of every needed node
     for (uint64_t e = 0; e < in.nB; ++e) {
         const uint64_t w0 = in.edgesB[2 * e], w1 = in.edgesB[2 * e + 1];
         const uint32_t a = (uint32_t)(w0 >> 32), b = (uint32_t)w0;
         const uint32_t type = (uint32_t)(w1 >> 20) & 3u, length = (uint32_t)(w1 & 0xFFFFFu);
-        const uint32_t ia = w.slot.find(a), ib = w.slot.find(b);
-        if (ia != kNone) w.adj[ia].push_back(HEdge{ b, ib, (uint8_t)type, 0, length });
+        const uint32_t ia = eb_a[e], ib = eb_b[e];
+        if (ia != kNone) w.push(ia, HEdge{ b, ib, (uint8_t)type, 0, length });
         if (ib != kNone) {
             const uint32_t la = in.edgesB_len[e] & 0xFFFFu, lb = in.edgesB_len[e] >> 16;
-            w.adj[ib].push_back(HEdge{ a, ia, (uint8_t)rev_type(type), 0, (la - (lb - length)) & 0xFFFFFu });
+            w.push(ib, HEdge{ a, ia, (uint8_t)rev_type(type), 0, (la - (lb - length)) & 0xFFFFFu });
         }
     }
 
@@ -185,25 +262,25 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
     for (uint32_t i = 0; i < nS; ++i) {
         if (w.state[i] != 0) continue;
         queue.clear();
-        size_t start = 0;
+        size_t qs = 0;
         queue.push_back(i);
-        while (start < queue.size()) {
-            const uint32_t n1 = queue[start++];
+        while (qs < queue.size()) {
+            const uint32_t n1 = queue[qs++];
             if (w.state[n1] == 0) w.insert_all(n1);
-            if (w.adj[n1].empty()) continue;                                 // :525
+            if (w.size[n1] == 0) continue;                                   // :525
             if (w.state[n1] == 1) {
-                for (size_t x = 0; x < w.adj[n1].size(); ++x) {
-                    const uint32_t n2 = w.adj[n1][x].node;
+                for (uint32_t x = 0; x < w.size[n1]; ++x) {
+                    const uint32_t n2 = w.list(n1)[x].node;
                     if (w.state[n2] == 0) { queue.push_back(n2); w.insert_all(n2); }
                 }
                 w.mark_transitive(n1);
             }
             if (w.state[n1] == 2) {
-                for (size_t x = 0; x < w.adj[n1].size(); ++x) {
-                    const uint32_t n2 = w.adj[n1][x].node;
+                for (uint32_t x = 0; x < w.size[n1]; ++x) {
+                    const uint32_t n2 = w.list(n1)[x].node;
                     if (w.state[n2] != 1) continue;
-                    for (size_t y = 0; y < w.adj[n2].size(); ++y) {
-                        const uint32_t n3 = w.adj[n2][y].node;
+                    for (uint32_t y = 0; y < w.size[n2]; ++y) {
+                        const uint32_t n3 = w.list(n2)[y].node;
                         if (w.state[n3] == 0) { queue.push_back(n3); w.insert_all(n3); }
                     }
                     w.mark_transitive(n2);
@@ -219,32 +296,28 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
     // independently -- here on all host cores (the quadratic part of the phase: sum over nodes of degree^2).
     {
         std::vector<uint32_t> todo;
-        for (uint32_t i = 0; i < nS; ++i) if (w.state[i] == 2) todo.push_back(i);
-        unsigned T = std::thread::hardware_concurrency();
-        if (T > 32) T = 32;
-        if (T < 1 || todo.size() < 4096) T = 1;
-        const size_t n_nodes = w.adj.size();
-        auto work = [&](unsigned t) {
+        for (uint32_t i = 0; i < nS; ++i) if (w.state[i] == 2 && w.size[i] > 0) todo.push_back(i);
+        on_all_cores(todo.size(), [&](unsigned t, unsigned T) {
             std::vector<uint8_t> scratch(n_nodes, 0);
             for (size_t x = t; x < todo.size(); x += T) w.compute_marks(todo[x], scratch);
-        };
-        if (T == 1) work(0);
-        else {
-            std::vector<std::thread> pool;
-            for (unsigned t = 0; t < T; ++t) pool.emplace_back(work, t);
-            for (auto &th : pool) th.join();
-        }
+        });
         for (uint32_t i : todo) w.remove_marked(i);
     }
 
     // what convertGraph consumes from the lists of S reads (overlapGraph.cpp:93-112)
     out.edges.clear();
+    {
+        size_t kept = 0;
+        for (uint32_t i = 0; i < nS; ++i) kept += w.size[i];
+        out.edges.reserve(kept + 2);      // every kept entry appears from both ends; the larger-id end emits it
+    }
     for (uint32_t i = 0; i < nS; ++i) {
         const uint32_t a = w.node_id[i];
-        for (const HEdge &e : w.adj[i])
-            if (e.id > a) {
-                out.edges.push_back(((uint64_t)a << 32) | e.id);
-                out.edges.push_back(((uint64_t)e.type << 20) | e.length);
+        const HEdge *l = w.list(i);
+        for (uint32_t x = 0; x < w.size[i]; ++x)
+            if (l[x].id > a) {
+                out.edges.push_back(((uint64_t)a << 32) | l[x].id);
+                out.edges.push_back(((uint64_t)l[x].type << 20) | l[x].length);
             }
     }
     out.inserted = w.inserted;
