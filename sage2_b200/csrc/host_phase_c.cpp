@@ -180,7 +180,8 @@ struct Walk {
 template <typename Fn>
 void on_all_cores(size_t work_items, Fn fn)
 {
-    unsigned T = std::thread::hardware_concurrency();
+    static const unsigned forced = [] { const char *e = getenv("SAGE2GPU_HOST_THREADS"); return e ? (unsigned)atoi(e) : 0u; }();
+    unsigned T = forced ? forced : std::thread::hardware_concurrency();
     if (T > 32) T = 32;
     if (T < 1 || work_items < 4096) T = 1;
     if (T == 1) { fn(0u, 1u); return; }
