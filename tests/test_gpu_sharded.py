@@ -137,6 +137,15 @@ def test_cfg2_sharded_full_size():
             np.testing.assert_array_equal(e[f], want[f])
 
 
+def _host_gib():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
+
+
+@pytest.mark.skipif(_host_gib() < 40, reason="cfg4 needs about 25 GiB of host memory for its 33 M synthetic reads")
 def test_cfg4_sharded_equals_single_table():
     """cfg4 at full size (33.3 M reads, 27.9 M unique, 2 % repeats: masked keys, 94,560 reads left for phase C, host walk):
     the sharded build (one shard, peer-memory transport, 54 routed batches) gives the single-table build's edge list."""
