@@ -606,13 +606,11 @@ void stage_route_post(Context &c, int what, u64 first, u64 count, int exact, u64
     DevBuf<unsigned long long> d_cnt(world, st);
     SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, world * sizeof(unsigned long long), st));
     RouteDst D = {}, C = {};
-    const int qw = exact ? 2 : 1;
     for (int g = 0; g < world; ++g) {
         D.dst[g] = (u64 *)(m.peer[g] + mb_off_queries(world)) + (u64)rank * m.cap * 2;      // my segment in owner g's mailbox
         D.qoff[g] = (u64)g * m.cap;
         C.dst[g] = (u64 *)(m.peer[g] + mb_off_counts()) + rank;
     }
-    (void)qw;
     if (n > 0) {
         c.rt_qmap.alloc((u64)world * m.cap, st);
         c.rt_wslot.alloc(n * (u64)c.rt_wstride, st);
