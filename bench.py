@@ -287,17 +287,20 @@ def run_ours(args):
     alt = None
     if world > 1 and not args.no_alt_table:
         layout["sharded"] = not sharded
-        xstats.clear()
-        for _ in range(3):
-            step_device()
-        xstats.clear()
-        a_ms, _, a_launches, a_stage = timed(step_device, args.steps)
-        alt = {"table": "sharded" if layout["sharded"] else "replicated",
-               "exchange": (args.exchange if peers_ok else "nccl") if layout["sharded"] else "nccl",
-               "ms_per_step": a_ms / args.steps,
-               "value": n_reads / (a_ms / args.steps / 1000.0), "unit": UNIT, "sent_bytes_per_rank_and_step": comm["sent"],
-               "gpu_launches": a_launches, "stage_ms": a_stage,
-               "exchange_wall_ms_per_step": {kk: (vv / args.steps) for kk, vv in xstats.items()}}
+        try:
+            xstats.clear()
+            for _ in range(3):
+                step_device()
+            xstats.clear()
+            a_ms, _, a_launches, a_stage = timed(step_device, args.steps)
+            alt = {"table": "sharded" if layout["sharded"] else "replicated",
+                   "exchange": (args.exchange if peers_ok else "nccl") if layout["sharded"] else "nccl",
+                   "ms_per_step": a_ms / args.steps,
+                   "value": n_reads / (a_ms / args.steps / 1000.0), "unit": UNIT, "sent_bytes_per_rank_and_step": comm["sent"],
+                   "gpu_launches": a_launches, "stage_ms": a_stage,
+                   "exchange_wall_ms_per_step": {kk: (vv / args.steps) for kk, vv in xstats.items()}}
+        except Exception as ex:      # the headline above stands; the failure is reported, not hidden
+            alt = {"table": "sharded" if layout["sharded"] else "replicated", "error": repr(ex)[:300]}
         layout["sharded"] = sharded
         comm["sent"] = main_sent
 
