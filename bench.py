@@ -201,7 +201,12 @@ def run_ours(args):
     comm = {"sent": 0, "h2d": 0}
 
     # the mailbox transport needs peer access between all GPUs of the job (NVLink / NVSwitch box); otherwise NCCL
-    peers_ok = all(torch.cuda.can_device_access_peer(local, d) for d in range(world) if d != local) if world > 1 else True
+    peers_ok = True
+    if world > 1:
+        try:
+            peers_ok = torch.cuda.device_count() >= world and all(torch.cuda.can_device_access_peer(local, d) for d in range(world) if d != local)
+        except Exception:
+            peers_ok = False
     if world > 1:
         t_ok = torch.tensor([1 if peers_ok else 0], device="cuda")
         dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
