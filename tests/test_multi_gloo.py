@@ -91,3 +91,34 @@ def test_partitioned_upload_reassembles_the_input(world, tmp_path):
         assert ok_b == 1 and ok_o == 1
         total += int(moved)
     assert total == b.nbytes + off.nbytes
+
+
+def _requests_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got = {}
+
+        def steps():      # the request kinds of multi.run_dist that the sharded steps use besides all-to-all
+            got["boxes"] = yield ("mailboxes", {"handle": bytes([rank]) * 64, "ptr": 1234 + rank})
+            got["barrier"] = yield ("barrier",)
+            got["max"] = yield ("max", 10 * rank)
+            got["counts"] = yield ("counts", [rank * 100 + d for d in range(world)])
+            got["a2a"] = yield ("a2a", torch.arange(world * 2, dtype=torch.int64) + 1000 * rank, [2] * world, [2] * world)
+
+        stats = {}
+        multi.run_dist(steps(), rank, world, "cpu", stats)
+        assert [b["handle"][0] for b in got["boxes"]] == list(range(world)) and all("ptr" not in b for b in got["boxes"])
+        assert got["max"] == 10 * (world - 1)
+        assert got["counts"] == [s * 100 + rank for s in range(world)]
+        assert got["a2a"].tolist() == [1000 * s + 2 * rank + i for s in range(world) for i in range(2)]
+        assert stats["n_a2a"] == 1 and stats["n_barrier"] == 1
+        open(os.path.join(out, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_requests_over_gloo(tmp_path):
+    world = 3
+    mp.spawn(_requests_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
