@@ -217,7 +217,9 @@ __device__ __forceinline__ u64 make_item(int jj, bool first, bool inl, u64 paylo
 // ------------------------------------------------------------------------------------------------
 // K4: phase A
 // ------------------------------------------------------------------------------------------------
-template <int SW, int MINB, bool ROUTED>
+// ORDERED (experimental, off by default): the batch is processed in the order of the id list P.ids instead of id order
+// (a min-hash order that keeps overlapping reads together in time); results do not depend on it.
+template <int SW, int MINB, bool ROUTED, bool ORDERED = false>
 __global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32, MINB)
 phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, uint8_t *__restrict__ flag5,
                u32 *__restrict__ cont_max, unsigned long long *__restrict__ counters)
@@ -240,7 +242,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
 
     const u64 n_batch = ROUTED ? P.n : P.hi - P.lo;
     for (u64 sb = (u64)blockIdx.x * WARPS + warp; sb < n_batch; sb += nwarps) {
-        const u64 i = (ROUTED && P.ids) ? (u64)P.ids[sb] : P.lo + sb;
+        const u64 i = ((ROUTED || ORDERED) && P.ids) ? (u64)P.ids[sb] : P.lo + sb;
         if (lane < SW) { Xf[lane] = P.F[i * SWS + lane]; Xr[lane] = P.RC[i * SWS + lane]; }
         __syncwarp();
         const int len1 = (int)(Xf[SW - 1] & 0xFFFF);
@@ -632,6 +634,63 @@ static void launch_phase_a(Context &c, const SearchParams &P, unsigned long long
 }
 
 template <int SW>
+static void launch_phase_a_ordered(Context &c, const SearchParams &P, unsigned long long *d_counters)
+{
+    constexpr int WARPS = SearchCfg<SW>::WARPS;
+    constexpr int MINB = SW <= 8 ? 4 : 1;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_kernel<SW, MINB, false, true>, WARPS * 32, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    phase_a_kernel<SW, MINB, false, true><<<search_grid(P.hi - P.lo, WARPS, blocks_per_sm), WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p,
+                                                                                                                   c.cont_max.p, d_counters);
+}
+
+// ---- experimental read schedule (SAGE2GPU_READ_ORDER=minhash): min-hash of the window keys per read, ids sorted by it ----
+__global__ void __launch_bounds__(256) minhash_kernel(const u64 *__restrict__ F, int SW, int SWS, int h, u64 lo, u64 n,
+                                                      u64 *__restrict__ key, u32 *__restrict__ id)
+{
+    __shared__ u64 sX[8][kMaxWords];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 *X = sX[warp];
+    const u64 nwarps = (u64)gridDim.x * 8;
+    for (u64 s = (u64)blockIdx.x * 8 + warp; s < n; s += nwarps) {
+        const u64 i = lo + s;
+        __syncwarp();
+        for (int w = lane; w < SW; w += 32) X[w] = F[i * SWS + w];
+        __syncwarp();
+        const int W = rec_len(X, SW) - h + 1;
+        u64 m = ~0ull;
+        for (int j = lane; j < W; j += 32) {
+            u64 v0, v1;
+            extract_key(X, SW, j, h, v0, v1);
+            const u64 hsh = hash_key(v0, v1);
+            m = hsh < m ? hsh : m;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const u64 y = __shfl_xor_sync(0xffffffffu, m, o); m = y < m ? y : m; }
+        if (lane == 0) { key[s] = m; id[s] = (u32)i; }
+    }
+}
+
+// ids of [lo, hi) in min-hash order -> out (device array owned by the caller's arena scope)
+static const u32 *minhash_order(Context &c, u64 lo, u64 hi, DevBuf<u64> &ka, DevBuf<u64> &kb, DevBuf<u32> &va, DevBuf<u32> &vb)
+{
+    cudaStream_t st = c.stream;
+    const u64 n = hi - lo;
+    ka.alloc(n, st); kb.alloc(n, st); va.alloc(n, st); vb.alloc(n, st);
+    u64 g = (n + 7) / 8;
+    if (g > (u64)kSMs * 8) g = (u64)kSMs * 8;
+    minhash_kernel<<<(unsigned)g, 256, 0, st>>>(c.F.p, c.SW, c.SWS, c.h, lo, n, ka.p, va.p);
+    SG_LAUNCHED();
+    SortCols cols;
+    cols.a[0] = ka.p; cols.a[1] = kb.p; cols.b[0] = cols.b[1] = nullptr; cols.v[0] = va.p; cols.v[1] = vb.p;
+    const int cur = radix_sort_bits(cols, 0, n, false, 32, 64, st);      // the top 32 bits cluster well enough
+    return cols.v[cur];
+}
+
+template <int SW>
 static void launch_phase_a_routed(Context &c, const SearchParams &P, unsigned long long *d_counters)
 {
     if constexpr (SW <= 8) launch_phase_a_v<SW, 4, true>(c, P, d_counters);
@@ -712,7 +771,15 @@ void stage_phase_a(Context &c, int rank, int world)
     cudaEvent_t e0, e1;
     SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
     SG_CUDA(cudaEventRecord(e0, st));
-    if (P.hi > P.lo) {
+    static const bool by_minhash = [] { const char *e = getenv("SAGE2GPU_READ_ORDER"); return e && e[0] == 'm'; }();
+    DevBuf<u64> oka, okb;
+    DevBuf<u32> ova, ovb;
+    if (P.hi > P.lo && by_minhash) {        // experimental schedule, see launch_phase_a_ordered
+        P.ids = minhash_order(c, P.lo, P.hi, oka, okb, ova, ovb);
+        SG_CUDA(cudaEventRecord(e0, st));    // the ordering is not part of the search kernel's time (it is part of the stage's)
+        SG_DISPATCH_SW(c.SW, launch_phase_a_ordered<SWC>(c, P, d_counters.p));
+        SG_LAUNCHED();
+    } else if (P.hi > P.lo) {
         SG_DISPATCH_SW(c.SW, launch_phase_a<SWC>(c, P, d_counters.p));
         SG_LAUNCHED();
     }
