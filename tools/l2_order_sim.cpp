@@ -31,7 +31,7 @@ struct Lru {
 
 struct KeyHash { size_t operator()(const std::pair<u64, u64> &k) const { return (size_t)hash_key(k.first, k.second); } };
 
-extern "C" void l2sim(const u64 *F, const u64 *RC, const uint16_t *len, u64 U, int SW, int k, u64 cache_lines, double *out /*[8]*/)
+extern "C" void l2sim(const u64 *F, const u64 *RC, const uint16_t *len, u64 U, int SW, int k, u64 cache_lines, u64 inflight, double *out /*[8]*/)
 {
     const int h = hash_len_for(k);
     std::unordered_map<std::pair<u64, u64>, std::vector<u32>, KeyHash> table;
@@ -59,9 +59,14 @@ extern "C" void l2sim(const u64 *F, const u64 *RC, const uint16_t *len, u64 U, i
         if (mode == 1) std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return minhash[a] < minhash[b]; });
         Lru slot_c(cache_lines);      // one cache for everything, statistics by kind
         u64 slot_hits = 0, slot_req = 0, rec_hits = 0, rec_req = 0;
-        for (u64 x = 0; x < U; ++x) {
+        // `inflight` reads advance together, 32 windows at a time each (the kernel's resident warps), then the next group
+        for (u64 x0 = 0; x0 < U; x0 += inflight)
+        for (int jb = 0; jb < 1024; jb += 32) {
+          bool any = false;
+          for (u64 x = x0; x < U && x < x0 + inflight; ++x) {
             const u64 i = order[x];
-            for (int j = 0; j + h <= (int)len[i]; ++j) {
+            for (int j = jb; j < jb + 32 && j + h <= (int)len[i]; ++j) {
+                any = true;
                 u64 v0, v1;
                 extract_key(F + i * SW, SW, j, h, v0, v1);
                 const u64 hsh = hash_key(v0, v1);
@@ -79,6 +84,8 @@ extern "C" void l2sim(const u64 *F, const u64 *RC, const uint16_t *len, u64 U, i
                     rec_hits += slot_c.hits - b2; ++rec_req;
                 }
             }
+          }
+          if (!any) break;
         }
         out[4 * mode + 0] = (double)slot_req; out[4 * mode + 1] = (double)slot_hits;
         out[4 * mode + 2] = (double)rec_req; out[4 * mode + 3] = (double)rec_hits;

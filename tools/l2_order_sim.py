@@ -22,7 +22,7 @@ def main():
     so = "/tmp/l2_order_sim.so"
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", so, os.path.join(ROOT, "tools", "l2_order_sim.cpp")])
     lib = C.CDLL(so)
-    lib.l2sim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+    lib.l2sim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
     g = synth.random_genome(4_600_000 // scale, 4600)
     reads = synth.paired_reads(g, 150, 100, seed=4601, mu=450, sigma=30)
     b, off = synth.concat(reads)
@@ -36,12 +36,13 @@ def main():
     L.hemu_free(h)
     cache_lines = (126 << 20) // 128 // scale
     out = np.zeros(8, np.float64)
-    lib.l2sim(F.ctypes.data, RC.ctypes.data, ln.ctypes.data, U, SW, 63, cache_lines, out.ctypes.data)
+    inflight = max(1, 148 * 32 // scale)        # resident warps of the search kernel, scaled like the cache
+    lib.l2sim(F.ctypes.data, RC.ctypes.data, ln.ctypes.data, U, SW, 63, cache_lines, inflight, out.ctypes.data)
     for mode, name in enumerate(("id order (today)", "min-hash order")):
         sr, sh, rr, rh = out[4 * mode:4 * mode + 4]
         print(f"{name:18s}: slot lines {sr:.3g} requests, {100 * sh / sr:.1f} % hits; partner records {rr:.3g} requests, {100 * rh / rr:.1f} % hits; "
               f"misses {sr - sh + rr - rh:.3g} lines")
-    print(f"(U = {U}, cache = {cache_lines} lines = 126 MB / {scale})")
+    print(f"(U = {U}, cache = {cache_lines} lines = 126 MB / {scale}, {inflight} reads in flight)")
 
 
 if __name__ == "__main__":
