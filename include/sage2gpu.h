@@ -187,6 +187,18 @@ int sage2gpu_run_steps123(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t
  * (granule 32/64); 2: a 64-byte granule fetched by a lane pair, one 256-bit load each. */
 int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int granule_bytes, uint64_t n_loads, int mode, double *gbps);
 
+/* Parity gate of the measurements (no reference counterpart): order-sensitive 64-bit digests of the resident unique
+ * reads (what ReadLoader::saveReadsInFile would write, readLoader.cpp:270-287: id, frequency, length, forward bases)
+ * and of the canonical edge list (what OverlapGraph::saveOverlapGraphInFile would write, overlapGraph.cpp:338-369:
+ * position, from, to, type, both overhangs).  tests/digest.py computes the same sums from the reference's own files.
+ * Either pointer may be NULL. */
+int sage2gpu_digest(sage2gpu_ctx *ctx, uint64_t *reads_digest, uint64_t *edges_digest);
+
+/* Run-time options.  "read_order": schedule of the phase-A search (results do not depend on it): 0 = id order,
+ * 1 = min-hash order (reads that share k-mers are searched together, so slot sectors and partner records hit L2),
+ * -1 = the default. */
+int sage2gpu_set_option(sage2gpu_ctx *ctx, const char *name, int64_t value);
+
 int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *out);
 /* Number of CUDA kernels this library has launched in this process so far (monotonic). */
 uint64_t sage2gpu_kernel_launches(void);

@@ -51,7 +51,7 @@ EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2g
            "sage2gpu_build_hash_table_shard", "sage2gpu_phase_a_sharded_begin", "sage2gpu_route_begin", "sage2gpu_shard_answer",
            "sage2gpu_route_finish", "sage2gpu_phase_a_routed", "sage2gpu_phase_a_sharded_end", "sage2gpu_phase_b",
            "sage2gpu_map_reads", "sage2gpu_mailbox_create", "sage2gpu_mailbox_open", "sage2gpu_route_post", "sage2gpu_answer_post",
-           "sage2gpu_route_collect", "sage2gpu_mailbox_barrier"]
+           "sage2gpu_route_collect", "sage2gpu_mailbox_barrier", "sage2gpu_digest", "sage2gpu_set_option"]
 
 _lib = None
 
@@ -120,6 +120,8 @@ def load_library():
         lib.sage2gpu_write_reads.argtypes = [vp, C.c_char_p]
         lib.sage2gpu_write_graph3.argtypes = [vp, C.c_char_p]
         lib.sage2gpu_measure_gather.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+        lib.sage2gpu_digest.argtypes = [vp, u64p, u64p]
+        lib.sage2gpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         lib.sage2gpu_stream.argtypes = [vp]
         lib.sage2gpu_stream.restype = vp
         lib.sage2gpu_kernel_launches.argtypes = []
@@ -355,6 +357,15 @@ class Sage2Gpu:
         n = C.c_uint64()
         self._check(self._lib.sage2gpu_get_edges_packed(self._h, out_ptr, int(capacity), C.byref(n)), "get_edges_packed")
         return int(n.value)
+
+    def digest(self, reads: bool = True, edges: bool = True) -> dict:
+        """Order-sensitive digests of the resident reads / edge list (definitions: tests/digest.py)."""
+        r, e = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sage2gpu_digest(self._h, C.byref(r) if reads else None, C.byref(e) if edges else None), "digest")
+        return {"reads": int(r.value) if reads else None, "edges": int(e.value) if edges else None}
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.sage2gpu_set_option(self._h, name.encode(), int(value)), "set_option")
 
     def write_reads(self, path: str):
         self._check(self._lib.sage2gpu_write_reads(self._h, path.encode()), "write_reads")

@@ -592,6 +592,26 @@ int sage2gpu_measure_gather(sage2gpu_ctx *ctx, uint64_t footprint_bytes, int gra
     });
 }
 
+int sage2gpu_digest(sage2gpu_ctx *ctx, uint64_t *reads_digest, uint64_t *edges_digest)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        sg::u64 r = 0, e = 0;
+        sg::stage_digest(c, reads_digest ? &r : nullptr, edges_digest ? &e : nullptr);
+        if (reads_digest) *reads_digest = r;
+        if (edges_digest) *edges_digest = e;
+    });
+}
+
+int sage2gpu_set_option(sage2gpu_ctx *ctx, const char *name, int64_t value)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(name != nullptr, "null option name");
+        const std::string n(name);
+        if (n == "read_order") { SG_CHECK(value >= -1 && value <= 1, "read_order: -1 default, 0 id order, 1 min-hash order"); c.opt_read_order = (int)value; }
+        else throw sg::CudaError("unknown option: " + n);
+    });
+}
+
 uint64_t sage2gpu_kernel_launches(void) { return sg::launch_counter(); }
 
 int sage2gpu_write_reads(sage2gpu_ctx *ctx, const char *path)

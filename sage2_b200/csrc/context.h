@@ -56,6 +56,8 @@ struct Context {
     cudaStream_t stream = nullptr;
     std::string last_error;
     int min_overlap = 0, h = 0, SW = 0, SWS = 0;     // SW = words per record, SWS = storage stride of F / RC
+    // run-time options (sage2gpu_set_option); -1 = take the default / the environment variable
+    int opt_read_order = -1;    // phase A schedule: 0 id order, 1 min-hash order (SAGE2GPU_READ_ORDER)
     Counters cnt;
     Timers tm;
 
@@ -143,6 +145,8 @@ void stage_phase_a_sharded_end(Context &c);
 float stage_map_reads(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident, int64_t *ids, uint8_t *good);
 void stage_phase_b(Context &c);
 void stage_phase_c_and_finalize(Context &c);
+// digest.cu: order-sensitive digests of the unique reads / the edge list (parity gate of the measurements)
+void stage_digest(Context &c, u64 *reads_digest, u64 *edges_digest);
 // device-side text formatters of the reference's -s files (format.cu); false = short write
 bool write_reads_text(Context &c, FILE *f);
 bool write_graph3_text(Context &c, FILE *f);

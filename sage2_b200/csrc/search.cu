@@ -771,7 +771,8 @@ void stage_phase_a(Context &c, int rank, int world)
     cudaEvent_t e0, e1;
     SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
     SG_CUDA(cudaEventRecord(e0, st));
-    static const bool by_minhash = [] { const char *e = getenv("SAGE2GPU_READ_ORDER"); return e && e[0] == 'm'; }();
+    static const bool env_minhash = [] { const char *e = getenv("SAGE2GPU_READ_ORDER"); return e && e[0] == 'm'; }();
+    const bool by_minhash = c.opt_read_order < 0 ? env_minhash : c.opt_read_order == 1;
     DevBuf<u64> oka, okb;
     DevBuf<u32> ova, ovb;
     if (P.hi > P.lo && by_minhash) {        // experimental schedule, see launch_phase_a_ordered

@@ -52,17 +52,20 @@ def paired_reads(genome: np.ndarray, read_len: int, coverage: float, seed: int,
     ins = np.rint(rng.normal(mu, sigma, size=n_pairs)).astype(np.int64)
     ins = np.clip(ins, 2 * read_len, G)
     start = (rng.random(n_pairs) * (G - ins + 1)).astype(np.int64)
-    ar = np.arange(read_len, dtype=np.int64)
-    m1 = genome[start[:, None] + ar[None, :]]
-    # mate 2: reverse complement of the last read_len bases of the fragment
-    m2 = _COMP[genome[(start + ins - 1)[:, None] - ar[None, :]]]
     # whole fragments are sampled from either strand with equal probability
     flip = rng.random(n_pairs) < 0.5
-    a = np.where(flip[:, None], m2, m1)
-    b = np.where(flip[:, None], m1, m2)
+    ar = np.arange(read_len, dtype=np.int64)
     codes = np.empty((2 * n_pairs, read_len), dtype=np.uint8)
-    codes[0::2] = a
-    codes[1::2] = b
+    step = 1 << 20          # pairs per block: bounds the index temporaries (same bytes as one big gather)
+    for p0 in range(0, n_pairs, step):
+        p1 = min(n_pairs, p0 + step)
+        st, en = start[p0:p1], (start[p0:p1] + ins[p0:p1] - 1)
+        m1 = genome[st[:, None] + ar[None, :]]
+        # mate 2: reverse complement of the last read_len bases of the fragment
+        m2 = _COMP[genome[en[:, None] - ar[None, :]]]
+        f = flip[p0:p1, None]
+        codes[2 * p0:2 * p1:2] = np.where(f, m2, m1)
+        codes[2 * p0 + 1:2 * p1:2] = np.where(f, m1, m2)
     if err_rate > 0.0:
         errs = rng.random(codes.shape) < err_rate
         shift = rng.integers(1, 4, size=codes.shape, dtype=np.uint8)

@@ -121,25 +121,93 @@ def test_input_order_does_not_matter():
     np.testing.assert_array_equal(e1, gpu.edges())
 
 
-def test_cfg2_full_size_properties():
-    """BASELINE config #2 at full size: structural invariants that do not need the oracle."""
+BIG = json.load(open(os.path.join(HERE, "golden", "golden_big.json")))
+
+
+def _md5_file(path):
+    h = hashlib.md5()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 22), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def _check_against_big_golden(gpu, name, tmp_path=None):
+    """Counters + digests (+ the bytes of the -s files) against what the UNMODIFIED reference produced for the same
+    full-size input (`SAGE2 -s -M 3`, tests/golden/make_golden_big.py)."""
+    g, c = BIG[name], gpu.counters()
+    assert c["good_reads"] == g["good_reads"] and c["unique_reads"] == g["unique_reads"]
+    assert c["keys_over_threshold"] == g["over_threshold"]
+    assert (c["contained_ext"], c["contained_size"], c["left_to_explore"]) == (g["contained_ext"], g["contained_size"], g["left_to_explore"])
+    assert (c["edges_inserted_c"], c["transitive_removed"]) == (g["edges_inserted"], g["transitive_removed"])
+    assert c["n_edges"] == g["n_edges"]
+    d = gpu.digest()
+    assert d["edges"] == g["edges_digest"] and d["reads"] == g["reads_digest"]
+    if tmp_path is not None:
+        gpu.write_graph3(str(tmp_path / "g.graph3"))
+        assert _md5_file(tmp_path / "g.graph3") == g["graph3_md5"]
+        os.remove(tmp_path / "g.graph3")
+        gpu.write_reads(str(tmp_path / "g.reads"))
+        assert _md5_file(tmp_path / "g.reads") == g["reads_md5"]
+        os.remove(tmp_path / "g.reads")
+
+
+def test_cfg2_full_size_byte_identical_to_reference(tmp_path):
+    """BASELINE config #2 at full size: `.reads` / `.graph3` md5, counters and digests of the unmodified reference."""
     reads, k = _get("cfg2")
     b, off = synth.concat(reads)
     gpu = api.Sage2Gpu(0)
     gpu.run_steps123(b, off, k)
-    c = gpu.counters()
-    assert c["good_reads"] == len(reads)
     r = gpu.reads()
     assert int(r["frequency"].astype(np.int64).sum()) == len(reads)         # dedupe conserves reads
-    e = gpu.edges()
-    assert c["n_edges"] == len(e) > 0
-    assert np.all(e["from"] < e["to"]) and np.all(e["to"] <= c["unique_reads"])
-    key = (e["from"].astype(np.uint64) << np.uint64(34)) | (e["to"].astype(np.uint64) << np.uint64(2)) | e["type"].astype(np.uint64)
-    assert np.all(np.diff(key.astype(np.int64)) > 0)                        # canonical order, (from,to,type) unique
-    # fixed-length reads: the twin overhang equals the overhang, and an error-free random genome is a chain
-    assert np.all(e["delta"] == e["delta_twin"])
-    assert c["contained_ext"] + c["left_to_explore"] + c["contained_size"] == c["unique_reads"]
-    assert c["left_to_explore"] <= 8
+    _check_against_big_golden(gpu, "cfg2", tmp_path)
+    # the same through the min-hash schedule of phase A (results must not depend on the order reads are searched in)
+    for order in (0, 1):
+        gpu.set_option("read_order", order)
+        gpu.run_steps123(b, off, k)
+        _check_against_big_golden(gpu, "cfg2")
+
+
+@pytest.mark.skipif("cfg4" not in BIG, reason="no cfg4 golden committed")
+def test_cfg4_full_size_byte_identical_to_reference(tmp_path):
+    """BASELINE config #4 (100 Mbp + 2 % repeats, 33.3 M reads, -k 75) at full size against the unmodified reference."""
+    reads, k = _get("cfg4")
+    b, off = synth.concat(reads)
+    del reads
+    gpu = api.Sage2Gpu(0)
+    gpu.run_steps123(b, off, k)
+    _check_against_big_golden(gpu, "cfg4", tmp_path if os.environ.get("SAGE2_TEST_CFG4_FILES") else None)
+
+
+def test_digest_equals_numpy_definition():
+    """sage2gpu_digest against tests/digest.py on the arrays the C ABI returns (small sets, ragged lengths)."""
+    import digest
+    for name in ("varlen_err", "mixed", "rep", "empty"):
+        reads, k = _get(name)
+        b, off = synth.concat(reads)
+        gpu = api.Sage2Gpu(0)
+        gpu.run_steps123(b, off, k)
+        d, e, r = gpu.digest(), gpu.edges(), gpu.reads()
+        assert d["edges"] == digest.edges_digest_total(e)
+        U = len(r["length"])
+        rows = []
+        for i in range(U):
+            codes = _decode(r["fwd"][int(r["byte_off"][i]):int(r["byte_off"][i + 1])], int(r["length"][i]))
+            rows.append(bytes(np.frombuffer(b"ACGT", np.uint8)[codes]))
+        want = digest.finish(digest.reads_digest_ragged(np.arange(1, U + 1), r["frequency"], r["length"], rows), U)
+        assert d["reads"] == want
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_minhash_read_order_changes_nothing(name):
+    """SAGE2GPU_READ_ORDER=minhash / set_option("read_order", 1): phase A in min-hash order must give the oracle's graph."""
+    reads, k = _get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    gpu = api.Sage2Gpu(0)
+    gpu.set_option("read_order", 1)
+    gpu.run_steps123(b, off, k)
+    _compare(o, gpu)
 
 
 @pytest.mark.parametrize("name,world", [("rep", 2), ("deep_varlen", 3), ("varlen_err", 4)])
@@ -216,21 +284,19 @@ def _check_edges_are_exact_overlaps(gpu, k, sample=3000, seed=5):
 
 
 @pytest.mark.parametrize("name", ["cfg3-40", "cfg3-60", "cfg3-90"])
-def test_cfg3_k_sweep_full_size(name):
-    """BASELINE config #3 (k = 40 / 60 / 90 on the cfg2 reads) at full size through size-independent properties."""
+def test_cfg3_k_sweep_full_size(name, tmp_path):
+    """BASELINE config #3 (k = 40 / 60 / 90 on the cfg2 reads) at full size: the unmodified reference's counters,
+    digests and `.graph3` bytes, plus oracle-independent properties."""
     reads, k = _get(name)
     b, off = synth.concat(reads)
     gpu = api.Sage2Gpu(0)
     gpu.run_steps123(b, off, k)
     c = gpu.counters()
     assert c["hash_len"] == min(k, 64) and c["good_reads"] == len(reads)
-    assert c["unique_reads"] == 2239082                      # k does not change the read set (all reads are longer than k)
     assert c["window_probes"] == c["unique_reads"] * (150 - min(k, 64) + 1)
-    e = gpu.edges()
-    assert np.all(e["from"] < e["to"])
-    key = (e["from"].astype(np.uint64) << np.uint64(34)) | (e["to"].astype(np.uint64) << np.uint64(2)) | e["type"].astype(np.uint64)
-    assert np.all(np.diff(key.astype(np.int64)) > 0)
-    assert c["contained_ext"] + c["left_to_explore"] + c["contained_size"] == c["unique_reads"]
+    _check_against_big_golden(gpu, name)
+    gpu.write_graph3(str(tmp_path / "g.graph3"))
+    assert _md5_file(tmp_path / "g.graph3") == BIG[name]["graph3_md5"]
     assert _check_edges_are_exact_overlaps(gpu, k) > 0
 
 

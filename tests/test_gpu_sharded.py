@@ -11,7 +11,7 @@ import torch
 import datasets
 from oracle import oracle
 from sage2_b200 import api, multi, synth
-from test_gpu_parity import _compare
+from test_gpu_parity import _compare, BIG
 
 pytestmark = pytest.mark.gpu
 
@@ -112,7 +112,8 @@ def test_sharded_context_refuses_the_local_search():
 
 
 def test_cfg2_sharded_full_size():
-    """cfg2 at full size over 4 shards on one GPU: the edge list equals the single-table build's."""
+    """cfg2 at full size over 4 shards on one GPU: the edge list equals the single-table build's AND the unmodified
+    reference's (digests of its own `.reads` / `.graph3`, tests/golden/golden_big.json)."""
     reads, k = synth.config("cfg2")
     b, off = synth.concat(reads)
     ref = api.Sage2Gpu(0)
@@ -135,6 +136,9 @@ def test_cfg2_sharded_full_size():
         assert len(e) == len(want)
         for f in ("from", "to", "type", "delta", "delta_twin"):
             np.testing.assert_array_equal(e[f], want[f])
+    for g in gpus:
+        d = g.digest()
+        assert d["edges"] == BIG["cfg2"]["edges_digest"] and d["reads"] == BIG["cfg2"]["reads_digest"]
 
 
 def _host_gib():
@@ -163,3 +167,7 @@ def test_cfg4_sharded_equals_single_table():
     got = g.edges()
     for f in ("from", "to", "type", "delta", "delta_twin"):
         np.testing.assert_array_equal(got[f], want[f])
+    if "cfg4" in BIG:      # ... and the unmodified reference's own result
+        d = g.digest()
+        assert d["edges"] == BIG["cfg4"]["edges_digest"] and d["reads"] == BIG["cfg4"]["reads_digest"]
+        assert c["n_edges"] == BIG["cfg4"]["n_edges"]
