@@ -282,6 +282,7 @@ class Job:
         self.torch.cuda.synchronize()
 
     def build_graph(self):
+        """Table + graph on reads this rank has already organised (the sharded layout; one GPU)."""
         gpu, args, multi = self.gpu, self.args, self.multi
         if self.sharded:       # key-hash shard per GPU, window probes routed to their owners
             gpu.build_hash_table_shard(self.rank, self.world)
@@ -292,22 +293,29 @@ class Job:
         gpu.build_hash_table()
         return multi.build_overlap_graph(gpu, self.rank, self.world, self.dev)
 
+    def steps123(self, bases_ptr, off_ptr, on_device):
+        """Steps 1-3 on input every rank can see.  Replicated table over several GPUs: every stage partitioned (key range of
+        the reads, key-hash shard of the table, id slice of the search), results all-gathered (multi.partitioned_graph_steps)."""
+        if self.world > 1 and not self.sharded and not self.args.replicate_stages:
+            return self.multi.build_partitioned(self.gpu, self.rank, self.world, self.dev, bases_ptr, off_ptr, self.n_reads, self.k, on_device,
+                                                stats=self.xstats)
+        self.gpu.load_reads_ptr(bases_ptr, off_ptr, self.n_reads, self.k, device=on_device)
+        return self.build_graph()
+
     def step_device(self):
-        self.gpu.load_reads_ptr(self.d_bases.data_ptr(), self.d_off.data_ptr(), self.n_reads, self.k, device=True)
-        self.comm["sent"] = self.build_graph()
+        self.comm["sent"] = self.steps123(self.d_bases.data_ptr(), self.d_off.data_ptr(), True)
 
     def step_host(self):
         # the call a user of the C ABI makes: host buffers in, edge list back in host memory
         torch, gpu = self.torch, self.gpu
         if self.world == 1:
-            gpu.load_reads_ptr(self.h_bases.data_ptr(), self.h_off.data_ptr(), self.n_reads, self.k, device=False)
+            self.steps123(self.h_bases.data_ptr(), self.h_off.data_ptr(), False)
             self.comm["h2d"] = self.nbytes_in
         else:       # each rank moves 1/N of the input over PCIe, NVLink all-gather completes it
             # (on torch's own stream: pinned tensors must not be tied to the library's stream, which dies first)
             tb, to, self.comm["h2d"] = self.multi.upload_partitioned(self.h_bases, self.h_off, self.rank, self.world, self.dev)
             torch.cuda.current_stream(self.dev).synchronize()
-            gpu.load_reads_ptr(tb.data_ptr(), to.data_ptr(), self.n_reads, self.k, device=True)
-        self.build_graph()
+            self.steps123(tb.data_ptr(), to.data_ptr(), True)
         if self.h_edges is None:
             self.h_edges = torch.empty(2 * max(1, gpu.counters()["n_edges"]), dtype=torch.int64).pin_memory()
         gpu.edges_packed_into(self.h_edges.data_ptr(), self.h_edges.numel() // 2)
@@ -519,6 +527,9 @@ def run_ours(args):
                             f"({'kernel stores into peer-memory mailboxes over NVLink' if args.exchange == 'p2p' else 'NCCL all-to-all'}), "
                             f"phase A partitioned by read id ({comm['sent']} B sent per rank and step)") if sharded else
                            "single GPU" if world == 1 else
+                           (f"{world} GPUs: every stage partitioned (reads organised by key range, table built by key-hash shard, phase A "
+                            f"by read id), reads / table / phase-A arrays all-gathered over NVLink ({comm['sent']} B contributed per rank)")
+                           if not args.replicate_stages else
                            f"{world} GPUs: reads + table replicated, phase A partitioned by read id, "
                            f"one NCCL exchange (all-gather + all-reduce MAX, {comm['sent']} B sent per rank)"),
                        table=args.table, read_order=args.read_order or "default",
@@ -557,6 +568,8 @@ def main():
                     help="N > 1: every GPU holds the whole table, or one key-hash shard of it with routed probes (SURVEY 8(e))")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="--table sharded: routed probes through peer-memory mailboxes (kernel stores over NVLink) or NCCL all-to-all")
+    ap.add_argument("--replicate-stages", action="store_true",
+                    help="N > 1, replicated table: every rank organises all reads and builds the whole table (the round-1 layout)")
     ap.add_argument("--no-alt-table", action="store_true", help="N > 1: do not also time the other table layout")
     ap.add_argument("--batch-reads", type=int, default=1 << 20, help="reads per routed batch (--table sharded)")
     ap.add_argument("--no-gather", action="store_true", help="skip the random-gather ceiling microbenchmark")

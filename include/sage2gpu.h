@@ -41,6 +41,7 @@ typedef struct {
     uint64_t record_words;      /* 64-bit words per packed read record */
     uint64_t probe_restarts;    /* reads redone with verified probes after a tag collision */
     uint64_t phase_c_on_device; /* 1 when phase C ran on the device (order-independent input), 0 for the host walk */
+    uint64_t fast_path_reads;   /* phase-A reads certified by the superstring scan (the rest took the hit-by-hit kernel) */
 } sage2gpu_counters;
 
 /* Stage times in milliseconds (CUDA events on the context's stream; host part by steady_clock). */
@@ -121,6 +122,35 @@ int sage2gpu_phase_a_buffers(sage2gpu_ctx *ctx, void **right_ext, void **left_ex
                              uint64_t *reads_per_rank, uint64_t *unique_reads);
 int sage2gpu_finish_graph(sage2gpu_ctx *ctx);
 
+/* ---- Several GPUs, every stage partitioned ----------------------------------------------------------
+ * The packed reads end up replicated on every GPU, as north_star asks, but no GPU does another GPU's work:
+ *
+ *   load_reads_partition(rank, world)   organizeReads (readLoader.cpp:215-260) for the reads whose leading bases fall into
+ *                                       this rank's key range: every rank sees the whole input, derives the same splitters
+ *                                       from a histogram of the leading 6 bases and sorts + dedupes only its range;
+ *                                       *unique_local = its number of unique reads.  Equal reads share a range, so the
+ *                                       ranks' runs concatenate to the global sorted order (read ids stay the reference's).
+ *   [all-gather of the counts]          reads_gather_layout(counts): device arrays of the total size with this rank's run
+ *                                       in its place (records: uint64 x record_stride_words per read; lengths,
+ *                                       frequencies: uint16); [first, first + counts[rank]) is this rank's id range
+ *   [all-gather of the three arrays, variable block sizes]   reads_gather_finish(): reverse complements, done.
+ *   build_hash_table_shard(rank, world) hashPrefixesAndSuffix (hashTable.cpp:70-128) for the keys this rank owns;
+ *   table_shard_info, [all-gather of the entry counts], table_gather_layout(entry_counts): room for all shards back to
+ *                                       back (slots: slots_per_shard uint64 per shard; entries: uint32), own shard in place
+ *   [all-gather of both arrays]         table_gather_finish(): the complete table on every GPU; probes stay local
+ *   phase_a_partition(rank, world) + exchange of phase_a_buffers + finish_graph as before.
+ * The exchanges are the host's (NCCL through sage2_b200/multi.py, or peer copies inside one process). */
+int sage2gpu_load_reads_partition(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int min_overlap,
+                                  int on_device, int rank, int world, uint64_t *unique_local);
+int sage2gpu_reads_gather_layout(sage2gpu_ctx *ctx, const uint64_t *counts, void **records, void **lengths, void **frequencies,
+                                 uint64_t *first, uint64_t *total, uint64_t *record_stride_words);
+int sage2gpu_reads_gather_finish(sage2gpu_ctx *ctx);
+int sage2gpu_table_shard_info(sage2gpu_ctx *ctx, uint64_t *slots, uint64_t *entries, uint64_t *distinct_keys, uint64_t *keys_over_threshold);
+int sage2gpu_table_gather_layout(sage2gpu_ctx *ctx, const uint64_t *entry_counts, void **slots, void **entries, uint64_t *slots_per_shard,
+                                 uint64_t *entries_first);
+int sage2gpu_table_gather_finish(sage2gpu_ctx *ctx, const uint64_t *entry_counts, const uint64_t *distinct_keys,
+                                 const uint64_t *keys_over_threshold);
+
 /* ---- The table sharded by key hash (north_star) ---------------------------------------------------
  * The reads stay on every GPU; shard `rank` of `world` indexes only the keys whose hash it owns, so the table of a
  * data set is spread over the GPUs of the box.  A window probe of HashTable::hashTableSearch (hashTable.cpp:193-231)
@@ -196,7 +226,7 @@ int sage2gpu_digest(sage2gpu_ctx *ctx, uint64_t *reads_digest, uint64_t *edges_d
 
 /* Run-time options.  "read_order": schedule of the phase-A search (results do not depend on it): 0 = id order,
  * 1 = min-hash order (reads that share k-mers are searched together, so slot sectors and partner records hit L2),
- * -1 = the default. */
+ * -1 = the default.  "fast_scan": 1 = phase A tries the superstring scan first (default), 0 = hit-by-hit kernel only. */
 int sage2gpu_set_option(sage2gpu_ctx *ctx, const char *name, int64_t value);
 
 int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *out);

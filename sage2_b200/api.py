@@ -28,7 +28,8 @@ class Counters(C.Structure):
         "hash_len", "distinct_keys", "keys_over_threshold", "table_capacity",
         "contained_ext", "contained_size", "left_to_explore",
         "edges_phase_b", "candidates_c", "edges_inserted_c", "transitive_removed",
-        "n_edges", "compare_calls", "window_probes", "slow_path_reads", "record_words", "probe_restarts", "phase_c_on_device")]
+        "n_edges", "compare_calls", "window_probes", "slow_path_reads", "record_words", "probe_restarts", "phase_c_on_device",
+        "fast_path_reads")]
 
 
 class Timers(C.Structure):
@@ -51,7 +52,9 @@ EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2g
            "sage2gpu_build_hash_table_shard", "sage2gpu_phase_a_sharded_begin", "sage2gpu_route_begin", "sage2gpu_shard_answer",
            "sage2gpu_route_finish", "sage2gpu_phase_a_routed", "sage2gpu_phase_a_sharded_end", "sage2gpu_phase_b",
            "sage2gpu_map_reads", "sage2gpu_mailbox_create", "sage2gpu_mailbox_open", "sage2gpu_route_post", "sage2gpu_answer_post",
-           "sage2gpu_route_collect", "sage2gpu_mailbox_barrier", "sage2gpu_digest", "sage2gpu_set_option"]
+           "sage2gpu_route_collect", "sage2gpu_mailbox_barrier", "sage2gpu_digest", "sage2gpu_set_option",
+           "sage2gpu_load_reads_partition", "sage2gpu_reads_gather_layout", "sage2gpu_reads_gather_finish",
+           "sage2gpu_table_shard_info", "sage2gpu_table_gather_layout", "sage2gpu_table_gather_finish"]
 
 _lib = None
 
@@ -120,6 +123,12 @@ def load_library():
         lib.sage2gpu_write_reads.argtypes = [vp, C.c_char_p]
         lib.sage2gpu_write_graph3.argtypes = [vp, C.c_char_p]
         lib.sage2gpu_measure_gather.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+        lib.sage2gpu_load_reads_partition.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, u64p]
+        lib.sage2gpu_reads_gather_layout.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p, u64p, u64p]
+        lib.sage2gpu_reads_gather_finish.argtypes = [vp]
+        lib.sage2gpu_table_shard_info.argtypes = [vp, u64p, u64p, u64p, u64p]
+        lib.sage2gpu_table_gather_layout.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), u64p, u64p]
+        lib.sage2gpu_table_gather_finish.argtypes = [vp, u64p, u64p, u64p]
         lib.sage2gpu_digest.argtypes = [vp, u64p, u64p]
         lib.sage2gpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         lib.sage2gpu_stream.argtypes = [vp]
@@ -208,6 +217,42 @@ class Sage2Gpu:
 
     def finish_graph(self):
         self._check(self._lib.sage2gpu_finish_graph(self._h), "finish_graph")
+
+    # ---- several GPUs, every stage partitioned (include/sage2gpu.h) --------------------------------------------
+    def load_reads_partition(self, bases_ptr: int, offsets_ptr: int, n_reads: int, min_overlap: int, device: bool, rank: int, world: int) -> int:
+        """organizeReads for this rank's key range; returns its number of unique reads."""
+        u = C.c_uint64()
+        self._check(self._lib.sage2gpu_load_reads_partition(self._h, bases_ptr, offsets_ptr, int(n_reads), int(min_overlap), int(bool(device)),
+                                                            int(rank), int(world), C.byref(u)), "load_reads_partition")
+        return int(u.value)
+
+    def reads_gather_layout(self, counts) -> dict:
+        cs = (C.c_uint64 * len(counts))(*[int(x) for x in counts])
+        p = [C.c_void_p() for _ in range(3)]
+        first, total, stride = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sage2gpu_reads_gather_layout(self._h, cs, *(C.byref(x) for x in p), C.byref(first), C.byref(total), C.byref(stride)),
+                    "reads_gather_layout")
+        return {"records": p[0].value or 0, "lengths": p[1].value or 0, "frequencies": p[2].value or 0, "first": int(first.value),
+                "total": int(total.value), "stride": int(stride.value), "counts": [int(x) for x in counts]}
+
+    def reads_gather_finish(self):
+        self._check(self._lib.sage2gpu_reads_gather_finish(self._h), "reads_gather_finish")
+
+    def table_shard_info(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self._lib.sage2gpu_table_shard_info(self._h, *(C.byref(x) for x in v)), "table_shard_info")
+        return {"slots": int(v[0].value), "entries": int(v[1].value), "distinct": int(v[2].value), "over": int(v[3].value)}
+
+    def table_gather_layout(self, entry_counts) -> dict:
+        cs = (C.c_uint64 * len(entry_counts))(*[int(x) for x in entry_counts])
+        ps, pe = C.c_void_p(), C.c_void_p()
+        sps, ef = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sage2gpu_table_gather_layout(self._h, cs, C.byref(ps), C.byref(pe), C.byref(sps), C.byref(ef)), "table_gather_layout")
+        return {"slots": ps.value or 0, "entries": pe.value or 0, "slots_per_shard": int(sps.value), "entries_first": int(ef.value)}
+
+    def table_gather_finish(self, entry_counts, distinct, over):
+        mk = lambda a: (C.c_uint64 * len(a))(*[int(x) for x in a])
+        self._check(self._lib.sage2gpu_table_gather_finish(self._h, mk(entry_counts), mk(distinct), mk(over)), "table_gather_finish")
 
     # ---- sharded table (include/sage2gpu.h, "The table sharded by key hash") ----------------------------------
     def build_hash_table_shard(self, rank: int, world: int):

@@ -51,7 +51,7 @@ int guarded(sage2gpu_ctx *ctx, Fn fn)
     }
 }
 
-void load_common(sg::Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n, int k, bool dev)
+void load_common(sg::Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n, int k, bool dev, int rank = 0, int world = 1)
 {
     SG_CHECK(k >= 1 && k < 65535, "min_overlap out of range");
     SG_CHECK(n == 0 || (bases != nullptr && offsets != nullptr), "null input");
@@ -64,7 +64,7 @@ void load_common(sg::Context &c, const uint8_t *bases, const int64_t *offsets, i
     }
     {
         StageTimer t(c.stream);
-        sg::stage_organize_reads(c);
+        sg::stage_organize_reads(c, rank, world);
         c.tm.sort_reads = t.stop();
     }
 }
@@ -165,6 +165,73 @@ int sage2gpu_load_reads(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *
 int sage2gpu_load_reads_device(sage2gpu_ctx *ctx, const uint8_t *d_bases, const int64_t *d_offsets, int64_t n_reads, int min_overlap)
 {
     return guarded(ctx, [&](sg::Context &c) { load_common(c, d_bases, d_offsets, n_reads, min_overlap, true); });
+}
+
+// ---- several GPUs: the reads organised by key range, one range per rank (reads.cu) -----------------------------------
+int sage2gpu_load_reads_partition(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int min_overlap,
+                                  int on_device, int rank, int world, uint64_t *unique_local)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        load_common(c, bases, offsets, n_reads, min_overlap, on_device != 0, rank, world);
+        if (unique_local) *unique_local = world > 1 ? c.rp_local : c.cnt.unique_reads;
+    });
+}
+
+int sage2gpu_reads_gather_layout(sage2gpu_ctx *ctx, const uint64_t *counts, void **records, void **lengths, void **frequencies,
+                                 uint64_t *first, uint64_t *total, uint64_t *record_stride_words)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::u64 f = 0, tot = 0;
+        sg::stage_reads_gather_layout(c, (const sg::u64 *)counts, records, lengths, frequencies, &f, &tot);
+        if (first) *first = f;
+        if (total) *total = tot;
+        if (record_stride_words) *record_stride_words = (uint64_t)c.SWS;
+        c.tm.sort_reads += t.stop();
+    });
+}
+
+int sage2gpu_reads_gather_finish(sage2gpu_ctx *ctx)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_reads_gather_finish(c);
+        c.tm.sort_reads += t.stop();
+    });
+}
+
+// ---- several GPUs, replicated table: one key-hash shard built per rank, the shards all-gathered (table.cu) --------------
+int sage2gpu_table_shard_info(sage2gpu_ctx *ctx, uint64_t *slots, uint64_t *entries, uint64_t *distinct_keys, uint64_t *keys_over_threshold)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.have_table, "no table built");
+        if (slots) *slots = c.cap;
+        if (entries) *entries = c.tb_entries;
+        if (distinct_keys) *distinct_keys = c.cnt.distinct_keys;
+        if (keys_over_threshold) *keys_over_threshold = c.cnt.keys_over_threshold;
+    });
+}
+
+int sage2gpu_table_gather_layout(sage2gpu_ctx *ctx, const uint64_t *entry_counts, void **slots, void **entries, uint64_t *slots_per_shard,
+                                 uint64_t *entries_first)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::u64 sps = 0, ef = 0;
+        sg::stage_table_gather_layout(c, (const sg::u64 *)entry_counts, slots, entries, &sps, &ef);
+        if (slots_per_shard) *slots_per_shard = sps;
+        if (entries_first) *entries_first = ef;
+        c.tm.build_table += t.stop();
+    });
+}
+
+int sage2gpu_table_gather_finish(sage2gpu_ctx *ctx, const uint64_t *entry_counts, const uint64_t *distinct_keys, const uint64_t *keys_over_threshold)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_table_gather_finish(c, (const sg::u64 *)entry_counts, (const sg::u64 *)distinct_keys, (const sg::u64 *)keys_over_threshold);
+        c.tm.build_table += t.stop();
+    });
 }
 
 // ---- streamed upload: the FASTA/Q parser fills one pinned chunk while the previous one is copied ----
@@ -480,6 +547,7 @@ int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *o)
     o->record_words = (uint64_t)ctx->c.SW;
     o->probe_restarts = n.probe_restarts;
     o->phase_c_on_device = n.phase_c_on_device;
+    o->fast_path_reads = n.fast_path_reads;
     return SAGE2GPU_OK;
 }
 
@@ -608,6 +676,7 @@ int sage2gpu_set_option(sage2gpu_ctx *ctx, const char *name, int64_t value)
         SG_CHECK(name != nullptr, "null option name");
         const std::string n(name);
         if (n == "read_order") { SG_CHECK(value >= -1 && value <= 1, "read_order: -1 default, 0 id order, 1 min-hash order"); c.opt_read_order = (int)value; }
+        else if (n == "fast_scan") { SG_CHECK(value >= -1 && value <= 1, "fast_scan: -1 default, 0 off, 1 on"); c.opt_fast_scan = (int)value; }
         else throw sg::CudaError("unknown option: " + n);
     });
 }

@@ -21,6 +21,7 @@ struct Counters {
     u64 window_probes = 0;   // U*W
     u64 slow_path_reads = 0; // reads that left the parallel fast mode for the exact sequential chain
     u64 probe_restarts = 0;  // reads redone with verified probes after a 24-bit tag collision
+    u64 fast_path_reads = 0;     // reads of phase A certified by the superstring scan (search_fast.cu)
     u64 phase_c_on_device = 0;   // 1: phase C was marked and filtered on the device (symmetric candidate set), 0: host walk
 };
 
@@ -57,6 +58,7 @@ struct Context {
     std::string last_error;
     int min_overlap = 0, h = 0, SW = 0, SWS = 0;     // SW = words per record, SWS = storage stride of F / RC
     // run-time options (sage2gpu_set_option); -1 = take the default / the environment variable
+    int opt_fast_scan = -1;     // phase A: 1 superstring scan first, 0 general kernel only (SAGE2GPU_PA_FAST)
     int opt_read_order = -1;    // phase A schedule: 0 id order, 1 min-hash order (SAGE2GPU_READ_ORDER)
     Counters cnt;
     Timers tm;
@@ -78,11 +80,17 @@ struct Context {
     DevBuf<u64> F, RC;          // [U*SWS] records (SW words used, stride SWS = storage_words(SW))
     DevBuf<uint16_t> len, freq; // [U]
 
+    // reads organised by key range over several GPUs (stage_organize_reads with world > 1)
+    int rp_rank = 0, rp_world = 1;
+    u64 rp_local = 0, rp_first = 0, rp_total = 0;
+
     // prefix/suffix table
     DevBuf<u64> slots;          // [cap]
     DevBuf<u32> entries;        // [4U]
     u64 cap = 0;
     int tb_rank = 0, tb_world = 1;   // which key-hash shard the table holds (0 / 1: all keys)
+    int tb_shards = 1;               // > 1: the complete table assembled from that many shards (stage_table_gather_*)
+    u64 tb_entries = 0;              // entries[] elements in use
 
     // phase A output
     DevBuf<u64> extR, extL;     // [U] ext_pack
@@ -122,8 +130,12 @@ void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets
 // parse.cu: record splitting of raw FASTA/FASTQ text on the device; false = irregular layout, nothing appended
 bool stage_parse_text_chunk(Context &c, const uint8_t *text, u64 n_bytes, bool final, int &marker, u64 max_records, u64 &consumed, u64 &n_records);
 void stage_remove_uploaded(Context &c, u64 first, u64 count);
-void stage_organize_reads(Context &c);
+void stage_organize_reads(Context &c, int rank = 0, int world = 1);   // world > 1: this rank's key range of the reads only
+void stage_reads_gather_layout(Context &c, const u64 *counts, void **F, void **len, void **freq, u64 *first, u64 *total);
+void stage_reads_gather_finish(Context &c);
 void stage_build_table(Context &c, int rank = 0, int world = 1);   // key-hash shard `rank` of `world`
+void stage_table_gather_layout(Context &c, const u64 *entry_counts, void **slots, void **entries, u64 *slots_per_shard, u64 *entries_first);
+void stage_table_gather_finish(Context &c, const u64 *entry_counts, const u64 *distinct, const u64 *over);
 void stage_phase_a(Context &c, int rank = 0, int world = 1);   // rank's slice of the reads; arrays padded to world * chunk
 // sharded table (shard.cu, search.cu)
 void stage_phase_a_sharded_begin(Context &c, int rank, int world);

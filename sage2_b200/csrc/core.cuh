@@ -265,6 +265,9 @@ SG_HD u64 partition_chunk(u64 U, int world) { return world <= 1 ? U : (U + (u64)
 // from hash bits 24..33: disjoint from the slot tag (bits 0..23) and from the bits home_sector() consumes.
 constexpr int kMaxWorld = 64;
 SG_HD int key_owner(u64 hsh, int world) { return world <= 1 ? 0 : (int)(((hsh >> 24) & 0x3FFull) % (u64)world); }
+// A complete table assembled from `shards` key-hash shards laid out back to back (nsec sectors each): a probe starts in
+// the shard that owns its key and wraps inside it.  shards == 1: the plain table.
+SG_HD u64 shard_base_sector(u64 hsh, u64 nsec, int shards) { return shards <= 1 ? 0ull : (u64)key_owner(hsh, shards) * nsec; }
 // Answer of an owner to one routed window probe = a slot word without its tag: count << 33 | payload, payload =
 // the only entry (count 1), a representative entry (count >= 100, tag probes only) or the offset of the bucket's
 // run in the entry stream the owner returns alongside.  0 = absent.

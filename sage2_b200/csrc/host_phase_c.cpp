@@ -11,6 +11,7 @@
 // with id > a after the walk, i.e. exactly what convertGraph would consume (overlapGraph.cpp:103).
 #include "host_phase_c.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
 #include <chrono>
@@ -257,6 +258,7 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
         }
     }
 
+    const auto t_setup = std::chrono::steady_clock::now();
     // buildOverlapGraphEconomy, economyGraph.cpp:513-564
     std::vector<uint32_t> queue;
     queue.reserve(nS);
@@ -290,6 +292,7 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
         }
     }
 
+    const auto t_walk = std::chrono::steady_clock::now();
     // Marking and removal, after the walk.  When the reference marks a node, every neighbour already has all its
     // edges (insertAllEdgesOfRead ran for it and nothing is appended to an explored node's list), the node's own list
     // was sorted at the end of its insertAllEdgesOfRead, and a node's marked edges are removed only after all its
@@ -305,6 +308,7 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
         for (uint32_t i : todo) w.remove_marked(i);
     }
 
+    const auto t_mark = std::chrono::steady_clock::now();
     // what convertGraph consumes from the lists of S reads (overlapGraph.cpp:93-112)
     out.edges.clear();
     {
@@ -323,7 +327,14 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
     }
     out.inserted = w.inserted;
     out.removed = w.removed;
-    return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const auto t_end = std::chrono::steady_clock::now();
+    if (getenv("SAGE2GPU_PHASE_C_TIMING")) {
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
+        fprintf(stderr, "[phase C host] nS %llu nC %llu nB %llu nodes %zu pool %llu | setup %.2f walk %.2f mark %.2f emit %.2f ms\n",
+                (unsigned long long)in.nS, (unsigned long long)nC, (unsigned long long)in.nB, n_nodes, (unsigned long long)total,
+                ms(t0, t_setup), ms(t_setup, t_walk), ms(t_walk, t_mark), ms(t_mark, t_end));
+    }
+    return std::chrono::duration<float, std::milli>(t_end - t0).count();
 }
 
 }  // namespace sg

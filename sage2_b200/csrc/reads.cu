@@ -511,16 +511,57 @@ static void refine_long_runs(Context &c, const u64 *rec, const u64 *key, u32 *pe
     SG_LAUNCHED();
 }
 
-void stage_organize_reads(Context &c)
+// ---- several GPUs: rank r organises the reads whose leading bases fall into its key range ------------------------
+// Every rank holds all packed records (the input is replicated or all-gathered), so the splitters -- quantiles of a
+// 4096-bin histogram of the leading 6 bases -- come out identical everywhere without an exchange; equal records share
+// a bin, so the dedupe stays local and the ranks' unique runs concatenate to the global sorted order.
+constexpr int kSplitBits = 12;
+__global__ void __launch_bounds__(256) split_hist_kernel(const u64 *__restrict__ key, u64 n, u32 *__restrict__ hist)
+{
+    __shared__ u32 sh[1 << kSplitBits];
+    for (int b = threadIdx.x; b < (1 << kSplitBits); b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) atomicAdd(&sh[key[i] >> (64 - kSplitBits)], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < (1 << kSplitBits); b += blockDim.x) if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+__global__ void __launch_bounds__(256) split_flag_kernel(const u64 *__restrict__ key, u64 n, u32 lo_bin, u32 hi_bin, u32 *__restrict__ flag)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(key[i] >> (64 - kSplitBits));
+        flag[i] = (b >= lo_bin && b < hi_bin) ? 1u : 0u;
+    }
+}
+__global__ void __launch_bounds__(256) split_compact_kernel(const u64 *__restrict__ key, const u32 *__restrict__ val, const u32 *__restrict__ flag,
+                                                            const u32 *__restrict__ idx, u64 n, u64 *__restrict__ okey, u32 *__restrict__ oval)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if (flag[i]) { okey[idx[i]] = key[i]; oval[idx[i]] = val[i]; }
+}
+__global__ void __launch_bounds__(256) revcomp_range_kernel(const u64 *__restrict__ F, u64 *__restrict__ RC, const uint16_t *__restrict__ len,
+                                                            u64 lo, u64 hi, int SW, int SWS)
+{
+    for (u64 u = lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; u < hi; u += (u64)gridDim.x * blockDim.x) {
+        u64 f[kMaxWords], r[kMaxWords];
+        for (int w = 0; w < SW; ++w) f[w] = F[u * SWS + w];
+        revcomp_record(f, r, SW, (int)len[u]);
+        for (int w = 0; w < SWS; ++w) RC[u * SWS + w] = w < SW ? r[w] : 0ull;
+    }
+}
+
+void stage_organize_reads(Context &c, int rank, int world)
 {
     cudaStream_t st = c.stream;
     ArenaScope arena_scope(c.arena, st);
-    const u64 n = c.n_input, n_good = c.cnt.good_reads;
+    SG_CHECK(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad rank / world");
+    const u64 n = c.n_input;
+    u64 n_good = c.cnt.good_reads;
     const int SW = c.SW;
     c.cnt.unique_reads = 0;
+    c.rp_rank = rank; c.rp_world = world; c.rp_local = 0;
     if (n == 0 || n_good == 0) {
         c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
-        c.have_reads = true;
+        c.have_reads = world == 1;
         return;
     }
     DevBuf<u64> &rec = c.raw;      // packed canonical records in input order (bad reads all-ones)
@@ -536,8 +577,42 @@ void stage_organize_reads(Context &c)
     }
     SortCols cols;
     cols.a[0] = ka.p; cols.a[1] = kb.p; cols.b[0] = cols.b[1] = nullptr; cols.v[0] = va.p; cols.v[1] = vb.p;
-    const int kSortSkipBits = sort_skip_bits(n_good);
-    int cur = radix_sort_bits(cols, 0, n_good, false, kSortSkipBits, 64, st);      // 4 .. 6 passes on the leading bases
+    const int kSortSkipBits = sort_skip_bits(n_good);       // from the global count: the same passes on every rank
+    int cur = 0;
+    if (world > 1) {        // keep this rank's key range only
+        const int nbins = 1 << kSplitBits;
+        DevBuf<u32> hist(nbins, st);
+        SG_CUDA(cudaMemsetAsync(hist.p, 0, nbins * sizeof(u32), st));
+        split_hist_kernel<<<kSMs * 4, 256, 0, st>>>(ka.p, n_good, hist.p);
+        SG_LAUNCHED();
+        std::vector<u32> h(nbins);
+        SG_CUDA(cudaMemcpyAsync(h.data(), hist.p, nbins * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        // bin boundaries: rank r takes bins [bound[r], bound[r+1]); bound[r] = first bin whose prefix reaches r * n_good / world
+        std::vector<u32> bound(world + 1, (u32)nbins);
+        bound[0] = 0;
+        u64 pre = 0;
+        int r = 1;
+        for (int b = 0; b < nbins && r < world; ++b) {
+            while (r < world && pre >= (n_good * (u64)r + (u64)world - 1) / (u64)world) bound[r++] = (u32)b;
+            pre += h[b];
+        }
+        u64 n_part = 0;
+        for (u32 b = bound[rank]; b < bound[rank + 1]; ++b) n_part += h[b];
+        DevBuf<u32> sflag(n_good, st), sidx(n_good, st);
+        split_flag_kernel<<<big_grid(n_good), 256, 0, st>>>(ka.p, n_good, bound[rank], bound[rank + 1], sflag.p);
+        SG_LAUNCHED();
+        exclusive_scan_u32(sflag.p, sidx.p, n_good, nullptr, st);
+        split_compact_kernel<<<big_grid(n_good), 256, 0, st>>>(ka.p, va.p, sflag.p, sidx.p, n_good, kb.p, vb.p);
+        SG_LAUNCHED();
+        cur = 1;
+        n_good = n_part;
+        if (n_good == 0) {
+            c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
+            return;
+        }
+    }
+    cur = radix_sort_bits(cols, cur, n_good, false, kSortSkipBits, 64, st);      // 4 .. 6 passes on the leading bases
     DevBuf<u32> d_flags(2, st);          // [0] tie-run overflow, [1] unique count
     SG_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(u32), st));
     {
@@ -571,6 +646,52 @@ void stage_organize_reads(Context &c)
     SG_LAUNCHED();
     freq_kernel<<<big_grid(U), 256, 0, st>>>(start.p, U, n_good, c.freq.p);
     SG_LAUNCHED();
+    c.rp_local = U;
+    c.have_reads = world == 1;      // several GPUs: complete only after the ranks' runs were gathered (stage_reads_gather_*)
+}
+
+// The ranks' unique runs -> the global arrays.  counts[q] = unique reads of rank q (the host all-gathered them): this rank's
+// run moves to its place in arrays of the total size, whose device pointers go back to the host for the all-gather.
+void stage_reads_gather_layout(Context &c, const u64 *counts, void **F, void **len, void **freq, u64 *first, u64 *total)
+{
+    cudaStream_t st = c.stream;
+    SG_CHECK(c.rp_world > 1 && counts != nullptr, "sage2gpu_load_reads_partition must run first");
+    SG_CHECK(counts[c.rp_rank] == c.rp_local, "this rank's count does not match its organised reads");
+    u64 tot = 0, base = 0;
+    for (int q = 0; q < c.rp_world; ++q) { if (q < c.rp_rank) base += counts[q]; tot += counts[q]; }
+    SG_CHECK(tot < 0x3FFFFFFFull, "at most 2^30-1 unique reads");
+    c.SWS = storage_words(c.SW);
+    DevBuf<u64> Fg;
+    DevBuf<uint16_t> lg, fg;
+    Fg.persistent = lg.persistent = fg.persistent = true;
+    Fg.alloc((size_t)tot * c.SWS, st); lg.alloc(tot, st); fg.alloc(tot, st);
+    if (c.rp_local) {
+        SG_CUDA(cudaMemcpyAsync(Fg.p + base * c.SWS, c.F.p, (size_t)c.rp_local * c.SWS * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(lg.p + base, c.len.p, (size_t)c.rp_local * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(fg.p + base, c.freq.p, (size_t)c.rp_local * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+    }
+    c.F = std::move(Fg); c.len = std::move(lg); c.freq = std::move(fg);
+    c.RC.alloc((size_t)tot * c.SWS, st);
+    SG_CUDA(cudaStreamSynchronize(st));
+    c.rp_first = base; c.rp_total = tot;
+    if (F) *F = c.F.p;
+    if (len) *len = c.len.p;
+    if (freq) *freq = c.freq.p;
+    if (first) *first = base;
+    if (total) *total = tot;
+}
+
+// after the all-gather: reverse complements of all reads (utils.cpp:73-91 on packed words), the reads are complete
+void stage_reads_gather_finish(Context &c)
+{
+    cudaStream_t st = c.stream;
+    SG_CHECK(c.rp_world > 1, "sage2gpu_load_reads_partition must run first");
+    const u64 U = c.rp_total;
+    if (U) {
+        revcomp_range_kernel<<<big_grid(U, 128), 128, 0, st>>>(c.F.p, c.RC.p, c.len.p, 0, U, c.SW, c.SWS);
+        SG_LAUNCHED();
+    }
+    c.cnt.unique_reads = U;
     c.have_reads = true;
 }
 

@@ -21,89 +21,18 @@
 //              state to core.cuh's ExtState and the rest of the read runs the reference's sequential
 //              chain hit by hit (EXACT mode) -- still with parallel fetch and verification.
 #include <stdlib.h>
-#include "context.h"
+#include "search_common.cuh"
 
 namespace sg {
 
-struct SearchParams {
-    const u64 *F, *RC;
-    const u64 *slots;
-    const u32 *entries;
-    u64 nsec, U;
-    u64 lo, hi;         // phase A handles read indices [lo, hi)
-    int h, k;
-    // ROUTED kernels (sharded table, shard.cu): the probes of a batch of reads were answered by the shards that
-    // own their keys.  The batch is ids[0..n) (0-based read indices) or lo + [0..n); the answer word of window j
-    // of the s-th read is wslot[s * wstride + j] (core.cuh answer_encode) and `entries` is the batch's own entry
-    // stream.  Untrusted answers (tag probes) are proven in the kernel; a collision sets redo[s] and skips the read.
-    const u64 *wslot;
-    const u32 *ids;
-    uint8_t *redo;
-    u64 n;
-    u32 wstride;
-    int trusted;
-};
-
-// 256-bit read-only load: one 32-byte sector per lane and instruction (LDG.E.256 on sm_100a)
-__device__ __forceinline__ void ldg256(const u64 *p, u64 (&v)[4])
-{
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
-}
-// the same with an L2 eviction priority: the slot index is re-read by every read (keep: evict_last), a partner record
-// is needed once per overlap and should not push the index out (evict_first)
-__device__ __forceinline__ void ldg256_keep(const u64 *p, u64 (&v)[4])
-{
-    asm volatile("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
-}
-__device__ __forceinline__ void ldg256_stream(const u64 *p, u64 (&v)[4])
-{
-    asm volatile("ld.global.nc.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
-}
+// search_fast.cu
+bool launch_phase_a_fast(Context &c, const SearchParams &P, unsigned long long *d_counters, u32 *redo_ids, unsigned *redo_count);
 
 // FAST-mode scan state of one read (warp-uniform): first right hit, last left hit, last hit of each side
 struct FastState {
     u32 Rid = 0, Rtype = 0, Rlen = 0, Lid = 0, Ltype = 0, Llen = 0, connections = 0;
     int cJR = 0, cLenR = 0, firstJR = 0, cJL = 0, cLenL = 0;
 };
-
-template <int SW>
-struct SearchCfg {
-    static constexpr int WARPS = SW <= 8 ? 8 : (SW <= 16 ? 4 : 2);
-    static constexpr int SWS = SW <= 4 ? 4 : (SW <= 8 ? 8 : (SW <= 16 ? 16 : 32));   // == storage_words(SW): F / RC stride
-    static constexpr int LPI = SWS / 4;          // lanes that fetch one partner record together (one sector each)
-    static constexpr int SWP = SWS + 1;          // odd record stride in shared memory (bank spread) + the word read past
-};
-
-template <int SW>
-__device__ __forceinline__ u64 t_window32(const u64 *X, int s)
-{
-    const int i = s >> 5, sh = (s & 31) * 2;
-    const u64 a = i < SW ? X[i] : 0ull;
-    const u64 b = (i + 1) < SW ? X[i + 1] : 0ull;
-    return sh == 0 ? a : ((a << sh) | (b >> (64 - sh)));
-}
-
-template <int SW>
-__device__ __forceinline__ void t_extract_key(const u64 *X, int j, int h, u64 &v0, u64 &v1)
-{
-    if (h <= 32) { v0 = 0; v1 = t_window32<SW>(X, j) >> (64 - 2 * h); }
-    else { v0 = t_window32<SW>(X, j) >> (64 - 2 * (h - 32)); v1 = t_window32<SW>(X, j + h - 32); }
-}
-
-// masks of the first h bases (the hash key) inside the first two words of a compare
-__device__ __forceinline__ void key_masks(int h, u64 &km0, u64 &km1)
-{
-    km0 = h >= 32 ? ~0ull : ~(~0ull >> (2 * h));
-    km1 = h <= 32 ? 0ull : (h >= 64 ? ~0ull : ~(~0ull >> (2 * (h - 32))));
-}
-
-// 64 bits starting `s` bits (0..63) into the 128-bit string a:b, by two 32-bit funnel shifts
-__device__ __forceinline__ u64 funnel64(u64 a, u64 b, bool upper, unsigned s5)
-{
-    const u32 ah = (u32)(a >> 32), al = (u32)a, bh = (u32)(b >> 32), bl = (u32)b;
-    const u32 x0 = upper ? al : ah, x1 = upper ? bh : al, x2 = upper ? bl : bh;
-    return ((u64)__funnelshift_l(x1, x0, s5) << 32) | __funnelshift_l(x2, x1, s5);
-}
 
 // X[start+t] == Y[t] for t in [0, ov), ov = min(lenY, lenX-start): X is indexed dynamically (a shared
 // memory record with one readable word after it), Y statically (registers or a pointer).  Whole words
@@ -163,43 +92,6 @@ __device__ __forceinline__ bool overlap_equal_from(const u64 *X, int lenX, int s
     return acc == 0;
 }
 
-// hashTableSearch (hashTable.cpp:193-231) on the sector index.  cnt == 0: absent (or masked).
-// `exact`: confirm every tag match by re-extracting the key from the bucket's first read (:203-220);
-// otherwise only masked keys are confirmed here and the caller proves the key in stage 2.
-template <int SW>
-__device__ __forceinline__ void probe_window(const SearchParams &P, u64 v0, u64 v1, bool exact, u64 &payload, u32 &cnt)
-{
-    payload = 0; cnt = 0;
-    const u64 hsh = hash_key(v0, v1);
-    const u64 tag = slot_tag(hsh);
-    u64 sec = home_sector(hsh, P.nsec);
-    for (;;) {
-        u64 s[4];
-        ldg256_keep(P.slots + kSlotsPerSector * sec, s);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const u64 slot = s[t];
-            if (slot == 0) return;
-            if (slot_get_tag(slot) != tag) continue;
-            const u32 c = slot_get_count(slot);
-            if (exact || c >= (u32)kHashThreshold) {
-                const u32 ent = (c == 1 || c >= (u32)kHashThreshold) ? (u32)slot_get_payload(slot) : __ldg(&P.entries[slot_get_payload(slot)]);
-                const u64 rid = ent >> 2;
-                const int type = (int)(ent & 3);
-                const u64 *X = ((type & 2) ? P.RC : P.F) + rid * SearchCfg<SW>::SWS;
-                const int l = (int)(__ldg(&X[SW - 1]) & 0xFFFF);
-                u64 w0, w1;
-                t_extract_key<SW>(X, (type & 1) ? l - P.h : 0, P.h, w0, w1);
-                if (w0 != v0 || w1 != v1) continue;            // tag collision: keep probing
-                if (c >= (u32)kHashThreshold) return;         // masked key reads as absent (:203)
-            }
-            payload = slot_get_payload(slot); cnt = c;
-            return;
-        }
-        sec = (sec + 1 == P.nsec) ? 0 : sec + 1;
-    }
-}
-
 template <int SW>
 __device__ __forceinline__ void load_record(const u64 *src, u64 (&q)[SW])
 {
@@ -240,7 +132,7 @@ phase_a_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, u
     unsigned calls = 0, probes = 0, n_exact = 0, n_restart = 0;      // per warp: far below 2^32
     if (lane == 0) { Xf[SW] = 0; Xr[SW] = 0; prevR[SW] = 0; prevL[SW] = 0; }
 
-    const u64 n_batch = ROUTED ? P.n : P.hi - P.lo;
+    const u64 n_batch = ROUTED ? P.n : ((ORDERED && P.n_dev) ? (u64)*P.n_dev : P.hi - P.lo);
     for (u64 sb = (u64)blockIdx.x * WARPS + warp; sb < n_batch; sb += nwarps) {
         const u64 i = ((ROUTED || ORDERED) && P.ids) ? (u64)P.ids[sb] : P.lo + sb;
         if (lane < SW) { Xf[lane] = P.F[i * SWS + lane]; Xr[lane] = P.RC[i * SWS + lane]; }
@@ -729,8 +621,9 @@ static SearchParams make_params(const Context &c)
 {
     SearchParams P;
     P.F = c.F.p; P.RC = c.RC.p; P.slots = c.slots.p; P.entries = c.entries.p;
-    P.nsec = c.cap / kSlotsPerSector; P.U = c.cnt.unique_reads; P.lo = 0; P.hi = P.U; P.h = c.h; P.k = c.min_overlap;
-    P.wslot = nullptr; P.ids = nullptr; P.redo = nullptr; P.n = 0; P.wstride = 0; P.trusted = 0;
+    P.shards = c.tb_shards > 1 ? c.tb_shards : 1;
+    P.nsec = c.cap / kSlotsPerSector / (u64)P.shards; P.U = c.cnt.unique_reads; P.lo = 0; P.hi = P.U; P.h = c.h; P.k = c.min_overlap;
+    P.wslot = nullptr; P.ids = nullptr; P.redo = nullptr; P.n = 0; P.wstride = 0; P.trusted = 0; P.n_dev = nullptr;
     return P;
 }
 
@@ -772,12 +665,26 @@ void stage_phase_a(Context &c, int rank, int world)
     SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
     SG_CUDA(cudaEventRecord(e0, st));
     static const bool env_minhash = [] { const char *e = getenv("SAGE2GPU_READ_ORDER"); return e && e[0] == 'm'; }();
+    static const bool env_fast = [] { const char *e = getenv("SAGE2GPU_PA_FAST"); return !(e && e[0] == '0'); }();
     const bool by_minhash = c.opt_read_order < 0 ? env_minhash : c.opt_read_order == 1;
+    const bool fast = (c.opt_fast_scan < 0 ? env_fast : c.opt_fast_scan == 1) && c.SW <= 8;
     DevBuf<u64> oka, okb;
-    DevBuf<u32> ova, ovb;
-    if (P.hi > P.lo && by_minhash) {        // experimental schedule, see launch_phase_a_ordered
+    DevBuf<u32> ova, ovb, redo_ids;
+    DevBuf<unsigned> redo_n;
+    if (P.hi > P.lo && by_minhash) {        // schedule that keeps overlapping reads together in time
         P.ids = minhash_order(c, P.lo, P.hi, oka, okb, ova, ovb);
         SG_CUDA(cudaEventRecord(e0, st));    // the ordering is not part of the search kernel's time (it is part of the stage's)
+    }
+    if (P.hi > P.lo && fast) {
+        // the superstring scan first (search_fast.cu); the general kernel then takes the reads it could not certify
+        redo_ids.alloc(P.hi - P.lo, st); redo_n.alloc(1, st);
+        SG_CUDA(cudaMemsetAsync(redo_n.p, 0, sizeof(unsigned), st));
+        launch_phase_a_fast(c, P, d_counters.p, redo_ids.p, redo_n.p);
+        SearchParams P2 = P;
+        P2.ids = redo_ids.p; P2.n_dev = redo_n.p;
+        SG_DISPATCH_SW(c.SW, launch_phase_a_ordered<SWC>(c, P2, d_counters.p));
+        SG_LAUNCHED();
+    } else if (P.hi > P.lo && by_minhash) {
         SG_DISPATCH_SW(c.SW, launch_phase_a_ordered<SWC>(c, P, d_counters.p));
         SG_LAUNCHED();
     } else if (P.hi > P.lo) {
@@ -792,6 +699,13 @@ void stage_phase_a(Context &c, int rank, int world)
     c.cnt.window_probes = h[1];
     c.cnt.slow_path_reads = h[2];
     c.cnt.probe_restarts = h[3];
+    c.cnt.fast_path_reads = 0;
+    if (redo_n.p) {
+        unsigned nr = 0;
+        SG_CUDA(cudaMemcpyAsync(&nr, redo_n.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        c.cnt.fast_path_reads = (P.hi - P.lo) - nr;
+    }
     cudaEventElapsedTime(&c.tm.phase_a_kernel, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     c.have_phase_a = true;

@@ -143,7 +143,7 @@ void stage_build_table(Context &c, int rank, int world)
     ArenaScope arena_scope(c.arena, st);
     SG_CHECK(c.have_reads, "organize_reads must run before build_hash_table");
     SG_CHECK(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad rank / world");
-    c.tb_rank = rank; c.tb_world = world;
+    c.tb_rank = rank; c.tb_world = world; c.tb_shards = 1; c.tb_entries = 0;
     const u64 U = c.cnt.unique_reads;
     const int SW = c.SW, h = c.h;
     c.cnt.distinct_keys = 0; c.cnt.keys_over_threshold = 0; c.cap = 0; c.cnt.table_capacity = 0;
@@ -183,6 +183,7 @@ void stage_build_table(Context &c, int rank, int world)
     SG_CHECK(h_overflow == 0, "slot index of this table shard is full (key split too uneven)");
 
     c.entries.alloc(M, st);
+    c.tb_entries = M;
     if (M) {
         table_offsets_kernel<<<big_grid(cap), 256, 0, st>>>(c.slots.p, cap, run.p, off.p);
         SG_LAUNCHED();
@@ -199,6 +200,65 @@ void stage_build_table(Context &c, int rank, int world)
     c.cnt.distinct_keys = h_cnt[0];
     c.cnt.keys_over_threshold = h_cnt[1];
     c.have_table = true;
+}
+
+// ---- several GPUs, replicated table: every rank builds one key-hash shard, the shards are all-gathered ---------------
+// layout: room for all shards back to back (equal slot counts; entry runs of shard q behind those of shards < q), this
+// rank's shard moved to its place; the host all-gathers both arrays; finish: the run offsets stored in the slots of
+// shard q become offsets into the joint entries[] array.
+__global__ void __launch_bounds__(256) table_rebase_kernel(u64 *__restrict__ slots, u64 cap_shard, u64 ebase)
+{
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < cap_shard; s += (u64)gridDim.x * blockDim.x) {
+        const u64 v = slots[s];
+        if (v == 0) continue;
+        const u32 c = slot_get_count(v);
+        if (c >= 2 && c < (u32)kHashThreshold) slots[s] = (v & ~0x1FFFFFFFFull) | (slot_get_payload(v) + ebase);
+    }
+}
+
+void stage_table_gather_layout(Context &c, const u64 *entry_counts, void **slots, void **entries, u64 *slots_per_shard, u64 *entries_first)
+{
+    cudaStream_t st = c.stream;
+    SG_CHECK(c.have_table && c.tb_world > 1 && c.tb_shards == 1, "sage2gpu_build_hash_table_shard must run first");
+    SG_CHECK(entry_counts && entry_counts[c.tb_rank] == c.tb_entries, "this rank's entry count does not match its shard");
+    const int world = c.tb_world;
+    const u64 cap_shard = c.cap;
+    u64 tot = 0, base = 0;
+    for (int q = 0; q < world; ++q) { if (q < c.tb_rank) base += entry_counts[q]; tot += entry_counts[q]; }
+    SG_CHECK(tot < 0xFFFFFFFFull && cap_shard * (u64)world < (1ull << 40), "table too large");
+    DevBuf<u64> sg;
+    DevBuf<u32> eg;
+    sg.persistent = eg.persistent = true;
+    sg.alloc((size_t)cap_shard * world, st); eg.alloc(tot, st);
+    SG_CUDA(cudaMemcpyAsync(sg.p + (size_t)c.tb_rank * cap_shard, c.slots.p, (size_t)cap_shard * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    if (c.tb_entries) SG_CUDA(cudaMemcpyAsync(eg.p + base, c.entries.p, (size_t)c.tb_entries * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    c.slots = std::move(sg); c.entries = std::move(eg);
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (slots) *slots = c.slots.p;
+    if (entries) *entries = c.entries.p;
+    if (slots_per_shard) *slots_per_shard = cap_shard;
+    if (entries_first) *entries_first = base;
+}
+
+void stage_table_gather_finish(Context &c, const u64 *entry_counts, const u64 *distinct, const u64 *over)
+{
+    cudaStream_t st = c.stream;
+    SG_CHECK(c.have_table && c.tb_world > 1 && c.tb_shards == 1 && entry_counts, "sage2gpu_table_gather_layout must run first");
+    const int world = c.tb_world;
+    const u64 cap_shard = c.cap;
+    u64 ebase = 0, d = 0, o = 0;
+    for (int q = 0; q < world; ++q) {
+        if (ebase) { table_rebase_kernel<<<big_grid(cap_shard), 256, 0, st>>>(c.slots.p + (size_t)q * cap_shard, cap_shard, ebase); SG_LAUNCHED(); }
+        ebase += entry_counts[q];
+        if (distinct) d += distinct[q];
+        if (over) o += over[q];
+    }
+    c.tb_entries = ebase;
+    c.tb_shards = world; c.tb_world = 1; c.tb_rank = 0;
+    c.cap = cap_shard * (u64)world;
+    c.cnt.table_capacity = c.cap;
+    if (distinct) c.cnt.distinct_keys = d;
+    if (over) c.cnt.keys_over_threshold = o;
 }
 
 }  // namespace sg

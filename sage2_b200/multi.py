@@ -71,6 +71,20 @@ def build_overlap_graph(gpu, rank: int, world: int, device=None) -> int:
     return sent
 
 
+def build_partitioned(gpu, rank: int, world: int, device, bases_ptr: int, offsets_ptr: int, n_reads: int, k: int, on_device: bool,
+                      stats: dict | None = None) -> int:
+    """One process per GPU (torchrun): steps 1-3 with every stage partitioned; returns the bytes this rank contributed."""
+    if world == 1:
+        gpu.load_reads_ptr(bases_ptr, offsets_ptr, n_reads, k, on_device)
+        gpu.build_hash_table()
+        gpu.build_overlap_graph()
+        return 0
+    sent = [0]
+    steps = partitioned_graph_steps(gpu, rank, world, device_view_fn(device), bases_ptr, offsets_ptr, n_reads, k, on_device, sent)
+    run_dist(steps, rank, world, device, stats)
+    return sent[0]
+
+
 def upload_partitioned(h_bases: torch.Tensor, h_offsets: torch.Tensor, rank: int, world: int, device) -> tuple:
     """Host -> device of the raw reads with every rank moving only its 1/world share over PCIe; the shares are
     then all-gathered over NVLink.  h_* are (pinned) host tensors holding the WHOLE input on every rank.
@@ -120,7 +134,7 @@ def host_view(ptr: int, n: int, typestr: str) -> torch.Tensor:
 def device_view_fn(device):
     def view(ptr: int, n: int, typestr: str) -> torch.Tensor:
         if n == 0 or not ptr:
-            return torch.zeros(0, dtype={"<i8": torch.int64, "<i4": torch.int32, "|u1": torch.uint8}[typestr], device=device)
+            return torch.zeros(0, dtype={"<i8": torch.int64, "<i4": torch.int32, "<i2": torch.int16, "|u1": torch.uint8}[typestr], device=device)
         return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
     return view
 
@@ -207,6 +221,68 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
     gpu.finish_graph()
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Every stage partitioned, results replicated by all-gathers (include/sage2gpu.h "Several GPUs, every stage partitioned"):
+# rank r sorts + dedupes the reads of its key range, builds the table shard of the keys it owns and searches its slice of
+# the read ids; the unique reads, the table shards and the phase-A arrays are all-gathered over NVLink.  Two more requests:
+#     ("gather_counts", values)            -> the lists of all ranks, by rank
+#     ("gather_var", full, counts)         -> in place: rank q's block of `full` (counts[q] elements, blocks back to back)
+#                                             is filled from rank q; this rank's block is already in place
+# ---------------------------------------------------------------------------------------------------------------
+
+def partitioned_graph_steps(gpu, rank: int, world: int, view, bases_ptr: int, offsets_ptr: int, n_reads: int, k: int, on_device: bool,
+                            sent: list | None = None):
+    """Generator: steps 1-3 over `world` ranks; every rank holds the whole input (replicated, or all-gathered before)."""
+    sent = sent if sent is not None else [0]
+    u_local = gpu.load_reads_partition(bases_ptr, offsets_ptr, n_reads, k, on_device, rank, world)
+    counts = [c[0] for c in (yield ("gather_counts", [u_local]))]
+    lay = gpu.reads_gather_layout(counts)
+    tot, stride = lay["total"], lay["stride"]
+    yield ("gather_var", view(lay["records"], tot * stride, "<i8"), [c * stride for c in counts])
+    yield ("gather_var", view(lay["lengths"], tot, "<i2"), counts)
+    yield ("gather_var", view(lay["frequencies"], tot, "<i2"), counts)
+    sent[0] += counts[rank] * (8 * stride + 4)
+    gpu.reads_gather_finish()
+    gpu.build_hash_table_shard(rank, world)
+    info = gpu.table_shard_info()
+    infos = yield ("gather_counts", [info["entries"], info["distinct"], info["over"]])
+    ec = [x[0] for x in infos]
+    tl = gpu.table_gather_layout(ec)
+    yield ("gather_var", view(tl["slots"], tl["slots_per_shard"] * world, "<i8"), [tl["slots_per_shard"]] * world)
+    yield ("gather_var", view(tl["entries"], sum(ec), "<i4"), ec)
+    sent[0] += 8 * tl["slots_per_shard"] + 4 * ec[rank]
+    gpu.table_gather_finish(ec, [x[1] for x in infos], [x[2] for x in infos])
+    gpu.phase_a_partition(rank, world)
+    yield ("phase_a", gpu.phase_a_buffers())
+    gpu.finish_graph()
+
+
+def _gather_var_dist(full: torch.Tensor, counts, rank: int, world: int):
+    """All-gather of blocks of different sizes: equal blocks in place, otherwise through a padded copy."""
+    if len(set(counts)) == 1 and full.is_cuda:
+        c = counts[0]
+        if c:
+            dist.all_gather_into_tensor(full, full[rank * c:(rank + 1) * c])
+        return
+    m = max(counts)
+    if m == 0:
+        return
+    offs = [sum(counts[:q]) for q in range(world)]
+    mine = torch.zeros(m, dtype=full.dtype, device=full.device)
+    mine[:counts[rank]] = full[offs[rank]:offs[rank] + counts[rank]]
+    if full.is_cuda:
+        tmp = torch.empty(m * world, dtype=full.dtype, device=full.device)
+        dist.all_gather_into_tensor(tmp, mine)
+        parts = [tmp[q * m:q * m + counts[q]] for q in range(world)]
+    else:      # gloo
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        parts = [parts[q][:counts[q]] for q in range(world)]
+    for q in range(world):
+        if q != rank and counts[q]:
+            full[offs[q]:offs[q] + counts[q]] = parts[q]
+
+
 def run_dist(gen, rank: int, world: int, device, stats: dict | None = None) -> int:
     """Serve one rank's requests with torch.distributed (NCCL for CUDA tensors, gloo on the CPU).  Returns bytes sent.
     stats (optional): wall milliseconds spent in the exchanges, by request kind, are added to it."""
@@ -236,6 +312,22 @@ def run_dist(gen, rank: int, world: int, device, stats: dict | None = None) -> i
                 t = torch.tensor([req[1]], dtype=torch.int64, device=device)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 val = int(t.item())
+            elif kind == "gather_counts":
+                t = torch.tensor(req[1], dtype=torch.int64, device=device)
+                out = torch.empty(world * t.numel(), dtype=torch.int64, device=device)
+                if cuda:
+                    dist.all_gather_into_tensor(out, t)
+                else:
+                    parts = [torch.empty_like(t) for _ in range(world)]
+                    dist.all_gather(parts, t)
+                    out = torch.cat(parts)
+                val = out.view(world, -1).tolist()
+            elif kind == "gather_var":
+                _gather_var_dist(req[1], req[2], rank, world)
+                if cuda:
+                    torch.cuda.current_stream(device).synchronize()       # the library reads it on its own stream
+                sent += req[2][rank] * req[1].element_size()
+                val = None
             elif kind == "barrier":           # every rank's library call before it has returned (= its stream is drained)
                 t = torch.zeros(1, dtype=torch.int32, device=device)
                 dist.all_reduce(t)
@@ -290,6 +382,19 @@ def run_local(gens: list, views_of=None) -> None:
                 torch.cuda.synchronize()
         elif kind == "max":
             vals = [max(r[1] for r in reqs)] * world
+        elif kind == "gather_counts":
+            vals = [[list(r[1]) for r in reqs]] * world
+        elif kind == "gather_var":
+            counts = reqs[0][2]
+            offs = [sum(counts[:q]) for q in range(world)]
+            for q in range(world):
+                blk = reqs[q][1][offs[q]:offs[q] + counts[q]].clone()
+                for r in range(world):
+                    if r != q and counts[q]:
+                        reqs[r][1][offs[q]:offs[q] + counts[q]] = blk
+            if reqs[0][1].is_cuda:
+                torch.cuda.synchronize()
+            vals = [None] * world
         elif kind in ("barrier", "device_barrier"):      # one process drives the ranks in turn: nothing to wait for
             vals = [0] * world
         elif kind == "mailboxes":             # one process: plain pointers

@@ -75,10 +75,10 @@ class EmuRun:
                          "over_limit": mk(p[2], C.c_uint8, np.uint8), "contained_by": mk(p[3], C.c_uint32, np.int32)}
                 exchange(views, n // world)
             L.hemu_finish(h)
-        sz = np.zeros(13, dtype=np.uint64)
+        sz = np.zeros(14, dtype=np.uint64)
         L.hemu_sizes(h, sz.ctypes.data)
         (self.U, self.SW, self.N, self.total_bp, self.n_edges, self.over, self.distinct, self.compare_calls,
-         self.inserted, self.removed, self.contained, self.contained_size, self.slow_reads) = (int(x) for x in sz)
+         self.inserted, self.removed, self.contained, self.contained_size, self.slow_reads, self.fast_reads) = (int(x) for x in sz)
         U, SW, E = self.U, self.SW, self.n_edges
         self.F = np.zeros(U * SW, np.uint64); self.RC = np.zeros(U * SW, np.uint64)
         self.len = np.zeros(U, np.uint16); self.freq = np.zeros(U, np.uint16)
@@ -110,7 +110,7 @@ class EmuShard:
             self.h = None
 
     def _sizes(self):
-        sz = np.zeros(13, dtype=np.uint64)
+        sz = np.zeros(14, dtype=np.uint64)
         self.L.hemu_sizes(self.h, sz.ctypes.data)
         return [int(x) for x in sz]
 

@@ -28,7 +28,7 @@ struct Emu {
     std::map<std::pair<u64, u64>, std::vector<u32>> table;
     std::vector<uint8_t> flag5;
     std::vector<u32> cont_max;
-    u64 over = 0, distinct = 0, compare_calls = 0, inserted = 0, removed = 0, contained = 0, contained_size = 0, slow_reads = 0;
+    u64 over = 0, distinct = 0, compare_calls = 0, inserted = 0, removed = 0, contained = 0, contained_size = 0, slow_reads = 0, fast_reads = 0;
     // ---- the sharded table (emulation of csrc/shard.cu: same buffers, same wire format) ----
     int max_len = 1, tb_rank = 0, tb_world = 1;
     std::map<u64, std::pair<u64, u64>> by_hash;      // owned keys by their 64-bit hash (what a tag probe can see)
@@ -133,6 +133,93 @@ void alloc_phase_a(Emu &e, int rank, int world)
     e.compare_calls = 0; e.slow_reads = 0; e.restarts = 0;
 }
 
+// ---- the superstring fast path of phase_a_fast_kernel (search_fast.cu) ------------------------------------------------
+// Per side a "superstring" S = read i (right side) or its reverse complement (left side) followed by the bases the hits
+// seen so far agree on beyond its end.  Every gated item is compared ONCE against S: a mismatch inside read i's span
+// means "not a hit", a mismatch beyond it means two hits disagree (anomaly).  Per round of 32 items the hit that reaches
+// furthest extends S and the other hits of the round are checked on the part S did not cover before.  No anomaly and
+// at most one hit per side and window: the reference's chain (economyGraph.cpp:94-437) reduces to "first right hit,
+// last left hit, not ambiguous".  Anything else is left to the general scan (returns false, no side effects kept).
+struct FastOut { u32 Rid, Rtype, Rlen, Lid, Ltype, Llen, connections; u64 calls; std::vector<std::pair<u32, u32>> cont; };
+
+static int base_at(const u64 *rec, int p) { return (int)((rec[p >> 5] >> (62 - 2 * (p & 31))) & 3); }
+
+template <typename ItemT>
+bool fast_certify(const Emu &e, u64 i, const std::vector<ItemT> &items, FastOut &o, size_t cap_items, int max_windows)
+{
+    const int SW = e.SW, k = e.k, h = e.h;
+    const u64 *Xf = &e.F[i * SW], *Xr = &e.RC[i * SW];
+    const int len1 = e.len[i];
+    if (len1 - h + 1 > max_windows || items.size() > cap_items) return false;
+    std::vector<uint8_t> S[2];          // [0] right side: read i; [1] left side: its reverse complement
+    for (int p = 0; p < len1; ++p) { S[0].push_back((uint8_t)base_at(Xf, p)); S[1].push_back((uint8_t)base_at(Xr, p)); }
+    int lastJ[2] = { -1, -1 };
+    bool hasR = false, hasL = false;
+    int bestRj = 0, bestLj = 0;
+    o = FastOut();
+    o.Rid = o.Rtype = o.Rlen = o.Lid = o.Ltype = o.Llen = o.connections = 0; o.calls = 0;
+    struct H { int jj, side, s, len2, type; u32 rid2; const u64 *Q; };
+    std::vector<H> hits;
+    // the kernel's order: the gated right items from the last window down, then the gated left items from the first up
+    std::vector<ItemT> order;
+    for (size_t x = items.size(); x-- > 0;) {
+        const u32 rid2 = items[x].ent >> 2;
+        const int type = (int)(items[x].ent & 3);
+        if (!(type & 1) && rid2 != (u32)i && gate_right(items[x].jj, len1, k)) order.push_back(items[x]);
+    }
+    for (size_t x = 0; x < items.size(); ++x) {
+        const u32 rid2 = items[x].ent >> 2;
+        const int type = (int)(items[x].ent & 3);
+        if ((type & 1) && rid2 != (u32)i && gate_left(items[x].jj, k, h)) order.push_back(items[x]);
+    }
+    for (size_t r0 = 0; r0 < order.size(); r0 += 32) {
+        hits.clear();
+        for (size_t x = r0; x < std::min(order.size(), r0 + 32); ++x) {
+            const int j = order[x].jj;
+            const u32 rid2 = order[x].ent >> 2;
+            const int type = (int)(order[x].ent & 3);
+            const bool right = !(type & 1);
+            const u64 *Q = (partner_uses_rc(type) ? &e.RC[0] : &e.F[0]) + (u64)rid2 * SW;
+            const int len2 = e.len[rid2], side = right ? 0 : 1, s = right ? j : len1 - j - h, xlen = len1 - s;
+            o.calls++;
+            const int ov = std::min(len2, (int)S[side].size() - s);
+            int first_bad = -1;
+            for (int t = 0; t < ov; ++t) if (base_at(Q, t) != S[side][s + t]) { first_bad = t; break; }
+            const bool contained = len2 <= xlen;
+            if (first_bad >= 0 && first_bad < std::min(xlen, len2)) continue;           // differs inside read i: not a hit
+            if (contained) { o.cont.push_back(std::make_pair(rid2, (u32)(i + 1))); continue; }
+            if (first_bad >= 0) return false;                                             // disagrees with an earlier hit
+            hits.push_back(H{ j, side, s, len2, type, rid2, Q });
+        }
+        for (int side = 0; side < 2; ++side) {
+            int best = -1, nside = 0;
+            for (size_t x = 0; x < hits.size(); ++x) {
+                if (hits[x].side != side) continue;
+                nside++;
+                if (hits[x].jj == lastJ[side]) return false;                              // two hits of one side in one window
+                for (size_t y = 0; y < x; ++y) if (hits[y].side == side && hits[y].jj == hits[x].jj) return false;
+                if (best < 0 || hits[x].s + hits[x].len2 > hits[best].s + hits[best].len2) best = (int)x;
+            }
+            if (!nside) continue;
+            const int old = (int)S[side].size();
+            const H &m = hits[best];
+            for (int pos = old; pos < m.s + m.len2; ++pos) S[side].push_back((uint8_t)base_at(m.Q, pos - m.s));
+            for (const H &q : hits) {
+                if (q.side != side) continue;
+                for (int t = std::max(0, old - q.s); t < q.len2; ++t) if (base_at(q.Q, t) != S[side][q.s + t]) return false;
+                lastJ[side] = q.jj;
+            }
+        }
+        for (const H &q : hits) {
+            if (q.side == 0) { if (!hasR || q.jj < bestRj) { o.Rid = q.rid2 + 1; o.Rtype = (u32)(q.type >> 1); o.Rlen = (u32)(q.len2 - (len1 - q.jj)); hasR = true; bestRj = q.jj; } }
+            else if (!hasL || q.jj > bestLj) { o.Lid = q.rid2 + 1; o.Ltype = (u32)(q.type >> 1); o.Llen = (u32)(q.len2 - q.jj - h); hasL = true; bestLj = q.jj; }
+        }
+        o.connections += (u32)hits.size();
+    }
+    (void)hasL;
+    return true;
+}
+
 // Phase A of the reads ids[0..n) (or first + [0..n)); redo[s] is set, and the read skipped, when a lookup fails its proof
 void scan_reads(Emu &e, const u32 *ids, u64 first, u64 n, const Lookup &lookup, uint8_t *redo)
 {
@@ -145,6 +232,7 @@ void scan_reads(Emu &e, const u32 *ids, u64 first, u64 n, const Lookup &lookup, 
     auto &cont_max = e.cont_max;
     std::vector<u64> prevR(SW), prevL(SW);
     const bool exact_only = getenv("SAGE2_EMUL_EXACT_ONLY") != nullptr;
+    const bool fast_first = !exact_only && getenv("SAGE2_EMUL_NO_FAST") == nullptr;
     struct Item { int jj; u32 ent; };
     struct Hit { int jj; bool right; u32 rid2; int type; int len2; const u64 *Q; };
     std::vector<Item> items;
@@ -164,6 +252,18 @@ void scan_reads(Emu &e, const u32 *ids, u64 first, u64 n, const Lookup &lookup, 
             for (int x = 0; x < cnt; ++x) items.push_back(Item{ j, ents[x] });
         }
         if (collision) { redo[sb] = 1; e.restarts++; continue; }
+        if (fast_first) {       // phase_a_fast_kernel first; the general scan below only sees what it could not certify
+            FastOut fo;
+            if (fast_certify(e, i, items, fo, 192, 128)) {
+                for (auto &cm : fo.cont) cont_max[cm.first] = std::max(cont_max[cm.first], cm.second);
+                e.compare_calls += fo.calls;
+                e.fast_reads++;
+                flag5[i] = fo.connections > kConnectionsLimit;
+                e.extR[i] = ext_pack(fo.Rid, fo.Rtype, fo.Rlen);
+                e.extL[i] = ext_pack(fo.Lid, fo.Ltype, fo.Llen);
+                continue;
+            }
+        }
         ExtState st;
         ext_init(st);
         bool exact = exact_only, hasR = false, hasL = false;
@@ -559,7 +659,7 @@ void hemu_sizes(void *p, uint64_t *o)
     Emu *e = (Emu *)p;
     o[0] = e->U; o[1] = (u64)e->SW; o[2] = e->good; o[3] = e->total_bp; o[4] = e->edges.size() / 2; o[5] = e->over;
     o[6] = e->distinct; o[7] = e->compare_calls; o[8] = e->inserted; o[9] = e->removed; o[10] = e->contained;
-    o[11] = e->contained_size; o[12] = e->slow_reads;
+    o[11] = e->contained_size; o[12] = e->slow_reads; o[13] = e->fast_reads;
 }
 void hemu_copy(void *p, uint64_t *F, uint64_t *RC, uint16_t *len, uint16_t *freq, uint64_t *extR, uint64_t *extL,
                uint8_t *expl_a, uint8_t *expl_b, uint64_t *edges)

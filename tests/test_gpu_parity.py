@@ -199,6 +199,30 @@ def test_digest_equals_numpy_definition():
 
 
 @pytest.mark.parametrize("name", SMALL)
+def test_general_kernel_alone_equals_oracle(name):
+    """Phase A without the superstring scan (set_option("fast_scan", 0)): the hit-by-hit kernel on every read."""
+    reads, k = _get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    gpu = api.Sage2Gpu(0)
+    gpu.set_option("fast_scan", 0)
+    gpu.run_steps123(b, off, k)
+    assert gpu.counters()["fast_path_reads"] == 0
+    _compare(o, gpu)
+
+
+def test_superstring_scan_takes_the_clean_reads():
+    """The fast path certifies every read of an error-free random genome and leaves contradicting hits to the general kernel."""
+    for name, lo, hi in (("clean", 1.0, 1.0), ("rep", 0.9, 1.0), ("err", 0.05, 0.6), ("deep", 0.0, 0.2)):
+        reads, k = _get(name)
+        b, off = synth.concat(reads)
+        gpu = api.Sage2Gpu(0)
+        gpu.run_steps123(b, off, k)
+        c = gpu.counters()
+        assert lo <= c["fast_path_reads"] / c["unique_reads"] <= hi, (name, c["fast_path_reads"], c["unique_reads"])
+
+
+@pytest.mark.parametrize("name", SMALL)
 def test_minhash_read_order_changes_nothing(name):
     """SAGE2GPU_READ_ORDER=minhash / set_option("read_order", 1): phase A in min-hash order must give the oracle's graph."""
     reads, k = _get(name)
