@@ -67,7 +67,8 @@ const char *sage2gpu_last_error(const sage2gpu_ctx *ctx);
  * (readLoader.cpp:133-260; isGoodRead utils.cpp:144, insertReadIntoList readLoader.cpp:179).
  * `bases` = the read sequences concatenated (ASCII, any case), read r = bases[offsets[r],
  * offsets[r+1]).  Host buffers (pinned memory makes the upload asynchronous).  Reads with
- * length <= min_overlap or a non-ACGT character are dropped exactly like the reference does. */
+ * length <= min_overlap or a non-ACGT character are dropped exactly like the reference does.  Limit of this build: reads
+ * of up to 1016 bases (the reference has none); a longer read makes the call fail rather than renumber the reads. */
 int sage2gpu_load_reads(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
                         int64_t n_reads, int min_overlap);
 /* Same, with both buffers already resident in this context's device memory. */
@@ -198,7 +199,8 @@ int sage2gpu_phase_a_sharded_end(sage2gpu_ctx *ctx);
 int sage2gpu_mailbox_create(sage2gpu_ctx *ctx, int rank, int world, uint64_t max_reads_per_batch, void *ipc_handle_out, void **local_ptr);
 int sage2gpu_mailbox_open(sage2gpu_ctx *ctx, int peer_rank, const void *ipc_handle, void *ptr);
 /* The barrier between the three steps, on the device: every rank stores its barrier count into the peers' mailboxes and
- * waits for theirs (all ranks must call it the same number of times; gives up with an error after a few seconds). */
+ * waits for theirs (all ranks must call it the same number of times).  A peer that never arrives ends the wait with an
+ * error after 60 s (environment SAGE2GPU_BARRIER_TIMEOUT_S); the mailbox is released then and has to be created again. */
 int sage2gpu_mailbox_barrier(sage2gpu_ctx *ctx);
 int sage2gpu_route_post(sage2gpu_ctx *ctx, int what, uint64_t first, uint64_t count, int exact, uint64_t *n_reads, uint64_t *bytes_sent);
 int sage2gpu_answer_post(sage2gpu_ctx *ctx, int exact, uint64_t *bytes_sent);

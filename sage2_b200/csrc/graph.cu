@@ -67,6 +67,15 @@ __global__ void __launch_bounds__(256) phase_b_edges_kernel(const u64 *__restric
     }
 }
 
+__global__ void __launch_bounds__(256) sum_u32_kernel(const u32 *__restrict__ v, u64 n, unsigned long long *__restrict__ out)
+{
+    unsigned long long acc = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) acc += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 __global__ void __launch_bounds__(256) flag_state0_kernel(const uint8_t *__restrict__ explored, u64 U, u32 *__restrict__ flag)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += (u64)gridDim.x * blockDim.x) flag[i] = explored[i] == 0;
@@ -230,10 +239,18 @@ void stage_phase_c_and_finalize(Context &c)
         compact_ids_kernel<<<big_grid(U), 256, 0, st>>>(flag.p, idx.p, U, s_ids.p);
         SG_LAUNCHED();
         launch_phase_c_candidates(c, s_ids.p, nS, counts.p, nullptr, nullptr, false);
+        // the candidate total is not bounded by 4U (error-rich data): sum it in 64 bits before the 32-bit scan
+        DevBuf<unsigned long long> d_c64(1, st);
+        SG_CUDA(cudaMemsetAsync(d_c64.p, 0, sizeof(unsigned long long), st));
+        sum_u32_kernel<<<big_grid(nS), 256, 0, st>>>(counts.p, nS, d_c64.p);
+        SG_LAUNCHED();
         exclusive_scan_u32(counts.p, offs.p, nS, d_ctotal.p, st);
         u32 nC = 0;
+        unsigned long long nC64 = 0;
         SG_CUDA(cudaMemcpyAsync(&nC, d_ctotal.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(&nC64, d_c64.p, sizeof(nC64), cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaStreamSynchronize(st));
+        SG_CHECK(nC64 < 0xFFFFFFFFull, "more than 2^32 phase-C candidates: not supported (split the input)");
         DevBuf<u64> cand(nC, st);
         if (nC) launch_phase_c_candidates(c, s_ids.p, nS, counts.p, offs.p, cand.p, true);
         c.cnt.candidates_c = nC;

@@ -286,7 +286,9 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     int max_len = 0;
     SG_CUDA(cudaMemcpyAsync(&max_len, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
-    if (max_len > 32 * kMaxWords - 8) max_len = 32 * kMaxWords - 8;   // longer reads are dropped as bad
+    // The reference has no length limit; this build packs reads of up to 1016 bases (kMaxWords 64-bit words per record).
+    // Dropping a longer read silently would renumber every read after it, so the call fails instead.
+    SG_CHECK(max_len <= 32 * kMaxWords - 8, "a read is longer than 1016 bases: not supported by this build of libsage2gpu");
     if (max_len < 1) max_len = 1;
     c.max_len = max_len;
     c.SW = words_for_len(max_len);

@@ -392,6 +392,15 @@ void stage_route_begin(Context &c, int what, u64 first, u64 count, int exact, in
 
 // Owner side.  `queries` (device): the streams received from source 0, 1, .. world-1 back to back,
 // counts_per_source[s] queries each.  Answers in the same order; entry stream of source s = entry_counts[s] words.
+__global__ void __launch_bounds__(256) sum_runlen_kernel(const u32 *__restrict__ v, u64 n, unsigned long long *__restrict__ out)
+{
+    unsigned long long acc = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) acc += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 void stage_shard_answer(Context &c, const void *queries, const u64 *counts_per_source, int exact, int world, void **responses, void **entries,
                         u64 *entry_counts)
 {
@@ -416,14 +425,22 @@ void stage_shard_answer(Context &c, const void *queries, const u64 *counts_per_s
     const ShardView T = shard_view(c, fake_mask);
     answer_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>((const u64 *)queries, nq, exact, T, c.an_resp.p, runlen.p);
     SG_LAUNCHED();
+    // up to 99 entries per query: the grand total is checked in 64 bits before the 32-bit scan is trusted
+    DevBuf<unsigned long long> d_t64(1, st);
+    SG_CUDA(cudaMemsetAsync(d_t64.p, 0, sizeof(unsigned long long), st));
+    sum_runlen_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>(runlen.p, nq, d_t64.p);
+    SG_LAUNCHED();
     exclusive_scan_u32(runlen.p, off.p, nq + 1, d_total.p, st);
     seg_totals_kernel<<<1, kMaxWorld, 0, st>>>(off.p, d_seg.p, world, d_ecnt.p);
     SG_LAUNCHED();
     u32 total = 0;
     u64 h_ecnt[kMaxWorld];
+    unsigned long long total64 = 0;
+    SG_CUDA(cudaMemcpyAsync(&total64, d_t64.p, sizeof(total64), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(&total, d_total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_ecnt, d_ecnt.p, world * sizeof(u64), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
+    SG_CHECK(total64 < 0xFFFFFFFFull, "more than 2^32 bucket entries in one routed batch: use smaller batches");
     c.an_entries.alloc(total, st);
     if (total) {
         answer_runs_kernel<<<sm_grid(nq, 256, 8), 256, 0, st>>>(c.an_resp.p, runlen.p, off.p, nq, d_seg.p, world, c.entries.p, c.an_entries.p);
@@ -495,9 +512,13 @@ void stage_mailbox_create(Context &c, int rank, int world, u64 cap_windows, void
     SG_CHECK(cap_windows >= 1 && cap_windows < 0xFFFFFFFFull && (u64)world * cap_windows < (1ull << 33), "bad mailbox capacity");
     stage_mailbox_destroy(c);
     Mailbox &m = c.mb;
-    // entry segments: every bucket entry of every window in the worst case + the holes the chunked reservation of
-    // answer_fused_kernel can leave (one chunk per warp of its grid)
-    m.world = world; m.rank = rank; m.cap = cap_windows; m.ecap = cap_windows + (u64)kSMs * 8 * 8 * kEntryChunk;
+    // entry segments: room for `factor` bucket entries per window on average (entries travel only for buckets of 2..99
+    // reads: 0.25 per window at cfg2, < 0.1 at cfg4; SAGE2GPU_MAILBOX_ENTRY_FACTOR raises it for repeat-rich or very deep
+    // data) + the holes the chunked reservation of answer_fused_kernel can leave.  This is NOT a worst case (a bucket holds
+    // up to 99 entries): a batch that needs more fails loudly ("entry stream exceeds the mailbox capacity") and the
+    // caller reruns with a larger factor, smaller batches or the NCCL transport, which sizes its buffers exactly.
+    static const u64 efactor = [] { const char *e = getenv("SAGE2GPU_MAILBOX_ENTRY_FACTOR"); const long v = e ? atol(e) : 2; return (u64)(v < 1 ? 1 : v); }();
+    m.world = world; m.rank = rank; m.cap = cap_windows; m.ecap = efactor * cap_windows + (u64)kSMs * 8 * 8 * kEntryChunk;
     SG_CHECK((u64)world * m.ecap < (1ull << 33), "mailbox too large for the 33-bit answer payload");
     m.bytes = mb_bytes(world, m.cap, m.ecap);
     SG_CUDA(cudaMalloc((void **)&m.base, m.bytes));          // plain cudaMalloc: pool memory cannot be exported through IPC
@@ -551,9 +572,11 @@ __global__ void publish_counts_kernel(const unsigned long long *__restrict__ cnt
 // Barrier between the ranks ON THE DEVICE: one thread per peer stores this rank's epoch into the peer's mailbox (after a
 // system-scope fence: everything this rank stored into peer memory before is visible first) and then waits until the
 // peer's epoch has arrived here.  Stream-ordered, no host round trip through a collective.  A peer that never arrives
-// (a dead rank) ends the wait after ~4 s with an error instead of hanging the GPU.
+// (a dead rank) ends the wait after 60 s (SAGE2GPU_BARRIER_TIMEOUT_S) with an error instead of hanging the GPU; the
+// mailbox is released then, because the ranks' epochs no longer agree.
 __global__ void mailbox_barrier_kernel(const __grid_constant__ RouteDst D /* dst[g] = flags[rank] in peer g's mailbox */,
-                                       const volatile u64 *__restrict__ my_flags, u64 epoch, int world, int rank, u32 *__restrict__ timed_out)
+                                       const volatile u64 *__restrict__ my_flags, u64 epoch, int world, int rank, long long timeout_clocks,
+                                       u32 *__restrict__ timed_out)
 {
     const int g = threadIdx.x;
     if (g >= world || g == rank) return;
@@ -562,7 +585,7 @@ __global__ void mailbox_barrier_kernel(const __grid_constant__ RouteDst D /* dst
     const long long t0 = clock64();
     while (my_flags[g] < epoch) {
         __nanosleep(200);
-        if (clock64() - t0 > 8000000000ll) { *timed_out = 1; break; }
+        if (clock64() - t0 > timeout_clocks) { *timed_out = 1; break; }
     }
     __threadfence_system();
 }
@@ -582,12 +605,20 @@ void stage_mailbox_barrier(Context &c)
     DevBuf<u32> d_to(1, st);
     SG_CUDA(cudaMemsetAsync(d_to.p, 0, sizeof(u32), st));
     ++m.epoch;
-    mailbox_barrier_kernel<<<1, kMaxWorld, 0, st>>>(D, (const volatile u64 *)(m.base + mb_off_flags(m.world)), m.epoch, m.world, m.rank, d_to.p);
+    // a peer may be late by seconds (lazy module load, allocator stalls, uneven batches): 60 s by default
+    // (SAGE2GPU_BARRIER_TIMEOUT_S), counted in SM clocks at ~2 GHz
+    static const long long timeout_clocks = [] { const char *e = getenv("SAGE2GPU_BARRIER_TIMEOUT_S"); const long v = e ? atol(e) : 60; return (long long)(v < 1 ? 1 : v) * 2000000000ll; }();
+    mailbox_barrier_kernel<<<1, kMaxWorld, 0, st>>>(D, (const volatile u64 *)(m.base + mb_off_flags(m.world)), m.epoch, m.world, m.rank, timeout_clocks, d_to.p);
     SG_LAUNCHED();
     u32 h_to = 0;
     SG_CUDA(cudaMemcpyAsync(&h_to, d_to.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
-    SG_CHECK(h_to == 0, "mailbox barrier timed out: a peer rank never arrived");
+    if (h_to != 0) {
+        // this rank has already published its epoch, so the peers pass this barrier: the mailbox is unusable from here on
+        // (the epochs of the ranks no longer agree).  Drop it; the next build has to create and open the mailboxes again.
+        stage_mailbox_destroy(c);
+        throw CudaError("mailbox barrier timed out: a peer rank never arrived (mailbox released; create it again)");
+    }
 }
 
 void stage_route_post(Context &c, int what, u64 first, u64 count, int exact, u64 *n_reads)

@@ -201,8 +201,17 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
         n = min(batch_reads, first + count - lo)
         yield from route(0, lo, n, False)
         redo += gpu.phase_a_routed()
+    def fit_mailbox(n_list):
+        # a list batch (redo reads, reads left for phase C) travels as ONE batch: the mailboxes of all ranks grow to hold
+        # the largest list any rank has (error-rich data sends most reads through phase C)
+        need = yield ("max", n_list)
+        if p2p and need > getattr(gpu, "mailbox_batch_reads", 0):
+            yield from mailbox_steps(gpu, rank, world, need)
+        return need
+
     if (yield ("max", redo)):
         # 24-bit tag collisions (about U*W / 2^24 reads): those reads once more, with probes the owners verify
+        yield from fit_mailbox(redo)
         yield from route(2, 0, 0, True)
         left = gpu.phase_a_routed()
         if left:
@@ -210,6 +219,8 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
     gpu.phase_a_sharded_end()
     yield ("phase_a", gpu.phase_a_buffers())
     gpu.phase_b()
+    cnt = gpu.counters()
+    yield from fit_mailbox(cnt.get("left_to_explore", cnt.get("unique_reads", 0)))
     if p2p:
         posted = gpu.route_post(1, 0, 0, True)          # reads left for phase C: identical list on every rank
         if posted[0]:
@@ -267,6 +278,9 @@ def _gather_var_dist(full: torch.Tensor, counts, rank: int, world: int):
     m = max(counts)
     if m == 0:
         return
+    if not full.is_cuda and full.dtype != torch.uint8:      # gloo moves bytes (it has no 16-bit integer type)
+        es = full.element_size()
+        return _gather_var_dist(full.view(torch.uint8), [c * es for c in counts], rank, world)
     offs = [sum(counts[:q]) for q in range(world)]
     mine = torch.zeros(m, dtype=full.dtype, device=full.device)
     mine[:counts[rank]] = full[offs[rank]:offs[rank] + counts[rank]]
@@ -283,78 +297,84 @@ def _gather_var_dist(full: torch.Tensor, counts, rank: int, world: int):
             full[offs[q]:offs[q] + counts[q]] = parts[q]
 
 
+def serve_one(req, rank: int, world: int, device, sent: list | None = None):
+    """Serve ONE exchange request of a step generator with torch.distributed (NCCL for CUDA tensors, gloo on the CPU)."""
+    sent = sent if sent is not None else [0]
+    cuda = torch.device(device).type == "cuda"
+    kind = req[0]
+    if kind == "counts":
+        t = torch.tensor(req[1], dtype=torch.int64, device=device)
+        out = torch.empty_like(t)
+        dist.all_to_all_single(out, t)
+        sent[0] += 8 * (world - 1)
+        return out.tolist()
+    if kind == "a2a":
+        send, sc, rc = req[1], req[2], req[3]
+        out = torch.empty(sum(rc), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(out, send, rc, sc)
+        if cuda:
+            torch.cuda.current_stream(device).synchronize()       # the library reads it on its own stream
+        sent[0] += (sum(sc) - sc[rank]) * send.element_size()
+        return out
+    if kind == "max":
+        t = torch.tensor([req[1]], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
+    if kind == "gather_counts":
+        t = torch.tensor(req[1], dtype=torch.int64, device=device)
+        if cuda:
+            out = torch.empty(world * t.numel(), dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(out, t)
+        else:
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            out = torch.cat(parts)
+        return out.view(world, -1).tolist()
+    if kind == "gather_var":
+        _gather_var_dist(req[1], req[2], rank, world)
+        if cuda:
+            torch.cuda.current_stream(device).synchronize()       # the library reads it on its own stream
+        sent[0] += req[2][rank] * req[1].element_size()
+        return None
+    if kind == "barrier":           # every rank's library call before it has returned (= its stream is drained)
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.all_reduce(t)
+        return int(t.item())
+    if kind == "device_barrier":    # flags in the peers' mailboxes, written and awaited by a kernel (csrc/shard.cu)
+        req[1].mailbox_barrier()
+        return 0
+    if kind == "mailboxes":         # CUDA IPC handles of all ranks (other processes cannot use the pointer)
+        boxes = [None] * world
+        dist.all_gather_object(boxes, {"handle": req[1]["handle"]})
+        return boxes
+    if kind == "phase_a":
+        bufs = req[1]
+        views = req[2] if len(req) > 2 else device_views(bufs, world, device)
+        sent[0] += exchange_phase_a(views, bufs["chunk"], rank, world)
+        if cuda:
+            torch.cuda.current_stream(device).synchronize()
+        return None
+    raise ValueError(kind)
+
+
 def run_dist(gen, rank: int, world: int, device, stats: dict | None = None) -> int:
     """Serve one rank's requests with torch.distributed (NCCL for CUDA tensors, gloo on the CPU).  Returns bytes sent.
     stats (optional): wall milliseconds spent in the exchanges, by request kind, are added to it."""
     import time
-    sent = 0
-    cuda = torch.device(device).type == "cuda"
+    sent = [0]
     try:
         req = next(gen)
         while True:
-            kind = req[0]
             t0 = time.perf_counter()
-            if kind == "counts":
-                t = torch.tensor(req[1], dtype=torch.int64, device=device)
-                out = torch.empty_like(t)
-                dist.all_to_all_single(out, t)
-                val = out.tolist()
-                sent += 8 * (world - 1)
-            elif kind == "a2a":
-                send, sc, rc = req[1], req[2], req[3]
-                out = torch.empty(sum(rc), dtype=send.dtype, device=send.device)
-                dist.all_to_all_single(out, send, rc, sc)
-                if cuda:
-                    torch.cuda.current_stream(device).synchronize()       # the library reads it on its own stream
-                sent += (sum(sc) - sc[rank]) * send.element_size()
-                val = out
-            elif kind == "max":
-                t = torch.tensor([req[1]], dtype=torch.int64, device=device)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                val = int(t.item())
-            elif kind == "gather_counts":
-                t = torch.tensor(req[1], dtype=torch.int64, device=device)
-                out = torch.empty(world * t.numel(), dtype=torch.int64, device=device)
-                if cuda:
-                    dist.all_gather_into_tensor(out, t)
-                else:
-                    parts = [torch.empty_like(t) for _ in range(world)]
-                    dist.all_gather(parts, t)
-                    out = torch.cat(parts)
-                val = out.view(world, -1).tolist()
-            elif kind == "gather_var":
-                _gather_var_dist(req[1], req[2], rank, world)
-                if cuda:
-                    torch.cuda.current_stream(device).synchronize()       # the library reads it on its own stream
-                sent += req[2][rank] * req[1].element_size()
-                val = None
-            elif kind == "barrier":           # every rank's library call before it has returned (= its stream is drained)
-                t = torch.zeros(1, dtype=torch.int32, device=device)
-                dist.all_reduce(t)
-                val = int(t.item())
-            elif kind == "device_barrier":    # flags in the peers' mailboxes, written and awaited by a kernel (csrc/shard.cu)
-                req[1].mailbox_barrier()
-                val = 0
-            elif kind == "mailboxes":         # CUDA IPC handles of all ranks (other processes cannot use the pointer)
-                boxes = [None] * world
-                dist.all_gather_object(boxes, {"handle": req[1]["handle"]})
-                val = boxes
-            elif kind == "phase_a":
-                bufs = req[1]
-                views = req[2] if len(req) > 2 else device_views(bufs, world, device)
-                sent += exchange_phase_a(views, bufs["chunk"], rank, world)
-                if cuda:
-                    torch.cuda.current_stream(device).synchronize()
-                val = None
-            else:
-                raise ValueError(kind)
+            val = serve_one(req, rank, world, device, sent)
             if stats is not None:
+                kind = req[0]
                 stats[kind] = stats.get(kind, 0.0) + (time.perf_counter() - t0) * 1e3
                 stats["n_" + kind] = stats.get("n_" + kind, 0) + 1
             req = gen.send(val)
     except StopIteration:
         pass
-    return sent
+    return sent[0]
 
 
 def run_local(gens: list, views_of=None) -> None:

@@ -250,3 +250,81 @@ def unpack_edges(w: np.ndarray):
     w0, w1 = w[0::2], w[1::2]
     return (w0 >> np.uint64(32)).astype(np.uint64), (w0 & np.uint64(0xFFFFFFFF)).astype(np.uint64), \
         ((w1 >> np.uint64(20)) & np.uint64(3)).astype(np.uint32), (w1 & np.uint64(0xFFFFF)).astype(np.uint32)
+
+
+class EmuPart:
+    """One rank of the fully partitioned build on the CPU: the methods multi.partitioned_graph_steps calls on
+    api.Sage2Gpu, with host buffers (tests/host_emul.cpp restates reads.cu's key-range organise; the table is rebuilt
+    from the gathered reads, so its two all-gathers carry nothing here)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.L.hemu_prepare_partition.restype = C.c_void_p
+        self.L.hemu_prepare_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        self.L.hemu_reads_gather_layout.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                    C.POINTER(C.c_void_p)]
+        self.L.hemu_reads_gather_finish.argtypes = [C.c_void_p]
+        self.h = None
+
+    def load_reads_partition(self, bases_ptr, offsets_ptr, n_reads, k, on_device, rank, world):
+        u = C.c_uint64()
+        self.rank, self.world = rank, world
+        self.h = self.L.hemu_prepare_partition(bases_ptr, offsets_ptr, n_reads, k, rank, world, C.byref(u))
+        return int(u.value)
+
+    def _sizes(self):
+        sz = np.zeros(14, dtype=np.uint64)
+        self.L.hemu_sizes(self.h, sz.ctypes.data)
+        return [int(x) for x in sz]
+
+    def reads_gather_layout(self, counts):
+        cs = (C.c_uint64 * len(counts))(*counts)
+        p = [C.c_void_p() for _ in range(3)]
+        self.L.hemu_reads_gather_layout(self.h, cs, self.rank, self.world, *(C.byref(x) for x in p))
+        return {"records": p[0].value or 0, "lengths": p[1].value or 0, "frequencies": p[2].value or 0, "first": sum(counts[:self.rank]),
+                "total": sum(counts), "stride": self._sizes()[1], "counts": list(counts)}
+
+    def reads_gather_finish(self):
+        self.L.hemu_reads_gather_finish(self.h)
+
+    def build_hash_table_shard(self, rank, world):
+        pass
+
+    def table_shard_info(self):
+        sz = self._sizes()
+        return {"slots": 0, "entries": 0, "distinct": sz[6], "over": sz[5]}
+
+    def table_gather_layout(self, entry_counts):
+        return {"slots": 0, "entries": 0, "slots_per_shard": 0, "entries_first": 0}
+
+    def table_gather_finish(self, entry_counts, distinct, over):
+        pass
+
+    def phase_a_partition(self, rank, world):
+        self.L.hemu_phase_a(self.h, rank, world)
+
+    def phase_a_buffers(self):
+        p = [C.c_void_p() for _ in range(4)]
+        n = int(self.L.hemu_phase_a_arrays(self.h, *(C.byref(x) for x in p)))
+        return {"right": p[0].value or 0, "left": p[1].value or 0, "over_limit": p[2].value or 0, "contained_by": p[3].value or 0,
+                "chunk": n // self.world, "unique_reads": self._sizes()[0]}
+
+    def finish_graph(self):
+        self.L.hemu_finish(self.h)
+
+    def result(self):
+        sz = self._sizes()
+        U, SW, E = sz[0], sz[1], sz[4]
+        F = np.zeros(U * SW, np.uint64); RC = np.zeros(U * SW, np.uint64)
+        ln = np.zeros(U, np.uint16); fr = np.zeros(U, np.uint16)
+        eR = np.zeros(U, np.uint64); eL = np.zeros(U, np.uint64)
+        xa = np.zeros(U, np.uint8); xb = np.zeros(U, np.uint8)
+        edges = np.zeros(2 * E, np.uint64)
+        self.L.hemu_copy(self.h, *(a.ctypes.data for a in (F, RC, ln, fr, eR, eL, xa, xb, edges)))
+        return {"U": U, "len": ln, "freq": fr, "F": F.reshape(U, SW), "RC": RC.reshape(U, SW), "edges": edges, "distinct": sz[6], "over": sz[5],
+                "compare_calls": sz[7]}
+
+    def close(self):
+        if self.h:
+            self.L.hemu_free(self.h)
+            self.h = None

@@ -58,7 +58,26 @@ void pack_record(const uint8_t *s, int len, int SW, u64 *rec, bool rc)
     rec[SW - 1] |= (u64)len;
 }
 
-void prepare(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
+// reverse complements + K3, once the unique reads are complete
+void finish_reads(Emu &e)
+{
+    const int SW = e.SW, h = e.h;
+    const u64 U = e.U = e.len.size();
+    e.RC.resize(U * SW);
+    for (u64 i = 0; i < U; ++i) revcomp_record(&e.F[i * SW], &e.RC[i * SW], SW, e.len[i]);
+    auto &table = e.table;
+    table.clear();
+    for (u64 i = 0; i < U; ++i)
+        for (int t = 0; t < 4; ++t) {
+            u64 v0, v1;
+            entry_key(&e.F[i * SW], &e.RC[i * SW], SW, e.len[i], h, t, v0, v1);
+            table[std::make_pair(v0, v1)].push_back((u32)(i * 4 + t));
+        }
+    e.distinct = table.size(); e.over = 0;
+    for (auto &kv : table) if (kv.second.size() >= (size_t)kHashThreshold) e.over++;
+}
+
+void prepare(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k, int rank = 0, int world = 1)
 {
     e.k = k; e.h = hash_len_for(k); e.total = (u64)n;
     const int h = e.h;
@@ -85,6 +104,24 @@ void prepare(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
         recs.push_back(q < f ? q : f);
         e.good++; e.total_bp += (u64)l;
     }
+    if (world > 1) {
+        // reads.cu, stage_organize_reads with world > 1: quantile splitters of a 4096-bin histogram of the leading 6 bases
+        const int nbins = 1 << 12;
+        std::vector<u64> hist(nbins, 0);
+        for (auto &r : recs) hist[r[0] >> 52]++;
+        std::vector<u32> bound(world + 1, (u32)nbins);
+        bound[0] = 0;
+        u64 pre = 0;
+        int r = 1;
+        const u64 n_good = recs.size();
+        for (int b = 0; b < nbins && r < world; ++b) {
+            while (r < world && pre >= (n_good * (u64)r + (u64)world - 1) / (u64)world) bound[r++] = (u32)b;
+            pre += hist[b];
+        }
+        std::vector<std::vector<u64>> mine;
+        for (auto &rec : recs) { const u32 b = (u32)(rec[0] >> 52); if (b >= bound[rank] && b < bound[rank + 1]) mine.push_back(rec); }
+        recs.swap(mine);
+    }
     // K2
     std::sort(recs.begin(), recs.end());
     for (size_t i = 0; i < recs.size(); ++i) {
@@ -95,21 +132,8 @@ void prepare(Emu &e, const uint8_t *bases, const int64_t *off, int64_t n, int k)
         }
         e.freq.back()++;
     }
-    const u64 U = e.U = e.len.size();
-    e.RC.resize(U * SW);
-    for (u64 i = 0; i < U; ++i) revcomp_record(&e.F[i * SW], &e.RC[i * SW], SW, e.len[i]);
-
-    // K3
-    auto &table = e.table;
-    for (u64 i = 0; i < U; ++i)
-        for (int t = 0; t < 4; ++t) {
-            u64 v0, v1;
-            entry_key(&e.F[i * SW], &e.RC[i * SW], SW, e.len[i], h, t, v0, v1);
-            table[std::make_pair(v0, v1)].push_back((u32)(i * 4 + t));
-        }
-    e.distinct = table.size();
-    for (auto &kv : table) if (kv.second.size() >= (size_t)kHashThreshold) e.over++;
-
+    e.U = e.len.size();
+    if (world == 1) finish_reads(e);
 }
 
 Lookup local_table(Emu &e)
@@ -617,6 +641,30 @@ void *hemu_prepare(const uint8_t *bases, const int64_t *off, int64_t n, int k)
     prepare(*e, bases, off, n, k);
     return e;
 }
+// every stage partitioned (include/sage2gpu.h): this rank's key range of the reads ...
+void *hemu_prepare_partition(const uint8_t *bases, const int64_t *off, int64_t n, int k, int rank, int world, uint64_t *unique_local)
+{
+    Emu *e = new Emu();
+    prepare(*e, bases, off, n, k, rank, world);
+    *unique_local = e->U;
+    return e;
+}
+// ... arrays of the total size with this rank's run in place (the caller all-gathers them) ...
+void hemu_reads_gather_layout(void *p, const uint64_t *counts, int rank, int world, uint64_t **F, uint16_t **len, uint16_t **freq)
+{
+    Emu *e = (Emu *)p;
+    u64 tot = 0, base = 0;
+    for (int q = 0; q < world; ++q) { if (q < rank) base += counts[q]; tot += counts[q]; }
+    std::vector<u64> Fg(tot * e->SW, 0);
+    std::vector<uint16_t> lg(tot, 0), fg(tot, 0);
+    std::copy(e->F.begin(), e->F.end(), Fg.begin() + base * e->SW);
+    std::copy(e->len.begin(), e->len.end(), lg.begin() + base);
+    std::copy(e->freq.begin(), e->freq.end(), fg.begin() + base);
+    e->F.swap(Fg); e->len.swap(lg); e->freq.swap(fg);
+    *F = e->F.data(); *len = e->len.data(); *freq = e->freq.data();
+}
+// ... and the reads are complete: reverse complements, table
+void hemu_reads_gather_finish(void *p) { finish_reads(*(Emu *)p); }
 void hemu_phase_a(void *p, int rank, int world) { phase_a(*(Emu *)p, rank, world); }
 // pointers to the padded phase-A arrays (u64, u64, u8, u32) and their length
 uint64_t hemu_phase_a_arrays(void *p, uint64_t **extR, uint64_t **extL, uint8_t **flag5, uint32_t **cont_max)

@@ -122,3 +122,69 @@ def test_exchange_requests_over_gloo(tmp_path):
     world = 3
     mp.spawn(_requests_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+# ---- every stage partitioned (multi.partitioned_graph_steps) over gloo ---------------------------------------------------
+
+def _part_worker(rank, world, port, name, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        reads, k = datasets.get(name)
+        b, off = synth.concat(reads)
+        g = emul.EmuPart()
+        views = {}
+
+        def view(ptr, n, ts):
+            return multi.host_view(ptr, n, ts)
+
+        steps = multi.partitioned_graph_steps(g, rank, world, view, b.ctypes.data, off.ctypes.data, len(off) - 1, k, False)
+
+        def serve():
+            # run_dist with the phase-A exchange on host views of the emulator's arrays
+            req = next(steps)
+            while True:
+                if req[0] == "phase_a":
+                    bufs = req[1]
+                    n = bufs["chunk"] * world
+                    tv = {"right": multi.host_view(bufs["right"], n, "<i8"), "left": multi.host_view(bufs["left"], n, "<i8"),
+                          "over_limit": multi.host_view(bufs["over_limit"], n, "|u1"), "contained_by": multi.host_view(bufs["contained_by"], n, "<i4")}
+                    multi.exchange_phase_a(tv, bufs["chunk"], rank, world)
+                    val = None
+                else:
+                    val = multi.serve_one(req, rank, world, "cpu")
+                try:
+                    req = steps.send(val)
+                except StopIteration:
+                    return
+        serve()
+        r = g.result()
+        np.save(os.path.join(out, f"edges{rank}.npy"), r["edges"])
+        np.save(os.path.join(out, f"freq{rank}.npy"), r["freq"])
+        np.save(os.path.join(out, f"F{rank}.npy"), r["F"])
+        np.save(os.path.join(out, f"calls{rank}.npy"), np.array([r["compare_calls"], r["U"]]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,world", [("rep", 2), ("varlen_err", 3), ("hicopy", 2), ("single", 2), ("allbad", 2)])
+def test_every_stage_partitioned_over_gloo(name, world, tmp_path):
+    mp.spawn(_part_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    reads, k = datasets.get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    calls = 0
+    for r in range(world):
+        a, bb, t, d = emul.unpack_edges(np.load(tmp_path / f"edges{r}.npy"))
+        assert len(a) == o.n_edges
+        np.testing.assert_array_equal(a, o.edges["from"])
+        np.testing.assert_array_equal(bb, o.edges["to"])
+        np.testing.assert_array_equal(t, o.edges["type"])
+        np.testing.assert_array_equal(d, o.edges["delta"])
+        np.testing.assert_array_equal(np.load(tmp_path / f"freq{r}.npy"), o.frequency[1:])
+        c = np.load(tmp_path / f"calls{r}.npy")
+        assert c[1] == o.U
+        calls += int(c[0])
+        F = np.load(tmp_path / f"F{r}.npy")
+        np.testing.assert_array_equal(emul.records_to_bytes(F, o.length[1:]), o.fwd)
+    assert calls == o.compare_calls
