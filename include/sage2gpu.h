@@ -40,7 +40,8 @@ typedef struct {
     uint64_t slow_path_reads;   /* reads whose extension chain ran hit by hit (ambiguity / multi-hit windows) */
     uint64_t record_words;      /* 64-bit words per packed read record */
     uint64_t probe_restarts;    /* reads redone with verified probes after a tag collision */
-    uint64_t phase_c_on_device; /* 1 when phase C ran on the device (order-independent input), 0 for the host walk */
+    uint64_t phase_c_on_device; /* phase C lists / marks / filtering: 1 on the device (order-independent input), 2 on the device with
+                                   the traversal order from the host, 0 whole walk on the host */
     uint64_t fast_path_reads;   /* phase-A reads certified by the superstring scan (the rest took the hit-by-hit kernel) */
 } sage2gpu_counters;
 

@@ -22,7 +22,7 @@ struct Counters {
     u64 slow_path_reads = 0; // reads that left the parallel fast mode for the exact sequential chain
     u64 probe_restarts = 0;  // reads redone with verified probes after a 24-bit tag collision
     u64 fast_path_reads = 0;     // reads of phase A certified by the superstring scan (search_fast.cu)
-    u64 phase_c_on_device = 0;   // 1: phase C was marked and filtered on the device (symmetric candidate set), 0: host walk
+    u64 phase_c_on_device = 0;   // lists / marks / filtering of phase C: 1 device, 2 device with the host's traversal order, 0 host walk
 };
 
 struct Timers {   // milliseconds, CUDA events on the context stream

@@ -13,8 +13,9 @@ namespace sg {
 
 void launch_phase_c_candidates(Context &c, const u32 *s_ids, u64 nS, u32 *counts, const u32 *offsets, u64 *cand, bool fill);
 // phase_c_device.cu
+bool phase_c_is_symmetric(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand);
 bool device_phase_c(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand, u64 nC,
-                    const u64 *selB, const u32 *selLen, u64 nSel, DevBuf<u64> &out, u64 &n_out, u64 &removed);
+                    const u64 *selB, const u32 *selLen, u64 nSel, const u32 *d_order, DevBuf<u64> &out, u64 &n_out, u64 &inserted, u64 &removed);
 
 static unsigned big_grid(u64 n, unsigned block = 256)
 {
@@ -233,7 +234,7 @@ void stage_phase_c_and_finalize(Context &c)
     DevBuf<u64> dev_c_edges;           // the same when phase C ran on the device
     u64 n_dev_c = 0;
     bool c_on_device = false;
-    float host_ms = 0.f;
+    float host_ms = 0.f, host_order_ms = 0.f;
     if (nS > 0) {
         DevBuf<u32> s_ids(nS, st), counts(nS, st), offs(nS, st), d_ctotal(1, st);
         compact_ids_kernel<<<big_grid(U), 256, 0, st>>>(flag.p, idx.p, U, s_ids.p);
@@ -280,36 +281,61 @@ void stage_phase_c_and_finalize(Context &c)
                 SG_LAUNCHED();
             }
         }
-        // ---- phase C on the device when the traversal order cannot matter (phase_c_device.cu) -----------
+        // ---- phase C: lists, marks and filtering on the device (phase_c_device.cu); the host contributes the traversal
+        // order when the candidate set is not symmetric, and the whole walk only when a list is too long for a warp
         const bool force_host = getenv("SAGE2GPU_PHASE_C_HOST") != nullptr;       // test knob: always take the walk
-        u64 removed_dev = 0;
-        if (!force_host)
-            c_on_device = device_phase_c(c, s_ids.p, idx.p, nS, counts.p, offs.p, cand.p, nC, selB.p, selLen.p, nSel, dev_c_edges, n_dev_c, removed_dev);
-        c.cnt.phase_c_on_device = c_on_device ? 1 : 0;
+        // the walk's input, fetched once (for the traversal order or for the whole walk)
+        PhaseCInput in;
+        std::vector<u32> h_sids, h_off, h_selLen;
+        std::vector<u64> h_cand, h_selB;
+        std::vector<uint16_t> h_slen;
+        bool have_input = false;
+        auto fetch_input = [&]() {
+            if (have_input) return;
+            h_sids.resize(nS); h_off.resize((size_t)nS + 1); h_selLen.resize(nSel); h_cand.resize(nC); h_selB.resize(2 * (u64)nSel); h_slen.resize(nS);
+            SG_CUDA(cudaMemcpyAsync(h_sids.data(), s_ids.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaMemcpyAsync(h_off.data(), offs.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaMemcpyAsync(h_slen.data(), sLen.p, nS * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+            if (nC) SG_CUDA(cudaMemcpyAsync(h_cand.data(), cand.p, nC * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            if (nSel) {
+                SG_CUDA(cudaMemcpyAsync(h_selB.data(), selB.p, 2 * (u64)nSel * sizeof(u64), cudaMemcpyDeviceToHost, st));
+                SG_CUDA(cudaMemcpyAsync(h_selLen.data(), selLen.p, nSel * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            }
+            SG_CUDA(cudaStreamSynchronize(st));
+            h_off[nS] = nC;
+            in.nS = nS; in.s_ids = h_sids.data(); in.s_len = h_slen.data(); in.cand_off = h_off.data();
+            in.cand = h_cand.data(); in.nB = nSel; in.edgesB = h_selB.data(); in.edgesB_len = h_selLen.data();
+            have_input = true;
+        };
+        u64 removed_dev = 0, inserted_dev = 0;
+        if (!force_host) {
+            DevBuf<u32> d_order;
+            const u32 *order = nullptr;
+            if (!phase_c_is_symmetric(c, s_ids.p, idx.p, nS, counts.p, offs.p, cand.p)) {
+                // which end point inserts an overlap depends on the breadth-first traversal (economyGraph.cpp:513-564, :605):
+                // that part stays sequential, on the host; everything else follows from its order
+                fetch_input();
+                std::vector<u32> h_order;
+                host_order_ms = run_host_phase_c_order(in, h_order);
+                d_order.alloc(nS, st);
+                SG_CUDA(cudaMemcpyAsync(d_order.p, h_order.data(), nS * sizeof(u32), cudaMemcpyHostToDevice, st));
+                SG_CUDA(cudaStreamSynchronize(st));
+                order = d_order.p;
+                c.cnt.phase_c_on_device = 2;
+            } else c.cnt.phase_c_on_device = 1;
+            c_on_device = device_phase_c(c, s_ids.p, idx.p, nS, counts.p, offs.p, cand.p, nC, selB.p, selLen.p, nSel, order, dev_c_edges, n_dev_c,
+                                         inserted_dev, removed_dev);
+        }
         if (c_on_device) {
-            c.cnt.edges_inserted_c = nC;               // every overlap was found from both ends: 2 entries per pair
+            c.cnt.edges_inserted_c = inserted_dev;
             c.cnt.transitive_removed = removed_dev;
             SG_CUDA(cudaEventRecord(ev1, st));
         } else {
-        PhaseCInput in;
-        std::vector<u32> h_sids(nS), h_off((size_t)nS + 1), h_selLen(nSel);
-        std::vector<u64> h_cand(nC), h_selB(2 * (u64)nSel);
-        std::vector<uint16_t> h_slen(nS);
-        SG_CUDA(cudaMemcpyAsync(h_sids.data(), s_ids.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(h_off.data(), offs.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(h_slen.data(), sLen.p, nS * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
-        if (nC) SG_CUDA(cudaMemcpyAsync(h_cand.data(), cand.p, nC * sizeof(u64), cudaMemcpyDeviceToHost, st));
-        if (nSel) {
-            SG_CUDA(cudaMemcpyAsync(h_selB.data(), selB.p, 2 * (u64)nSel * sizeof(u64), cudaMemcpyDeviceToHost, st));
-            SG_CUDA(cudaMemcpyAsync(h_selLen.data(), selLen.p, nSel * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        }
+        c.cnt.phase_c_on_device = 0;
+        fetch_input();
         SG_CUDA(cudaEventRecord(ev1, st));
-        SG_CUDA(cudaStreamSynchronize(st));
-        h_off[nS] = nC;
-        in.nS = nS; in.s_ids = h_sids.data(); in.s_len = h_slen.data(); in.cand_off = h_off.data();
-        in.cand = h_cand.data(); in.nB = nSel; in.edgesB = h_selB.data(); in.edgesB_len = h_selLen.data();
         PhaseCOutput out;
-        host_ms = run_host_phase_c(in, out);
+        host_ms += run_host_phase_c(in, out);
         if (const char *dump = getenv("SAGE2GPU_DUMP_PHASE_C")) {      // test knob: the walk's input and output, for tools/phase_c_bench
             if (FILE *f = fopen(dump, "wb")) {
                 const u64 hdr[6] = { nS, nC, nSel, out.edges.size(), out.inserted, out.removed };
@@ -348,7 +374,7 @@ void stage_phase_c_and_finalize(Context &c)
         SG_CUDA(cudaEventRecord(ev2, st));
         SG_CUDA(cudaEventSynchronize(ev2));
         c.have_graph = true; c.rt_for_c = false;
-        c.tm.phase_c_host = host_ms;
+        c.tm.phase_c_host = host_ms + host_order_ms;
         cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
         return;
     }
@@ -395,8 +421,8 @@ void stage_phase_c_and_finalize(Context &c)
     float ms01 = 0, ms12 = 0;
     cudaEventElapsedTime(&ms01, ev0, ev1);
     cudaEventElapsedTime(&ms12, ev1, ev2);
-    c.tm.phase_c_dev = ms01;
-    c.tm.phase_c_host = host_ms;
+    c.tm.phase_c_dev = ms01 - host_order_ms > 0 ? ms01 - host_order_ms : 0;
+    c.tm.phase_c_host = host_ms + host_order_ms;
     c.tm.sort_edges = ms12 - host_ms > 0 ? ms12 - host_ms : 0;
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
     c.have_graph = true; c.rt_for_c = false;

@@ -89,6 +89,8 @@ struct Walk {
     std::vector<uint8_t> state;                    // 0/1/2 for S nodes, 4 for everything else
     std::vector<uint32_t> node_id, node_len;
     uint64_t inserted = 0, removed = 0;
+    std::vector<uint32_t> *order = nullptr;        // when set: order[s] = position of S read s in the exploration sequence
+    uint32_t explored_so_far = 0;
 
     explicit Walk(const PhaseCInput &i) : in(i) {}
 
@@ -121,6 +123,7 @@ struct Walk {
     {
         if (state[n1] != 0) return;
         state[n1] = 1;
+        if (order) (*order)[n1] = explored_so_far++;
         const uint32_t s = n1;    // S nodes occupy local slots 0..nS-1 in s_ids order
         uint64_t cnt = 0;
         for (uint32_t q = in.cand_off[s]; q < in.cand_off[s + 1]; ++q) {
@@ -193,10 +196,13 @@ void on_all_cores(size_t work_items, Fn fn)
 
 }  // namespace
 
-float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
+static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uint32_t> *order)
 {
+    PhaseCOutput dummy;
+    PhaseCOutput &out = outp ? *outp : dummy;
     const auto t0 = std::chrono::steady_clock::now();
     Walk w(in);
+    if (order) { order->assign(in.nS, 0); w.order = order; }
     w.slot.init(in.nS + 2 * in.nB);
     w.state.reserve(in.nS + 2 * in.nB); w.node_id.reserve(in.nS + 2 * in.nB); w.node_len.reserve(in.nS + 2 * in.nB);
     for (uint64_t s = 0; s < in.nS; ++s) w.node(in.s_ids[s] + 1, 0, in.s_len[s]);
@@ -293,6 +299,12 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
     }
 
     const auto t_walk = std::chrono::steady_clock::now();
+    if (!outp) {        // the caller only wants the exploration order: lists, marks and filtering are rebuilt on the device
+        if (getenv("SAGE2GPU_PHASE_C_TIMING"))
+            fprintf(stderr, "[phase C host, order only] nS %llu nC %llu | setup %.2f walk %.2f ms\n", (unsigned long long)in.nS, (unsigned long long)nC,
+                    std::chrono::duration<float, std::milli>(t_setup - t0).count(), std::chrono::duration<float, std::milli>(t_walk - t_setup).count());
+        return std::chrono::duration<float, std::milli>(t_walk - t0).count();
+    }
     // Marking and removal, after the walk.  When the reference marks a node, every neighbour already has all its
     // edges (insertAllEdgesOfRead ran for it and nothing is appended to an explored node's list), the node's own list
     // was sorted at the end of its insertAllEdgesOfRead, and a node's marked edges are removed only after all its
@@ -336,5 +348,11 @@ float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out)
     }
     return std::chrono::duration<float, std::milli>(t_end - t0).count();
 }
+
+float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out) { return run_walk(in, &out, nullptr); }
+
+// The traversal alone (economyGraph.cpp:513-564): order[s] = when S read s was explored (insertAllEdgesOfRead ran for it).
+// That order is all the final lists depend on: an overlap is inserted by whichever end point is explored first (:605).
+float run_host_phase_c_order(const PhaseCInput &in, std::vector<uint32_t> &order) { return run_walk(in, nullptr, &order); }
 
 }  // namespace sg

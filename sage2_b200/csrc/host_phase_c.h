@@ -25,5 +25,7 @@ struct PhaseCOutput {
 
 // returns elapsed host milliseconds
 float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out);
+// the traversal alone: order[s] = position of S read s in the exploration sequence (lists / marks / filtering elsewhere)
+float run_host_phase_c_order(const PhaseCInput &in, std::vector<uint32_t> &order);
 
 }  // namespace sg

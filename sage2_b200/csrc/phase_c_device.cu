@@ -10,9 +10,12 @@
 //   * the final lists depend on the traversal order only through WHICH endpoint inserted an overlap.  If every
 //     candidate (a -> b, type, overhang) has its twin (b -> a, reverse type, twin overhang) in b's own candidate list,
 //     either endpoint inserts the same two entries and list[a] = a's own candidates + a's phase-B entries.
-// So: check that the candidate set is symmetric (it is not when a read contains another one -- variable read lengths --
-// or when one of the two h-mers of an overlap is a masked key); if it is, build, sort, mark and filter every list on the
-// device, one warp per read; if it is not (or a list exceeds the per-warp capacity) the caller falls back to the walk.
+// So the lists are a function of the EXPLORATION ORDER alone: overlap {a, b} enters both lists with the candidate record
+// of the end point explored first.  If the candidate set is symmetric the order is immaterial and nothing runs on the
+// host; if it is not (a read contains another one -- variable read lengths -- or one of the two h-mers of an overlap is a
+// masked key) the host does the traversal only (host_phase_c.cpp, run_host_phase_c_order) and hands over the order.  Either
+// way every list is built, sorted, marked and filtered here, one warp per read.  A list longer than the per-warp
+// capacity sends the whole phase to the host walk.
 #include "context.h"
 
 namespace sg {
@@ -90,11 +93,55 @@ struct PcHash {
     }
 };
 
-// one warp per read of S: list = own candidates + phase-B half edges, sorted by compareLengthBased (:853-871), marked
-// like markTransitiveEdge, filtered like removeTransitiveEdges; survivors with id > read go to `out`
-__global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__restrict__ s_ids, const u32 *__restrict__ sidx, u64 nS,
-                                                                 const u32 *__restrict__ counts, const u32 *__restrict__ offs, const u64 *__restrict__ cand,
-                                                                 const uint8_t *__restrict__ explored, const u64 *__restrict__ pb_owner, const u64 *__restrict__ pb_rec, u64 n_pb,
+// Half edges of phase C.  An overlap {a, b} of two S reads is inserted by whichever end point is explored first
+// (insertAllEdgesOfRead skips partners that were explored already, :605), with THAT read's candidate record and the
+// twin computed from it (insertEdgeEconomy, :813-849).  order[s] = position of S read s in the exploration sequence;
+// without it (symmetric candidate sets: either end point inserts the same two entries) the S index serves.
+__global__ void __launch_bounds__(256) pc_cand_half_edges_kernel(const u32 *__restrict__ s_ids, const u32 *__restrict__ sidx, u64 nS,
+                                                                  const u32 *__restrict__ counts, const u32 *__restrict__ offs, const u64 *__restrict__ cand,
+                                                                  const uint16_t *__restrict__ len, const u32 *__restrict__ order,
+                                                                  u64 *__restrict__ owner, u64 *__restrict__ rec, unsigned long long *__restrict__ n_out)
+{
+    const int lane = threadIdx.x & 31;
+    const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nS; s += nwarps) {
+        const u32 a = s_ids[s] + 1, la = len[a - 1];
+        const u32 base = offs[s], m = counts[s];
+        const u32 oa = order ? order[s] : (u32)s;
+        for (u32 x0 = 0; x0 < m; x0 += 32) {
+            const u32 x = x0 + lane;
+            bool keep = false;
+            u64 cw = 0;
+            u32 b = 0;
+            if (x < m) {
+                cw = cand[base + x];
+                b = (u32)(cw >> 32);
+                const u32 sb = sidx[b - 1];
+                keep = oa < (order ? order[sb] : sb);
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            if (km == 0) continue;
+            unsigned long long pos = 0;
+            if (lane == 0) pos = atomicAdd(n_out, 2ull * (unsigned long long)__popc(km));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (keep) {
+                const u64 at = pos + 2ull * (u64)__popc(km & ((1u << lane) - 1u));
+                const u32 t = (u32)(cw >> 20) & 3u;
+                u32 d = (u32)(cw & 0xFFFFFu);
+                if (d & 0x80000u) d |= 0xFFF00000u;
+                const u32 lb = len[b - 1];
+                owner[at] = a;     rec[at] = cw;
+                owner[at + 1] = b; rec[at + 1] = ((u64)a << 32) | ((u64)pc_rev(t) << 20) | ((la - (lb - d)) & 0xFFFFFu);
+            }
+        }
+    }
+}
+
+// one warp per read of S: list = its half edges (phase C + phase B) out of the owner-sorted array, sorted by
+// compareLengthBased (:853-871), marked like markTransitiveEdge, filtered like removeTransitiveEdges; survivors with
+// id > read go to `out`
+__global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__restrict__ s_ids, u64 nS,
+                                                                 const u64 *__restrict__ he_owner, const u64 *__restrict__ he_rec, u64 n_he,
                                                                  u64 *__restrict__ out, unsigned long long *__restrict__ counters /*[0] out, [1] removed*/,
                                                                  u32 *__restrict__ flags)
 {
@@ -108,19 +155,16 @@ __global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__res
     unsigned long long removed = 0;
     for (u64 s = (u64)blockIdx.x * PC_WARPS + warp; s < nS; s += nwarps) {
         const u32 n = s_ids[s] + 1;
-        const u32 cnt = counts[s], base = offs[s];
         u64 plo, phi;
-        pc_range(pb_owner, n_pb, n, plo, phi);
-        const u32 d = cnt + (u32)(phi - plo);
-        if (d > (u32)PC_MAXD) { if (lane == 0) atomicOr(&flags[0], 2u); continue; }
+        pc_range(he_owner, n_he, n, plo, phi);
+        const u32 d = (u32)(phi - plo);
+        if (phi - plo > (u64)PC_MAXD) { if (lane == 0) atomicOr(&flags[0], 2u); continue; }
         if (d == 0) continue;
         u32 P = 1;
         while (P < d) P <<= 1;
         __syncwarp();
         for (u32 x = lane; x < P; x += 32) {
-            u64 cw = 0;
-            if (x < cnt) cw = cand[base + x];
-            else if (x < d) cw = pb_rec[plo + (x - cnt)];
+            const u64 cw = x < d ? he_rec[plo + x] : 0ull;
             // length desc, id desc, type desc  ==  one descending 54-bit key
             key[x] = x < d ? (((cw & 0xFFFFFull) << 34) | ((cw >> 32) << 2) | ((cw >> 20) & 3ull)) : 0ull;
         }
@@ -150,18 +194,10 @@ __global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__res
             const u32 ida = (u32)(key[x] >> 2), t1 = (u32)key[x] & 3u;
             const int sa = H.find(ida);
             if (H.st[sa] == 1) {
-                if (explored[ida - 1] == 0) {
-                    const u32 sx = sidx[ida - 1], bx = offs[sx], mx = counts[sx];
-                    for (u32 y = lane; y < mx; y += 32) {
-                        const u64 cw = cand[bx + y];
-                        const int sf = H.find((u32)(cw >> 32));
-                        if (sf >= 0 && H.st[sf] == 1 && pc_rule(t1, (u32)(cw >> 20) & 3u)) H.st[sf] = 2;
-                    }
-                }
                 u64 qlo, qhi;
-                pc_range(pb_owner, n_pb, ida, qlo, qhi);
+                pc_range(he_owner, n_he, ida, qlo, qhi);
                 for (u64 y = qlo + lane; y < qhi; y += 32) {
-                    const u64 cw = pb_rec[y];
+                    const u64 cw = he_rec[y];
                     const int sf = H.find((u32)(cw >> 32));
                     if (sf >= 0 && H.st[sf] == 1 && pc_rule(t1, (u32)(cw >> 20) & 3u)) H.st[sf] = 2;
                 }
@@ -193,12 +229,10 @@ static unsigned pc_grid(u64 n, unsigned per_block)
     return (unsigned)g;
 }
 
-// true: `out` holds n_out (w0,w1) records owned by the S reads; false: not applicable, use the host walk
-bool device_phase_c(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand, u64 nC,
-                    const u64 *selB, const u32 *selLen, u64 nSel, DevBuf<u64> &out, u64 &n_out, u64 &removed)
+// every candidate has its twin in the other read's list?  (then the traversal order cannot matter)
+bool phase_c_is_symmetric(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand)
 {
     cudaStream_t st = c.stream;
-    const u64 U = c.cnt.unique_reads;
     DevBuf<u32> flags(1, st);
     SG_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(u32), st));
     pc_symmetry_kernel<<<pc_grid(nS, 8), 256, 0, st>>>(s_ids, sidx, nS, counts, offs, cand, c.len.p, flags.p);
@@ -206,35 +240,57 @@ bool device_phase_c(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const
     u32 h_flags = 0;
     SG_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
-    if (h_flags) return false;
+    return h_flags == 0;
+}
 
-    // phase-B half edges sorted by owner
-    const u64 n_pb = 2 * nSel;
-    DevBuf<u64> o0(n_pb, st), o1(n_pb, st), r0(n_pb, st), r1(n_pb, st);
-    const u64 *pb_owner = o0.p, *pb_rec = r0.p;
+// Lists, marks and filtering of phase C on the device.  d_order: exploration order of the S reads (device array, from the
+// host traversal) or null for symmetric candidate sets.  true: `out` holds n_out (w0,w1) records owned by the S reads;
+// false: a list exceeds the per-warp capacity, use the host walk.
+bool device_phase_c(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand, u64 nC,
+                    const u64 *selB, const u32 *selLen, u64 nSel, const u32 *d_order, DevBuf<u64> &out, u64 &n_out, u64 &inserted, u64 &removed)
+{
+    cudaStream_t st = c.stream;
+    const u64 U = c.cnt.unique_reads;
+    // half edges: phase B (both end points of every selected record) + phase C (inserting end point + twin), sorted by owner
+    const u64 n_pb = 2 * nSel, cap = n_pb + 2 * nC;
+    DevBuf<u64> o0(cap + 1, st), o1(cap + 1, st), r0(cap + 1, st), r1(cap + 1, st);
+    DevBuf<unsigned long long> cnt(3, st);
+    SG_CUDA(cudaMemsetAsync(cnt.p, 0, 3 * sizeof(unsigned long long), st));
     if (n_pb) {
         pc_half_edges_kernel<<<pc_grid(nSel, 256), 256, 0, st>>>(selB, selLen, nSel, o0.p, r0.p);
         SG_LAUNCHED();
+    }
+    if (nC) {
+        pc_cand_half_edges_kernel<<<pc_grid(nS, 8), 256, 0, st>>>(s_ids, sidx, nS, counts, offs, cand, c.len.p, d_order, o0.p + n_pb, r0.p + n_pb, cnt.p + 2);
+        SG_LAUNCHED();
+    }
+    unsigned long long n_c = 0;
+    SG_CUDA(cudaMemcpyAsync(&n_c, cnt.p + 2, sizeof(n_c), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    const u64 n_he = n_pb + n_c;
+    const u64 *he_owner = o0.p, *he_rec = r0.p;
+    if (n_he) {
         SortCols cols;
         cols.a[0] = o0.p; cols.a[1] = o1.p; cols.b[0] = r0.p; cols.b[1] = r1.p; cols.v[0] = cols.v[1] = nullptr;
         int id_bits = 1;
         while ((U >> id_bits) != 0) ++id_bits;
-        const int cur = radix_sort_bits(cols, 0, n_pb, false, 0, id_bits, st);
-        pb_owner = cols.a[cur]; pb_rec = cols.b[cur];
+        const int cur = radix_sort_bits(cols, 0, n_he, false, 0, id_bits, st);
+        he_owner = cols.a[cur]; he_rec = cols.b[cur];
     }
-    out.alloc(2 * (nC + n_pb) + 2, st);
-    DevBuf<unsigned long long> cnt(2, st);
-    SG_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(unsigned long long), st));
-    pc_node_kernel<<<pc_grid(nS, PC_WARPS), PC_WARPS * 32, 0, st>>>(s_ids, sidx, nS, counts, offs, cand, c.explored.p, pb_owner, pb_rec, n_pb,
-                                                                    out.p, cnt.p, flags.p);
+    out.alloc(2 * n_he + 2, st);
+    DevBuf<u32> flags(1, st);
+    SG_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(u32), st));
+    pc_node_kernel<<<pc_grid(nS, PC_WARPS), PC_WARPS * 32, 0, st>>>(s_ids, nS, he_owner, he_rec, n_he, out.p, cnt.p, flags.p);
     SG_LAUNCHED();
     unsigned long long h_cnt[2];
+    u32 h_flags = 0;
     SG_CUDA(cudaMemcpyAsync(h_cnt, cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     if (h_flags) return false;           // a list longer than PC_MAXD
     n_out = h_cnt[0];
     removed = h_cnt[1];
+    inserted = n_c;
     return true;
 }
 

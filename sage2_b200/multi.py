@@ -270,6 +270,9 @@ def partitioned_graph_steps(gpu, rank: int, world: int, view, bases_ptr: int, of
 
 def _gather_var_dist(full: torch.Tensor, counts, rank: int, world: int):
     """All-gather of blocks of different sizes: equal blocks in place, otherwise through a padded copy."""
+    if full.dtype != torch.uint8:      # bytes travel (neither NCCL nor gloo has a 16-bit integer type)
+        es = full.element_size()
+        return _gather_var_dist(full.view(torch.uint8), [c * es for c in counts], rank, world)
     if len(set(counts)) == 1 and full.is_cuda:
         c = counts[0]
         if c:
@@ -278,9 +281,6 @@ def _gather_var_dist(full: torch.Tensor, counts, rank: int, world: int):
     m = max(counts)
     if m == 0:
         return
-    if not full.is_cuda and full.dtype != torch.uint8:      # gloo moves bytes (it has no 16-bit integer type)
-        es = full.element_size()
-        return _gather_var_dist(full.view(torch.uint8), [c * es for c in counts], rank, world)
     offs = [sum(counts[:q]) for q in range(world)]
     mine = torch.zeros(m, dtype=full.dtype, device=full.device)
     mine[:counts[rank]] = full[offs[rank]:offs[rank] + counts[rank]]

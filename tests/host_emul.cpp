@@ -4,6 +4,7 @@
 // the `-m "not gpu"` suite check the bit arithmetic, the extension state machine, phase B and the
 // phase-C walk against the oracle without a GPU.  It is NOT a fallback: nothing in sage2_b200 links it.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -371,6 +372,64 @@ void scan_reads(Emu &e, const u32 *ids, u64 first, u64 n, const Lookup &lookup, 
     }
 }
 
+// ---- phase_c_device.cu restated: lists, marks and filtering of phase C from the exploration order ----------------------
+static u32 rev_t(u32 t) { return t == 0 ? 3u : (t == 3 ? 0u : t); }
+static bool tr_rule(u32 t1, u32 t2) { return ((t1 == 0 || t1 == 2) && (t2 == 0 || t2 == 1)) || ((t1 == 1 || t1 == 3) && (t2 == 2 || t2 == 3)); }
+void phase_c_from_order(const Emu &e, const PhaseCInput &in, const std::vector<u32> &order, std::vector<u64> &out, u64 &inserted, u64 &removed)
+{
+    std::map<u32, u32> sidx;                                     // read id (1-based) -> S index
+    for (u64 s = 0; s < in.nS; ++s) sidx[in.s_ids[s] + 1] = (u32)s;
+    std::map<u32, std::vector<u64>> lists;                       // owner id -> half-edge records id << 32 | type << 20 | overhang
+    for (u64 x = 0; x < in.nB; ++x) {
+        const u64 w0 = in.edgesB[2 * x], w1 = in.edgesB[2 * x + 1];
+        const u32 a = (u32)(w0 >> 32), b = (u32)w0, type = (u32)(w1 >> 20) & 3u, len = (u32)(w1 & 0xFFFFFu);
+        const u32 la = in.edgesB_len[x] & 0xFFFFu, lb = in.edgesB_len[x] >> 16;
+        lists[a].push_back(((u64)b << 32) | ((u64)type << 20) | len);
+        lists[b].push_back(((u64)a << 32) | ((u64)rev_t(type) << 20) | ((la - (lb - len)) & 0xFFFFFu));
+    }
+    inserted = 0; removed = 0;
+    for (u64 s = 0; s < in.nS; ++s) {
+        const u32 a = in.s_ids[s] + 1, la = e.len[a - 1];
+        for (u32 q = in.cand_off[s]; q < in.cand_off[s + 1]; ++q) {
+            const u64 cw = in.cand[q];
+            const u32 b = (u32)(cw >> 32), t = (u32)(cw >> 20) & 3u;
+            u32 d = (u32)(cw & 0xFFFFFu);
+            if (d & 0x80000u) d |= 0xFFF00000u;
+            if (!(order[s] < order[sidx.at(b)])) continue;
+            const u32 lb = e.len[b - 1];
+            lists[a].push_back(cw);
+            lists[b].push_back(((u64)a << 32) | ((u64)rev_t(t) << 20) | ((la - (lb - d)) & 0xFFFFFu));
+            inserted += 2;
+        }
+    }
+    auto key_of = [](u64 cw) { return ((cw & 0xFFFFFull) << 34) | ((cw >> 32) << 2) | ((cw >> 20) & 3ull); };
+    for (u64 s = 0; s < in.nS; ++s) {
+        const u32 n = in.s_ids[s] + 1;
+        auto it = lists.find(n);
+        if (it == lists.end()) continue;
+        std::vector<u64> key;
+        for (u64 cw : it->second) key.push_back(key_of(cw));
+        std::sort(key.begin(), key.end(), std::greater<u64>());               // length desc, id desc, type desc (:853-871)
+        std::map<u32, int> st;
+        for (u64 kx : key) st[(u32)(kx >> 2)] = 1;
+        for (u64 kx : key) {
+            const u32 ida = (u32)(kx >> 2), t1 = (u32)kx & 3u;
+            if (st[ida] != 1) continue;
+            auto jt = lists.find(ida);
+            if (jt == lists.end()) continue;
+            for (u64 cw : jt->second) {
+                auto f = st.find((u32)(cw >> 32));
+                if (f != st.end() && f->second == 1 && tr_rule(t1, (u32)(cw >> 20) & 3u)) f->second = 2;
+            }
+        }
+        for (u64 kx : key) {
+            const u32 id = (u32)(kx >> 2);
+            if (st[id] == 2) { removed++; continue; }
+            if (id > n) { out.push_back(((u64)n << 32) | id); out.push_back(((kx & 3ull) << 20) | (kx >> 34)); }
+        }
+    }
+}
+
 // rank's slice of the reads (sage2gpu_phase_a_partition); arrays padded to world * chunk
 void phase_a(Emu &e, int rank, int world)
 {
@@ -609,6 +668,24 @@ void finish_after_b(Emu &e)
         run_host_phase_c(in, out);
         e.inserted = out.inserted; e.removed = out.removed;
         all = out.edges;
+        // phase_c_device.cu on the CPU: the same records from the traversal ORDER alone (run_host_phase_c_order): half
+        // edges of every overlap from the end point explored first, lists sorted, marked and filtered read by read
+        if (!getenv("SAGE2_EMUL_NO_ORDER_CHECK")) {
+            std::vector<u32> order;
+            run_host_phase_c_order(in, order);
+            std::vector<u64> got;
+            u64 ins2 = 0, rem2 = 0;
+            phase_c_from_order(e, in, order, got, ins2, rem2);
+            std::vector<std::pair<u64, u64>> A, B;
+            for (size_t x = 0; x < all.size(); x += 2) A.emplace_back(all[x], all[x + 1]);
+            for (size_t x = 0; x < got.size(); x += 2) B.emplace_back(got[x], got[x + 1]);
+            std::sort(A.begin(), A.end()); std::sort(B.begin(), B.end());
+            if (A != B || ins2 != out.inserted || rem2 != out.removed) {
+                fprintf(stderr, "host_emul: phase C from the traversal order differs from the walk (%zu vs %zu records, inserted %llu vs %llu, removed %llu vs %llu)\n",
+                        B.size(), A.size(), (unsigned long long)ins2, (unsigned long long)out.inserted, (unsigned long long)rem2, (unsigned long long)out.removed);
+                abort();
+            }
+        }
     }
     for (size_t x = 0; x < edgesB.size(); x += 2)
         if (e.explored_b[(edgesB[x] >> 32) - 1] != 0) { all.push_back(edgesB[x]); all.push_back(edgesB[x + 1]); }
