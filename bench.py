@@ -74,30 +74,14 @@ def make_workload(name: str, genome_size: int | None = None):
 
 
 def cached_workload(name: str, rank: int, world: int, barrier):
-    """The full-size read set, generated once per box (rank 0) and memory-mapped by everybody."""
-    best = None
-    for d in ("/dev/shm", tempfile.gettempdir()):
-        try:
-            st = os.statvfs(d)
-            if st.f_bavail * st.f_frsize > (12 << 30) and os.access(d, os.W_OK):
-                best = d
-                break
-        except OSError:
-            pass
-    if best is None:
-        return make_workload(name)
-    path = os.path.join(best, f"sage2_bench_{name}_v2.npy")
-    meta = path + ".json"
-    if rank == 0 and not (os.path.exists(path) and os.path.exists(meta)):
-        reads, k, cfg = make_workload(name)
-        tmp = path + f".{os.getpid()}.tmp.npy"
-        np.save(tmp, reads)
-        os.replace(tmp, path)
-        json.dump({"k": k, "cfg": cfg}, open(meta, "w"))
-        del reads
-    barrier()
-    m = json.load(open(meta))
-    return np.load(path, mmap_mode="r"), m["k"], m["cfg"]
+    """The full-size read set, generated once per box (rank 0) and memory-mapped by everybody (sage2_b200.synth.config_cached,
+    the cache the full-size tests use too)."""
+    from sage2_b200 import synth
+    reads, k = synth.config_cached(name, wait=barrier)
+    cfg = {"workload": SHAPES[name][0] if name in SHAPES else name, "name": name, "k": k}
+    if name in SHAPES:
+        cfg.update(genome_bp=SHAPES[name][1], read_len=SHAPES[name][2], coverage=SHAPES[name][3])
+    return reads, k, cfg
 
 
 def golden_for(name: str):
@@ -382,10 +366,12 @@ class Job:
         args, gpu, world = self.args, self.gpu, self.world
         for _ in range(max(3, warmup)):
             self.step_device()
+        self.xstats.clear()
         sampler = ClockSampler(self.local) if sample_clocks and self.rank == 0 and not os.environ.get("SAGE2_BENCH_NO_SAMPLER") else None
         dev_ms, wall_ms, launches, stage = self.timed(self.step_device, steps)
         counters = gpu.counters()
         clocks = sampler.stop() if sampler else None
+        xwall = {kk: (vv / steps) for kk, vv in self.xstats.items()} if self.xstats else None
         self.check_parity("device_resident")
         self.step_host()
         e2e_dev_ms, e2e_wall_ms, _, _ = self.timed(self.step_host, steps)
@@ -415,7 +401,7 @@ class Job:
             self.sharded = not self.sharded
             self.comm["sent"] = main_sent
         return dict(dev_ms=dev_ms, wall_ms=wall_ms, launches=launches, stage=stage, counters=counters, clocks=clocks,
-                    e2e_dev_ms=e2e_dev_ms, n_edges=n_edges, alt=alt, steps=steps)
+                    e2e_dev_ms=e2e_dev_ms, n_edges=n_edges, alt=alt, steps=steps, xwall=xwall)
 
     def roofline(self, m: dict, with_gather: bool) -> dict:
         peaks = {}
@@ -546,6 +532,7 @@ def run_ours(args):
         "wall_ms_per_step": m["wall_ms"] / steps,
         "stage_ms": stage,
         "alt_table": m["alt"],
+        "exchange_wall_ms_per_step": m.get("xwall"),
         "cfg2": extra,
         "per_step_ms": {"device_resident": per_step[0], "e2e": per_step[1]},
         "counters": {kk: counters[kk] for kk in ("good_reads", "unique_reads", "distinct_keys", "keys_over_threshold", "compare_calls",

@@ -136,7 +136,8 @@ int sage2gpu_finish_graph(sage2gpu_ctx *ctx);
  *                                       in its place (records: uint64 x record_stride_words per read; lengths,
  *                                       frequencies: uint16); [first, first + counts[rank]) is this rank's id range
  *   [all-gather of the three arrays, variable block sizes]   reads_gather_finish(): reverse complements, done.
- *   build_hash_table_shard(rank, world) hashPrefixesAndSuffix (hashTable.cpp:70-128) for the keys this rank owns;
+ *   build_hash_table_part(rank, world)  hashPrefixesAndSuffix (hashTable.cpp:70-128) for the keys this rank owns, built in its
+ *                                       place inside a slot array with room for all shards;
  *   table_shard_info, [all-gather of the entry counts], table_gather_layout(entry_counts): room for all shards back to
  *                                       back (slots: slots_per_shard uint64 per shard; entries: uint32), own shard in place
  *   [all-gather of both arrays]         table_gather_finish(): the complete table on every GPU; probes stay local
@@ -144,9 +145,29 @@ int sage2gpu_finish_graph(sage2gpu_ctx *ctx);
  * The exchanges are the host's (NCCL through sage2_b200/multi.py, or peer copies inside one process). */
 int sage2gpu_load_reads_partition(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int min_overlap,
                                   int on_device, int rank, int world, uint64_t *unique_local);
+/* The same with the INGEST partitioned too (inputs that no single GPU should hold as characters, e.g. config #5):
+ *   pack_slice(slice, max_read_length)  isGoodRead + canonical orientation + 2-bit pack (readLoader.cpp:146-213) of this
+ *                                       rank's slice of the input; max_read_length = longest read of the WHOLE read set
+ *                                       (it fixes the record stride on every rank); sums of *good_reads / *total_bp over
+ *                                       the ranks are the read set's counters
+ *   [all-gather of the slice sizes]     raw_gather_layout(counts): room for the packed records of all slices, own slice in place
+ *   [all-gather of the records, record_words uint64 per read; all-reduce of the counters]   raw_gather_finish(totals)
+ *   organize_partition(rank, world)     as load_reads_partition from here on. */
+int sage2gpu_pack_slice(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int min_overlap, int on_device,
+                        int max_read_length, uint64_t *good_reads, uint64_t *total_bp, uint64_t *record_words);
+int sage2gpu_raw_gather_layout(sage2gpu_ctx *ctx, int rank, int world, const uint64_t *counts, void **records, uint64_t *first, uint64_t *total);
+int sage2gpu_raw_gather_finish(sage2gpu_ctx *ctx, uint64_t total_reads, uint64_t good_reads, uint64_t total_bp);
+int sage2gpu_organize_partition(sage2gpu_ctx *ctx, int rank, int world, uint64_t *unique_local);
+/* Measurement aid (no reference counterpart): pairs [first_pair, first_pair + n_pairs) of a synthetic error-free paired-end
+ * read set (uniform-random genome of genome_bp bases that is a pure function of the seed, mates interleaved, insert size
+ * ~ N(insert_mean, insert_sd) clipped to >= 2 * read_length) written as characters into DEVICE buffers: d_bases
+ * (2 * n_pairs * read_length bytes), d_offsets (2 * n_pairs + 1).  Any rank can generate any slice. */
+int sage2gpu_synth_reads(sage2gpu_ctx *ctx, uint8_t *d_bases, int64_t *d_offsets, uint64_t first_pair, uint64_t n_pairs, uint64_t genome_bp,
+                         int read_length, float insert_mean, float insert_sd, uint64_t seed);
 int sage2gpu_reads_gather_layout(sage2gpu_ctx *ctx, const uint64_t *counts, void **records, void **lengths, void **frequencies,
                                  uint64_t *first, uint64_t *total, uint64_t *record_stride_words);
 int sage2gpu_reads_gather_finish(sage2gpu_ctx *ctx);
+int sage2gpu_build_hash_table_part(sage2gpu_ctx *ctx, int rank, int world);
 int sage2gpu_table_shard_info(sage2gpu_ctx *ctx, uint64_t *slots, uint64_t *entries, uint64_t *distinct_keys, uint64_t *keys_over_threshold);
 int sage2gpu_table_gather_layout(sage2gpu_ctx *ctx, const uint64_t *entry_counts, void **slots, void **entries, uint64_t *slots_per_shard,
                                  uint64_t *entries_first);

@@ -54,7 +54,9 @@ EXPORTS = ["sage2gpu_create", "sage2gpu_destroy", "sage2gpu_last_error", "sage2g
            "sage2gpu_map_reads", "sage2gpu_mailbox_create", "sage2gpu_mailbox_open", "sage2gpu_route_post", "sage2gpu_answer_post",
            "sage2gpu_route_collect", "sage2gpu_mailbox_barrier", "sage2gpu_digest", "sage2gpu_set_option",
            "sage2gpu_load_reads_partition", "sage2gpu_reads_gather_layout", "sage2gpu_reads_gather_finish",
-           "sage2gpu_table_shard_info", "sage2gpu_table_gather_layout", "sage2gpu_table_gather_finish"]
+           "sage2gpu_table_shard_info", "sage2gpu_table_gather_layout", "sage2gpu_table_gather_finish",
+           "sage2gpu_pack_slice", "sage2gpu_raw_gather_layout", "sage2gpu_raw_gather_finish", "sage2gpu_organize_partition",
+           "sage2gpu_synth_reads", "sage2gpu_build_hash_table_part"]
 
 _lib = None
 
@@ -124,8 +126,14 @@ def load_library():
         lib.sage2gpu_write_graph3.argtypes = [vp, C.c_char_p]
         lib.sage2gpu_measure_gather.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
         lib.sage2gpu_load_reads_partition.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, u64p]
+        lib.sage2gpu_pack_slice.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, u64p, u64p, u64p]
+        lib.sage2gpu_raw_gather_layout.argtypes = [vp, C.c_int, C.c_int, u64p, C.POINTER(vp), u64p, u64p]
+        lib.sage2gpu_raw_gather_finish.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
+        lib.sage2gpu_organize_partition.argtypes = [vp, C.c_int, C.c_int, u64p]
+        lib.sage2gpu_synth_reads.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_float, C.c_float, C.c_uint64]
         lib.sage2gpu_reads_gather_layout.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p, u64p, u64p]
         lib.sage2gpu_reads_gather_finish.argtypes = [vp]
+        lib.sage2gpu_build_hash_table_part.argtypes = [vp, C.c_int, C.c_int]
         lib.sage2gpu_table_shard_info.argtypes = [vp, u64p, u64p, u64p, u64p]
         lib.sage2gpu_table_gather_layout.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), u64p, u64p]
         lib.sage2gpu_table_gather_finish.argtypes = [vp, u64p, u64p, u64p]
@@ -226,6 +234,33 @@ class Sage2Gpu:
                                                             int(rank), int(world), C.byref(u)), "load_reads_partition")
         return int(u.value)
 
+    def pack_slice(self, bases_ptr: int, offsets_ptr: int, n_reads: int, min_overlap: int, device: bool, max_read_length: int) -> dict:
+        g, b, w = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sage2gpu_pack_slice(self._h, bases_ptr, offsets_ptr, int(n_reads), int(min_overlap), int(bool(device)),
+                                                  int(max_read_length), C.byref(g), C.byref(b), C.byref(w)), "pack_slice")
+        return {"good_reads": int(g.value), "total_bp": int(b.value), "record_words": int(w.value)}
+
+    def raw_gather_layout(self, rank: int, world: int, counts) -> dict:
+        cs = (C.c_uint64 * len(counts))(*[int(x) for x in counts])
+        p = C.c_void_p()
+        first, total = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sage2gpu_raw_gather_layout(self._h, int(rank), int(world), cs, C.byref(p), C.byref(first), C.byref(total)),
+                    "raw_gather_layout")
+        return {"records": p.value or 0, "first": int(first.value), "total": int(total.value)}
+
+    def raw_gather_finish(self, total_reads: int, good_reads: int, total_bp: int):
+        self._check(self._lib.sage2gpu_raw_gather_finish(self._h, int(total_reads), int(good_reads), int(total_bp)), "raw_gather_finish")
+
+    def organize_partition(self, rank: int, world: int) -> int:
+        u = C.c_uint64()
+        self._check(self._lib.sage2gpu_organize_partition(self._h, int(rank), int(world), C.byref(u)), "organize_partition")
+        return int(u.value)
+
+    def synth_reads(self, bases_ptr: int, offsets_ptr: int, first_pair: int, n_pairs: int, genome_bp: int, read_length: int,
+                    insert_mean: float = 450.0, insert_sd: float = 30.0, seed: int = 1):
+        self._check(self._lib.sage2gpu_synth_reads(self._h, bases_ptr, offsets_ptr, int(first_pair), int(n_pairs), int(genome_bp), int(read_length),
+                                                   float(insert_mean), float(insert_sd), int(seed)), "synth_reads")
+
     def reads_gather_layout(self, counts) -> dict:
         cs = (C.c_uint64 * len(counts))(*[int(x) for x in counts])
         p = [C.c_void_p() for _ in range(3)]
@@ -237,6 +272,9 @@ class Sage2Gpu:
 
     def reads_gather_finish(self):
         self._check(self._lib.sage2gpu_reads_gather_finish(self._h), "reads_gather_finish")
+
+    def build_hash_table_part(self, rank: int, world: int):
+        self._check(self._lib.sage2gpu_build_hash_table_part(self._h, int(rank), int(world)), "build_hash_table_part")
 
     def table_shard_info(self) -> dict:
         v = [C.c_uint64() for _ in range(4)]

@@ -177,6 +177,56 @@ int sage2gpu_load_reads_partition(sage2gpu_ctx *ctx, const uint8_t *bases, const
     });
 }
 
+int sage2gpu_pack_slice(sage2gpu_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, int min_overlap, int on_device,
+                        int max_read_length, uint64_t *good_reads, uint64_t *total_bp, uint64_t *record_words)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(min_overlap >= 1 && min_overlap < 65535, "min_overlap out of range");
+        SG_CHECK(max_read_length >= 1, "the longest read of the whole read set must be given");
+        c.min_overlap = min_overlap;
+        c.tm = sg::Timers();
+        StageTimer t(c.stream);
+        sg::stage_ingest_ascii(c, bases, offsets, n_reads, on_device != 0, max_read_length);
+        c.tm.ingest = t.stop();
+        if (good_reads) *good_reads = c.cnt.good_reads;
+        if (total_bp) *total_bp = c.cnt.total_bp;
+        if (record_words) *record_words = (uint64_t)c.SW;
+    });
+}
+
+int sage2gpu_raw_gather_layout(sage2gpu_ctx *ctx, int rank, int world, const uint64_t *counts, void **records, uint64_t *first, uint64_t *total)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::u64 f = 0, tot = 0;
+        sg::stage_raw_gather_layout(c, rank, world, (const sg::u64 *)counts, records, &f, &tot);
+        if (first) *first = f;
+        if (total) *total = tot;
+        c.tm.ingest += t.stop();
+    });
+}
+
+int sage2gpu_raw_gather_finish(sage2gpu_ctx *ctx, uint64_t total_reads, uint64_t good_reads, uint64_t total_bp)
+{
+    return guarded(ctx, [&](sg::Context &c) { sg::stage_raw_gather_finish(c, total_reads, good_reads, total_bp); });
+}
+
+int sage2gpu_organize_partition(sage2gpu_ctx *ctx, int rank, int world, uint64_t *unique_local)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_organize_reads(c, rank, world);
+        c.tm.sort_reads = t.stop();
+        if (unique_local) *unique_local = world > 1 ? c.rp_local : c.cnt.unique_reads;
+    });
+}
+
+int sage2gpu_synth_reads(sage2gpu_ctx *ctx, uint8_t *d_bases, int64_t *d_offsets, uint64_t first_pair, uint64_t n_pairs, uint64_t genome_bp,
+                         int read_length, float insert_mean, float insert_sd, uint64_t seed)
+{
+    return guarded(ctx, [&](sg::Context &c) { sg::stage_synth_reads(c, d_bases, d_offsets, first_pair, n_pairs, genome_bp, read_length, insert_mean, insert_sd, seed); });
+}
+
 int sage2gpu_reads_gather_layout(sage2gpu_ctx *ctx, const uint64_t *counts, void **records, void **lengths, void **frequencies,
                                  uint64_t *first, uint64_t *total, uint64_t *record_stride_words)
 {
@@ -201,6 +251,15 @@ int sage2gpu_reads_gather_finish(sage2gpu_ctx *ctx)
 }
 
 // ---- several GPUs, replicated table: one key-hash shard built per rank, the shards all-gathered (table.cu) --------------
+int sage2gpu_build_hash_table_part(sage2gpu_ctx *ctx, int rank, int world)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        StageTimer t(c.stream);
+        sg::stage_build_table(c, rank, world, true);
+        c.tm.build_table = t.stop();
+    });
+}
+
 int sage2gpu_table_shard_info(sage2gpu_ctx *ctx, uint64_t *slots, uint64_t *entries, uint64_t *distinct_keys, uint64_t *keys_over_threshold)
 {
     return guarded(ctx, [&](sg::Context &c) {

@@ -47,6 +47,7 @@ struct Context {
         // everything a context keeps between stages is persistent; stage-local temporaries use `arena`
         d_bases.persistent = d_offsets.persistent = up_d_bases.persistent = up_d_offsets.persistent = true;
         raw.persistent = F.persistent = RC.persistent = len.persistent = freq.persistent = true;
+        F_loc.persistent = len_loc.persistent = freq_loc.persistent = raw_slice.persistent = entries_loc.persistent = true;
         slots.persistent = entries.persistent = true;
         extR.persistent = extL.persistent = flag5.persistent = cont_max.persistent = explored.persistent = edges.persistent = true;
         rt_queries.persistent = rt_qmap.persistent = rt_wslot.persistent = rt_wentries.persistent = rt_ids.persistent = true;
@@ -83,6 +84,13 @@ struct Context {
     // reads organised by key range over several GPUs (stage_organize_reads with world > 1)
     int rp_rank = 0, rp_world = 1;
     u64 rp_local = 0, rp_first = 0, rp_total = 0;
+    u64 rg_total = 0;           // reads of all slices after stage_raw_gather_layout
+    // this rank's unique run before it moves into the global arrays (grow-only, kept between calls)
+    DevBuf<u64> F_loc;
+    DevBuf<uint16_t> len_loc, freq_loc;
+    DevBuf<u64> raw_slice;      // this rank's packed slice of a partitioned ingest (the joint array is `raw`)
+    DevBuf<u32> entries_loc;    // this rank's shard's entry runs before they move into the joint entries[] array
+    bool tb_joint = false;      // the shard was built in its place inside a slot array with room for all shards
 
     // prefix/suffix table
     DevBuf<u64> slots;          // [cap]
@@ -125,7 +133,11 @@ struct Context {
 };
 
 // stages (each throws sg::CudaError)
-void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident);
+void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident, int forced_max_len = 0);
+void stage_raw_gather_layout(Context &c, int rank, int world, const u64 *counts, void **raw, u64 *first, u64 *total);
+void stage_raw_gather_finish(Context &c, u64 total_reads, u64 good_reads, u64 total_bp);
+// synth.cu: synthetic paired-end reads generated on the device (measurement aid)
+void stage_synth_reads(Context &c, uint8_t *d_bases, int64_t *d_offsets, u64 first_pair, u64 n_pairs, u64 genome_bp, int read_len, float mu, float sigma, u64 seed);
 void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads);
 // parse.cu: record splitting of raw FASTA/FASTQ text on the device; false = irregular layout, nothing appended
 bool stage_parse_text_chunk(Context &c, const uint8_t *text, u64 n_bytes, bool final, int &marker, u64 max_records, u64 &consumed, u64 &n_records);
@@ -133,7 +145,7 @@ void stage_remove_uploaded(Context &c, u64 first, u64 count);
 void stage_organize_reads(Context &c, int rank = 0, int world = 1);   // world > 1: this rank's key range of the reads only
 void stage_reads_gather_layout(Context &c, const u64 *counts, void **F, void **len, void **freq, u64 *first, u64 *total);
 void stage_reads_gather_finish(Context &c);
-void stage_build_table(Context &c, int rank = 0, int world = 1);   // key-hash shard `rank` of `world`
+void stage_build_table(Context &c, int rank = 0, int world = 1, bool joint = false);   // key-hash shard `rank` of `world`; joint: inside an array with room for all shards
 void stage_table_gather_layout(Context &c, const u64 *entry_counts, void **slots, void **entries, u64 *slots_per_shard, u64 *entries_first);
 void stage_table_gather_finish(Context &c, const u64 *entry_counts, const u64 *distinct, const u64 *over);
 void stage_phase_a(Context &c, int rank = 0, int world = 1);   // rank's slice of the reads; arrays padded to world * chunk

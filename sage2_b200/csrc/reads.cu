@@ -250,7 +250,7 @@ void stage_upload_chunk(Context &c, const uint8_t *bases, const int64_t *offsets
     c.up_bases += (u64)nb;
 }
 
-void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident)
+void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets, int64_t n_reads, bool device_resident, int forced_max_len)
 {
     cudaStream_t st = c.stream;
     ArenaScope arena_scope(c.arena, st);
@@ -262,7 +262,7 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     c.cnt.total_reads = (u64)n_reads;
     c.h = hash_len_for(c.min_overlap);
     c.cnt.hash_len = (u64)c.h;
-    if (n_reads == 0) { c.SW = 1; c.max_len = 0; return; }
+    if (n_reads == 0 && forced_max_len <= 0) { c.SW = 1; c.max_len = 0; return; }
 
     const uint8_t *d_b = bases;
     const int64_t *d_o = offsets;
@@ -281,14 +281,17 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     SG_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int), st));
     unsigned g = grid_for((u64)n_reads, K1_WARPS * 32, 4);
     if (g > kSMs * 8) g = kSMs * 8;
-    max_len_kernel<<<g, K1_WARPS * 32, 0, st>>>(d_o, (u64)n_reads, d_max.p);
-    SG_LAUNCHED();
+    if (n_reads > 0) { max_len_kernel<<<g, K1_WARPS * 32, 0, st>>>(d_o, (u64)n_reads, d_max.p); SG_LAUNCHED(); }
     int max_len = 0;
     SG_CUDA(cudaMemcpyAsync(&max_len, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     // The reference has no length limit; this build packs reads of up to 1016 bases (kMaxWords 64-bit words per record).
     // Dropping a longer read silently would renumber every read after it, so the call fails instead.
     SG_CHECK(max_len <= 32 * kMaxWords - 8, "a read is longer than 1016 bases: not supported by this build of libsage2gpu");
+    if (forced_max_len > 0) {       // a slice of a read set that several GPUs pack: the record stride follows the longest read of ALL slices
+        SG_CHECK(max_len <= forced_max_len, "a read of this slice is longer than the maximum given for the whole read set");
+        max_len = forced_max_len;
+    }
     if (max_len < 1) max_len = 1;
     c.max_len = max_len;
     c.SW = words_for_len(max_len);
@@ -297,9 +300,10 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
         for (int s : kStrides) if (s >= c.SW) { c.SW = s; break; }
     }
 
-    // K1
-    c.raw.alloc((size_t)n_reads * c.SW, st);
-    DevBuf<u64> &rec = c.raw;
+    // K1 (a slice of a partitioned ingest is packed into a buffer of its own: the joint array is c.raw)
+    DevBuf<u64> &rec = forced_max_len > 0 ? c.raw_slice : c.raw;
+    rec.alloc((size_t)n_reads * c.SW, st);
+    if (n_reads == 0) { c.cnt.good_reads = 0; c.cnt.total_bp = 0; c.cnt.avg_len = 0; return; }
     DevBuf<unsigned long long> d_cnt(2, st);
     SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), st));
     int rpb = K1T_STAGE / (max_len > 0 ? max_len : 1);           // reads per block of the thread-per-read kernel
@@ -360,6 +364,7 @@ __global__ void unique_flag_kernel(const u64 *__restrict__ rec, const u32 *__res
     }
 }
 
+template <bool WITH_RC>
 __global__ void unique_write_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ perm, const u32 *__restrict__ flag,
                                     const u32 *__restrict__ uidx, u64 n_good, int SW, int SWS,
                                     u64 *__restrict__ F, u64 *__restrict__ RC, uint16_t *__restrict__ len, u32 *__restrict__ start)
@@ -371,8 +376,8 @@ __global__ void unique_write_kernel(const u64 *__restrict__ rec, const u32 *__re
         u64 f[kMaxWords], r[kMaxWords];
         for (int w = 0; w < SW; ++w) f[w] = a[w];
         const int l = rec_len(f, SW);
-        revcomp_record(f, r, SW, l);
-        for (int w = 0; w < SWS; ++w) { F[(u64)u * SWS + w] = w < SW ? f[w] : 0ull; RC[(u64)u * SWS + w] = w < SW ? r[w] : 0ull; }
+        if (WITH_RC) revcomp_record(f, r, SW, l);
+        for (int w = 0; w < SWS; ++w) { F[(u64)u * SWS + w] = w < SW ? f[w] : 0ull; if (WITH_RC) RC[(u64)u * SWS + w] = w < SW ? r[w] : 0ull; }
         len[u] = (uint16_t)l;
         start[u] = (u32)i;
     }
@@ -562,7 +567,7 @@ void stage_organize_reads(Context &c, int rank, int world)
     c.cnt.unique_reads = 0;
     c.rp_rank = rank; c.rp_world = world; c.rp_local = 0;
     if (n == 0 || n_good == 0) {
-        c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
+        if (world == 1) { c.F.release(); c.RC.release(); c.len.release(); c.freq.release(); }
         c.have_reads = world == 1;
         return;
     }
@@ -609,10 +614,7 @@ void stage_organize_reads(Context &c, int rank, int world)
         SG_LAUNCHED();
         cur = 1;
         n_good = n_part;
-        if (n_good == 0) {
-            c.F.release(); c.RC.release(); c.len.release(); c.freq.release();
-            return;
-        }
+        if (n_good == 0) return;
     }
     cur = radix_sort_bits(cols, cur, n_good, false, kSortSkipBits, 64, st);      // 4 .. 6 passes on the leading bases
     DevBuf<u32> d_flags(2, st);          // [0] tie-run overflow, [1] unique count
@@ -639,14 +641,22 @@ void stage_organize_reads(Context &c, int rank, int world)
     const u32 U = h_flags[1];
     c.cnt.unique_reads = U;
     c.SWS = storage_words(SW);
-    c.F.alloc((size_t)U * c.SWS, st);
-    c.RC.alloc((size_t)U * c.SWS, st);
-    c.len.alloc(U, st);
-    c.freq.alloc(U, st);
+    // several GPUs: the run goes to buffers of its own and moves into the global arrays once the ranks' counts are known
+    // (all of them grow-only: no multi-GB allocation per call)
+    DevBuf<u64> &Fo = world > 1 ? c.F_loc : c.F;
+    DevBuf<uint16_t> &lo = world > 1 ? c.len_loc : c.len, &fo = world > 1 ? c.freq_loc : c.freq;
+    Fo.alloc((size_t)U * c.SWS, st);
+    lo.alloc(U, st);
+    fo.alloc(U, st);
     DevBuf<u32> start(U, st);
-    unique_write_kernel<<<big_grid(n_good, 128), 128, 0, st>>>(rec.p, perm, flag.p, uidx.p, n_good, SW, c.SWS, c.F.p, c.RC.p, c.len.p, start.p);
+    if (world > 1) {
+        unique_write_kernel<false><<<big_grid(n_good, 128), 128, 0, st>>>(rec.p, perm, flag.p, uidx.p, n_good, SW, c.SWS, Fo.p, nullptr, lo.p, start.p);
+    } else {
+        c.RC.alloc((size_t)U * c.SWS, st);
+        unique_write_kernel<true><<<big_grid(n_good, 128), 128, 0, st>>>(rec.p, perm, flag.p, uidx.p, n_good, SW, c.SWS, Fo.p, c.RC.p, lo.p, start.p);
+    }
     SG_LAUNCHED();
-    freq_kernel<<<big_grid(U), 256, 0, st>>>(start.p, U, n_good, c.freq.p);
+    freq_kernel<<<big_grid(U), 256, 0, st>>>(start.p, U, n_good, fo.p);
     SG_LAUNCHED();
     c.rp_local = U;
     c.have_reads = world == 1;      // several GPUs: complete only after the ranks' runs were gathered (stage_reads_gather_*)
@@ -663,17 +673,12 @@ void stage_reads_gather_layout(Context &c, const u64 *counts, void **F, void **l
     for (int q = 0; q < c.rp_world; ++q) { if (q < c.rp_rank) base += counts[q]; tot += counts[q]; }
     SG_CHECK(tot < 0x3FFFFFFFull, "at most 2^30-1 unique reads");
     c.SWS = storage_words(c.SW);
-    DevBuf<u64> Fg;
-    DevBuf<uint16_t> lg, fg;
-    Fg.persistent = lg.persistent = fg.persistent = true;
-    Fg.alloc((size_t)tot * c.SWS, st); lg.alloc(tot, st); fg.alloc(tot, st);
+    c.F.alloc((size_t)tot * c.SWS, st); c.RC.alloc((size_t)tot * c.SWS, st); c.len.alloc(tot, st); c.freq.alloc(tot, st);
     if (c.rp_local) {
-        SG_CUDA(cudaMemcpyAsync(Fg.p + base * c.SWS, c.F.p, (size_t)c.rp_local * c.SWS * sizeof(u64), cudaMemcpyDeviceToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(lg.p + base, c.len.p, (size_t)c.rp_local * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(fg.p + base, c.freq.p, (size_t)c.rp_local * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(c.F.p + base * c.SWS, c.F_loc.p, (size_t)c.rp_local * c.SWS * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(c.len.p + base, c.len_loc.p, (size_t)c.rp_local * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(c.freq.p + base, c.freq_loc.p, (size_t)c.rp_local * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
     }
-    c.F = std::move(Fg); c.len = std::move(lg); c.freq = std::move(fg);
-    c.RC.alloc((size_t)tot * c.SWS, st);
     SG_CUDA(cudaStreamSynchronize(st));
     c.rp_first = base; c.rp_total = tot;
     if (F) *F = c.F.p;
@@ -695,6 +700,36 @@ void stage_reads_gather_finish(Context &c)
     }
     c.cnt.unique_reads = U;
     c.have_reads = true;
+}
+
+// ---- several GPUs, partitioned ingest: every rank packs its slice of the input, the packed records are all-gathered ----
+// layout: room for the records of all slices back to back (counts[q] reads of rank q), this rank's slice in place
+void stage_raw_gather_layout(Context &c, int rank, int world, const u64 *counts, void **raw, u64 *first, u64 *total)
+{
+    cudaStream_t st = c.stream;
+    SG_CHECK(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && counts, "bad rank / world");
+    SG_CHECK(counts[rank] == c.n_input, "this rank's count does not match its packed slice");
+    u64 tot = 0, base = 0;
+    for (int q = 0; q < world; ++q) { if (q < rank) base += counts[q]; tot += counts[q]; }
+    SG_CHECK(tot < 0x3FFFFFFFull, "at most 2^30-1 reads");
+    c.raw.alloc((size_t)tot * c.SW, st);
+    if (c.n_input) SG_CUDA(cudaMemcpyAsync(c.raw.p + base * c.SW, c.raw_slice.p, (size_t)c.n_input * c.SW * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (raw) *raw = c.raw.p;
+    if (first) *first = base;
+    if (total) *total = tot;
+    c.rg_total = tot;
+}
+
+// after the all-gather: the context holds the packed records of the whole input; the counters are the sums over the slices
+void stage_raw_gather_finish(Context &c, u64 total_reads, u64 good_reads, u64 total_bp)
+{
+    SG_CHECK(c.rg_total == total_reads, "sage2gpu_raw_gather_layout must run first");
+    c.n_input = total_reads;
+    c.cnt.total_reads = total_reads;
+    c.cnt.good_reads = good_reads;
+    c.cnt.total_bp = total_bp;
+    c.cnt.avg_len = good_reads ? total_bp / good_reads : 0;        // readLoader.cpp:161 integer division
 }
 
 }  // namespace sg

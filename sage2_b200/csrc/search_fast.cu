@@ -31,36 +31,27 @@ constexpr int kFastWindows = 128;    // windows of one read (the window travels 
 
 // hashTableSearch (hashTable.cpp:193-231) on the sector index with a branch-free sector test: the slots of a sector fill
 // in order, so empty slots are a suffix and "no tag match + an empty slot" means absent.  A tag match counts as found
-// (proven by the compare of the bucket's first entry).
-// One sector: 0 = decided (payload / cnt set; cnt 0 = absent), 1 = masked key (>= 100 entries: probe_window confirms it
-// through its representative read), 2 = full sector without a match: the next sector decides.
-__device__ __forceinline__ int sector_resolve(const u64 (&s)[4], u64 tag, u64 &payload, u32 &cnt)
-{
-    const bool m0 = (s[0] >> 40) == tag && s[0] != 0, m1 = (s[1] >> 40) == tag && s[1] != 0;
-    const bool m2 = (s[2] >> 40) == tag && s[2] != 0, m3 = (s[3] >> 40) == tag && s[3] != 0;
-    const u64 cand = m0 ? s[0] : (m1 ? s[1] : (m2 ? s[2] : (m3 ? s[3] : 0ull)));
-    if (cand != 0) {
-        const u32 c = slot_get_count(cand);
-        if (c >= (u32)kHashThreshold) return 1;
-        payload = slot_get_payload(cand); cnt = c;
-        return 0;
-    }
-    return s[3] == 0 ? 0 : 2;
-}
-__device__ __forceinline__ const u64 *sector_ptr(const SearchParams &P, u64 hsh, u64 sec)
-{
-    return P.slots + kSlotsPerSector * (shard_base_sector(hsh, P.nsec, P.shards) + sec);
-}
-// the probe sequence from sector `sec` on; false = masked key
-__device__ __forceinline__ bool probe_sectors_from(const SearchParams &P, u64 hsh, u64 sec, u64 &payload, u32 &cnt)
+// (proven by the compare of the bucket's first entry).  Returns false for a masked key (>= 100 entries), which
+// probe_window confirms through its representative read.
+__device__ __forceinline__ bool probe_sectors(const SearchParams &P, u64 hsh, u64 &payload, u32 &cnt)
 {
     const u64 tag = slot_tag(hsh);
+    const u64 *shard = P.slots + kSlotsPerSector * shard_base_sector(hsh, P.nsec, P.shards);
+    u64 sec = home_sector(hsh, P.nsec);
     payload = 0; cnt = 0;
     for (;;) {
         u64 s[4];
-        ldg256_keep(sector_ptr(P, hsh, sec), s);
-        const int r = sector_resolve(s, tag, payload, cnt);
-        if (r != 2) return r == 0;
+        ldg256_keep(shard + kSlotsPerSector * sec, s);
+        const bool m0 = (s[0] >> 40) == tag && s[0] != 0, m1 = (s[1] >> 40) == tag && s[1] != 0;
+        const bool m2 = (s[2] >> 40) == tag && s[2] != 0, m3 = (s[3] >> 40) == tag && s[3] != 0;
+        const u64 cand = m0 ? s[0] : (m1 ? s[1] : (m2 ? s[2] : (m3 ? s[3] : 0ull)));
+        if (cand != 0) {
+            const u32 c = slot_get_count(cand);
+            if (c >= (u32)kHashThreshold) return false;
+            payload = slot_get_payload(cand); cnt = c;
+            return true;
+        }
+        if (s[3] == 0) return true;                  // room left in this sector: the key is absent
         sec = (sec + 1 == P.nsec) ? 0 : sec + 1;
     }
 }
@@ -121,8 +112,7 @@ __device__ __forceinline__ u64 window_signed(const u64 *M, int s)
     return M[0] >> (2 * (-s));
 }
 
-// kFastAhead: chunks of 32 windows whose home sectors are requested before the first one is used
-template <int SW, int MINB, int kFastAhead>
+template <int SW, int MINB>
 __global__ void __launch_bounds__(SearchCfg<SW>::WARPS * 32, MINB)
 phase_a_fast_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ extL, uint8_t *__restrict__ flag5,
                     u32 *__restrict__ cont_max, unsigned long long *__restrict__ counters, u32 *__restrict__ redo_ids,
@@ -169,49 +159,14 @@ phase_a_fast_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ ex
         // unless they are the first of their bucket, which proves the bucket's key.
         int Tr = 0, Tl = 0;
         unsigned my_probes = 0;
-        // the home sectors of the first kFastAhead * 32 windows are requested together (one dependent memory round trip
-        // instead of one per 32 windows); a probe that its home sector does not decide continues on its own
-        u64 hv[kFastAhead], sv[kFastAhead][4];
-#pragma unroll
-        for (int c = 0; c < kFastAhead; ++c) {
-            const int j = 32 * c + lane;
-            hv[c] = 0;
-            sv[c][0] = sv[c][1] = sv[c][2] = sv[c][3] = 0;
-            if (j < W && !punt) {
-                u64 v0, v1;
-                t_extract_key<SW>(SR, j, P.h, v0, v1);
-                hv[c] = hash_key(v0, v1);
-                ldg256_keep(sector_ptr(P, hv[c], home_sector(hv[c], P.nsec)), sv[c]);
-            }
-        }
         for (int base = 0; base < W && !punt; base += 32) {
             const int j = base + lane;
             u64 payload = 0;
             u32 cnt = 0;
             if (j < W) {
-                bool decided = false;
-                u64 hsh = 0;
-                u64 sec = 0;
-#pragma unroll
-                for (int c = 0; c < kFastAhead; ++c)
-                    if (base == 32 * c) {
-                        hsh = hv[c];
-                        sec = home_sector(hsh, P.nsec);
-                        const int r = sector_resolve(sv[c], slot_tag(hsh), payload, cnt);
-                        decided = r == 0;
-                        if (r == 2) { sec = (sec + 1 == P.nsec) ? 0 : sec + 1; decided = probe_sectors_from(P, hsh, sec, payload, cnt); }
-                        if (!decided) {     // masked key
-                            u64 v0, v1;
-                            t_extract_key<SW>(SR, j, P.h, v0, v1);
-                            probe_window<SW>(P, v0, v1, false, payload, cnt);
-                        }
-                    }
-                if (base >= 32 * kFastAhead) {
-                    u64 v0, v1;
-                    t_extract_key<SW>(SR, j, P.h, v0, v1);
-                    hsh = hash_key(v0, v1);
-                    if (!probe_sectors_from(P, hsh, home_sector(hsh, P.nsec), payload, cnt)) probe_window<SW>(P, v0, v1, false, payload, cnt);
-                }
+                u64 v0, v1;
+                t_extract_key<SW>(SR, j, P.h, v0, v1);
+                if (!probe_sectors(P, hash_key(v0, v1), payload, cnt)) probe_window<SW>(P, v0, v1, false, payload, cnt);
                 my_probes++;
             }
             const bool gR = gate_right(j, len1, P.k), gL = gate_left(j, P.k, P.h);
@@ -369,34 +324,31 @@ phase_a_fast_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ ex
     if (lane == 0) { atomicAdd(&counters[0], (unsigned long long)calls); atomicAdd(&counters[1], (unsigned long long)probes); }
 }
 
-template <int SW, int MINB, int AHEAD>
+template <int SW, int MINB>
 static void launch_fast_v(Context &c, const SearchParams &P, unsigned long long *d_counters, u32 *redo_ids, unsigned *redo_count)
 {
     constexpr int WARPS = SearchCfg<SW>::WARPS;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_fast_kernel<SW, MINB, AHEAD>, WARPS * 32, 0));
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, phase_a_fast_kernel<SW, MINB>, WARPS * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     u64 g = (P.hi - P.lo + WARPS - 1) / WARPS;
     if (g > (u64)kSMs * blocks_per_sm) g = (u64)kSMs * blocks_per_sm;
     if (g == 0) g = 1;
-    phase_a_fast_kernel<SW, MINB, AHEAD><<<(unsigned)g, WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters, redo_ids,
-                                                                                   redo_count);
+    phase_a_fast_kernel<SW, MINB><<<(unsigned)g, WARPS * 32, 0, c.stream>>>(P, c.extR.p, c.extL.p, c.flag5.p, c.cont_max.p, d_counters, redo_ids,
+                                                                            redo_count);
 }
 
 // The superstring scan of reads [P.lo, P.hi) (in the order of P.ids when given); the reads it could not certify are
 // appended to redo_ids (*redo_count of them).  false: no instantiation for this record stride (long reads).
 bool launch_phase_a_fast(Context &c, const SearchParams &P, unsigned long long *d_counters, u32 *redo_ids, unsigned *redo_count)
 {
-    static const int ahead = [] { const char *e = getenv("SAGE2GPU_PAF_AHEAD"); return e ? atoi(e) : 3; }();
     switch (c.SW) {
-#define SG_FAST_CASE(SWV)                                                                                        \
-        case SWV:                                                                                                \
-            if (ahead <= 1) launch_fast_v<SWV, 4, 1>(c, P, d_counters, redo_ids, redo_count);                    \
-            else if (ahead == 2) launch_fast_v<SWV, 4, 2>(c, P, d_counters, redo_ids, redo_count);               \
-            else launch_fast_v<SWV, 4, 3>(c, P, d_counters, redo_ids, redo_count);                               \
-            break;
+        // 4 resident blocks per SM (64 registers): 3 blocks (79 registers) and 5 blocks (48 registers, spills) were measured
+        // slower, 12.3 / 11.8 ms against 10.1 ms at cfg2; requesting the home sectors of several window chunks before the
+        // first is used was slower too (10.9 / 11.6 / 13.1 ms for 1 / 2 / 3 chunks ahead): the kernel is not short of loads in flight
+#define SG_FAST_CASE(SWV) case SWV: launch_fast_v<SWV, 4>(c, P, d_counters, redo_ids, redo_count); break;
         SG_FAST_CASE(2) SG_FAST_CASE(3) SG_FAST_CASE(4) SG_FAST_CASE(5) SG_FAST_CASE(6) SG_FAST_CASE(8)
 #undef SG_FAST_CASE
         default: return false;

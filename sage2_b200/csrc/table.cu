@@ -137,18 +137,17 @@ static unsigned big_grid(u64 n, unsigned block = 256)
 
 // rank / world: the key-hash shard this context holds (0 / 1 = the whole table).  A shard indexes only the keys
 // with key_owner(hash) == rank; every context still streams all 4U entries (the reads are replicated).
-void stage_build_table(Context &c, int rank, int world)
+void stage_build_table(Context &c, int rank, int world, bool joint)
 {
     cudaStream_t st = c.stream;
     ArenaScope arena_scope(c.arena, st);
     SG_CHECK(c.have_reads, "organize_reads must run before build_hash_table");
     SG_CHECK(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad rank / world");
-    c.tb_rank = rank; c.tb_world = world; c.tb_shards = 1; c.tb_entries = 0;
+    c.tb_rank = rank; c.tb_world = world; c.tb_shards = 1; c.tb_entries = 0; c.tb_joint = joint && world > 1;
     const u64 U = c.cnt.unique_reads;
     const int SW = c.SW, h = c.h;
     c.cnt.distinct_keys = 0; c.cnt.keys_over_threshold = 0; c.cap = 0; c.cnt.table_capacity = 0;
-    c.slots.release(); c.entries.release();
-    if (U == 0) { c.have_table = true; return; }
+    if (U == 0) { c.slots.release(); c.entries.release(); c.have_table = true; return; }
     const u64 n = 4 * U;
     SG_CHECK(n < 0xFFFFFFFFull, "at most 2^30-1 unique reads per context");
 
@@ -159,18 +158,21 @@ void stage_build_table(Context &c, int rank, int world)
     if (nsec < 256) nsec = 256;
     const u64 cap = nsec * kSlotsPerSector;
     SG_CHECK(cap < 0xFFFFFFFFull, "slot index too large for one context");
-    c.slots.alloc(cap, st);
-    SG_CUDA(cudaMemsetAsync(c.slots.p, 0, cap * sizeof(u64), st));
+    // joint: the shard is built in its place inside an array with room for all shards (stage_table_gather_* completes it)
+    c.slots.alloc(c.tb_joint ? cap * (u64)world : cap, st);
+    u64 *const slots = c.slots.p + (c.tb_joint ? (u64)rank * cap : 0);
+    DevBuf<u32> &entries = c.tb_joint ? c.entries_loc : c.entries;
+    SG_CUDA(cudaMemsetAsync(slots, 0, cap * sizeof(u64), st));
 
     DevBuf<u32> where(n, st), d_overflow(1, st);
     SG_CUDA(cudaMemsetAsync(d_overflow.p, 0, sizeof(u32), st));
-    table_insert_kernel<<<big_grid(n), 256, 0, st>>>(c.F.p, c.RC.p, c.len.p, U, SW, c.SWS, h, c.slots.p, nsec, where.p, rank, world, d_overflow.p);
+    table_insert_kernel<<<big_grid(n), 256, 0, st>>>(c.F.p, c.RC.p, c.len.p, U, SW, c.SWS, h, slots, nsec, where.p, rank, world, d_overflow.p);
     SG_LAUNCHED();
 
     DevBuf<u32> run(cap, st), off(cap, st), d_total(1, st);
     DevBuf<unsigned long long> d_cnt(2, st);
     SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), st));
-    table_runs_kernel<<<big_grid(cap), 256, 0, st>>>(c.slots.p, cap, run.p, d_cnt.p);
+    table_runs_kernel<<<big_grid(cap), 256, 0, st>>>(slots, cap, run.p, d_cnt.p);
     SG_LAUNCHED();
     exclusive_scan_u32(run.p, off.p, cap, d_total.p, st);
     u32 M = 0;
@@ -182,16 +184,16 @@ void stage_build_table(Context &c, int rank, int world)
     SG_CUDA(cudaStreamSynchronize(st));
     SG_CHECK(h_overflow == 0, "slot index of this table shard is full (key split too uneven)");
 
-    c.entries.alloc(M, st);
+    entries.alloc(M, st);
     c.tb_entries = M;
     if (M) {
-        table_offsets_kernel<<<big_grid(cap), 256, 0, st>>>(c.slots.p, cap, run.p, off.p);
+        table_offsets_kernel<<<big_grid(cap), 256, 0, st>>>(slots, cap, run.p, off.p);
         SG_LAUNCHED();
         DevBuf<u32> cursor(M, st);
         SG_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)M * sizeof(u32), st));
-        table_fill_kernel<<<big_grid(n), 256, 0, st>>>(c.slots.p, where.p, n, cursor.p, c.entries.p);
+        table_fill_kernel<<<big_grid(n), 256, 0, st>>>(slots, where.p, n, cursor.p, entries.p);
         SG_LAUNCHED();
-        table_order_kernel<<<big_grid(cap), 256, 0, st>>>(c.slots.p, cap, c.entries.p);
+        table_order_kernel<<<big_grid(cap), 256, 0, st>>>(slots, cap, entries.p);
         SG_LAUNCHED();
         SG_CUDA(cudaStreamSynchronize(st));     // cursor / where lifetimes end here
     }
@@ -226,13 +228,9 @@ void stage_table_gather_layout(Context &c, const u64 *entry_counts, void **slots
     u64 tot = 0, base = 0;
     for (int q = 0; q < world; ++q) { if (q < c.tb_rank) base += entry_counts[q]; tot += entry_counts[q]; }
     SG_CHECK(tot < 0xFFFFFFFFull && cap_shard * (u64)world < (1ull << 40), "table too large");
-    DevBuf<u64> sg;
-    DevBuf<u32> eg;
-    sg.persistent = eg.persistent = true;
-    sg.alloc((size_t)cap_shard * world, st); eg.alloc(tot, st);
-    SG_CUDA(cudaMemcpyAsync(sg.p + (size_t)c.tb_rank * cap_shard, c.slots.p, (size_t)cap_shard * sizeof(u64), cudaMemcpyDeviceToDevice, st));
-    if (c.tb_entries) SG_CUDA(cudaMemcpyAsync(eg.p + base, c.entries.p, (size_t)c.tb_entries * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-    c.slots = std::move(sg); c.entries = std::move(eg);
+    SG_CHECK(c.tb_joint, "the shard must be built with sage2gpu_build_hash_table_part for the gather");
+    c.entries.alloc(tot, st);
+    if (c.tb_entries) SG_CUDA(cudaMemcpyAsync(c.entries.p + base, c.entries_loc.p, (size_t)c.tb_entries * sizeof(u32), cudaMemcpyDeviceToDevice, st));
     SG_CUDA(cudaStreamSynchronize(st));
     if (slots) *slots = c.slots.p;
     if (entries) *entries = c.entries.p;

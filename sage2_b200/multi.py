@@ -241,11 +241,8 @@ def sharded_graph_steps(gpu, rank: int, world: int, view, batch_reads: int = 1 <
 #                                             is filled from rank q; this rank's block is already in place
 # ---------------------------------------------------------------------------------------------------------------
 
-def partitioned_graph_steps(gpu, rank: int, world: int, view, bases_ptr: int, offsets_ptr: int, n_reads: int, k: int, on_device: bool,
-                            sent: list | None = None):
-    """Generator: steps 1-3 over `world` ranks; every rank holds the whole input (replicated, or all-gathered before)."""
-    sent = sent if sent is not None else [0]
-    u_local = gpu.load_reads_partition(bases_ptr, offsets_ptr, n_reads, k, on_device, rank, world)
+def _partitioned_from_organized(gpu, rank: int, world: int, view, u_local: int, sent: list):
+    """The steps after this rank has organised the reads of its key range (u_local unique reads)."""
     counts = [c[0] for c in (yield ("gather_counts", [u_local]))]
     lay = gpu.reads_gather_layout(counts)
     tot, stride = lay["total"], lay["stride"]
@@ -254,7 +251,7 @@ def partitioned_graph_steps(gpu, rank: int, world: int, view, bases_ptr: int, of
     yield ("gather_var", view(lay["frequencies"], tot, "<i2"), counts)
     sent[0] += counts[rank] * (8 * stride + 4)
     gpu.reads_gather_finish()
-    gpu.build_hash_table_shard(rank, world)
+    gpu.build_hash_table_part(rank, world)
     info = gpu.table_shard_info()
     infos = yield ("gather_counts", [info["entries"], info["distinct"], info["over"]])
     ec = [x[0] for x in infos]
@@ -268,6 +265,35 @@ def partitioned_graph_steps(gpu, rank: int, world: int, view, bases_ptr: int, of
     gpu.finish_graph()
 
 
+def partitioned_graph_steps(gpu, rank: int, world: int, view, bases_ptr: int, offsets_ptr: int, n_reads: int, k: int, on_device: bool,
+                            sent: list | None = None):
+    """Generator: steps 1-3 over `world` ranks; every rank holds the whole input (replicated, or all-gathered before)."""
+    sent = sent if sent is not None else [0]
+    u_local = gpu.load_reads_partition(bases_ptr, offsets_ptr, n_reads, k, on_device, rank, world)
+    yield from _partitioned_from_organized(gpu, rank, world, view, u_local, sent)
+
+
+def partitioned_slice_steps(gpu, rank: int, world: int, view, bases_ptr: int, offsets_ptr: int, n_slice: int, k: int, on_device: bool,
+                            max_read_length: int, sent: list | None = None):
+    """Generator: the same with the ingest partitioned too -- every rank holds (and packs) only its slice of the input, the
+    packed records are all-gathered (4 x fewer bytes than the characters, and no rank ever holds all characters)."""
+    sent = sent if sent is not None else [0]
+    info = gpu.pack_slice(bases_ptr, offsets_ptr, n_slice, k, on_device, max_read_length)
+    infos = yield ("gather_counts", [n_slice, info["good_reads"], info["total_bp"]])
+    counts = [x[0] for x in infos]
+    lay = gpu.raw_gather_layout(rank, world, counts)
+    sw = info["record_words"]
+    yield ("gather_var", view(lay["records"], lay["total"] * sw, "<i8"), [c * sw for c in counts])
+    sent[0] += 8 * sw * n_slice
+    gpu.raw_gather_finish(sum(counts), sum(x[1] for x in infos), sum(x[2] for x in infos))
+    u_local = gpu.organize_partition(rank, world)
+    if world == 1:
+        gpu.build_hash_table()
+        gpu.build_overlap_graph()
+        return
+    yield from _partitioned_from_organized(gpu, rank, world, view, u_local, sent)
+
+
 def _gather_var_dist(full: torch.Tensor, counts, rank: int, world: int):
     """All-gather of blocks of different sizes: equal blocks in place, otherwise through a padded copy."""
     if full.dtype != torch.uint8:      # bytes travel (neither NCCL nor gloo has a 16-bit integer type)
@@ -278,23 +304,23 @@ def _gather_var_dist(full: torch.Tensor, counts, rank: int, world: int):
         if c:
             dist.all_gather_into_tensor(full, full[rank * c:(rank + 1) * c])
         return
-    m = max(counts)
-    if m == 0:
+    if max(counts) == 0:
         return
+    # blocks of different sizes: grouped sends / receives straight between the blocks (no padded copy: at config #5 the
+    # records of the unique reads alone are 35 GB)
     offs = [sum(counts[:q]) for q in range(world)]
-    mine = torch.zeros(m, dtype=full.dtype, device=full.device)
-    mine[:counts[rank]] = full[offs[rank]:offs[rank] + counts[rank]]
-    if full.is_cuda:
-        tmp = torch.empty(m * world, dtype=full.dtype, device=full.device)
-        dist.all_gather_into_tensor(tmp, mine)
-        parts = [tmp[q * m:q * m + counts[q]] for q in range(world)]
-    else:      # gloo
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine)
-        parts = [parts[q][:counts[q]] for q in range(world)]
+    mine = full[offs[rank]:offs[rank] + counts[rank]]
+    ops = []
     for q in range(world):
-        if q != rank and counts[q]:
-            full[offs[q]:offs[q] + counts[q]] = parts[q]
+        if q == rank:
+            continue
+        if counts[rank]:
+            ops.append(dist.P2POp(dist.isend, mine, q))
+        if counts[q]:
+            ops.append(dist.P2POp(dist.irecv, full[offs[q]:offs[q] + counts[q]], q))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
 
 
 def serve_one(req, rank: int, world: int, device, sent: list | None = None):

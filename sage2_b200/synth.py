@@ -149,3 +149,42 @@ def config(name: str):
         g = add_repeats(random_genome(1_000_000, 40), 20, 1000, 41)
         return paired_reads(g, 150, 50, seed=42, mu=450, sigma=30), 75
     raise KeyError(name)
+
+
+def config_cached(name: str, wait=None):
+    """config(name) through a per-box cache (/dev/shm or the temp directory): the big workloads take a minute to generate
+    and are used by several tests and by every bench.py run.  Returns (reads memory-mapped read-only, k).
+    wait: optional callable run between "the file is written" and "the file is read" (a barrier when several ranks share
+    the box and only one of them generates)."""
+    import json
+    import os
+    import tempfile
+    best = None
+    for d in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            st = os.statvfs(d)
+            if st.f_bavail * st.f_frsize > (12 << 30) and os.access(d, os.W_OK):
+                best = d
+                break
+        except OSError:
+            pass
+    if best is None:
+        if wait:
+            wait()
+        return config(name)
+    path = os.path.join(best, f"sage2_synth_{name}_v2.npy")
+    meta = path + ".json"
+    if (wait is None or os.environ.get("RANK", "0") == "0") and not (os.path.exists(path) and os.path.exists(meta)):
+        reads, k = config(name)
+        tmp = path + f".{os.getpid()}.tmp.npy"
+        np.save(tmp, reads)
+        os.replace(tmp, path)
+        with open(meta + ".tmp", "w") as f:
+            json.dump({"k": k}, f)
+        os.replace(meta + ".tmp", meta)
+        del reads
+    if wait:
+        wait()
+    with open(meta) as f:
+        k = json.load(f)["k"]
+    return np.load(path, mmap_mode="r"), k

@@ -287,7 +287,7 @@ class EmuPart:
     def reads_gather_finish(self):
         self.L.hemu_reads_gather_finish(self.h)
 
-    def build_hash_table_shard(self, rank, world):
+    def build_hash_table_part(self, rank, world):
         pass
 
     def table_shard_info(self):

@@ -26,7 +26,12 @@ def _md5(path):
 
 
 def _get(name):
-    return datasets.get(name) if name in datasets.DATASETS else synth.config(name)
+    if name in datasets.DATASETS:
+        return datasets.get(name)
+    if name == "cfg2" or name.startswith("cfg3-"):       # cfg3 = the cfg2 reads with another k
+        reads, _ = synth.config_cached("cfg2")
+        return reads, (63 if name == "cfg2" else int(name.split("-")[1]))
+    return synth.config(name)
 
 
 def _run_gpu(reads, k):
@@ -154,7 +159,7 @@ def _check_against_big_golden(gpu, name, tmp_path=None):
 
 def test_cfg2_full_size_byte_identical_to_reference(tmp_path):
     """BASELINE config #2 at full size: `.reads` / `.graph3` md5, counters and digests of the unmodified reference."""
-    reads, k = _get("cfg2")
+    reads, k = synth.config_cached("cfg2")
     b, off = synth.concat(reads)
     gpu = api.Sage2Gpu(0)
     gpu.run_steps123(b, off, k)
@@ -171,7 +176,7 @@ def test_cfg2_full_size_byte_identical_to_reference(tmp_path):
 @pytest.mark.skipif("cfg4" not in BIG, reason="no cfg4 golden committed")
 def test_cfg4_full_size_byte_identical_to_reference(tmp_path):
     """BASELINE config #4 (100 Mbp + 2 % repeats, 33.3 M reads, -k 75) at full size against the unmodified reference."""
-    reads, k = _get("cfg4")
+    reads, k = synth.config_cached("cfg4")
     b, off = synth.concat(reads)
     del reads
     gpu = api.Sage2Gpu(0)

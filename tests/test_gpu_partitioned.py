@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _run(name, world):
-    reads, k = datasets.get(name) if name in datasets.DATASETS else synth.config(name)
+    reads, k = datasets.get(name) if name in datasets.DATASETS else synth.config_cached(name)
     b, off = synth.concat(reads)
     dev = torch.device("cuda", 0)
     tb, to = torch.from_numpy(b).to(dev), torch.from_numpy(off).to(dev)
@@ -62,3 +62,42 @@ def test_partitioned_cfg2_full_size_equals_reference():
         d, c = g.digest(), g.counters()
         assert d["edges"] == BIG["cfg2"]["edges_digest"] and d["reads"] == BIG["cfg2"]["reads_digest"]
         assert c["n_edges"] == BIG["cfg2"]["n_edges"] and c["unique_reads"] == BIG["cfg2"]["unique_reads"]
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_device_generated_slices_equal_oracle(world):
+    """Config-#5 path at a size the oracle handles: every rank generates its slice of a synthetic read set ON THE DEVICE
+    (sage2gpu_synth_reads), packs it (sage2gpu_pack_slice), the packed records are all-gathered and the rest runs partitioned;
+    the characters, copied back, go through the oracle."""
+    G, L, k, n_pairs = 150_000, 100, 45, 26_000
+    dev = torch.device("cuda", 0)
+    view = multi.device_view_fn(dev)
+    gpus = [api.Sage2Gpu(0) for _ in range(world)]
+    chunk = -(-n_pairs // world)
+    slices, steps = [], []
+    for r, g in enumerate(gpus):
+        p0, p1 = min(n_pairs, r * chunk), min(n_pairs, (r + 1) * chunk)
+        n = 2 * (p1 - p0)
+        tb = torch.empty(max(1, n * L), dtype=torch.uint8, device=dev)
+        to = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        g.synth_reads(tb.data_ptr(), to.data_ptr(), p0, p1 - p0, G, L, 300.0, 20.0, 7)
+        slices.append((tb, to, n))
+        steps.append(multi.partitioned_slice_steps(g, r, world, view, tb.data_ptr(), to.data_ptr(), n, k, True, L))
+    multi.run_local(steps)
+    bases = np.concatenate([tb[:n * L].cpu().numpy() for tb, _, n in slices])
+    reads = bases.reshape(-1, L)
+    assert set(np.unique(reads)) <= set(b"ACGT")
+    # mates of a pair come from one fragment: mate 2 is the reverse complement of a stretch downstream of mate 1 (or the other way round)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    assert o.U > 0.9 * len(reads) * 0.5 and o.n_edges > 0
+    for g in gpus:
+        c = g.counters()
+        assert c["good_reads"] == len(reads) and c["unique_reads"] == o.U
+        e = g.edges()
+        assert len(e) == o.n_edges
+        for f in ("from", "to", "type", "delta", "delta_twin"):
+            np.testing.assert_array_equal(e[f], o.edges[f])
+        r = g.reads()
+        np.testing.assert_array_equal(r["frequency"], o.frequency[1:])
+        np.testing.assert_array_equal(r["fwd"], o.fwd)

@@ -114,7 +114,7 @@ def test_sharded_context_refuses_the_local_search():
 def test_cfg2_sharded_full_size():
     """cfg2 at full size over 4 shards on one GPU: the edge list equals the single-table build's AND the unmodified
     reference's (digests of its own `.reads` / `.graph3`, tests/golden/golden_big.json)."""
-    reads, k = synth.config("cfg2")
+    reads, k = synth.config_cached("cfg2")
     b, off = synth.concat(reads)
     ref = api.Sage2Gpu(0)
     ref.run_steps123(b, off, k)
@@ -153,7 +153,7 @@ def _host_gib():
 def test_cfg4_sharded_equals_single_table():
     """cfg4 at full size (33.3 M reads, 27.9 M unique, 2 % repeats: masked keys, 94,560 reads left for phase C, host walk):
     the sharded build (one shard, peer-memory transport, 54 routed batches) gives the single-table build's edge list."""
-    reads, k = synth.config("cfg4")
+    reads, k = synth.config_cached("cfg4")
     b, off = synth.concat(reads)
     del reads
     g = api.Sage2Gpu(0)
