@@ -174,6 +174,18 @@ int sage2gpu_table_gather_layout(sage2gpu_ctx *ctx, const uint64_t *entry_counts
 int sage2gpu_table_gather_finish(sage2gpu_ctx *ctx, const uint64_t *entry_counts, const uint64_t *distinct_keys,
                                  const uint64_t *keys_over_threshold);
 
+/* ---- One process, several GPUs (host/sage2gpu_main.cpp --devices): the exchanges of the partitioned build as peer copies ----
+ * load_finish_packed   = sage2gpu_load_finish without organizeReads: the streamed upload is filtered and packed
+ *                        (readLoader.cpp:146-213) and stays this context's slice, as after pack_slice; *max_read_length is what
+ *                        the other contexts pass to pack_slice (with 0 reads) before raw_gather_layout
+ * peer_copy            bytes from src's device memory into dst's (cudaMemcpyPeer): the all-gathers between the *_gather_layout
+ *                        and *_gather_finish calls
+ * phase_a_import       rank src_rank's slice of the phase-A arrays of `src` into `ctx` (+ element-wise maximum of the
+ *                        containment ids): the exchange of sage2gpu_phase_a_buffers */
+int sage2gpu_load_finish_packed(sage2gpu_ctx *ctx, uint64_t *n_reads, int *max_read_length, uint64_t *good_reads, uint64_t *total_bp);
+int sage2gpu_peer_copy(sage2gpu_ctx *dst, void *dst_ptr, sage2gpu_ctx *src, const void *src_ptr, uint64_t n_bytes);
+int sage2gpu_phase_a_import(sage2gpu_ctx *ctx, sage2gpu_ctx *src, int src_rank);
+
 /* ---- The table sharded by key hash (north_star) ---------------------------------------------------
  * The reads stay on every GPU; shard `rank` of `world` indexes only the keys whose hash it owns, so the table of a
  * data set is spread over the GPUs of the box.  A window probe of HashTable::hashTableSearch (hashTable.cpp:193-231)
@@ -250,7 +262,8 @@ int sage2gpu_digest(sage2gpu_ctx *ctx, uint64_t *reads_digest, uint64_t *edges_d
 
 /* Run-time options.  "read_order": schedule of the phase-A search (results do not depend on it): 0 = id order,
  * 1 = min-hash order (reads that share k-mers are searched together, so slot sectors and partner records hit L2),
- * -1 = the default.  "fast_scan": 1 = phase A tries the superstring scan first (default), 0 = hit-by-hit kernel only. */
+ * -1 = the default.  "low_memory": 1 = every buffer is released as soon as no later stage of the step needs it (the table
+ * before the edge sort, the packed input after organizeReads ...; for read sets near the capacity of the GPU).  "fast_scan": 1 = phase A tries the superstring scan first (default), 0 = hit-by-hit kernel only. */
 int sage2gpu_set_option(sage2gpu_ctx *ctx, const char *name, int64_t value);
 
 int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *out);

@@ -39,6 +39,10 @@ int guarded(sage2gpu_ctx *ctx, Fn fn)
     try {
         SG_CUDA(cudaSetDevice(ctx->c.device));
         fn(ctx->c);
+        if (ctx->c.opt_low_memory) {       // the stage's workspace goes back to the driver instead of waiting for the next stage
+            SG_CUDA(cudaStreamSynchronize(ctx->c.stream));
+            ctx->c.arena.destroy();
+        }
         ctx->c.last_error.clear();
         return SAGE2GPU_OK;
     } catch (const sg::CudaError &e) {
@@ -225,6 +229,42 @@ int sage2gpu_synth_reads(sage2gpu_ctx *ctx, uint8_t *d_bases, int64_t *d_offsets
                          int read_length, float insert_mean, float insert_sd, uint64_t seed)
 {
     return guarded(ctx, [&](sg::Context &c) { sg::stage_synth_reads(c, d_bases, d_offsets, first_pair, n_pairs, genome_bp, read_length, insert_mean, insert_sd, seed); });
+}
+
+// ---- helpers of a single-process multi-GPU host (host/sage2gpu_main.cpp --devices): no torch, no NCCL ---------------------
+int sage2gpu_load_finish_packed(sage2gpu_ctx *ctx, uint64_t *n_reads, int *max_read_length, uint64_t *good_reads, uint64_t *total_bp)
+{
+    return guarded(ctx, [&](sg::Context &c) {
+        SG_CHECK(c.up_open, "sage2gpu_load_begin must be called first");
+        c.up_open = false;
+        SG_CUDA(cudaEventSynchronize(c.up_event));
+        StageTimer t(c.stream);
+        // pass 1 finds the longest read, pass 2 packs with that stride into the slice buffer (the joint array comes later)
+        sg::stage_ingest_ascii(c, c.up_d_bases.p, c.up_d_offsets.p, (int64_t)c.up_reads, true, -1);
+        c.up_d_bases.release(); c.up_d_offsets.release();
+        c.tm.ingest = t.stop();
+        if (n_reads) *n_reads = c.n_input;
+        if (max_read_length) *max_read_length = c.max_len;
+        if (good_reads) *good_reads = c.cnt.good_reads;
+        if (total_bp) *total_bp = c.cnt.total_bp;
+    });
+}
+
+int sage2gpu_peer_copy(sage2gpu_ctx *dst, void *dst_ptr, sage2gpu_ctx *src, const void *src_ptr, uint64_t n_bytes)
+{
+    if (!dst || !src) return SAGE2GPU_ERR_ARG;
+    return guarded(dst, [&](sg::Context &c) {
+        if (n_bytes == 0) return;
+        SG_CHECK(dst_ptr && src_ptr, "null pointer");
+        // both contexts' streams are idle between the stages of the host's schedule; a synchronous peer copy keeps it simple
+        SG_CUDA(cudaMemcpyPeer(dst_ptr, c.device, src_ptr, src->c.device, (size_t)n_bytes));
+    });
+}
+
+int sage2gpu_phase_a_import(sage2gpu_ctx *ctx, sage2gpu_ctx *src, int src_rank)
+{
+    if (!ctx || !src) return SAGE2GPU_ERR_ARG;
+    return guarded(ctx, [&](sg::Context &c) { sg::stage_phase_a_import(c, src->c, src_rank); });
 }
 
 int sage2gpu_reads_gather_layout(sage2gpu_ctx *ctx, const uint64_t *counts, void **records, void **lengths, void **frequencies,
@@ -735,6 +775,7 @@ int sage2gpu_set_option(sage2gpu_ctx *ctx, const char *name, int64_t value)
         SG_CHECK(name != nullptr, "null option name");
         const std::string n(name);
         if (n == "read_order") { SG_CHECK(value >= -1 && value <= 1, "read_order: -1 default, 0 id order, 1 min-hash order"); c.opt_read_order = (int)value; }
+        else if (n == "low_memory") { SG_CHECK(value == 0 || value == 1, "low_memory: 0 or 1"); c.opt_low_memory = (int)value; }
         else if (n == "fast_scan") { SG_CHECK(value >= -1 && value <= 1, "fast_scan: -1 default, 0 off, 1 on"); c.opt_fast_scan = (int)value; }
         else throw sg::CudaError("unknown option: " + n);
     });

@@ -59,6 +59,7 @@ struct Context {
     std::string last_error;
     int min_overlap = 0, h = 0, SW = 0, SWS = 0;     // SW = words per record, SWS = storage stride of F / RC
     // run-time options (sage2gpu_set_option); -1 = take the default / the environment variable
+    int opt_low_memory = 0;     // 1: buffers are released as soon as a stage no longer needs them (config #5: 620 M reads on 180 GB)
     int opt_fast_scan = -1;     // phase A: 1 superstring scan first, 0 general kernel only (SAGE2GPU_PA_FAST)
     int opt_read_order = -1;    // phase A schedule: 0 id order, 1 min-hash order (SAGE2GPU_READ_ORDER)
     Counters cnt;
@@ -148,7 +149,8 @@ void stage_reads_gather_finish(Context &c);
 void stage_build_table(Context &c, int rank = 0, int world = 1, bool joint = false);   // key-hash shard `rank` of `world`; joint: inside an array with room for all shards
 void stage_table_gather_layout(Context &c, const u64 *entry_counts, void **slots, void **entries, u64 *slots_per_shard, u64 *entries_first);
 void stage_table_gather_finish(Context &c, const u64 *entry_counts, const u64 *distinct, const u64 *over);
-void stage_phase_a(Context &c, int rank = 0, int world = 1);   // rank's slice of the reads; arrays padded to world * chunk
+void stage_phase_a(Context &c, int rank = 0, int world = 1);
+void stage_phase_a_import(Context &c, Context &src, int src_rank);   // single-process multi-GPU host: rank src_rank's slice of the phase-A arrays   // rank's slice of the reads; arrays padded to world * chunk
 // sharded table (shard.cu, search.cu)
 void stage_phase_a_sharded_begin(Context &c, int rank, int world);
 void stage_route_begin(Context &c, int what, u64 first, u64 count, int exact, int world, void **queries, u64 *counts);

@@ -355,6 +355,11 @@ void stage_phase_c_and_finalize(Context &c)
         SG_CUDA(cudaEventRecord(ev1, st));
     }
 
+    if (c.opt_low_memory) {     // the table is not needed after the candidate scan: its memory serves the edge sort
+        SG_CUDA(cudaStreamSynchronize(st));
+        c.slots.release(); c.entries.release(); c.entries_loc.release();
+        c.have_table = false;
+    }
     // ---- assemble the final record set on device --------------------------------------------------
     const u64 nH = c_on_device ? n_dev_c : host_c_edges.size() / 2;
     DevBuf<u32> eflag, eidx, d_keep(1, st);

@@ -262,7 +262,7 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     c.cnt.total_reads = (u64)n_reads;
     c.h = hash_len_for(c.min_overlap);
     c.cnt.hash_len = (u64)c.h;
-    if (n_reads == 0 && forced_max_len <= 0) { c.SW = 1; c.max_len = 0; return; }
+    if (n_reads == 0 && forced_max_len <= 0) { c.SW = 1; c.max_len = 0; c.raw_slice.alloc(0, st); return; }
 
     const uint8_t *d_b = bases;
     const int64_t *d_o = offsets;
@@ -301,7 +301,7 @@ void stage_ingest_ascii(Context &c, const uint8_t *bases, const int64_t *offsets
     }
 
     // K1 (a slice of a partitioned ingest is packed into a buffer of its own: the joint array is c.raw)
-    DevBuf<u64> &rec = forced_max_len > 0 ? c.raw_slice : c.raw;
+    DevBuf<u64> &rec = forced_max_len != 0 ? c.raw_slice : c.raw;       // < 0: a slice whose own longest read decides
     rec.alloc((size_t)n_reads * c.SW, st);
     if (n_reads == 0) { c.cnt.good_reads = 0; c.cnt.total_bp = 0; c.cnt.avg_len = 0; return; }
     DevBuf<unsigned long long> d_cnt(2, st);
@@ -660,6 +660,7 @@ void stage_organize_reads(Context &c, int rank, int world)
     SG_LAUNCHED();
     c.rp_local = U;
     c.have_reads = world == 1;      // several GPUs: complete only after the ranks' runs were gathered (stage_reads_gather_*)
+    if (c.opt_low_memory) { SG_CUDA(cudaStreamSynchronize(st)); c.raw.release(); }      // the packed input is not needed again
 }
 
 // The ranks' unique runs -> the global arrays.  counts[q] = unique reads of rank q (the host all-gathered them): this rank's
@@ -700,6 +701,7 @@ void stage_reads_gather_finish(Context &c)
     }
     c.cnt.unique_reads = U;
     c.have_reads = true;
+    if (c.opt_low_memory) { SG_CUDA(cudaStreamSynchronize(st)); c.F_loc.release(); c.len_loc.release(); c.freq_loc.release(); }
 }
 
 // ---- several GPUs, partitioned ingest: every rank packs its slice of the input, the packed records are all-gathered ----
@@ -730,6 +732,7 @@ void stage_raw_gather_finish(Context &c, u64 total_reads, u64 good_reads, u64 to
     c.cnt.good_reads = good_reads;
     c.cnt.total_bp = total_bp;
     c.cnt.avg_len = good_reads ? total_bp / good_reads : 0;        // readLoader.cpp:161 integer division
+    if (c.opt_low_memory) { SG_CUDA(cudaStreamSynchronize(c.stream)); c.raw_slice.release(); }
 }
 
 }  // namespace sg

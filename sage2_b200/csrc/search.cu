@@ -711,6 +711,33 @@ void stage_phase_a(Context &c, int rank, int world)
     c.have_phase_a = true;
 }
 
+// ---- single-process multi-GPU host: the phase-A arrays of rank src_rank's slice come over from its context -------------
+__global__ void __launch_bounds__(256) max_merge_kernel(u32 *__restrict__ dst, const u32 *__restrict__ src, u64 n)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) { const u32 v = src[i]; if (v > dst[i]) dst[i] = v; }
+}
+
+void stage_phase_a_import(Context &c, Context &src, int src_rank)
+{
+    cudaStream_t st = c.stream;
+    ArenaScope arena_scope(c.arena, st);
+    SG_CHECK(c.have_phase_a && src.have_phase_a && c.pa_chunk == src.pa_chunk && c.pa_world == src.pa_world, "both contexts must have searched slices of the same partition");
+    SG_CHECK(src_rank >= 0 && src_rank < c.pa_world, "bad source rank");
+    const u64 chunk = c.pa_chunk, off = (u64)src_rank * chunk, padded = chunk * (u64)c.pa_world;
+    if (chunk == 0) return;
+    SG_CUDA(cudaMemcpyPeerAsync(c.extR.p + off, c.device, src.extR.p + off, src.device, chunk * sizeof(u64), st));
+    SG_CUDA(cudaMemcpyPeerAsync(c.extL.p + off, c.device, src.extL.p + off, src.device, chunk * sizeof(u64), st));
+    SG_CUDA(cudaMemcpyPeerAsync(c.flag5.p + off, c.device, src.flag5.p + off, src.device, chunk, st));
+    // economyGraph.cpp:735 -- the largest id that found the read contained: element-wise maximum over the ranks' arrays
+    DevBuf<u32> tmp(padded, st);
+    SG_CUDA(cudaMemcpyPeerAsync(tmp.p, c.device, src.cont_max.p, src.device, padded * sizeof(u32), st));
+    unsigned g = grid_for(padded, 256, 4);
+    if (g > kSMs * 16u) g = kSMs * 16u;
+    max_merge_kernel<<<g, 256, 0, st>>>(c.cont_max.p, tmp.p, padded);
+    SG_LAUNCHED();
+    SG_CUDA(cudaStreamSynchronize(st));
+}
+
 // ---- phase A over a sharded table: begin (allocate the slice's arrays) / one routed batch / end ------------------
 void stage_phase_a_sharded_begin(Context &c, int rank, int world)
 {

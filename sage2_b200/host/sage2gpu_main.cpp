@@ -7,7 +7,9 @@
 //
 // Flags are the reference's: -f/--fileInput, -l/--listInput, -k/--minOverlap, -o/--outputDir,
 // -p/--prefix, -i/--inputPrefix, -m/--minStep, -M/--maxStep, -s/--saveAll, -d/--debug, -h/--help.
-// Added: --device N (CUDA ordinal), --reference PATH.
+// Added: --device N (CUDA ordinal), --reference PATH, --devices LIST (several GPUs in ONE process: one context per listed
+// device, every stage partitioned -- reads organised by key range, table built by key-hash shard, search by id slice --
+// and the all-gathers between the stages done as peer copies; no NCCL, no Python; same files out).
 //
 // Differences, all stated in the log: steps 1-3 are one device pass, so a restart at -m 2 / -m 3
 // recomputes from the input files instead of loading <prefix>.reads / <prefix>.hashTable (results are
@@ -27,8 +29,11 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <functional>
+#include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sage2gpu.h"
@@ -41,6 +46,7 @@ namespace {
 struct Options {
     int minStep = 1, maxStep = 7, minOverlap = 0, device = 0;
     bool saveAll = false, debugging = false, parseOnly = false;
+    std::vector<int> devices;       // --devices: one context per listed GPU, every stage partitioned, peer copies between them
     std::string fileInput, listInput, outputDir, prefixName = "untitled", inputPrefix, referenceBin;
 };
 
@@ -84,6 +90,20 @@ void printListOfArgs()
                  "\t--reference <path>      SAGE2 binary that runs steps 4-7 from the files written here\n\n";
 }
 
+// "0,1,2" or "0-3" (or a mix); a device may be listed twice (two contexts on one GPU)
+std::vector<int> parseDevices(const char *arg)
+{
+    std::vector<int> v;
+    std::stringstream ss(arg);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) {
+        const size_t dash = tok.find('-', 1);
+        if (dash != std::string::npos) { for (int d = atoi(tok.substr(0, dash).c_str()); d <= atoi(tok.substr(dash + 1).c_str()); ++d) v.push_back(d); }
+        else if (!tok.empty()) v.push_back(atoi(tok.c_str()));
+    }
+    return v;
+}
+
 void parseArgs(int argc, char **argv, Options &o)
 {
     static struct option long_options[] = {
@@ -93,7 +113,8 @@ void parseArgs(int argc, char **argv, Options &o)
         { "inputPrefix", required_argument, 0, 'i' }, { "minStep", required_argument, 0, 'm' },
         { "maxStep", required_argument, 0, 'M' },  { "saveAll", no_argument, 0, 's' },
         { "debug", no_argument, 0, 'd' },          { "device", required_argument, 0, 1001 },
-        { "reference", required_argument, 0, 1002 }, { "parse-only", no_argument, 0, 1003 }, { 0, 0, 0, 0 } };
+        { "reference", required_argument, 0, 1002 }, { "parse-only", no_argument, 0, 1003 },
+        { "devices", required_argument, 0, 1004 }, { 0, 0, 0, 0 } };
     bool fFlag = false, lFlag = false;
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "hf:l:k:o:p:i:m:M:sd", long_options, &idx)) != -1) {
@@ -117,6 +138,7 @@ void parseArgs(int argc, char **argv, Options &o)
             case 1001: o.device = atoi(optarg); break;
             case 1002: o.referenceBin = optarg; break;
             case 1003: o.parseOnly = true; break;
+            case 1004: o.devices = parseDevices(optarg); break;
             case '?': std::cout << "\n"; exit(0);
             default: std::cout << "[ERROR] Wrong command line arguments!\n\n"; exit(0);
         }
@@ -196,6 +218,12 @@ public:
     {
         flush();
         if (sage2gpu_load_finish(ctx_) != 0) printError("CUDA", sage2gpu_last_error(ctx_));
+    }
+    // several GPUs: filter + pack only; organizeReads follows partitioned over the contexts
+    void finishPacked(uint64_t &n_reads, int &max_len, uint64_t &good, uint64_t &bp)
+    {
+        flush();
+        if (sage2gpu_load_finish_packed(ctx_, &n_reads, &max_len, &good, &bp) != 0) printError("CUDA", sage2gpu_last_error(ctx_));
     }
     // everything added so far is on the device after this
     void sync()
@@ -424,6 +452,143 @@ int runReference(const Options &o, int fromStep)
 
 }  // namespace
 
+// ---- several GPUs in one process ---------------------------------------------------------------------------------
+// One context per device, one host thread per context and stage (the library calls block), peer copies between the
+// stages.  The steps are those of sage2_b200/multi.py::partitioned_slice_steps with context 0 holding the whole input as
+// its "slice" (it received the streamed upload) and the others an empty one.
+struct MultiGpu {
+    std::vector<sage2gpu_ctx *> ctx;
+    int G() const { return (int)ctx.size(); }
+    void each(const std::function<void(int)> &fn)
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < G(); ++r) th.emplace_back(fn, r);
+        for (auto &t : th) t.join();
+    }
+    void check(int r, int rc) { if (rc != 0) printError("CUDA", std::string("device context ") + std::to_string(r) + ": " + sage2gpu_last_error(ctx[r])); }
+    // all-gather of blocks: block q (bytes[q] bytes at byte offset off[q]) of every context's array comes from context q
+    void gather(const std::vector<void *> &ptr, const std::vector<uint64_t> &off, const std::vector<uint64_t> &bytes)
+    {
+        each([&](int r) {
+            for (int q = 0; q < G(); ++q)
+                if (q != r && bytes[q]) check(r, sage2gpu_peer_copy(ctx[r], (char *)ptr[r] + off[q], ctx[q], (const char *)ptr[q] + off[q], bytes[q]));
+        });
+    }
+};
+
+// steps 1 (after the upload into context 0) to 3; the result is complete in every context
+void runPartitioned(MultiGpu &m, Uploader &up, int k)
+{
+    const int G = m.G();
+    uint64_t N = 0, good = 0, bp = 0;
+    int max_len = 0;
+    up.finishPacked(N, max_len, good, bp);
+    std::vector<uint64_t> counts(G, 0), zero(G, 0);
+    counts[0] = N;
+    m.each([&](int r) {
+        if (r > 0) m.check(r, sage2gpu_pack_slice(m.ctx[r], nullptr, nullptr, 0, k, 1, max_len > 0 ? max_len : 1, nullptr, nullptr, nullptr));
+    });
+    sage2gpu_counters c0;
+    sage2gpu_get_counters(m.ctx[0], &c0);
+    const uint64_t SW = c0.record_words;
+    std::vector<void *> p(G, nullptr), p2(G, nullptr), p3(G, nullptr);
+    m.each([&](int r) { m.check(r, sage2gpu_raw_gather_layout(m.ctx[r], r, G, counts.data(), &p[r], nullptr, nullptr)); });
+    {
+        std::vector<uint64_t> off(G, 0), bytes(G, 0);
+        bytes[0] = N * SW * 8;
+        m.gather(p, off, bytes);
+    }
+    std::vector<uint64_t> uloc(G, 0);
+    m.each([&](int r) {
+        m.check(r, sage2gpu_raw_gather_finish(m.ctx[r], N, good, bp));
+        m.check(r, sage2gpu_organize_partition(m.ctx[r], r, G, &uloc[r]));
+    });
+    std::vector<uint64_t> stride(G, 0);
+    m.each([&](int r) { m.check(r, sage2gpu_reads_gather_layout(m.ctx[r], uloc.data(), &p[r], &p2[r], &p3[r], nullptr, nullptr, &stride[r])); });
+    {
+        std::vector<uint64_t> off(G, 0), bytes(G, 0), off2(G, 0), bytes2(G, 0);
+        uint64_t acc = 0;
+        for (int q = 0; q < G; ++q) { off[q] = acc * stride[0] * 8; bytes[q] = uloc[q] * stride[0] * 8; off2[q] = acc * 2; bytes2[q] = uloc[q] * 2; acc += uloc[q]; }
+        m.gather(p, off, bytes);
+        m.gather(p2, off2, bytes2);
+        m.gather(p3, off2, bytes2);
+    }
+    std::vector<uint64_t> ec(G, 0), dk(G, 0), ov(G, 0), sps(G, 0);
+    m.each([&](int r) {
+        m.check(r, sage2gpu_reads_gather_finish(m.ctx[r]));
+        m.check(r, sage2gpu_build_hash_table_part(m.ctx[r], r, G));
+        m.check(r, sage2gpu_table_shard_info(m.ctx[r], nullptr, &ec[r], &dk[r], &ov[r]));
+    });
+    m.each([&](int r) { m.check(r, sage2gpu_table_gather_layout(m.ctx[r], ec.data(), &p[r], &p2[r], &sps[r], nullptr)); });
+    {
+        std::vector<uint64_t> off(G, 0), bytes(G, 0), off2(G, 0), bytes2(G, 0);
+        uint64_t acc = 0;
+        for (int q = 0; q < G; ++q) { off[q] = (uint64_t)q * sps[0] * 8; bytes[q] = sps[0] * 8; off2[q] = acc * 4; bytes2[q] = ec[q] * 4; acc += ec[q]; }
+        m.gather(p, off, bytes);
+        m.gather(p2, off2, bytes2);
+    }
+    m.each([&](int r) {
+        m.check(r, sage2gpu_table_gather_finish(m.ctx[r], ec.data(), dk.data(), ov.data()));
+        m.check(r, sage2gpu_phase_a_partition(m.ctx[r], r, G));
+    });
+    m.each([&](int r) {
+        for (int q = 0; q < G; ++q) if (q != r) m.check(r, sage2gpu_phase_a_import(m.ctx[r], m.ctx[q], q));
+    });
+    m.each([&](int r) { m.check(r, sage2gpu_finish_graph(m.ctx[r])); });
+}
+
+// --devices with more than one entry: steps 1-3 partitioned over the listed GPUs, the same files and log lines out
+int runOnSeveralDevices(const Options &o, const std::string &base)
+{
+    MultiGpu m;
+    for (int d : o.devices) {
+        sage2gpu_ctx *c = nullptr;
+        if (sage2gpu_create(&c, d) != 0) printError("CUDA", "no usable CUDA device " + std::to_string(d) + " (libsage2gpu has no CPU fallback)");
+        m.ctx.push_back(c);
+    }
+    logStream << "Devices: " << m.G() << " contexts (one per listed GPU), every stage partitioned, peer copies between the stages.\n";
+    banner("STEP 1", "                                          organizing reads");
+    auto t0 = std::chrono::steady_clock::now();
+    {
+        Uploader up(m.ctx[0], o.minOverlap);
+        if (!o.listInput.empty()) loadFromList(up, o.listInput);
+        else readDataset(up, o.fileInput, "");
+        logStream << "Parsed and uploaded in " << seconds_since(t0) << " sec.\n";
+        banner("STEPS 2-3", "                             building hash table and overlap graph");
+        auto t1 = std::chrono::steady_clock::now();
+        runPartitioned(m, up, o.minOverlap);
+        logStream << "Functions organizeReads() .. sortEconomyGraph() on " << m.G() << " devices in " << seconds_since(t1) << " sec.\n";
+    }
+    sage2gpu_counters cnt;
+    sage2gpu_get_counters(m.ctx[0], &cnt);
+    logStream << std::setw(20) << "Total reads: " << cnt.total_reads << "\n";
+    logStream << std::setw(20) << "Good reads: " << cnt.good_reads << "\n";
+    logStream << std::setw(20) << "Bad reads: " << cnt.total_reads - cnt.good_reads << "\n";
+    logStream << "\t" << std::setw(21) << "Average read length: " << cnt.avg_len << "\n";
+    logStream << "\tNumber of unique reads: " << cnt.unique_reads << "\n";
+    logStream << "\tSize of hash table: " << cnt.table_capacity << " slots, " << cnt.distinct_keys << " distinct keys\n";
+    logStream << "\tNumber of hashes over threshold: " << cnt.keys_over_threshold << "\n";
+    logStream << "\tTotal reads contained by extension: " << cnt.contained_ext << "\n";
+    logStream << "\tTotal reads contained by size: " << cnt.contained_size << "\n";
+    logStream << "\tTotal reads left to explore: " << cnt.left_to_explore << "\n";
+    logStream << "\tTotal edges inserted: " << cnt.edges_inserted_c << "\n";
+    logStream << "\tTotal transitive edges removed: " << cnt.transitive_removed << "\n";
+    logStream << "\tEdges in the overlap graph: " << cnt.n_edges << "\n";
+    if (sage2gpu_write_reads(m.ctx[0], (base + ".reads").c_str()) != 0) printError("OPEN_FILE", sage2gpu_last_error(m.ctx[0]));
+    // the graph from the LAST context: every context must hold the complete result
+    if (sage2gpu_write_graph3(m.ctx[m.G() - 1], (base + ".graph3").c_str()) != 0) printError("OPEN_FILE", sage2gpu_last_error(m.ctx[m.G() - 1]));
+    logStream.flush();
+    for (sage2gpu_ctx *c : m.ctx) sage2gpu_destroy(c);
+    if (o.maxStep <= 3) return 0;
+    if (o.referenceBin.empty()) {
+        std::cout << "sage2gpu: steps 1-3 done (" << base << ".reads, " << base << ".graph3); continue with SAGE2 -m 4 -i " << o.prefixName << "\n";
+        return 0;
+    }
+    logStream << "Running " << o.referenceBin << " -m 4 for steps 4-" << o.maxStep << ".\n";
+    logStream.close();
+    return runReference(o, 4);
+}
+
 int main(int argc, char **argv)
 {
     Options o;
@@ -472,6 +637,8 @@ int main(int argc, char **argv)
         logStream << "NOTE: steps 1-3 are one device pass; -m " << o.minStep << " recomputes them from the input files (same result).\n";
     logStream.flush();
 
+    if (o.devices.size() > 1) return runOnSeveralDevices(o, base);
+    if (o.devices.size() == 1) o.device = o.devices[0];
     sage2gpu_ctx *ctx = nullptr;
     if (sage2gpu_create(&ctx, o.device) != 0)
         printError("CUDA", "no usable CUDA device " + std::to_string(o.device) + " (libsage2gpu has no CPU fallback)");

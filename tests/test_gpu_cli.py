@@ -143,3 +143,29 @@ def test_two_mate_files_of_unequal_length(tmp_path):
         want = _run_cli(["-f", str(tmp_path / f"{name}_expected.fastq"), "-k", str(k)], tmp_path / f"{name}_w")
         assert got[:2] == want[:2]
         assert f"Good reads: {len(kept)}" in got[2].replace(",", "")
+
+
+def _devices_args():
+    import torch
+    out = [("0,0", "two contexts on one GPU"), ("0,0,0", "three contexts on one GPU")]
+    if torch.cuda.device_count() >= 2:
+        out.append(("0,1", "two GPUs"))
+    if torch.cuda.device_count() >= 4:
+        out.append(("0-3", "four GPUs"))
+    return out
+
+
+@pytest.mark.parametrize("name", ["mixed", "rep", "varlen_err", "hicopy", "cfg1"])
+def test_cli_several_devices_byte_identical_to_reference(name, tmp_path):
+    """`sage2gpu --devices LIST`: ONE process, one context per listed device, every stage partitioned, peer copies between
+    the stages (no NCCL, no Python).  Same bytes as the unmodified reference, from the first and from the last context."""
+    reads, k = _get(name)
+    fq = tmp_path / "in.fastq"
+    synth.write_fastq(str(fq), reads)
+    for devs, _ in _devices_args():
+        out = tmp_path / ("out_" + devs.replace(",", "_"))
+        subprocess.run([BIN, "-f", str(fq), "-k", str(k), "-o", str(out), "-p", "g", "-M", "3", "--devices", devs], check=True)
+        assert _md5(out / "g.reads") == GOLD[name]["reads_md5"], devs
+        assert _md5(out / "g.graph3") == GOLD[name]["graph3_md5"], devs
+        log = open(out / "g.log").read()
+        assert f"Number of unique reads: {GOLD[name]['unique_reads']}" in log

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--seed", type=int, default=31)
+    ap.add_argument("--low-memory", action="store_true", help="release every buffer as soon as no later stage needs it (full size needs it)")
     args = ap.parse_args()
 
     import torch
@@ -58,15 +59,12 @@ def main():
     p0, p1 = min(n_pairs, rank * chunk), min(n_pairs, (rank + 1) * chunk)
     n_slice = 2 * (p1 - p0)
     gpu = api.Sage2Gpu(local)
-    t0 = time.perf_counter()
-    d_bases = torch.empty(max(1, n_slice * L), dtype=torch.uint8, device=dev)
-    d_off = torch.empty(n_slice + 1, dtype=torch.int64, device=dev)
-    gpu.synth_reads(d_bases.data_ptr(), d_off.data_ptr(), p0, p1 - p0, args.genome_bp, L, 450.0, 30.0, args.seed)
-    torch.cuda.synchronize()
-    t_gen = time.perf_counter() - t0
+    if args.low_memory:
+        gpu.set_option("low_memory", 1)
     stream = torch.cuda.ExternalStream(gpu.stream_ptr(), device=dev)
     view = multi.device_view_fn(dev)
     xstats = {}
+    t_gen = [0.0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -77,12 +75,48 @@ def main():
     sent = [0]
 
     def step():
+        # the slice's characters exist only until they are packed (93 GB of them over the box at full size): generated at the
+        # start of every step (inside the timed region) and released as soon as sage2gpu_pack_slice has returned
         sent[0] = 0
-        steps = multi.partitioned_slice_steps(gpu, rank, world, view, d_bases.data_ptr(), d_off.data_ptr(), n_slice, args.k, True, L, sent)
+        t0 = time.perf_counter()
+        d_bases = torch.empty(max(1, n_slice * L), dtype=torch.uint8, device=dev)
+        d_off = torch.empty(n_slice + 1, dtype=torch.int64, device=dev)
+        gpu.synth_reads(d_bases.data_ptr(), d_off.data_ptr(), p0, p1 - p0, args.genome_bp, L, 450.0, 30.0, args.seed)
+        t_gen[0] = time.perf_counter() - t0
+        inner = multi.partitioned_slice_steps(gpu, rank, world, view, d_bases.data_ptr(), d_off.data_ptr(), n_slice, args.k, True, L, sent)
+
+        def steps():
+            nonlocal d_bases, d_off
+            try:
+                req = next(inner)              # sage2gpu_pack_slice has run: the characters can go
+            except StopIteration:
+                return
+            d_bases = d_off = None
+            torch.cuda.empty_cache()
+            while True:
+                val = yield req
+                try:
+                    req = inner.send(val)
+                except StopIteration:
+                    return
+
         if world == 1:
-            multi.run_local([steps])
+            multi.run_local([steps()])
         else:
-            multi.run_dist(steps, rank, world, dev, xstats)
+            multi.run_dist(steps(), rank, world, dev, xstats)
+
+    # peak device memory of this rank, sampled while the steps run
+    import threading
+    peak_used, stop = [0], threading.Event()
+
+    def sample():
+        torch.cuda.set_device(local)
+        while not stop.is_set():
+            free_b, total_b = torch.cuda.mem_get_info(dev)
+            peak_used[0] = max(peak_used[0], total_b - free_b)
+            stop.wait(0.01)
+    th = threading.Thread(target=sample, daemon=True)
+    th.start()
 
     for _ in range(args.warmup):
         step()
@@ -101,8 +135,9 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
     t = torch.tensor([ev0.elapsed_time(ev1) / args.steps, wall_ms], dtype=torch.float64, device=dev)
-    free_b, total_b = torch.cuda.mem_get_info(dev)
-    mem = torch.tensor([float(total_b - free_b)], dtype=torch.float64, device=dev)
+    stop.set()
+    th.join(timeout=1)
+    mem = torch.tensor([float(peak_used[0])], dtype=torch.float64, device=dev)
     c = gpu.counters()
     d = gpu.digest()
     dig = torch.tensor([d["reads"] & 0x7FFFFFFFFFFFFFFF, d["edges"] & 0x7FFFFFFFFFFFFFFF, c["compare_calls"], c["window_probes"], c["fast_path_reads"]],
@@ -135,7 +170,7 @@ def main():
             "workload": f"synthetic {args.genome_bp} bp random genome, {L} bp paired-end, {args.coverage}x, -k {args.k}, generated on the devices",
             "n_gpus": world, "input_reads": N, "ms_per_step": ms, "wall_ms_per_step": float(t[1]), "steps": args.steps, "warmup": args.warmup,
             "reads_per_sec": N / (ms / 1e3), "edges_per_sec": c["n_edges"] / (ms / 1e3),
-            "generate_s_per_rank": t_gen, "device_bytes_in_use_max": float(mem[0]),
+            "generate_s_per_rank_and_step": t_gen[0], "device_bytes_in_use_peak_max_over_ranks": float(mem[0]),
             "nvlink_bytes_contributed_per_rank_and_step": sent[0],
             "stage_ms_rank0": stage, "exchange_wall_ms_per_step_rank0": {kk: vv / args.steps for kk, vv in xstats.items()},
             "gpu_launches_rank0": launches,
