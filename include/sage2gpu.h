@@ -262,8 +262,9 @@ int sage2gpu_digest(sage2gpu_ctx *ctx, uint64_t *reads_digest, uint64_t *edges_d
 
 /* Run-time options.  "read_order": schedule of the phase-A search (results do not depend on it): 0 = id order,
  * 1 = min-hash order (reads that share k-mers are searched together, so slot sectors and partner records hit L2),
- * -1 = the default.  "low_memory": 1 = every buffer is released as soon as no later stage of the step needs it (the table
- * before the edge sort, the packed input after organizeReads ...; for read sets near the capacity of the GPU).  "fast_scan": 1 = phase A tries the superstring scan first (default), 0 = hit-by-hit kernel only. */
+ * -1 = the default.  "low_memory": 1 = the large buffers are released (and returned to the driver) as soon as no later stage of the step
+ * needs them -- the packed input after organizeReads, the table before the edge sort; 2 = the workspace too, after every
+ * call (for read sets near the capacity of the GPU).  "fast_scan": 1 = phase A tries the superstring scan first (default), 0 = hit-by-hit kernel only. */
 int sage2gpu_set_option(sage2gpu_ctx *ctx, const char *name, int64_t value);
 
 int sage2gpu_get_counters(const sage2gpu_ctx *ctx, sage2gpu_counters *out);

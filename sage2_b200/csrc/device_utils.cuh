@@ -136,6 +136,15 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// give the freed blocks of the stream-ordered pool back to the driver (low-memory mode: the workspace arena and other
+// allocators can then use them)
+inline void trim_default_pool(int device, cudaStream_t st)
+{
+    cudaStreamSynchronize(st);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+}
+
 constexpr int kSMs = 148;   // B200
 
 // every kernel launch of the library is followed by SG_LAUNCHED(): error check + launch count

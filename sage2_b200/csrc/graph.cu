@@ -205,6 +205,21 @@ __global__ void __launch_bounds__(256) join_edges_kernel(const u64 *__restrict__
         if (flag[e]) { edges[2 * (u64)idx[e]] = w0[e]; edges[2 * (u64)idx[e] + 1] = w1[e]; }
 }
 
+// ---- merge of two sorted record lists without common keys (kept phase-B records, phase-C records) -----------------------
+__device__ __forceinline__ bool rec_less2(u64 a0, u64 a1, u64 b0, u64 b1) { return a0 < b0 || (a0 == b0 && a1 < b1); }
+// records of X (nx) go to position i + |{y in Y : y < x_i}|
+__global__ void __launch_bounds__(256) merge_scatter_kernel(const u64 *__restrict__ x0, const u64 *__restrict__ x1, u64 nx,
+                                                             const u64 *__restrict__ y0, const u64 *__restrict__ y1, u64 ny,
+                                                             u64 *__restrict__ o0, u64 *__restrict__ o1)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k0 = x0[i], k1 = x1[i];
+        u64 lo = 0, hi = ny;
+        while (lo < hi) { const u64 m = (lo + hi) >> 1; if (rec_less2(y0[m], y1[m], k0, k1)) lo = m + 1; else hi = m; }
+        o0[i + lo] = k0; o1[i + lo] = k1;
+    }
+}
+
 void stage_phase_c_and_finalize(Context &c)
 {
     cudaStream_t st = c.stream;
@@ -235,6 +250,15 @@ void stage_phase_c_and_finalize(Context &c)
     u64 n_dev_c = 0;
     bool c_on_device = false;
     float host_ms = 0.f, host_order_ms = 0.f;
+    // kept phase-B records, sorted ahead of the merge (sort_kept_b)
+    DevBuf<u32> eflag, eidx, d_keep(1, st);
+    DevBuf<u64> ka0, ka1, kb0, kb1;
+    SortCols kcols;
+    int kcur = 0;
+    bool b_sorted = false;
+    u64 nKeep = nB;
+    int id_bits = 1;
+    while ((U >> id_bits) != 0) ++id_bits;                   // ids are 1..U
     if (nS > 0) {
         DevBuf<u32> s_ids(nS, st), counts(nS, st), offs(nS, st), d_ctotal(1, st);
         compact_ids_kernel<<<big_grid(U), 256, 0, st>>>(flag.p, idx.p, U, s_ids.p);
@@ -307,6 +331,31 @@ void stage_phase_c_and_finalize(Context &c)
             in.cand = h_cand.data(); in.nB = nSel; in.edgesB = h_selB.data(); in.edgesB_len = h_selLen.data();
             have_input = true;
         };
+        // the phase-B records that stay (owner not in S) are sorted now, asynchronously: the device works on them while the
+        // host computes the traversal order; the few records of phase C are merged in afterwards
+        auto sort_kept_b = [&]() {
+            if (b_sorted) return;
+            b_sorted = true;
+            nKeep = nB;
+            if (nB == 0) return;
+            eflag.alloc(nB, st); eidx.alloc(nB, st);
+            flag_keep_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, c.explored.p, eflag.p);
+            SG_LAUNCHED();
+            exclusive_scan_u32(eflag.p, eidx.p, nB, d_keep.p, st);
+            u32 k32 = 0;
+            SG_CUDA(cudaMemcpyAsync(&k32, d_keep.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaStreamSynchronize(st));
+            nKeep = k32;
+            if (nKeep == 0) return;
+            ka0.alloc(nKeep, st); ka1.alloc(nKeep, st); kb0.alloc(nKeep, st); kb1.alloc(nKeep, st);
+            split_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, eflag.p, eidx.p, ka0.p, kb0.p);
+            SG_LAUNCHED();
+            kcols.a[0] = ka0.p; kcols.a[1] = ka1.p; kcols.b[0] = kb0.p; kcols.b[1] = kb1.p; kcols.v[0] = kcols.v[1] = nullptr;
+            kcur = radix_sort_bits(kcols, 0, nKeep, false, 0, id_bits, st);           // w0: to
+            kcur = radix_sort_bits(kcols, kcur, nKeep, false, 32, 32 + id_bits, st);  // w0: from
+            order_pair_runs_kernel<<<big_grid(nKeep), 256, 0, st>>>(kcols.a[kcur], kcols.b[kcur], nKeep);
+            SG_LAUNCHED();
+        };
         u64 removed_dev = 0, inserted_dev = 0;
         if (!force_host) {
             DevBuf<u32> d_order;
@@ -315,6 +364,7 @@ void stage_phase_c_and_finalize(Context &c)
                 // which end point inserts an overlap depends on the breadth-first traversal (economyGraph.cpp:513-564, :605):
                 // that part stays sequential, on the host; everything else follows from its order
                 fetch_input();
+                sort_kept_b();          // queued behind the copies above: runs while the host walks
                 std::vector<u32> h_order;
                 host_order_ms = run_host_phase_c_order(in, h_order);
                 d_order.alloc(nS, st);
@@ -333,6 +383,7 @@ void stage_phase_c_and_finalize(Context &c)
         } else {
         c.cnt.phase_c_on_device = 0;
         fetch_input();
+        sort_kept_b();
         SG_CUDA(cudaEventRecord(ev1, st));
         PhaseCOutput out;
         host_ms += run_host_phase_c(in, out);
@@ -359,20 +410,24 @@ void stage_phase_c_and_finalize(Context &c)
         SG_CUDA(cudaStreamSynchronize(st));
         c.slots.release(); c.entries.release(); c.entries_loc.release();
         c.have_table = false;
+        trim_default_pool(c.device, st);
     }
     // ---- assemble the final record set on device --------------------------------------------------
+    // kept phase-B records (sorted above, or now) + the records of phase C (sorted here, few) -> one sorted list
     const u64 nH = c_on_device ? n_dev_c : host_c_edges.size() / 2;
-    DevBuf<u32> eflag, eidx, d_keep(1, st);
-    u64 nKeep = nB;
-    if (nS > 0 && nB > 0) {
-        eflag.alloc(nB, st); eidx.alloc(nB, st);
-        flag_keep_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, c.explored.p, eflag.p);
-        SG_LAUNCHED();
-        exclusive_scan_u32(eflag.p, eidx.p, nB, d_keep.p, st);
-        u32 k32 = 0;
-        SG_CUDA(cudaMemcpyAsync(&k32, d_keep.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaStreamSynchronize(st));
-        nKeep = k32;
+    if (nS == 0) nKeep = nB;        // no read reached phase C: every phase-B record stays
+    else if (!b_sorted) {           // (sort_kept_b is a lambda of the nS > 0 block: same steps when phase C never went to the host)
+        nKeep = nB;
+        if (nB) {
+            eflag.alloc(nB, st); eidx.alloc(nB, st);
+            flag_keep_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, c.explored.p, eflag.p);
+            SG_LAUNCHED();
+            exclusive_scan_u32(eflag.p, eidx.p, nB, d_keep.p, st);
+            u32 k32 = 0;
+            SG_CUDA(cudaMemcpyAsync(&k32, d_keep.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaStreamSynchronize(st));
+            nKeep = k32;
+        }
     }
     const u64 nAll = nKeep + nH;
     if (nAll == 0) {
@@ -383,42 +438,80 @@ void stage_phase_c_and_finalize(Context &c)
         cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
         return;
     }
-    DevBuf<u64> a0(nAll, st), a1(nAll, st), b0(nAll, st), b1(nAll, st);
-    if (nB) {
-        split_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, eflag.p, eidx.p, a0.p, b0.p);
+    const u64 *f0 = nullptr, *f1 = nullptr;     // the merged, sorted records
+    DevBuf<u64> a0, a1, b0, b1, m0, m1;
+    if (b_sorted) {
+        // phase C's records: sort them alone, then merge the two sorted lists (no key occurs in both: a kept phase-B record
+        // is owned by a read outside S, a phase-C record by a read of S)
+        a0.alloc(nH + 1, st); a1.alloc(nH + 1, st); b0.alloc(nH + 1, st); b1.alloc(nH + 1, st);
+        DevBuf<u64> tmp;
+        if (nH && c_on_device) {
+            split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(dev_c_edges.p, nH, nullptr, nullptr, a0.p, b0.p);
+            SG_LAUNCHED();
+        } else if (nH) {
+            tmp.alloc(2 * nH, st);
+            SG_CUDA(cudaMemcpyAsync(tmp.p, host_c_edges.data(), 2 * nH * sizeof(u64), cudaMemcpyHostToDevice, st));
+            split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(tmp.p, nH, nullptr, nullptr, a0.p, b0.p);
+            SG_LAUNCHED();
+            SG_CUDA(cudaStreamSynchronize(st));   // host_c_edges / tmp lifetime
+        }
+        SortCols cc;
+        cc.a[0] = a0.p; cc.a[1] = a1.p; cc.b[0] = b0.p; cc.b[1] = b1.p; cc.v[0] = cc.v[1] = nullptr;
+        int ccur = 0;
+        if (nH) {
+            ccur = radix_sort_bits(cc, ccur, nH, false, 0, id_bits, st);
+            ccur = radix_sort_bits(cc, ccur, nH, false, 32, 32 + id_bits, st);
+            order_pair_runs_kernel<<<big_grid(nH), 256, 0, st>>>(cc.a[ccur], cc.b[ccur], nH);
+            SG_LAUNCHED();
+        }
+        if (nH == 0) { f0 = kcols.a[kcur]; f1 = kcols.b[kcur]; }
+        else if (nKeep == 0) { f0 = cc.a[ccur]; f1 = cc.b[ccur]; }
+        else {
+            m0.alloc(nAll, st); m1.alloc(nAll, st);
+            merge_scatter_kernel<<<big_grid(nKeep), 256, 0, st>>>(kcols.a[kcur], kcols.b[kcur], nKeep, cc.a[ccur], cc.b[ccur], nH, m0.p, m1.p);
+            SG_LAUNCHED();
+            merge_scatter_kernel<<<big_grid(nH), 256, 0, st>>>(cc.a[ccur], cc.b[ccur], nH, kcols.a[kcur], kcols.b[kcur], nKeep, m0.p, m1.p);
+            SG_LAUNCHED();
+            f0 = m0.p; f1 = m1.p;
+        }
+        if (!f0) { f0 = kcols.a[kcur]; f1 = kcols.b[kcur]; }
+    } else {
+        a0.alloc(nAll, st); a1.alloc(nAll, st); b0.alloc(nAll, st); b1.alloc(nAll, st);
+        if (nB) {
+            split_edges_kernel<<<big_grid(nB), 256, 0, st>>>(c.edges.p, nB, nS > 0 ? eflag.p : nullptr, nS > 0 ? eidx.p : nullptr, a0.p, b0.p);
+            SG_LAUNCHED();
+        }
+        if (nH && c_on_device) {
+            split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(dev_c_edges.p, nH, nullptr, nullptr, a0.p + nKeep, b0.p + nKeep);
+            SG_LAUNCHED();
+        } else if (nH) {
+            DevBuf<u64> tmp(2 * nH, st);
+            SG_CUDA(cudaMemcpyAsync(tmp.p, host_c_edges.data(), 2 * nH * sizeof(u64), cudaMemcpyHostToDevice, st));
+            split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(tmp.p, nH, nullptr, nullptr, a0.p + nKeep, b0.p + nKeep);
+            SG_LAUNCHED();
+            SG_CUDA(cudaStreamSynchronize(st));   // host_c_edges / tmp lifetime
+        }
+        SortCols cols;
+        cols.a[0] = a0.p; cols.a[1] = a1.p; cols.b[0] = b0.p; cols.b[1] = b1.p; cols.v[0] = cols.v[1] = nullptr;
+        int cur = 0;
+        // stable LSD passes, least significant field first; the bit ranges are known, no reduction / host round trip
+        cur = radix_sort_bits(cols, cur, nAll, false, 0, id_bits, st);           // w0: to
+        cur = radix_sort_bits(cols, cur, nAll, false, 32, 32 + id_bits, st);     // w0: from
+        // several edges between one pair of reads are rare (tandem repeats, palindromes): order their
+        // (type, overhang) words in place instead of spending three more passes on every edge
+        order_pair_runs_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll);
         SG_LAUNCHED();
+        f0 = cols.a[cur]; f1 = cols.b[cur];
     }
-    if (nH && c_on_device) {
-        split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(dev_c_edges.p, nH, nullptr, nullptr, a0.p + nKeep, b0.p + nKeep);
-        SG_LAUNCHED();
-    } else if (nH) {
-        DevBuf<u64> tmp(2 * nH, st);
-        SG_CUDA(cudaMemcpyAsync(tmp.p, host_c_edges.data(), 2 * nH * sizeof(u64), cudaMemcpyHostToDevice, st));
-        split_edges_kernel<<<big_grid(nH), 256, 0, st>>>(tmp.p, nH, nullptr, nullptr, a0.p + nKeep, b0.p + nKeep);
-        SG_LAUNCHED();
-        SG_CUDA(cudaStreamSynchronize(st));   // host_c_edges / tmp lifetime
-    }
-    SortCols cols;
-    cols.a[0] = a0.p; cols.a[1] = a1.p; cols.b[0] = b0.p; cols.b[1] = b1.p; cols.v[0] = cols.v[1] = nullptr;
-    int cur = 0;
-    // stable LSD passes, least significant field first; the bit ranges are known, no reduction / host round trip
-    int id_bits = 1;
-    while ((U >> id_bits) != 0) ++id_bits;                   // ids are 1..U
-    cur = radix_sort_bits(cols, cur, nAll, false, 0, id_bits, st);           // w0: to
-    cur = radix_sort_bits(cols, cur, nAll, false, 32, 32 + id_bits, st);     // w0: from
-    // several edges between one pair of reads are rare (tandem repeats, palindromes): order their
-    // (type, overhang) words in place instead of spending three more passes on every edge
-    order_pair_runs_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll);
-    SG_LAUNCHED();
     DevBuf<u32> fflag(nAll, st), fidx(nAll, st), d_ne(1, st);
-    flag_first_edge_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll, fflag.p);
+    flag_first_edge_kernel<<<big_grid(nAll), 256, 0, st>>>(f0, f1, nAll, fflag.p);
     SG_LAUNCHED();
     exclusive_scan_u32(fflag.p, fidx.p, nAll, d_ne.p, st);
     u32 nE = 0;
     SG_CUDA(cudaMemcpyAsync(&nE, d_ne.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     c.edges.alloc(2 * (u64)nE, st);
-    join_edges_kernel<<<big_grid(nAll), 256, 0, st>>>(cols.a[cur], cols.b[cur], nAll, fflag.p, fidx.p, c.edges.p);
+    join_edges_kernel<<<big_grid(nAll), 256, 0, st>>>(f0, f1, nAll, fflag.p, fidx.p, c.edges.p);
     SG_LAUNCHED();
     SG_CUDA(cudaEventRecord(ev2, st));
     SG_CUDA(cudaEventSynchronize(ev2));

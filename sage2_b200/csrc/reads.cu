@@ -660,7 +660,7 @@ void stage_organize_reads(Context &c, int rank, int world)
     SG_LAUNCHED();
     c.rp_local = U;
     c.have_reads = world == 1;      // several GPUs: complete only after the ranks' runs were gathered (stage_reads_gather_*)
-    if (c.opt_low_memory) { SG_CUDA(cudaStreamSynchronize(st)); c.raw.release(); }      // the packed input is not needed again
+    if (c.opt_low_memory) { SG_CUDA(cudaStreamSynchronize(st)); c.raw.release(); trim_default_pool(c.device, st); }      // the packed input is not needed again
 }
 
 // The ranks' unique runs -> the global arrays.  counts[q] = unique reads of rank q (the host all-gathered them): this rank's

@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--seed", type=int, default=31)
-    ap.add_argument("--low-memory", action="store_true", help="release every buffer as soon as no later stage needs it (full size needs it)")
+    ap.add_argument("--low-memory", type=int, default=0, help="1: release the large buffers as soon as no later stage needs them (full size needs it); 2: the workspace too")
     args = ap.parse_args()
 
     import torch
@@ -60,7 +60,7 @@ def main():
     n_slice = 2 * (p1 - p0)
     gpu = api.Sage2Gpu(local)
     if args.low_memory:
-        gpu.set_option("low_memory", 1)
+        gpu.set_option("low_memory", args.low_memory)
     stream = torch.cuda.ExternalStream(gpu.stream_ptr(), device=dev)
     view = multi.device_view_fn(dev)
     xstats = {}
