@@ -221,6 +221,7 @@ int sage2gpu_organize_partition(sage2gpu_ctx *ctx, int rank, int world, uint64_t
         StageTimer t(c.stream);
         sg::stage_organize_reads(c, rank, world);
         c.tm.sort_reads = t.stop();
+        if (c.opt_low_memory) { SG_CUDA(cudaStreamSynchronize(c.stream)); c.arena.destroy(); }     // 25 GB of temporaries at 620 M reads
         if (unique_local) *unique_local = world > 1 ? c.rp_local : c.cnt.unique_reads;
     });
 }

@@ -129,6 +129,23 @@ __global__ void __launch_bounds__(256) gather_len_kernel(const u32 *__restrict__
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = len[ids[i]];
 }
 
+// what the host traversal needs besides the candidates: the S index of every candidate's read2, and which S reads own
+// phase-B records (their lists are not empty, economyGraph.cpp:525)
+__global__ void __launch_bounds__(256) cand_node_kernel(const u64 *__restrict__ cand, u64 nC, const u32 *__restrict__ sidx, u32 *__restrict__ node)
+{
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < nC; q += (u64)gridDim.x * blockDim.x) node[q] = sidx[(u32)(cand[q] >> 32) - 1];
+}
+__global__ void __launch_bounds__(256) has_b_kernel(const u64 *__restrict__ selB, u64 nSel, const uint8_t *__restrict__ explored, const u32 *__restrict__ sidx,
+                                                     uint8_t *__restrict__ has_b)
+{
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < nSel; e += (u64)gridDim.x * blockDim.x) {
+        const u64 w0 = selB[2 * e];
+        const u32 a = (u32)(w0 >> 32) - 1, b = (u32)w0 - 1;
+        if (explored[a] == 0) has_b[sidx[a]] = 1;
+        if (explored[b] == 0) has_b[sidx[b]] = 1;
+    }
+}
+
 void stage_phase_b(Context &c)
 {
     cudaStream_t st = c.stream;
@@ -313,10 +330,20 @@ void stage_phase_c_and_finalize(Context &c)
         std::vector<u32> h_sids, h_off, h_selLen;
         std::vector<u64> h_cand, h_selB;
         std::vector<uint16_t> h_slen;
+        std::vector<u32> h_cnode;
+        std::vector<uint8_t> h_hasb;
         bool have_input = false;
         auto fetch_input = [&]() {
             if (have_input) return;
             h_sids.resize(nS); h_off.resize((size_t)nS + 1); h_selLen.resize(nSel); h_cand.resize(nC); h_selB.resize(2 * (u64)nSel); h_slen.resize(nS);
+            h_cnode.resize(nC); h_hasb.resize(nS);
+            DevBuf<u32> d_cnode(nC, st);
+            DevBuf<uint8_t> d_hasb(nS, st);
+            SG_CUDA(cudaMemsetAsync(d_hasb.p, 0, nS, st));
+            if (nC) { cand_node_kernel<<<big_grid(nC), 256, 0, st>>>(cand.p, nC, idx.p, d_cnode.p); SG_LAUNCHED(); }
+            if (nSel) { has_b_kernel<<<big_grid(nSel), 256, 0, st>>>(selB.p, nSel, c.explored.p, idx.p, d_hasb.p); SG_LAUNCHED(); }
+            if (nC) SG_CUDA(cudaMemcpyAsync(h_cnode.data(), d_cnode.p, nC * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaMemcpyAsync(h_hasb.data(), d_hasb.p, nS, cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(h_sids.data(), s_ids.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(h_off.data(), offs.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(h_slen.data(), sLen.p, nS * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
@@ -329,6 +356,7 @@ void stage_phase_c_and_finalize(Context &c)
             h_off[nS] = nC;
             in.nS = nS; in.s_ids = h_sids.data(); in.s_len = h_slen.data(); in.cand_off = h_off.data();
             in.cand = h_cand.data(); in.nB = nSel; in.edgesB = h_selB.data(); in.edgesB_len = h_selLen.data();
+            in.cand_node = h_cnode.data(); in.has_b = h_hasb.data();
             have_input = true;
         };
         // the phase-B records that stay (owner not in S) are sorted now, asynchronously: the device works on them while the

@@ -196,6 +196,74 @@ void on_all_cores(size_t work_items, Fn fn)
 
 }  // namespace
 
+// buildOverlapGraphEconomy, economyGraph.cpp:513-564.  has_b: reads whose lists hold phase-B records that are not in the pool
+static void traverse(Walk &w, uint32_t nS, const uint8_t *has_b)
+{
+    std::vector<uint32_t> queue;
+    queue.reserve(nS);
+    for (uint32_t i = 0; i < nS; ++i) {
+        if (w.state[i] != 0) continue;
+        queue.clear();
+        size_t qs = 0;
+        queue.push_back(i);
+        while (qs < queue.size()) {
+            const uint32_t n1 = queue[qs++];
+            if (w.state[n1] == 0) w.insert_all(n1);
+            if (w.size[n1] == 0 && !(has_b && has_b[n1])) continue;          // :525
+            if (w.state[n1] == 1) {
+                for (uint32_t x = 0; x < w.size[n1]; ++x) {
+                    const uint32_t n2 = w.list(n1)[x].node;
+                    if (w.state[n2] == 0) { queue.push_back(n2); w.insert_all(n2); }
+                }
+                w.mark_transitive(n1);
+            }
+            if (w.state[n1] == 2) {
+                for (uint32_t x = 0; x < w.size[n1]; ++x) {
+                    const uint32_t n2 = w.list(n1)[x].node;
+                    if (w.state[n2] != 1) continue;
+                    for (uint32_t y = 0; y < w.size[n2]; ++y) {
+                        const uint32_t n3 = w.list(n2)[y].node;
+                        if (w.state[n3] == 0) { queue.push_back(n3); w.insert_all(n3); }
+                    }
+                    w.mark_transitive(n2);
+                }
+            }
+        }
+    }
+}
+
+// The traversal with S alone in play: node index = index in s_ids, candidate -> node from the device, no id map, no
+// phase-B entries in the lists (they lead to reads outside S, which the traversal never follows; only whether a list is
+// empty matters, :525).
+static float run_walk_lean(const PhaseCInput &in, Walk &w, std::chrono::steady_clock::time_point t0)
+{
+    const uint32_t nS = (uint32_t)in.nS;
+    const uint64_t nC = in.nS ? in.cand_off[in.nS] : 0;
+    static thread_local Workspace ws;
+    w.state.assign(nS, 0);
+    w.node_id.resize(nS); w.node_len.resize(nS);
+    for (uint32_t s = 0; s < nS; ++s) { w.node_id[s] = in.s_ids[s] + 1; w.node_len[s] = in.s_len[s]; }
+    w.cnode = in.cand_node;
+    std::vector<uint32_t> &room = ws.room;
+    room.assign(nS, 0);
+    for (uint32_t s = 0; s < nS; ++s) room[s] = in.cand_off[s + 1] - in.cand_off[s];
+    for (uint64_t q = 0; q < nC; ++q) room[in.cand_node[q]]++;
+    w.start.resize((size_t)nS + 1);
+    w.size.assign(nS, 0);
+    uint64_t total = 0;
+    for (uint32_t n = 0; n < nS; ++n) { w.start[n] = total; total += room[n]; }
+    w.start[nS] = total;
+    w.pool = ws.get_pool(total);
+    if (total && !w.pool) return -1.f;
+    const auto t_setup = std::chrono::steady_clock::now();
+    traverse(w, nS, in.has_b);
+    const auto t_walk = std::chrono::steady_clock::now();
+    if (getenv("SAGE2GPU_PHASE_C_TIMING"))
+        fprintf(stderr, "[phase C host, order only, lean] nS %llu nC %llu | setup %.2f walk %.2f ms\n", (unsigned long long)in.nS, (unsigned long long)nC,
+                std::chrono::duration<float, std::milli>(t_setup - t0).count(), std::chrono::duration<float, std::milli>(t_walk - t_setup).count());
+    return std::chrono::duration<float, std::milli>(t_walk - t0).count();
+}
+
 static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uint32_t> *order)
 {
     PhaseCOutput dummy;
@@ -203,6 +271,8 @@ static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uin
     const auto t0 = std::chrono::steady_clock::now();
     Walk w(in);
     if (order) { order->assign(in.nS, 0); w.order = order; }
+    const bool lean = !outp && in.cand_node && in.has_b;      // traversal only, with the device's node indices: S alone is in play
+    if (lean) return run_walk_lean(in, w, t0);
     w.slot.init(in.nS + 2 * in.nB);
     w.state.reserve(in.nS + 2 * in.nB); w.node_id.reserve(in.nS + 2 * in.nB); w.node_len.reserve(in.nS + 2 * in.nB);
     for (uint64_t s = 0; s < in.nS; ++s) w.node(in.s_ids[s] + 1, 0, in.s_len[s]);
@@ -265,38 +335,7 @@ static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uin
     }
 
     const auto t_setup = std::chrono::steady_clock::now();
-    // buildOverlapGraphEconomy, economyGraph.cpp:513-564
-    std::vector<uint32_t> queue;
-    queue.reserve(nS);
-    for (uint32_t i = 0; i < nS; ++i) {
-        if (w.state[i] != 0) continue;
-        queue.clear();
-        size_t qs = 0;
-        queue.push_back(i);
-        while (qs < queue.size()) {
-            const uint32_t n1 = queue[qs++];
-            if (w.state[n1] == 0) w.insert_all(n1);
-            if (w.size[n1] == 0) continue;                                   // :525
-            if (w.state[n1] == 1) {
-                for (uint32_t x = 0; x < w.size[n1]; ++x) {
-                    const uint32_t n2 = w.list(n1)[x].node;
-                    if (w.state[n2] == 0) { queue.push_back(n2); w.insert_all(n2); }
-                }
-                w.mark_transitive(n1);
-            }
-            if (w.state[n1] == 2) {
-                for (uint32_t x = 0; x < w.size[n1]; ++x) {
-                    const uint32_t n2 = w.list(n1)[x].node;
-                    if (w.state[n2] != 1) continue;
-                    for (uint32_t y = 0; y < w.size[n2]; ++y) {
-                        const uint32_t n3 = w.list(n2)[y].node;
-                        if (w.state[n3] == 0) { queue.push_back(n3); w.insert_all(n3); }
-                    }
-                    w.mark_transitive(n2);
-                }
-            }
-        }
-    }
+    traverse(w, nS, nullptr);
 
     const auto t_walk = std::chrono::steady_clock::now();
     if (!outp) {        // the caller only wants the exploration order: lists, marks and filtering are rebuilt on the device

@@ -16,6 +16,10 @@ struct PhaseCInput {
     const uint64_t *edgesB;     // [2*nB] canonical phase-B records (w0,w1), any order: every record with an
                                 // endpoint in S or adjacent (by a phase-B record) to a read in S
     const uint32_t *edgesB_len; // [nB] len(from) | len(to) << 16
+    // optional, for run_host_phase_c_order: what the device knows anyway, so that the traversal needs no id map and no
+    // phase-B adjacency (phase-B records are inert in the traversal: they lead to reads that are not in S)
+    const uint32_t *cand_node = nullptr;   // [nC] index in s_ids of every candidate's read2
+    const uint8_t *has_b = nullptr;        // [nS] the read has phase-B records (its list is not empty, economyGraph.cpp:525)
 };
 
 struct PhaseCOutput {

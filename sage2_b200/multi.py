@@ -294,6 +294,36 @@ def partitioned_slice_steps(gpu, rank: int, world: int, view, bases_ptr: int, of
     yield from _partitioned_from_organized(gpu, rank, world, view, u_local, sent)
 
 
+def partitioned_slice_sharded_steps(gpu, rank: int, world: int, view, bases_ptr: int, offsets_ptr: int, n_slice: int, k: int, on_device: bool,
+                                    max_read_length: int, batch_reads: int = 1 << 18, p2p: bool = True, sent: list | None = None):
+    """Generator: north_star's layout at full scale -- ingest and read organisation partitioned (as partitioned_slice_steps),
+    the packed reads replicated by all-gather, the TABLE sharded by key hash with the window probes routed to their owners
+    (sharded_graph_steps): for read sets whose table should not be held on every GPU (config #5: 29 GB)."""
+    sent = sent if sent is not None else [0]
+    info = gpu.pack_slice(bases_ptr, offsets_ptr, n_slice, k, on_device, max_read_length)
+    infos = yield ("gather_counts", [n_slice, info["good_reads"], info["total_bp"]])
+    counts = [x[0] for x in infos]
+    lay = gpu.raw_gather_layout(rank, world, counts)
+    sw = info["record_words"]
+    yield ("gather_var", view(lay["records"], lay["total"] * sw, "<i8"), [c * sw for c in counts])
+    sent[0] += 8 * sw * n_slice
+    gpu.raw_gather_finish(sum(counts), sum(x[1] for x in infos), sum(x[2] for x in infos))
+    u_local = gpu.organize_partition(rank, world)
+    if world > 1:
+        ucounts = [c[0] for c in (yield ("gather_counts", [u_local]))]
+        rl = gpu.reads_gather_layout(ucounts)
+        tot, stride = rl["total"], rl["stride"]
+        yield ("gather_var", view(rl["records"], tot * stride, "<i8"), [c * stride for c in ucounts])
+        yield ("gather_var", view(rl["lengths"], tot, "<i2"), ucounts)
+        yield ("gather_var", view(rl["frequencies"], tot, "<i2"), ucounts)
+        sent[0] += ucounts[rank] * (8 * stride + 4)
+        gpu.reads_gather_finish()
+    gpu.build_hash_table_shard(rank, world)
+    if p2p and getattr(gpu, "mailbox_batch_reads", 0) < batch_reads:
+        yield from mailbox_steps(gpu, rank, world, batch_reads)
+    yield from sharded_graph_steps(gpu, rank, world, view, batch_reads, p2p=p2p, sent=sent)
+
+
 def _gather_var_dist(full: torch.Tensor, counts, rank: int, world: int):
     """All-gather of blocks of different sizes: equal blocks in place, otherwise through a padded copy."""
     if full.dtype != torch.uint8:      # bytes travel (neither NCCL nor gloo has a 16-bit integer type)

@@ -672,7 +672,25 @@ void finish_after_b(Emu &e)
         // edges of every overlap from the end point explored first, lists sorted, marked and filtered read by read
         if (!getenv("SAGE2_EMUL_NO_ORDER_CHECK")) {
             std::vector<u32> order;
-            run_host_phase_c_order(in, order);
+            // as graph.cu hands it over: S index of every candidate's read2, S reads that own phase-B records
+            std::map<u32, u32> sidx;
+            for (u64 sx = 0; sx < in.nS; ++sx) sidx[in.s_ids[sx] + 1] = (u32)sx;
+            std::vector<u32> cnode(cand.size());
+            for (size_t q = 0; q < cand.size(); ++q) cnode[q] = sidx.at((u32)(cand[q] >> 32));
+            std::vector<uint8_t> hasb(in.nS, 0);
+            for (u64 x = 0; x < in.nB; ++x) {
+                const u32 a = (u32)(selB[2 * x] >> 32), b = (u32)selB[2 * x];
+                if (sidx.count(a)) hasb[sidx[a]] = 1;
+                if (sidx.count(b)) hasb[sidx[b]] = 1;
+            }
+            PhaseCInput in2 = in;
+            in2.cand_node = cnode.data(); in2.has_b = hasb.data();
+            run_host_phase_c_order(in2, order);
+            if (getenv("SAGE2_EMUL_CHECK_PLAIN_ORDER")) {       // the traversal with its own id map must give the same order
+                std::vector<u32> order2;
+                run_host_phase_c_order(in, order2);
+                if (order2 != order) { fprintf(stderr, "host_emul: lean traversal order differs\n"); abort(); }
+            }
             std::vector<u64> got;
             u64 ins2 = 0, rem2 = 0;
             phase_c_from_order(e, in, order, got, ins2, rem2);

@@ -38,6 +38,10 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--seed", type=int, default=31)
+    ap.add_argument("--table", default="replicated", choices=["replicated", "sharded"],
+                    help="replicated: every rank ends with the complete table (all-gather of the shards); sharded: north_star's layout, "
+                         "one key-hash shard per GPU, window probes routed through peer-memory mailboxes")
+    ap.add_argument("--batch-reads", type=int, default=1 << 18, help="reads per routed batch (--table sharded)")
     ap.add_argument("--low-memory", type=int, default=0, help="1: release the large buffers as soon as no later stage needs them (full size needs it); 2: the workspace too")
     args = ap.parse_args()
 
@@ -83,7 +87,11 @@ def main():
         d_off = torch.empty(n_slice + 1, dtype=torch.int64, device=dev)
         gpu.synth_reads(d_bases.data_ptr(), d_off.data_ptr(), p0, p1 - p0, args.genome_bp, L, 450.0, 30.0, args.seed)
         t_gen[0] = time.perf_counter() - t0
-        inner = multi.partitioned_slice_steps(gpu, rank, world, view, d_bases.data_ptr(), d_off.data_ptr(), n_slice, args.k, True, L, sent)
+        if args.table == "sharded":
+            inner = multi.partitioned_slice_sharded_steps(gpu, rank, world, view, d_bases.data_ptr(), d_off.data_ptr(), n_slice, args.k, True, L,
+                                                          batch_reads=args.batch_reads, p2p=True, sent=sent)
+        else:
+            inner = multi.partitioned_slice_steps(gpu, rank, world, view, d_bases.data_ptr(), d_off.data_ptr(), n_slice, args.k, True, L, sent)
 
         def steps():
             nonlocal d_bases, d_off
@@ -168,7 +176,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         line = {
             "workload": f"synthetic {args.genome_bp} bp random genome, {L} bp paired-end, {args.coverage}x, -k {args.k}, generated on the devices",
-            "n_gpus": world, "input_reads": N, "ms_per_step": ms, "wall_ms_per_step": float(t[1]), "steps": args.steps, "warmup": args.warmup,
+            "n_gpus": world, "table": args.table, "low_memory": args.low_memory, "input_reads": N, "ms_per_step": ms, "wall_ms_per_step": float(t[1]), "steps": args.steps, "warmup": args.warmup,
             "reads_per_sec": N / (ms / 1e3), "edges_per_sec": c["n_edges"] / (ms / 1e3),
             "generate_s_per_rank_and_step": t_gen[0], "device_bytes_in_use_peak_max_over_ranks": float(mem[0]),
             "nvlink_bytes_contributed_per_rank_and_step": sent[0],
