@@ -236,6 +236,14 @@ class Job:
         del reads, bases
         self.d_bases = self.h_bases.cuda(non_blocking=False)
         self.d_off = self.h_off.cuda(non_blocking=False)
+        # this rank's slice of the host input (N > 1, host-buffer leg): reads [lo, hi), offsets rebased to the slice
+        share = -(-self.n_reads // world)
+        self.sl_lo, self.sl_hi = min(self.n_reads, rank * share), min(self.n_reads, (rank + 1) * share)
+        sl = offsets[self.sl_lo:self.sl_hi + 1] - offsets[self.sl_lo]
+        self.h_sl_off = torch.from_numpy(np.ascontiguousarray(sl)).pin_memory()
+        self.sl_byte0 = int(offsets[self.sl_lo])
+        self.sl_bytes = int(offsets[self.sl_hi] - offsets[self.sl_lo])
+        self.max_len = int(np.max(np.diff(offsets))) if self.n_reads else 1
         self.gpu = api.Sage2Gpu(local)
         if args.read_order is not None:
             self.gpu.set_option("read_order", {"id": 0, "minhash": 1}[args.read_order])
@@ -295,7 +303,13 @@ class Job:
         if self.world == 1:
             self.steps123(self.h_bases.data_ptr(), self.h_off.data_ptr(), False)
             self.comm["h2d"] = self.nbytes_in
-        else:       # each rank moves 1/N of the input over PCIe, NVLink all-gather completes it
+        elif not self.sharded and not self.args.replicate_stages:
+            # each rank moves and packs 1/N of the input; the PACKED records are all-gathered over NVLink (4 x fewer bytes than
+            # the characters), every later stage is partitioned (multi.partitioned_slice_steps)
+            self.multi.build_partitioned_slices(gpu, self.rank, self.world, self.dev, self.h_bases.data_ptr() + self.sl_byte0,
+                                                self.h_sl_off.data_ptr(), self.sl_hi - self.sl_lo, self.k, False, self.max_len, stats=self.xstats)
+            self.comm["h2d"] = self.sl_bytes + 8 * (self.sl_hi - self.sl_lo + 1)
+        else:       # each rank moves 1/N of the input over PCIe, NVLink all-gather of the characters completes it
             # (on torch's own stream: pinned tensors must not be tied to the library's stream, which dies first)
             tb, to, self.comm["h2d"] = self.multi.upload_partitioned(self.h_bases, self.h_off, self.rank, self.world, self.dev)
             torch.cuda.current_stream(self.dev).synchronize()

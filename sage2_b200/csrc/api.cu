@@ -776,7 +776,7 @@ int sage2gpu_set_option(sage2gpu_ctx *ctx, const char *name, int64_t value)
         SG_CHECK(name != nullptr, "null option name");
         const std::string n(name);
         if (n == "read_order") { SG_CHECK(value >= -1 && value <= 1, "read_order: -1 default, 0 id order, 1 min-hash order"); c.opt_read_order = (int)value; }
-        else if (n == "low_memory") { SG_CHECK(value >= 0 && value <= 2, "low_memory: 0, 1 or 2"); c.opt_low_memory = (int)value; }
+        else if (n == "low_memory") { SG_CHECK(value >= 0 && value <= 2, "low_memory: 0, 1 or 2"); c.opt_low_memory = (int)value; c.arena.tight = value > 0; }
         else if (n == "fast_scan") { SG_CHECK(value >= -1 && value <= 1, "fast_scan: -1 default, 0 off, 1 on"); c.opt_fast_scan = (int)value; }
         else throw sg::CudaError("unknown option: " + n);
     });

@@ -40,13 +40,14 @@ struct Arena {
     std::vector<Block> blocks;
     size_t used = 0;            // bytes taken from the last block
     size_t peak = 0;            // high-water mark of the current scope over all blocks
+    bool tight = false;         // low-memory mode: blocks of exactly the size asked for, everything released at the end of the stage
     static size_t round(size_t b) { return (b + 255) & ~(size_t)255; }
     size_t total() const { size_t t = 0; for (const Block &b : blocks) t += b.cap; return t; }
     void *take(size_t bytes)
     {
         bytes = round(bytes ? bytes : 1);
         if (blocks.empty() || used + bytes > blocks.back().cap) {
-            size_t cap = std::max<size_t>(bytes, std::max<size_t>((size_t)64 << 20, total() / 2));
+            size_t cap = tight ? std::max<size_t>(bytes, (size_t)64 << 20) : std::max<size_t>(bytes, std::max<size_t>((size_t)64 << 20, total() / 2));
             char *p = nullptr;
             SG_CUDA(cudaMalloc((void **)&p, cap));
             blocks.push_back(Block{ p, cap });
@@ -64,6 +65,7 @@ struct Arena {
     // end of a stage: rewind; several blocks (growth during this stage) are merged into one
     void reset(cudaStream_t st)
     {
+        if (tight) { cudaStreamSynchronize(st); destroy(); return; }
         if (blocks.size() > 1) {
             const size_t want = total() + total() / 4;
             cudaStreamSynchronize(st);

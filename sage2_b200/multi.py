@@ -85,6 +85,19 @@ def build_partitioned(gpu, rank: int, world: int, device, bases_ptr: int, offset
     return sent[0]
 
 
+def build_partitioned_slices(gpu, rank: int, world: int, device, bases_ptr: int, offsets_ptr: int, n_slice: int, k: int, on_device: bool,
+                             max_read_length: int, stats: dict | None = None) -> int:
+    """One process per GPU: steps 1-3 from THIS RANK'S SLICE of the input (host or device buffers): the slice is packed
+    here, the packed records are all-gathered, every later stage is partitioned.  Returns the bytes this rank contributed."""
+    sent = [0]
+    steps = partitioned_slice_steps(gpu, rank, world, device_view_fn(device), bases_ptr, offsets_ptr, n_slice, k, on_device, max_read_length, sent)
+    if world == 1:
+        run_local([steps])
+    else:
+        run_dist(steps, rank, world, device, stats)
+    return sent[0]
+
+
 def upload_partitioned(h_bases: torch.Tensor, h_offsets: torch.Tensor, rank: int, world: int, device) -> tuple:
     """Host -> device of the raw reads with every rank moving only its 1/world share over PCIe; the shares are
     then all-gathered over NVLink.  h_* are (pinned) host tensors holding the WHOLE input on every rank.
