@@ -65,7 +65,11 @@ struct Arena {
     // end of a stage: rewind; several blocks (growth during this stage) are merged into one
     void reset(cudaStream_t st)
     {
-        if (tight) { cudaStreamSynchronize(st); destroy(); return; }
+        if (tight) {        // large workspaces go back to the driver, small ones (the routed batches of the sharded table) stay
+            if (total() > ((size_t)1 << 30)) { cudaStreamSynchronize(st); destroy(); }
+            used = 0;
+            if (blocks.size() <= 1) return;
+        }
         if (blocks.size() > 1) {
             const size_t want = total() + total() / 4;
             cudaStreamSynchronize(st);
