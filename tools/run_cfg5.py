@@ -182,9 +182,12 @@ def main():
             "nvlink_bytes_contributed_per_rank_and_step": sent[0],
             "stage_ms_rank0": stage, "exchange_wall_ms_per_step_rank0": {kk: vv / args.steps for kk, vv in xstats.items()},
             "gpu_launches_rank0": launches,
-            "phase_a": {"kernel_ms_rank0": ka, "algorithmic_bytes_all_ranks": abytes,
-                        "achieved_gbs_aggregate": abytes / (ka / 1e3) / 1e9, "hbm_copy_peak_gbs_per_gpu": peak,
-                        "frac_of_aggregate_copy_peak": abytes / (ka / 1e3) / 1e9 / (peak * world)},
+            # replicated table: the search kernel does all the phase-A work, its time is the denominator; sharded table: the probes run in
+            # the owners' answer kernels, so the whole phase-A stage (routing, answers, barriers, search) is
+            "phase_a": {"kernel_ms_rank0": ka, "stage_ms_rank0": stage["phase_a"], "algorithmic_bytes_all_ranks": abytes,
+                        "achieved_gbs_aggregate": abytes / ((ka if args.table == "replicated" else stage["phase_a"]) / 1e3) / 1e9,
+                        "hbm_copy_peak_gbs_per_gpu": peak,
+                        "frac_of_aggregate_copy_peak": abytes / ((ka if args.table == "replicated" else stage["phase_a"]) / 1e3) / 1e9 / (peak * world)},
             "counters_rank0": {kk: c[kk] for kk in ("good_reads", "unique_reads", "distinct_keys", "keys_over_threshold", "n_edges", "left_to_explore",
                                                      "contained_ext", "contained_size", "edges_inserted_c", "transitive_removed", "record_words",
                                                      "phase_c_on_device")},
