@@ -146,6 +146,34 @@ __global__ void __launch_bounds__(256) has_b_kernel(const u64 *__restrict__ selB
     }
 }
 
+// connected components of the candidate graph on the S reads (labels = smallest S index of the component): hooking on the
+// labels + pointer jumping, a few rounds over ~10^6 candidates.  The host walks the components independently.
+__global__ void __launch_bounds__(256) cc_init_kernel(u32 *__restrict__ label, u64 nS)
+{
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nS; s += (u64)gridDim.x * blockDim.x) label[s] = (u32)s;
+}
+__global__ void __launch_bounds__(256) cc_hook_kernel(const u32 *__restrict__ counts, const u32 *__restrict__ offs, const u32 *__restrict__ cnode, u64 nS,
+                                                       u32 *__restrict__ label, u32 *__restrict__ changed)
+{
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nS; s += (u64)gridDim.x * blockDim.x) {
+        const u32 base = offs[s], m = counts[s];
+        for (u32 x = 0; x < m; ++x) {
+            const u32 t = cnode[base + x];
+            const u32 ra = label[s], rb = label[t];
+            if (ra < rb) { atomicMin(&label[rb], ra); *changed = 1u; }
+            else if (rb < ra) { atomicMin(&label[ra], rb); *changed = 1u; }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) cc_jump_kernel(u32 *__restrict__ label, u64 nS)
+{
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nS; s += (u64)gridDim.x * blockDim.x) {
+        u32 l = label[s];
+        while (label[l] != l) l = label[l];
+        label[s] = l;
+    }
+}
+
 void stage_phase_b(Context &c)
 {
     cudaStream_t st = c.stream;
@@ -330,8 +358,9 @@ void stage_phase_c_and_finalize(Context &c)
         std::vector<u32> h_sids, h_off, h_selLen;
         std::vector<u64> h_cand, h_selB;
         std::vector<uint16_t> h_slen;
-        std::vector<u32> h_cnode;
+        std::vector<u32> h_cnode, h_comp;
         std::vector<uint8_t> h_hasb;
+        bool have_comp = false;
         bool have_input = false;
         auto fetch_input = [&]() {
             if (have_input) return;
@@ -344,6 +373,24 @@ void stage_phase_c_and_finalize(Context &c)
             if (nSel) { has_b_kernel<<<big_grid(nSel), 256, 0, st>>>(selB.p, nSel, c.explored.p, idx.p, d_hasb.p); SG_LAUNCHED(); }
             if (nC) SG_CUDA(cudaMemcpyAsync(h_cnode.data(), d_cnode.p, nC * sizeof(u32), cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(h_hasb.data(), d_hasb.p, nS, cudaMemcpyDeviceToHost, st));
+            // connected components of the candidate graph: the host walks them independently, on several threads
+            h_comp.resize(nS);
+            DevBuf<u32> d_comp(nS, st), d_changed(1, st);
+            cc_init_kernel<<<big_grid(nS), 256, 0, st>>>(d_comp.p, nS);
+            SG_LAUNCHED();
+            bool cc_done = nC == 0;
+            for (int round = 0; round < 64 && !cc_done; ++round) {
+                u32 h_changed = 0;
+                SG_CUDA(cudaMemsetAsync(d_changed.p, 0, sizeof(u32), st));
+                cc_hook_kernel<<<big_grid(nS), 256, 0, st>>>(counts.p, offs.p, d_cnode.p, nS, d_comp.p, d_changed.p);
+                SG_LAUNCHED();
+                cc_jump_kernel<<<big_grid(nS), 256, 0, st>>>(d_comp.p, nS);
+                SG_LAUNCHED();
+                SG_CUDA(cudaMemcpyAsync(&h_changed, d_changed.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+                SG_CUDA(cudaStreamSynchronize(st));
+                cc_done = h_changed == 0;
+            }
+            if (cc_done) { SG_CUDA(cudaMemcpyAsync(h_comp.data(), d_comp.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st)); have_comp = true; }
             SG_CUDA(cudaMemcpyAsync(h_sids.data(), s_ids.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(h_off.data(), offs.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(h_slen.data(), sLen.p, nS * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
@@ -356,7 +403,7 @@ void stage_phase_c_and_finalize(Context &c)
             h_off[nS] = nC;
             in.nS = nS; in.s_ids = h_sids.data(); in.s_len = h_slen.data(); in.cand_off = h_off.data();
             in.cand = h_cand.data(); in.nB = nSel; in.edgesB = h_selB.data(); in.edgesB_len = h_selLen.data();
-            in.cand_node = h_cnode.data(); in.has_b = h_hasb.data();
+            in.cand_node = h_cnode.data(); in.has_b = h_hasb.data(); in.comp = have_comp ? h_comp.data() : nullptr;
             have_input = true;
         };
         // the phase-B records that stay (owner not in S) are sorted now, asynchronously: the device works on them while the

@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <thread>
 
@@ -90,7 +91,7 @@ struct Walk {
     std::vector<uint32_t> node_id, node_len;
     uint64_t inserted = 0, removed = 0;
     std::vector<uint32_t> *order = nullptr;        // when set: order[s] = position of S read s in the exploration sequence
-    uint32_t explored_so_far = 0;
+    bool count_inserted = true;                    // off when several threads walk disjoint components
 
     explicit Walk(const PhaseCInput &i) : in(i) {}
 
@@ -119,11 +120,11 @@ struct Walk {
     }
 
     // insertAllEdgesOfRead, economyGraph.cpp:580-638
-    void insert_all(uint32_t n1)
+    void insert_all(uint32_t n1, uint32_t &counter)
     {
         if (state[n1] != 0) return;
         state[n1] = 1;
-        if (order) (*order)[n1] = explored_so_far++;
+        if (order) (*order)[n1] = counter++;
         const uint32_t s = n1;    // S nodes occupy local slots 0..nS-1 in s_ids order
         uint64_t cnt = 0;
         for (uint32_t q = in.cand_off[s]; q < in.cand_off[s + 1]; ++q) {
@@ -136,7 +137,7 @@ struct Walk {
             cnt++;
         }
         if (size[n1] > 1) std::sort(list(n1), list(n1) + size[n1], by_length_desc);   // :634
-        inserted += 2 * cnt;
+        if (count_inserted) inserted += 2 * cnt;
     }
 
     // markTransitiveEdge, economyGraph.cpp:643-679.  The walk only records that nf's marking is due (its position in the
@@ -196,24 +197,27 @@ void on_all_cores(size_t work_items, Fn fn)
 
 }  // namespace
 
-// buildOverlapGraphEconomy, economyGraph.cpp:513-564.  has_b: reads whose lists hold phase-B records that are not in the pool
-static void traverse(Walk &w, uint32_t nS, const uint8_t *has_b)
+// buildOverlapGraphEconomy, economyGraph.cpp:513-564, over the seed reads `seeds` in ascending order (all S reads, or the
+// reads of one connected component of the candidate graph: the traversal never leaves a component, and only the order
+// INSIDE a component decides which end point inserts an overlap).  has_b: reads whose lists hold phase-B records that are
+// not in the pool.
+static void traverse(Walk &w, const uint32_t *seeds, uint32_t n_seeds, uint32_t nS, const uint8_t *has_b, std::vector<uint32_t> &queue)
 {
-    std::vector<uint32_t> queue;
-    queue.reserve(nS);
-    for (uint32_t i = 0; i < nS; ++i) {
+    uint32_t counter = 0;
+    for (uint32_t k = 0; k < n_seeds; ++k) {
+        const uint32_t i = seeds ? seeds[k] : k;
         if (w.state[i] != 0) continue;
         queue.clear();
         size_t qs = 0;
         queue.push_back(i);
         while (qs < queue.size()) {
             const uint32_t n1 = queue[qs++];
-            if (w.state[n1] == 0) w.insert_all(n1);
+            if (w.state[n1] == 0) w.insert_all(n1, counter);
             if (w.size[n1] == 0 && !(has_b && has_b[n1])) continue;          // :525
             if (w.state[n1] == 1) {
                 for (uint32_t x = 0; x < w.size[n1]; ++x) {
                     const uint32_t n2 = w.list(n1)[x].node;
-                    if (w.state[n2] == 0) { queue.push_back(n2); w.insert_all(n2); }
+                    if (w.state[n2] == 0) { queue.push_back(n2); w.insert_all(n2, counter); }
                 }
                 w.mark_transitive(n1);
             }
@@ -223,13 +227,14 @@ static void traverse(Walk &w, uint32_t nS, const uint8_t *has_b)
                     if (w.state[n2] != 1) continue;
                     for (uint32_t y = 0; y < w.size[n2]; ++y) {
                         const uint32_t n3 = w.list(n2)[y].node;
-                        if (w.state[n3] == 0) { queue.push_back(n3); w.insert_all(n3); }
+                        if (w.state[n3] == 0) { queue.push_back(n3); w.insert_all(n3, counter); }
                     }
                     w.mark_transitive(n2);
                 }
             }
         }
     }
+    (void)nS;
 }
 
 // The traversal with S alone in play: node index = index in s_ids, candidate -> node from the device, no id map, no
@@ -256,10 +261,47 @@ static float run_walk_lean(const PhaseCInput &in, Walk &w, std::chrono::steady_c
     w.pool = ws.get_pool(total);
     if (total && !w.pool) return -1.f;
     const auto t_setup = std::chrono::steady_clock::now();
-    traverse(w, nS, in.has_b);
+    uint32_t n_comp = 1;
+    unsigned T = 1;
+    if (in.comp && nS >= in.comp_min_nodes) {
+        // connected components of the candidate graph (labels from the device): walked independently, on several threads
+        std::vector<uint32_t> cstart((size_t)nS + 2, 0), nodes(nS), cid(nS);
+        for (uint32_t s = 0; s < nS; ++s) cstart[in.comp[s] + 1]++;                 // comp[s] = a node index < nS (the component's label)
+        for (uint32_t c = 0; c < nS; ++c) cstart[c + 1] += cstart[c];
+        { std::vector<uint32_t> fill(cstart.begin(), cstart.end() - 1); for (uint32_t s = 0; s < nS; ++s) nodes[fill[in.comp[s]]++] = s; }      // ascending inside a component
+        std::vector<uint32_t> labels;                                               // non-empty components
+        for (uint32_t c = 0; c < nS; ++c) if (cstart[c + 1] > cstart[c]) labels.push_back(c);
+        n_comp = (uint32_t)labels.size();
+        static const unsigned forced = [] { const char *e = getenv("SAGE2GPU_HOST_THREADS"); return e ? (unsigned)atoi(e) : 0u; }();
+        T = forced ? forced : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        if (n_comp < 2 * T && in.comp_min_nodes > 1) T = 1;
+        w.count_inserted = false;
+        std::atomic<uint32_t> next(0);
+        auto work = [&]() {
+            std::vector<uint32_t> queue;
+            for (;;) {
+                const uint32_t k0 = next.fetch_add(64);                             // components in chunks of 64
+                if (k0 >= n_comp) break;
+                for (uint32_t k = k0; k < std::min(n_comp, k0 + 64); ++k) {
+                    const uint32_t c = labels[k];
+                    traverse(w, nodes.data() + cstart[c], cstart[c + 1] - cstart[c], nS, in.has_b, queue);
+                }
+            }
+        };
+        if (T == 1) work();
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < T; ++t) pool.emplace_back(work);
+            for (auto &th : pool) th.join();
+        }
+    } else {
+        std::vector<uint32_t> queue;
+        queue.reserve(nS);
+        traverse(w, nullptr, nS, nS, in.has_b, queue);
+    }
     const auto t_walk = std::chrono::steady_clock::now();
     if (getenv("SAGE2GPU_PHASE_C_TIMING"))
-        fprintf(stderr, "[phase C host, order only, lean] nS %llu nC %llu | setup %.2f walk %.2f ms\n", (unsigned long long)in.nS, (unsigned long long)nC,
+        fprintf(stderr, "[phase C host, order only, lean, %u components on %u threads] nS %llu nC %llu | setup %.2f walk %.2f ms\n", n_comp, T, (unsigned long long)in.nS, (unsigned long long)nC,
                 std::chrono::duration<float, std::milli>(t_setup - t0).count(), std::chrono::duration<float, std::milli>(t_walk - t_setup).count());
     return std::chrono::duration<float, std::milli>(t_walk - t0).count();
 }
@@ -335,7 +377,7 @@ static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uin
     }
 
     const auto t_setup = std::chrono::steady_clock::now();
-    traverse(w, nS, nullptr);
+    { std::vector<uint32_t> queue; queue.reserve(nS); traverse(w, nullptr, nS, nS, nullptr, queue); }
 
     const auto t_walk = std::chrono::steady_clock::now();
     if (!outp) {        // the caller only wants the exploration order: lists, marks and filtering are rebuilt on the device

@@ -20,6 +20,9 @@ struct PhaseCInput {
     // phase-B adjacency (phase-B records are inert in the traversal: they lead to reads that are not in S)
     const uint32_t *cand_node = nullptr;   // [nC] index in s_ids of every candidate's read2
     const uint8_t *has_b = nullptr;        // [nS] the read has phase-B records (its list is not empty, economyGraph.cpp:525)
+    const uint32_t *comp = nullptr;        // [nS] optional: label (an index < nS) of the read's connected component in the candidate graph;
+                                           // components are walked independently (the order inside a component is all that matters)
+    uint32_t comp_min_nodes = 4096;        // below this many S reads the components are not worth the threads
 };
 
 struct PhaseCOutput {

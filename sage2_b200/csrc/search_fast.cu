@@ -132,9 +132,6 @@ phase_a_fast_kernel(SearchParams P, u64 *__restrict__ extR, u64 *__restrict__ ex
     uint8_t *wins = sWin[warp];
     const u64 nwarps = (u64)gridDim.x * WARPS;
     unsigned calls = 0, probes = 0;
-    u64 km0, km1;
-    key_masks(P.h, km0, km1);
-    (void)km0; (void)km1;
 
     const u64 n_batch = P.hi - P.lo;
     for (u64 sb = (u64)blockIdx.x * WARPS + warp; sb < n_batch; sb += nwarps) {

@@ -685,8 +685,20 @@ void finish_after_b(Emu &e)
             }
             PhaseCInput in2 = in;
             in2.cand_node = cnode.data(); in2.has_b = hasb.data();
+            // connected components of the candidate graph (the device computes them by hooking + pointer jumping; here union-find):
+            // label = smallest S index of the component; walked independently on several threads
+            std::vector<u32> comp(in.nS);
+            for (u64 sx = 0; sx < in.nS; ++sx) comp[sx] = (u32)sx;
+            std::function<u32(u32)> find = [&](u32 x) { while (comp[x] != x) { comp[x] = comp[comp[x]]; x = comp[x]; } return x; };
+            for (u64 sx = 0; sx < in.nS; ++sx)
+                for (u32 q = in.cand_off[sx]; q < in.cand_off[sx + 1]; ++q) {
+                    const u32 a = find((u32)sx), b = find(cnode[q]);
+                    if (a < b) comp[b] = a; else if (b < a) comp[a] = b;
+                }
+            for (u64 sx = 0; sx < in.nS; ++sx) comp[sx] = find((u32)sx);
+            if (!getenv("SAGE2_EMUL_NO_COMPONENTS")) { in2.comp = comp.data(); in2.comp_min_nodes = 1; }
             run_host_phase_c_order(in2, order);
-            if (getenv("SAGE2_EMUL_CHECK_PLAIN_ORDER")) {       // the traversal with its own id map must give the same order
+            if (getenv("SAGE2_EMUL_CHECK_PLAIN_ORDER") && !in2.comp) {       // the traversal with its own id map must give the same order
                 std::vector<u32> order2;
                 run_host_phase_c_order(in, order2);
                 if (order2 != order) { fprintf(stderr, "host_emul: lean traversal order differs\n"); abort(); }
