@@ -137,11 +137,26 @@ __global__ void __launch_bounds__(256) pc_cand_half_edges_kernel(const u32 *__re
     }
 }
 
+// where the list of every half edge's far end sits in the owner-sorted array (the marking loop of pc_node_kernel walks
+// those lists one after the other: the two binary searches per step were its critical path)
+__global__ void __launch_bounds__(256) pc_target_range_kernel(const u64 *__restrict__ he_owner, const u64 *__restrict__ he_rec, u64 n_he,
+                                                               u64 *__restrict__ tlo, u32 *__restrict__ tcnt)
+{
+    for (u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x; x < n_he; x += (u64)gridDim.x * blockDim.x) {
+        u64 lo, hi;
+        pc_range(he_owner, n_he, he_rec[x] >> 32, lo, hi);
+        tlo[x] = lo;
+        tcnt[x] = (u32)(hi - lo);
+    }
+}
+
 // one warp per read of S: list = its half edges (phase C + phase B) out of the owner-sorted array, sorted by
 // compareLengthBased (:853-871), marked like markTransitiveEdge, filtered like removeTransitiveEdges; survivors with
-// id > read go to `out`
+// id > read go to `out`.  Sort key: length desc, id desc, type desc == one descending 54-bit number; the low 9 bits
+// carry the entry's place in the unsorted list (PC_MAXD = 512), which is where its far end's range was precomputed.
 __global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__restrict__ s_ids, u64 nS,
                                                                  const u64 *__restrict__ he_owner, const u64 *__restrict__ he_rec, u64 n_he,
+                                                                 const u64 *__restrict__ tlo, const u32 *__restrict__ tcnt,
                                                                  u64 *__restrict__ out, unsigned long long *__restrict__ counters /*[0] out, [1] removed*/,
                                                                  u32 *__restrict__ flags)
 {
@@ -165,8 +180,7 @@ __global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__res
         __syncwarp();
         for (u32 x = lane; x < P; x += 32) {
             const u64 cw = x < d ? he_rec[plo + x] : 0ull;
-            // length desc, id desc, type desc  ==  one descending 54-bit key
-            key[x] = x < d ? (((cw & 0xFFFFFull) << 34) | ((cw >> 32) << 2) | ((cw >> 20) & 3ull)) : 0ull;
+            key[x] = x < d ? (((cw & 0xFFFFFull) << 43) | ((cw >> 32) << 11) | (((cw >> 20) & 3ull) << 9) | (u64)x) : 0ull;
         }
         for (u32 x = lane; x < (u32)PC_HCAP; x += 32) { H.id[x] = 0; H.st[x] = 0; }
         __syncwarp();
@@ -183,35 +197,44 @@ __global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__res
                 __syncwarp();
             }
         for (u32 x = lane; x < d; x += 32) {
-            const u32 id = (u32)(key[x] >> 2);
+            const u32 id = (u32)(key[x] >> 11);
             for (u32 sl = PcHash::h(id) & (PC_HCAP - 1);; sl = (sl + 1) & (PC_HCAP - 1)) {
                 const u32 old = atomicCAS(&H.id[sl], 0u, id);
                 if (old == 0u || old == id) { H.st[sl] = 1; break; }
             }
         }
         __syncwarp();
-        for (u32 x = 0; x < d; ++x) {
-            const u32 ida = (u32)(key[x] >> 2), t1 = (u32)key[x] & 3u;
-            const int sa = H.find(ida);
-            if (H.st[sa] == 1) {
-                u64 qlo, qhi;
-                pc_range(he_owner, n_he, ida, qlo, qhi);
-                for (u64 y = qlo + lane; y < qhi; y += 32) {
-                    const u64 cw = he_rec[y];
-                    const int sf = H.find((u32)(cw >> 32));
-                    if (sf >= 0 && H.st[sf] == 1 && pc_rule(t1, (u32)(cw >> 20) & 3u)) H.st[sf] = 2;
+        for (u32 x0 = 0; x0 < d; x0 += 32) {
+            // 32 entries at a time: their far ends' ranges come in with one load per lane
+            const u64 my_key = x0 + lane < d ? key[x0 + lane] : 0ull;
+            u64 my_lo = 0;
+            u32 my_cnt = 0;
+            if (x0 + lane < d) { const u64 at = plo + (my_key & 511ull); my_lo = tlo[at]; my_cnt = tcnt[at]; }
+            const u32 m = d - x0 < 32u ? d - x0 : 32u;
+            for (u32 xx = 0; xx < m; ++xx) {
+                const u64 kx = __shfl_sync(0xffffffffu, my_key, xx);
+                const u64 qlo = __shfl_sync(0xffffffffu, my_lo, xx);
+                const u32 qn = __shfl_sync(0xffffffffu, my_cnt, xx);
+                const u32 ida = (u32)(kx >> 11), t1 = (u32)(kx >> 9) & 3u;
+                const int sa = H.find(ida);
+                if (H.st[sa] == 1) {
+                    for (u32 y = lane; y < qn; y += 32) {
+                        const u64 cw = he_rec[qlo + y];
+                        const int sf = H.find((u32)(cw >> 32));
+                        if (sf >= 0 && H.st[sf] == 1 && pc_rule(t1, (u32)(cw >> 20) & 3u)) H.st[sf] = 2;
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
         for (u32 x = lane; x < d; x += 32) {
             const u64 kx = key[x];
-            const u32 id = (u32)(kx >> 2);
+            const u32 id = (u32)(kx >> 11);
             if (H.st[H.find(id)] == 2) { removed++; continue; }
             if (id > n) {
                 const unsigned long long pos = atomicAdd(&counters[0], 1ull);
                 out[2 * pos] = ((u64)n << 32) | id;
-                out[2 * pos + 1] = ((kx & 3ull) << 20) | (kx >> 34);
+                out[2 * pos + 1] = (((kx >> 9) & 3ull) << 20) | (kx >> 43);
             }
         }
         __syncwarp();
@@ -280,7 +303,13 @@ bool device_phase_c(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const
     out.alloc(2 * n_he + 2, st);
     DevBuf<u32> flags(1, st);
     SG_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(u32), st));
-    pc_node_kernel<<<pc_grid(nS, PC_WARPS), PC_WARPS * 32, 0, st>>>(s_ids, nS, he_owner, he_rec, n_he, out.p, cnt.p, flags.p);
+    DevBuf<u64> tlo(n_he + 1, st);
+    DevBuf<u32> tcnt(n_he + 1, st);
+    if (n_he) {
+        pc_target_range_kernel<<<pc_grid(n_he, 256), 256, 0, st>>>(he_owner, he_rec, n_he, tlo.p, tcnt.p);
+        SG_LAUNCHED();
+    }
+    pc_node_kernel<<<pc_grid(nS, PC_WARPS), PC_WARPS * 32, 0, st>>>(s_ids, nS, he_owner, he_rec, n_he, tlo.p, tcnt.p, out.p, cnt.p, flags.p);
     SG_LAUNCHED();
     unsigned long long h_cnt[2];
     u32 h_flags = 0;
