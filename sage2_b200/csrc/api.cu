@@ -152,6 +152,7 @@ void sage2gpu_destroy(sage2gpu_ctx *ctx)
         c.cont_max.release(); c.explored.release(); c.edges.release();
         sg::stage_mailbox_destroy(c);
         c.arena.destroy();
+        c.pc_stage.release();
     }
     cudaStreamSynchronize(st);
     if (ctx->c.up_event) cudaEventDestroy(ctx->c.up_event);

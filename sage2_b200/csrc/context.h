@@ -110,6 +110,7 @@ struct Context {
     // edges
     DevBuf<u64> edges;          // [2*n_edges] (w0,w1) pairs, canonical sorted after finalize
     std::vector<u64> h_edges;   // host copy of final edges (w0,w1 interleaved)
+    PinnedBuf pc_stage;         // phase C: the lists of the host traversal land here
     bool have_reads = false, have_table = false, have_phase_a = false, have_phase_b = false, have_graph = false;
     u64 pa_chunk = 0;           // reads per rank in the last phase-A call (partition_chunk)
     int pa_world = 1;

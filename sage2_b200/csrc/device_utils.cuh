@@ -142,6 +142,25 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// page-locked host staging buffer of a context (grow-only): device -> host copies into it run at PCIe speed and do not
+// pass through the driver's bounce buffers
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void *ensure(size_t bytes)
+    {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            const size_t want = bytes + bytes / 4 + 4096;
+            SG_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+            cap = want;
+        }
+        return p;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 // give the freed blocks of the stream-ordered pool back to the driver (low-memory mode: the workspace arena and other
 // allocators can then use them)
 inline void trim_default_pool(int device, cudaStream_t st)

@@ -14,6 +14,8 @@ namespace sg {
 void launch_phase_c_candidates(Context &c, const u32 *s_ids, u64 nS, u32 *counts, const u32 *offsets, u64 *cand, bool fill);
 // phase_c_device.cu
 bool phase_c_is_symmetric(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand);
+bool phase_c_sorted_lists(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand, u64 nC,
+                          DevBuf<u32> &off, DevBuf<u32> &ent);
 bool device_phase_c(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand, u64 nC,
                     const u64 *selB, const u32 *selLen, u64 nSel, const u32 *d_order, DevBuf<u64> &out, u64 &n_out, u64 &inserted, u64 &removed);
 
@@ -129,12 +131,7 @@ __global__ void __launch_bounds__(256) gather_len_kernel(const u32 *__restrict__
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = len[ids[i]];
 }
 
-// what the host traversal needs besides the candidates: the S index of every candidate's read2, and which S reads own
-// phase-B records (their lists are not empty, economyGraph.cpp:525)
-__global__ void __launch_bounds__(256) cand_node_kernel(const u64 *__restrict__ cand, u64 nC, const u32 *__restrict__ sidx, u32 *__restrict__ node)
-{
-    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < nC; q += (u64)gridDim.x * blockDim.x) node[q] = sidx[(u32)(cand[q] >> 32) - 1];
-}
+// which S reads own phase-B records (their lists are not empty whatever the traversal does, economyGraph.cpp:525)
 __global__ void __launch_bounds__(256) has_b_kernel(const u64 *__restrict__ selB, u64 nSel, const uint8_t *__restrict__ explored, const u32 *__restrict__ sidx,
                                                      uint8_t *__restrict__ has_b)
 {
@@ -143,34 +140,6 @@ __global__ void __launch_bounds__(256) has_b_kernel(const u64 *__restrict__ selB
         const u32 a = (u32)(w0 >> 32) - 1, b = (u32)w0 - 1;
         if (explored[a] == 0) has_b[sidx[a]] = 1;
         if (explored[b] == 0) has_b[sidx[b]] = 1;
-    }
-}
-
-// connected components of the candidate graph on the S reads (labels = smallest S index of the component): hooking on the
-// labels + pointer jumping, a few rounds over ~10^6 candidates.  The host walks the components independently.
-__global__ void __launch_bounds__(256) cc_init_kernel(u32 *__restrict__ label, u64 nS)
-{
-    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nS; s += (u64)gridDim.x * blockDim.x) label[s] = (u32)s;
-}
-__global__ void __launch_bounds__(256) cc_hook_kernel(const u32 *__restrict__ counts, const u32 *__restrict__ offs, const u32 *__restrict__ cnode, u64 nS,
-                                                       u32 *__restrict__ label, u32 *__restrict__ changed)
-{
-    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nS; s += (u64)gridDim.x * blockDim.x) {
-        const u32 base = offs[s], m = counts[s];
-        for (u32 x = 0; x < m; ++x) {
-            const u32 t = cnode[base + x];
-            const u32 ra = label[s], rb = label[t];
-            if (ra < rb) { atomicMin(&label[rb], ra); *changed = 1u; }
-            else if (rb < ra) { atomicMin(&label[ra], rb); *changed = 1u; }
-        }
-    }
-}
-__global__ void __launch_bounds__(256) cc_jump_kernel(u32 *__restrict__ label, u64 nS)
-{
-    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nS; s += (u64)gridDim.x * blockDim.x) {
-        u32 l = label[s];
-        while (label[l] != l) l = label[l];
-        label[s] = l;
     }
 }
 
@@ -354,43 +323,13 @@ void stage_phase_c_and_finalize(Context &c)
         // order when the candidate set is not symmetric, and the whole walk only when a list is too long for a warp
         const bool force_host = getenv("SAGE2GPU_PHASE_C_HOST") != nullptr;       // test knob: always take the walk
         // the walk's input, fetched once (for the traversal order or for the whole walk)
+        // the input of the whole walk (only when a list is too long for the device, or on request)
         PhaseCInput in;
         std::vector<u32> h_sids, h_off, h_selLen;
         std::vector<u64> h_cand, h_selB;
         std::vector<uint16_t> h_slen;
-        std::vector<u32> h_cnode, h_comp;
-        std::vector<uint8_t> h_hasb;
-        bool have_comp = false;
-        bool have_input = false;
         auto fetch_input = [&]() {
-            if (have_input) return;
             h_sids.resize(nS); h_off.resize((size_t)nS + 1); h_selLen.resize(nSel); h_cand.resize(nC); h_selB.resize(2 * (u64)nSel); h_slen.resize(nS);
-            h_cnode.resize(nC); h_hasb.resize(nS);
-            DevBuf<u32> d_cnode(nC, st);
-            DevBuf<uint8_t> d_hasb(nS, st);
-            SG_CUDA(cudaMemsetAsync(d_hasb.p, 0, nS, st));
-            if (nC) { cand_node_kernel<<<big_grid(nC), 256, 0, st>>>(cand.p, nC, idx.p, d_cnode.p); SG_LAUNCHED(); }
-            if (nSel) { has_b_kernel<<<big_grid(nSel), 256, 0, st>>>(selB.p, nSel, c.explored.p, idx.p, d_hasb.p); SG_LAUNCHED(); }
-            if (nC) SG_CUDA(cudaMemcpyAsync(h_cnode.data(), d_cnode.p, nC * sizeof(u32), cudaMemcpyDeviceToHost, st));
-            SG_CUDA(cudaMemcpyAsync(h_hasb.data(), d_hasb.p, nS, cudaMemcpyDeviceToHost, st));
-            // connected components of the candidate graph: the host walks them independently, on several threads
-            h_comp.resize(nS);
-            DevBuf<u32> d_comp(nS, st), d_changed(1, st);
-            cc_init_kernel<<<big_grid(nS), 256, 0, st>>>(d_comp.p, nS);
-            SG_LAUNCHED();
-            bool cc_done = nC == 0;
-            for (int round = 0; round < 64 && !cc_done; ++round) {
-                u32 h_changed = 0;
-                SG_CUDA(cudaMemsetAsync(d_changed.p, 0, sizeof(u32), st));
-                cc_hook_kernel<<<big_grid(nS), 256, 0, st>>>(counts.p, offs.p, d_cnode.p, nS, d_comp.p, d_changed.p);
-                SG_LAUNCHED();
-                cc_jump_kernel<<<big_grid(nS), 256, 0, st>>>(d_comp.p, nS);
-                SG_LAUNCHED();
-                SG_CUDA(cudaMemcpyAsync(&h_changed, d_changed.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
-                SG_CUDA(cudaStreamSynchronize(st));
-                cc_done = h_changed == 0;
-            }
-            if (cc_done) { SG_CUDA(cudaMemcpyAsync(h_comp.data(), d_comp.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st)); have_comp = true; }
             SG_CUDA(cudaMemcpyAsync(h_sids.data(), s_ids.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(h_off.data(), offs.p, nS * sizeof(u32), cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(h_slen.data(), sLen.p, nS * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
@@ -403,8 +342,6 @@ void stage_phase_c_and_finalize(Context &c)
             h_off[nS] = nC;
             in.nS = nS; in.s_ids = h_sids.data(); in.s_len = h_slen.data(); in.cand_off = h_off.data();
             in.cand = h_cand.data(); in.nB = nSel; in.edgesB = h_selB.data(); in.edgesB_len = h_selLen.data();
-            in.cand_node = h_cnode.data(); in.has_b = h_hasb.data(); in.comp = have_comp ? h_comp.data() : nullptr;
-            have_input = true;
         };
         // the phase-B records that stay (owner not in S) are sorted now, asynchronously: the device works on them while the
         // host computes the traversal order; the few records of phase C are merged in afterwards
@@ -435,21 +372,39 @@ void stage_phase_c_and_finalize(Context &c)
         if (!force_host) {
             DevBuf<u32> d_order;
             const u32 *order = nullptr;
+            bool order_known = true;
             if (!phase_c_is_symmetric(c, s_ids.p, idx.p, nS, counts.p, offs.p, cand.p)) {
                 // which end point inserts an overlap depends on the breadth-first traversal (economyGraph.cpp:513-564, :605):
-                // that part stays sequential, on the host; everything else follows from its order
-                fetch_input();
-                sort_kept_b();          // queued behind the copies above: runs while the host walks
-                std::vector<u32> h_order;
-                host_order_ms = run_host_phase_c_order(in, h_order);
-                d_order.alloc(nS, st);
-                SG_CUDA(cudaMemcpyAsync(d_order.p, h_order.data(), nS * sizeof(u32), cudaMemcpyHostToDevice, st));
-                SG_CUDA(cudaStreamSynchronize(st));
-                order = d_order.p;
-                c.cnt.phase_c_on_device = 2;
+                // that part stays sequential, on the host; everything else follows from its order.  The device hands over
+                // every list already sorted (phase_c_sorted_lists), into page-locked memory.
+                DevBuf<u32> l_off, l_ent;
+                order_known = phase_c_sorted_lists(c, s_ids.p, idx.p, nS, counts.p, offs.p, cand.p, nC, l_off, l_ent);
+                if (order_known) {
+                    DevBuf<uint8_t> d_hasb(nS, st);
+                    SG_CUDA(cudaMemsetAsync(d_hasb.p, 0, nS, st));
+                    if (nSel) { has_b_kernel<<<big_grid(nSel), 256, 0, st>>>(selB.p, nSel, c.explored.p, idx.p, d_hasb.p); SG_LAUNCHED(); }
+                    const size_t off_bytes = ((size_t)nS + 1) * sizeof(u32), ent_bytes = 2 * (size_t)nC * sizeof(u32);
+                    char *stage = (char *)c.pc_stage.ensure(off_bytes + ent_bytes + nS);
+                    SG_CUDA(cudaMemcpyAsync(stage, l_off.p, off_bytes, cudaMemcpyDeviceToHost, st));
+                    if (nC) SG_CUDA(cudaMemcpyAsync(stage + off_bytes, l_ent.p, ent_bytes, cudaMemcpyDeviceToHost, st));
+                    SG_CUDA(cudaMemcpyAsync(stage + off_bytes + ent_bytes, d_hasb.p, nS, cudaMemcpyDeviceToHost, st));
+                    SG_CUDA(cudaStreamSynchronize(st));
+                    sort_kept_b();          // runs on the device while the host walks
+                    PhaseCLists lists;
+                    lists.nS = nS; lists.off = (const u32 *)stage; lists.ent = (const u32 *)(stage + off_bytes);
+                    lists.has_b = (const uint8_t *)(stage + off_bytes + ent_bytes);
+                    std::vector<u32> h_order;
+                    host_order_ms = run_host_phase_c_order_lists(lists, h_order);
+                    d_order.alloc(nS, st);
+                    SG_CUDA(cudaMemcpyAsync(d_order.p, h_order.data(), nS * sizeof(u32), cudaMemcpyHostToDevice, st));
+                    SG_CUDA(cudaStreamSynchronize(st));
+                    order = d_order.p;
+                    c.cnt.phase_c_on_device = 2;
+                }
             } else c.cnt.phase_c_on_device = 1;
-            c_on_device = device_phase_c(c, s_ids.p, idx.p, nS, counts.p, offs.p, cand.p, nC, selB.p, selLen.p, nSel, order, dev_c_edges, n_dev_c,
-                                         inserted_dev, removed_dev);
+            if (order_known)
+                c_on_device = device_phase_c(c, s_ids.p, idx.p, nS, counts.p, offs.p, cand.p, nC, selB.p, selLen.p, nSel, order, dev_c_edges, n_dev_c,
+                                             inserted_dev, removed_dev);
         }
         if (c_on_device) {
             c.cnt.edges_inserted_c = inserted_dev;

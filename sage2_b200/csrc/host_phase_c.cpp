@@ -14,7 +14,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
-#include <atomic>
 #include <chrono>
 #include <thread>
 
@@ -91,7 +90,6 @@ struct Walk {
     std::vector<uint32_t> node_id, node_len;
     uint64_t inserted = 0, removed = 0;
     std::vector<uint32_t> *order = nullptr;        // when set: order[s] = position of S read s in the exploration sequence
-    bool count_inserted = true;                    // off when several threads walk disjoint components
 
     explicit Walk(const PhaseCInput &i) : in(i) {}
 
@@ -137,7 +135,7 @@ struct Walk {
             cnt++;
         }
         if (size[n1] > 1) std::sort(list(n1), list(n1) + size[n1], by_length_desc);   // :634
-        if (count_inserted) inserted += 2 * cnt;
+        inserted += 2 * cnt;
     }
 
     // markTransitiveEdge, economyGraph.cpp:643-679.  The walk only records that nf's marking is due (its position in the
@@ -197,15 +195,11 @@ void on_all_cores(size_t work_items, Fn fn)
 
 }  // namespace
 
-// buildOverlapGraphEconomy, economyGraph.cpp:513-564, over the seed reads `seeds` in ascending order (all S reads, or the
-// reads of one connected component of the candidate graph: the traversal never leaves a component, and only the order
-// INSIDE a component decides which end point inserts an overlap).  has_b: reads whose lists hold phase-B records that are
-// not in the pool.
-static void traverse(Walk &w, const uint32_t *seeds, uint32_t n_seeds, uint32_t nS, const uint8_t *has_b, std::vector<uint32_t> &queue)
+// buildOverlapGraphEconomy, economyGraph.cpp:513-564
+static void traverse(Walk &w, uint32_t nS, std::vector<uint32_t> &queue)
 {
     uint32_t counter = 0;
-    for (uint32_t k = 0; k < n_seeds; ++k) {
-        const uint32_t i = seeds ? seeds[k] : k;
+    for (uint32_t i = 0; i < nS; ++i) {
         if (w.state[i] != 0) continue;
         queue.clear();
         size_t qs = 0;
@@ -213,7 +207,7 @@ static void traverse(Walk &w, const uint32_t *seeds, uint32_t n_seeds, uint32_t 
         while (qs < queue.size()) {
             const uint32_t n1 = queue[qs++];
             if (w.state[n1] == 0) w.insert_all(n1, counter);
-            if (w.size[n1] == 0 && !(has_b && has_b[n1])) continue;          // :525
+            if (w.size[n1] == 0) continue;          // :525
             if (w.state[n1] == 1) {
                 for (uint32_t x = 0; x < w.size[n1]; ++x) {
                     const uint32_t n2 = w.list(n1)[x].node;
@@ -234,76 +228,6 @@ static void traverse(Walk &w, const uint32_t *seeds, uint32_t n_seeds, uint32_t 
             }
         }
     }
-    (void)nS;
-}
-
-// The traversal with S alone in play: node index = index in s_ids, candidate -> node from the device, no id map, no
-// phase-B entries in the lists (they lead to reads outside S, which the traversal never follows; only whether a list is
-// empty matters, :525).
-static float run_walk_lean(const PhaseCInput &in, Walk &w, std::chrono::steady_clock::time_point t0)
-{
-    const uint32_t nS = (uint32_t)in.nS;
-    const uint64_t nC = in.nS ? in.cand_off[in.nS] : 0;
-    static thread_local Workspace ws;
-    w.state.assign(nS, 0);
-    w.node_id.resize(nS); w.node_len.resize(nS);
-    for (uint32_t s = 0; s < nS; ++s) { w.node_id[s] = in.s_ids[s] + 1; w.node_len[s] = in.s_len[s]; }
-    w.cnode = in.cand_node;
-    std::vector<uint32_t> &room = ws.room;
-    room.assign(nS, 0);
-    for (uint32_t s = 0; s < nS; ++s) room[s] = in.cand_off[s + 1] - in.cand_off[s];
-    for (uint64_t q = 0; q < nC; ++q) room[in.cand_node[q]]++;
-    w.start.resize((size_t)nS + 1);
-    w.size.assign(nS, 0);
-    uint64_t total = 0;
-    for (uint32_t n = 0; n < nS; ++n) { w.start[n] = total; total += room[n]; }
-    w.start[nS] = total;
-    w.pool = ws.get_pool(total);
-    if (total && !w.pool) return -1.f;
-    const auto t_setup = std::chrono::steady_clock::now();
-    uint32_t n_comp = 1;
-    unsigned T = 1;
-    if (in.comp && nS >= in.comp_min_nodes) {
-        // connected components of the candidate graph (labels from the device): walked independently, on several threads
-        std::vector<uint32_t> cstart((size_t)nS + 2, 0), nodes(nS), cid(nS);
-        for (uint32_t s = 0; s < nS; ++s) cstart[in.comp[s] + 1]++;                 // comp[s] = a node index < nS (the component's label)
-        for (uint32_t c = 0; c < nS; ++c) cstart[c + 1] += cstart[c];
-        { std::vector<uint32_t> fill(cstart.begin(), cstart.end() - 1); for (uint32_t s = 0; s < nS; ++s) nodes[fill[in.comp[s]]++] = s; }      // ascending inside a component
-        std::vector<uint32_t> labels;                                               // non-empty components
-        for (uint32_t c = 0; c < nS; ++c) if (cstart[c + 1] > cstart[c]) labels.push_back(c);
-        n_comp = (uint32_t)labels.size();
-        static const unsigned forced = [] { const char *e = getenv("SAGE2GPU_HOST_THREADS"); return e ? (unsigned)atoi(e) : 0u; }();
-        T = forced ? forced : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
-        if (n_comp < 2 * T && in.comp_min_nodes > 1) T = 1;
-        w.count_inserted = false;
-        std::atomic<uint32_t> next(0);
-        auto work = [&]() {
-            std::vector<uint32_t> queue;
-            for (;;) {
-                const uint32_t k0 = next.fetch_add(64);                             // components in chunks of 64
-                if (k0 >= n_comp) break;
-                for (uint32_t k = k0; k < std::min(n_comp, k0 + 64); ++k) {
-                    const uint32_t c = labels[k];
-                    traverse(w, nodes.data() + cstart[c], cstart[c + 1] - cstart[c], nS, in.has_b, queue);
-                }
-            }
-        };
-        if (T == 1) work();
-        else {
-            std::vector<std::thread> pool;
-            for (unsigned t = 0; t < T; ++t) pool.emplace_back(work);
-            for (auto &th : pool) th.join();
-        }
-    } else {
-        std::vector<uint32_t> queue;
-        queue.reserve(nS);
-        traverse(w, nullptr, nS, nS, in.has_b, queue);
-    }
-    const auto t_walk = std::chrono::steady_clock::now();
-    if (getenv("SAGE2GPU_PHASE_C_TIMING"))
-        fprintf(stderr, "[phase C host, order only, lean, %u components on %u threads] nS %llu nC %llu | setup %.2f walk %.2f ms\n", n_comp, T, (unsigned long long)in.nS, (unsigned long long)nC,
-                std::chrono::duration<float, std::milli>(t_setup - t0).count(), std::chrono::duration<float, std::milli>(t_walk - t_setup).count());
-    return std::chrono::duration<float, std::milli>(t_walk - t0).count();
 }
 
 static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uint32_t> *order)
@@ -313,8 +237,6 @@ static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uin
     const auto t0 = std::chrono::steady_clock::now();
     Walk w(in);
     if (order) { order->assign(in.nS, 0); w.order = order; }
-    const bool lean = !outp && in.cand_node && in.has_b;      // traversal only, with the device's node indices: S alone is in play
-    if (lean) return run_walk_lean(in, w, t0);
     w.slot.init(in.nS + 2 * in.nB);
     w.state.reserve(in.nS + 2 * in.nB); w.node_id.reserve(in.nS + 2 * in.nB); w.node_len.reserve(in.nS + 2 * in.nB);
     for (uint64_t s = 0; s < in.nS; ++s) w.node(in.s_ids[s] + 1, 0, in.s_len[s]);
@@ -377,7 +299,7 @@ static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uin
     }
 
     const auto t_setup = std::chrono::steady_clock::now();
-    { std::vector<uint32_t> queue; queue.reserve(nS); traverse(w, nullptr, nS, nS, nullptr, queue); }
+    { std::vector<uint32_t> queue; queue.reserve(nS); traverse(w, nS, queue); }
 
     const auto t_walk = std::chrono::steady_clock::now();
     if (!outp) {        // the caller only wants the exploration order: lists, marks and filtering are rebuilt on the device
@@ -432,8 +354,79 @@ static float run_walk(const PhaseCInput &in, PhaseCOutput *outp, std::vector<uin
 
 float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out) { return run_walk(in, &out, nullptr); }
 
-// The traversal alone (economyGraph.cpp:513-564): order[s] = when S read s was explored (insertAllEdgesOfRead ran for it).
-// That order is all the final lists depend on: an overlap is inserted by whichever end point is explored first (:605).
+// The walk's traversal alone: order[s] = when S read s was explored (insertAllEdgesOfRead ran for it).  That order is all the
+// final lists depend on: an overlap is inserted by whichever end point is explored first (:605).  (The product takes the order
+// from run_host_phase_c_order_lists; this one is what the tests hold it against.)
 float run_host_phase_c_order(const PhaseCInput &in, std::vector<uint32_t> &order) { return run_walk(in, nullptr, &order); }
+
+// The traversal of economyGraph.cpp:513-564 from the lists the device has sorted (PhaseCLists).  The list of read n as
+// insertAllEdgesOfRead leaves it (:580-638) = its own candidates towards reads that are still unexplored (:605) + the
+// twins that the reads explored BEFORE it pushed into its list, i.e. the twin entries whose owner is explored by now (an
+// explored owner met n unexplored, so it did insert).  Nothing is appended to a list after its read is explored.  So the
+// list is the device's static list under a filter on `state`, written once, in exploration order, into a compact pool;
+// the queue logic then reads those compact lists.  The traversal never follows phase-B records (they lead outside S);
+// only whether a list is empty matters (:525, has_b).
+float run_host_phase_c_order_lists(const PhaseCLists &in, std::vector<uint32_t> &order)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint32_t nS = (uint32_t)in.nS;
+    order.assign(nS, 0);
+    if (nS == 0) return 0.f;
+    static thread_local std::vector<uint32_t> pool, start, size, queue;
+    static thread_local std::vector<uint8_t> state;
+    pool.resize((size_t)in.off[nS] + 1);
+    start.assign(nS, 0); size.assign(nS, 0); state.assign(nS, 0);
+    queue.clear(); queue.reserve(nS);
+    uint32_t *P = pool.data();
+    uint8_t *st = state.data();
+    uint32_t top = 0, counter = 0;
+    auto explore = [&](uint32_t n) {      // insertAllEdgesOfRead
+        st[n] = 1;
+        order[n] = counter++;
+        const uint32_t s0 = top;
+        for (const uint32_t *e = in.ent + in.off[n], *ee = in.ent + in.off[n + 1]; e < ee; ++e) {
+            const uint32_t other = *e >> 1;
+            P[top] = other;
+            top += (uint32_t)((st[other] != 0) == (bool)(*e & 1u));      // own: partner unexplored; twin: owner explored
+        }
+        start[n] = s0; size[n] = top - s0;
+    };
+    for (uint32_t i = 0; i < nS; ++i) {
+        if (st[i] != 0) continue;
+        queue.clear();
+        size_t qs = 0;
+        queue.push_back(i);
+        while (qs < queue.size()) {
+            const uint32_t n1 = queue[qs++];
+            if (st[n1] == 0) explore(n1);
+            if (size[n1] == 0 && !in.has_b[n1]) continue;          // :525
+            if (st[n1] == 1) {
+                const uint32_t *l = P + start[n1];
+                for (uint32_t x = 0, e = size[n1]; x < e; ++x) {
+                    const uint32_t n2 = l[x];
+                    if (st[n2] == 0) { queue.push_back(n2); explore(n2); }
+                }
+                st[n1] = 2;         // markTransitiveEdge is due (the marks themselves are computed on the device)
+            }
+            if (st[n1] == 2) {
+                const uint32_t *l = P + start[n1];
+                for (uint32_t x = 0, e = size[n1]; x < e; ++x) {
+                    const uint32_t n2 = l[x];
+                    if (st[n2] != 1) continue;
+                    const uint32_t *l2 = P + start[n2];
+                    for (uint32_t y = 0, e2 = size[n2]; y < e2; ++y) {
+                        const uint32_t n3 = l2[y];
+                        if (st[n3] == 0) { queue.push_back(n3); explore(n3); }
+                    }
+                    st[n2] = 2;
+                }
+            }
+        }
+    }
+    const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("SAGE2GPU_PHASE_C_TIMING"))
+        fprintf(stderr, "[phase C host, order from the device's lists] nS %u entries %u | %.2f ms\n", nS, in.off[nS], ms);
+    return ms;
+}
 
 }  // namespace sg

@@ -16,13 +16,19 @@ struct PhaseCInput {
     const uint64_t *edgesB;     // [2*nB] canonical phase-B records (w0,w1), any order: every record with an
                                 // endpoint in S or adjacent (by a phase-B record) to a read in S
     const uint32_t *edgesB_len; // [nB] len(from) | len(to) << 16
-    // optional, for run_host_phase_c_order: what the device knows anyway, so that the traversal needs no id map and no
-    // phase-B adjacency (phase-B records are inert in the traversal: they lead to reads that are not in S)
-    const uint32_t *cand_node = nullptr;   // [nC] index in s_ids of every candidate's read2
-    const uint8_t *has_b = nullptr;        // [nS] the read has phase-B records (its list is not empty, economyGraph.cpp:525)
-    const uint32_t *comp = nullptr;        // [nS] optional: label (an index < nS) of the read's connected component in the candidate graph;
-                                           // components are walked independently (the order inside a component is all that matters)
-    uint32_t comp_min_nodes = 4096;        // below this many S reads the components are not worth the threads
+};
+
+// The traversal's input when the device has built and sorted every list a read can ever hold (phase_c_device.cu,
+// phase_c_sorted_lists): for S read n, in compareLengthBased order (economyGraph.cpp:853-871),
+//   * its own candidates, as n would insert them (entry = partner << 1), and
+//   * the twins of the candidates of OTHER reads that name n, as those reads would push them into n's list
+//     (insertEdgeEconomy, :813-849; entry = owner << 1 | 1).
+// partner / owner are S indices.  Which of them exist when n is explored is decided by the traversal alone.
+struct PhaseCLists {
+    uint64_t nS = 0;
+    const uint32_t *off = nullptr;       // [nS+1]
+    const uint32_t *ent = nullptr;       // [off[nS]]
+    const uint8_t *has_b = nullptr;      // [nS] the read has phase-B records (its list is not empty, economyGraph.cpp:525)
 };
 
 struct PhaseCOutput {
@@ -34,5 +40,8 @@ struct PhaseCOutput {
 float run_host_phase_c(const PhaseCInput &in, PhaseCOutput &out);
 // the traversal alone: order[s] = position of S read s in the exploration sequence (lists / marks / filtering elsewhere)
 float run_host_phase_c_order(const PhaseCInput &in, std::vector<uint32_t> &order);
+
+// the same traversal from the device's pre-sorted lists: no sort, no insertion into other reads' lists, no id map
+float run_host_phase_c_order_lists(const PhaseCLists &in, std::vector<uint32_t> &order);
 
 }  // namespace sg

@@ -24,6 +24,14 @@ constexpr int PC_MAXD = 512;        // entries per list handled on the device
 constexpr int PC_HCAP = 1024;       // per-warp hash capacity (ids of one list)
 constexpr int PC_WARPS = 4;
 
+static unsigned pc_grid(u64 n, unsigned per_block)
+{
+    u64 g = (n + per_block - 1) / per_block;
+    if (g > (u64)kSMs * 16) g = (u64)kSMs * 16;
+    if (g == 0) g = 1;
+    return (unsigned)g;
+}
+
 __device__ __forceinline__ u32 pc_rev(u32 t) { return t == 0 ? 3u : (t == 3 ? 0u : t); }
 __device__ __forceinline__ bool pc_rule(u32 t1, u32 t2)      // economyGraph.cpp:661-664
 {
@@ -244,12 +252,81 @@ __global__ void __launch_bounds__(PC_WARPS * 32) pc_node_kernel(const u32 *__res
     if (lane == 0 && removed) atomicAdd(&counters[1], removed);
 }
 
-static unsigned pc_grid(u64 n, unsigned per_block)
+// ---- the lists of the host traversal ---------------------------------------------------------------------------------
+// For asymmetric candidate sets the traversal (economyGraph.cpp:513-564) stays on the host, but everything it would sort or
+// look up is prepared here: for every S read the entries its list can ever hold -- its own candidates and the twins other
+// reads would push into it (insertEdgeEconomy, :813-849) -- in compareLengthBased order (:853-871).  One record per
+// potential entry: B = the list's read (S index), A = 55-bit sort key, complemented so that ascending = compareLengthBased:
+// (overhang20 << 34 | other read's S index << 2 | type) << 1 | twin.  S indices ascend with the ids, so they order like ids.
+constexpr u64 PC_KEYMASK = (1ull << 55) - 1ull;
+
+__global__ void __launch_bounds__(256) pc_list_records_kernel(const u32 *__restrict__ s_ids, const u32 *__restrict__ sidx, u64 nS,
+                                                               const u32 *__restrict__ counts, const u32 *__restrict__ offs, const u64 *__restrict__ cand,
+                                                               const uint16_t *__restrict__ len, u64 *__restrict__ A, u64 *__restrict__ B)
 {
-    u64 g = (n + per_block - 1) / per_block;
-    if (g > (u64)kSMs * 16) g = (u64)kSMs * 16;
-    if (g == 0) g = 1;
-    return (unsigned)g;
+    const int lane = threadIdx.x & 31;
+    const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nS; s += nwarps) {
+        const u32 a = s_ids[s] + 1, la = len[a - 1];
+        const u32 base = offs[s], m = counts[s];
+        for (u32 x = lane; x < m; x += 32) {
+            const u64 q = (u64)base + x, cw = cand[q];
+            const u32 b = (u32)(cw >> 32), t = (u32)(cw >> 20) & 3u, d20 = (u32)(cw & 0xFFFFFu);
+            const u32 d = (d20 & 0x80000u) ? (d20 | 0xFFF00000u) : d20;
+            const u32 sb = sidx[b - 1], lb = len[b - 1];
+            const u32 d2 = (la - (lb - d)) & 0xFFFFFu;
+            const u64 k_own = ((u64)d20 << 34) | ((u64)sb << 2) | t;
+            const u64 k_twin = ((u64)d2 << 34) | ((u64)s << 2) | pc_rev(t);
+            A[2 * q] = PC_KEYMASK ^ (k_own << 1);             B[2 * q] = s;
+            A[2 * q + 1] = PC_KEYMASK ^ ((k_twin << 1) | 1);  B[2 * q + 1] = sb == (u32)s ? nS : sb;     // a read never inserts an overlap with itself (:605)
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) pc_list_entries_kernel(const u64 *__restrict__ A, u64 n, u32 *__restrict__ ent)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = A[i] ^ PC_KEYMASK;
+        ent[i] = ((u32)(k >> 3) << 1) | (u32)(k & 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(256) pc_list_offsets_kernel(const u64 *__restrict__ B, u64 n, u64 nS, u32 *__restrict__ off)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= nS; i += (u64)gridDim.x * blockDim.x) {
+        u64 lo = 0, hi = n;
+        while (lo < hi) { const u64 m = (lo + hi) >> 1; if (B[m] < i) lo = m + 1; else hi = m; }
+        off[i] = (u32)lo;
+    }
+}
+
+// off[nS+1], ent[2 nC] on the device; false: too many entries for 32-bit offsets (the caller takes the host walk)
+bool phase_c_sorted_lists(Context &c, const u32 *s_ids, const u32 *sidx, u64 nS, const u32 *counts, const u32 *offs, const u64 *cand, u64 nC,
+                          DevBuf<u32> &off, DevBuf<u32> &ent)
+{
+    cudaStream_t st = c.stream;
+    const u64 n = 2 * nC;
+    if (n >= 0xFFFFFFFFull || nS >= 0x7FFFFFFFull) return false;
+    off.alloc(nS + 1, st);
+    ent.alloc(n + 1, st);
+    DevBuf<u64> a0(n + 1, st), a1(n + 1, st), b0(n + 1, st), b1(n + 1, st);
+    const u64 *B = b0.p;
+    if (n) {
+        pc_list_records_kernel<<<pc_grid(nS, 8), 256, 0, st>>>(s_ids, sidx, nS, counts, offs, cand, c.len.p, a0.p, b0.p);
+        SG_LAUNCHED();
+        SortCols cols;
+        cols.a[0] = a0.p; cols.a[1] = a1.p; cols.b[0] = b0.p; cols.b[1] = b1.p; cols.v[0] = cols.v[1] = nullptr;
+        int cur = radix_sort_varying(cols, 0, n, false, st);        // the key, then (stable) the list's read
+        int nbits = 1;
+        while ((nS >> nbits) != 0) ++nbits;
+        cur = radix_sort_bits(cols, cur, n, true, 0, nbits, st);
+        pc_list_entries_kernel<<<pc_grid(n, 256), 256, 0, st>>>(cols.a[cur], n, ent.p);
+        SG_LAUNCHED();
+        B = cols.b[cur];
+    }
+    pc_list_offsets_kernel<<<pc_grid(nS + 1, 256), 256, 0, st>>>(B, n, nS, off.p);
+    SG_LAUNCHED();
+    return true;
 }
 
 // every candidate has its twin in the other read's list?  (then the traversal order cannot matter)

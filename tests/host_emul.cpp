@@ -13,6 +13,7 @@
 #include <vector>
 #include "../sage2_b200/csrc/core.cuh"
 #include "../sage2_b200/csrc/host_phase_c.h"
+#include "phase_c_lists_ref.h"
 
 using namespace sg;
 
@@ -683,25 +684,14 @@ void finish_after_b(Emu &e)
                 if (sidx.count(a)) hasb[sidx[a]] = 1;
                 if (sidx.count(b)) hasb[sidx[b]] = 1;
             }
-            PhaseCInput in2 = in;
-            in2.cand_node = cnode.data(); in2.has_b = hasb.data();
-            // connected components of the candidate graph (the device computes them by hooking + pointer jumping; here union-find):
-            // label = smallest S index of the component; walked independently on several threads
-            std::vector<u32> comp(in.nS);
-            for (u64 sx = 0; sx < in.nS; ++sx) comp[sx] = (u32)sx;
-            std::function<u32(u32)> find = [&](u32 x) { while (comp[x] != x) { comp[x] = comp[comp[x]]; x = comp[x]; } return x; };
-            for (u64 sx = 0; sx < in.nS; ++sx)
-                for (u32 q = in.cand_off[sx]; q < in.cand_off[sx + 1]; ++q) {
-                    const u32 a = find((u32)sx), b = find(cnode[q]);
-                    if (a < b) comp[b] = a; else if (b < a) comp[a] = b;
-                }
-            for (u64 sx = 0; sx < in.nS; ++sx) comp[sx] = find((u32)sx);
-            if (!getenv("SAGE2_EMUL_NO_COMPONENTS")) { in2.comp = comp.data(); in2.comp_min_nodes = 1; }
-            run_host_phase_c_order(in2, order);
-            if (getenv("SAGE2_EMUL_CHECK_PLAIN_ORDER") && !in2.comp) {       // the traversal with its own id map must give the same order
+            // the traversal as graph.cu runs it: from the lists phase_c_sorted_lists prepares (here: tests/phase_c_lists_ref.h)
+            pc_ref::Lists lists = pc_ref::build(in, cnode);
+            lists.has_b = hasb;
+            run_host_phase_c_order_lists(lists.view(in.nS), order);
+            if (!getenv("SAGE2_EMUL_NO_PLAIN_ORDER_CHECK")) {       // the walk itself (its own id map, sort and insertions) must explore in the same order
                 std::vector<u32> order2;
                 run_host_phase_c_order(in, order2);
-                if (order2 != order) { fprintf(stderr, "host_emul: lean traversal order differs\n"); abort(); }
+                if (order2 != order) { fprintf(stderr, "host_emul: traversal order from the sorted lists differs from the walk's\n"); abort(); }
             }
             std::vector<u64> got;
             u64 ins2 = 0, rem2 = 0;

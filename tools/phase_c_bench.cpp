@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <vector>
 #include "../sage2_b200/csrc/host_phase_c.h"
+#include "../tests/phase_c_lists_ref.h"
 
 int main(int argc, char **argv)
 {
@@ -39,6 +40,26 @@ int main(int argc, char **argv)
                     (unsigned long long)out.inserted, (unsigned long long)hdr[4], (unsigned long long)out.removed, (unsigned long long)hdr[5]);
             return 3;
         }
+    }
+    // the traversal alone, as libsage2gpu runs it for asymmetric candidate sets: from the lists the device prepares (built here
+    // on the CPU, tests/phase_c_lists_ref.h).  It must explore in the same order as the walk.
+    {
+        std::vector<uint32_t> cnode(nC);
+        auto node_of = [&](uint32_t id1) { return (uint32_t)(std::lower_bound(s_ids.begin(), s_ids.end(), id1 - 1) - s_ids.begin()); };
+        auto in_s = [&](uint32_t id1) { const uint32_t n = node_of(id1); return n < nS && s_ids[n] == id1 - 1; };
+        for (uint64_t q = 0; q < nC; ++q) cnode[q] = node_of((uint32_t)(cand[q] >> 32));
+        pc_ref::Lists lists = pc_ref::build(in, cnode);
+        for (uint64_t e = 0; e < nB; ++e) {
+            const uint32_t a = (uint32_t)(selB[2 * e] >> 32), b = (uint32_t)selB[2 * e];
+            if (in_s(a)) lists.has_b[node_of(a)] = 1;
+            if (in_s(b)) lists.has_b[node_of(b)] = 1;
+        }
+        std::vector<uint32_t> order1, order2;
+        float b1 = 1e30f, b2 = 1e30f;
+        for (int r = 0; r < reps; ++r) b1 = std::min(b1, sg::run_host_phase_c_order(in, order1));
+        for (int r = 0; r < reps; ++r) b2 = std::min(b2, sg::run_host_phase_c_order_lists(lists.view(nS), order2));
+        printf("traversal only: walk %.2f ms, from the sorted lists %.2f ms, orders %s\n", b1, b2, order1 == order2 ? "identical" : "DIFFER");
+        if (order1 != order2) return 4;
     }
     printf("nS %llu  candidates %llu  phase-B records %llu  output words %llu : best of %d = %.2f ms, identical output\n",
            (unsigned long long)nS, (unsigned long long)nC, (unsigned long long)nB, (unsigned long long)nOut, reps, best);
