@@ -228,6 +228,20 @@ def test_superstring_scan_takes_the_clean_reads():
 
 
 @pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("how", ["direct", "bucketed"])
+def test_both_table_builds_equal_oracle(name, how, monkeypatch):
+    """The table is built entry by entry in read order (small indexes) or from (hash, entry) records bucketed by slot range
+    (indexes far larger than L2, csrc/table.cu); SAGE2GPU_TABLE_BUILD forces either on every data set."""
+    monkeypatch.setenv("SAGE2GPU_TABLE_BUILD", how)
+    reads, k = _get(name)
+    b, off = synth.concat(reads)
+    o = oracle.OracleRun(b, off, k)
+    gpu = api.Sage2Gpu(0)
+    gpu.run_steps123(b, off, k)
+    _compare(o, gpu)
+
+
+@pytest.mark.parametrize("name", SMALL)
 def test_minhash_read_order_changes_nothing(name):
     """SAGE2GPU_READ_ORDER=minhash / set_option("read_order", 1): phase A in min-hash order must give the oracle's graph."""
     reads, k = _get(name)

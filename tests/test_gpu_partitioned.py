@@ -55,6 +55,16 @@ def test_partitioned_build_equals_oracle(name, world):
     assert total_calls == o.compare_calls
 
 
+@pytest.mark.parametrize("name,world", [("rep", 3), ("hicopy", 2), ("hicopy", 8), ("varlen_err", 5), ("single", 2), ("empty", 3)])
+def test_partitioned_build_with_bucketed_table_shards(name, world, monkeypatch):
+    """The same with every table shard built from bucketed (hash, entry) records (csrc/table.cu: owned records compacted,
+    one radix pass, inserts in slot order); `hicopy` is the uneven key split that overflows the first compaction."""
+    monkeypatch.setenv("SAGE2GPU_TABLE_BUILD", "bucketed")
+    test_partitioned_build_equals_oracle(name, world)
+    monkeypatch.setenv("SAGE2GPU_TABLE_ROOM", "8")      # the compaction runs out of room and is repeated with room for all
+    test_partitioned_build_equals_oracle(name, world)
+
+
 def test_partitioned_cfg2_full_size_equals_reference():
     """cfg2 at full size over 4 ranks: digests of the unmodified reference's `.reads` / `.graph3` on every rank."""
     _, _, _, gpus = _run("cfg2", 4)
