@@ -337,7 +337,8 @@ void stage_build_table(Context &c, int rank, int world, bool joint)
     // bucketed build when the index is far larger than L2 (see the header); SAGE2GPU_TABLE_BUILD=direct|bucketed overrides
     const char *env = getenv("SAGE2GPU_TABLE_BUILD");
     const int forced = !env ? 0 : (env[0] == 'd' ? 1 : 2);
-    const bool bucketed = forced ? forced == 2 : cap * sizeof(u64) >= ((size_t)256 << 20);
+    // (not in low-memory mode: the records take 2.5 x the workspace of the direct build, and config #5 fits 180 GB with nothing to spare)
+    const bool bucketed = forced ? forced == 2 : (!c.opt_low_memory && cap * sizeof(u64) >= ((size_t)256 << 20));
     DevBuf<u32> where, d_overflow(1, st), v0, v1;
     DevBuf<u64> a0, a1;
     const u32 *recV = nullptr;
