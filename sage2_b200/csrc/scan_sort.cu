@@ -145,6 +145,9 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const u64 *__restri
     if (threadIdx.x <= mask) tile_hist[(u64)threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
+// One stable pass: the tile's records are first brought into digit order in shared memory, one column at a time, and then
+// written out position by position -- the records of one digit leave as contiguous runs (coalesced stores) instead of 4096
+// scattered 8-byte stores per tile.
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__restrict__ key, u64 n, int shift, u32 mask,
                                                                  const u32 *__restrict__ tile_off, u32 num_tiles,
                                                                  const u64 *__restrict__ a_in, u64 *__restrict__ a_out,
@@ -152,13 +155,19 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
                                                                  const u32 *__restrict__ v_in, u32 *__restrict__ v_out)
 {
     __shared__ u32 whist[RS_WARPS][256];
-    __shared__ u32 dbase[256];
+    __shared__ u32 dbase[256];           // global position of the tile's first record of digit d
+    __shared__ u32 dstart[256];          // position inside the tile of its first record of digit d
+    __shared__ u32 wsum[RS_WARPS];
+    __shared__ uint8_t sdig[RS_TILE];    // digit of the record at tile position j (after the reordering)
+    __shared__ u64 stage[RS_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
 
-    const u64 wbase = (u64)blockIdx.x * RS_TILE + (u64)warp * RS_WARP_ITEMS;
-    u32 packed[RS_ITEMS];    // digit | rank-in-warp << 8
+    const u64 tbase = (u64)blockIdx.x * RS_TILE;
+    const u64 wbase = tbase + (u64)warp * RS_WARP_ITEMS;
+    const u32 in_tile = (u32)((n - tbase) < (u64)RS_TILE ? (n - tbase) : (u64)RS_TILE);
+    u32 packed[RS_ITEMS];    // digit | rank-in-warp << 8, then the record's position inside the tile
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const u64 idx = wbase + (u64)r * 32 + lane;
@@ -174,24 +183,59 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
         packed[r] = valid ? (d | (rank << 8)) : 0xFFFFFFFFu;
     }
     __syncthreads();
-    // exclusive scan over warps for every digit + global base of (digit, tile)
+    // per digit: exclusive scan over the warps, the tile's total, the global base of (digit, tile)
+    u32 total;
     {
         const int d = threadIdx.x;
         u32 run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { const u32 t = whist[w][d]; whist[w][d] = run; run += t; }
+        total = run;
         dbase[d] = ((u32)d <= mask) ? tile_off[(u64)d * num_tiles + blockIdx.x] : 0u;
+    }
+    // exclusive scan of the totals over the digits -> where each digit starts inside the tile
+    u32 inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    {
+        u32 before = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) if (w < warp) before += wsum[w];
+        dstart[threadIdx.x] = before + inc - total;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         if (packed[r] == 0xFFFFFFFFu) continue;
-        const u64 idx = wbase + (u64)r * 32 + lane;
         const u32 d = packed[r] & 0xFF;
-        const u64 pos = (u64)dbase[d] + whist[warp][d] + (packed[r] >> 8);
-        a_out[pos] = a_in[idx];
-        if (b_in) b_out[pos] = b_in[idx];
-        if (v_in) v_out[pos] = v_in[idx];
+        const u32 lpos = dstart[d] + whist[warp][d] + (packed[r] >> 8);
+        sdig[lpos] = (uint8_t)d;
+        packed[r] = lpos;
+    }
+    // column a
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+        if (packed[r] != 0xFFFFFFFFu) stage[packed[r]] = a_in[wbase + (u64)r * 32 + lane];
+    __syncthreads();
+    for (u32 j = threadIdx.x; j < in_tile; j += RS_THREADS) { const u32 d = sdig[j]; a_out[(u64)dbase[d] + (j - dstart[d])] = stage[j]; }
+    if (b_in) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r)
+            if (packed[r] != 0xFFFFFFFFu) stage[packed[r]] = b_in[wbase + (u64)r * 32 + lane];
+        __syncthreads();
+        for (u32 j = threadIdx.x; j < in_tile; j += RS_THREADS) { const u32 d = sdig[j]; b_out[(u64)dbase[d] + (j - dstart[d])] = stage[j]; }
+    }
+    if (v_in) {
+        __syncthreads();
+        u32 *stage32 = reinterpret_cast<u32 *>(stage);
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r)
+            if (packed[r] != 0xFFFFFFFFu) stage32[packed[r]] = v_in[wbase + (u64)r * 32 + lane];
+        __syncthreads();
+        for (u32 j = threadIdx.x; j < in_tile; j += RS_THREADS) { const u32 d = sdig[j]; v_out[(u64)dbase[d] + (j - dstart[d])] = stage32[j]; }
     }
 }
 
