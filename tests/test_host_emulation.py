@@ -3,6 +3,8 @@
 tests/host_emul.cpp drives sage2_b200/csrc/core.cuh (the host/device primitives the kernels are built
 from) and host_phase_c.cpp sequentially; its every stage must equal the oracle's.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -102,3 +104,19 @@ def test_record_order_is_read_order():
             c = oracle.lib().sgo_string_compare(packed[i].ctypes.data, len(strs[i]), packed[j].ctypes.data, len(strs[j]))
             mine = (recs[i] > recs[j]) - (recs[i] < recs[j])
             assert mine == c, (strs[i], strs[j])
+
+
+def test_phase_c_traversal_from_device_lists_equals_the_walk_on_random_graphs(tmp_path):
+    """tests/phase_c_order_fuzz.cpp: the traversal graph.cu runs for asymmetric candidate sets (run_host_phase_c_order_lists, over
+    the lists phase_c_sorted_lists prepares) explores in the same order as the walk itself (economyGraph.cpp:513-638) on random
+    candidate graphs: asymmetric sets, several candidates per pair, self candidates, negative overhangs, phase-B records."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    exe = str(tmp_path / "phase_c_order_fuzz")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(here, "phase_c_order_fuzz.cpp"),
+                           os.path.join(root, "sage2_b200", "csrc", "host_phase_c.cpp")])
+    for seed in (1, 2, 3):
+        out = subprocess.run([exe, "300", str(seed)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        assert "same order" in out.stdout
